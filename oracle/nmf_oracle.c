@@ -320,6 +320,11 @@ static unsigned max_row_index(const unsigned char* bits, int k)
     return 0;
 }
 
+/* Work counters (diagnostics for sizing the GPU kernel; not part of the algorithm). */
+static double g_stat_solves = 0.0, g_stat_p3 = 0.0, g_stat_rounds = 0.0, g_stat_calls = 0.0;
+void orc_stats_get(double* out4) { out4[0] = g_stat_solves; out4[1] = g_stat_p3; out4[2] = g_stat_rounds; out4[3] = g_stat_calls; }
+void orc_stats_reset(void) { g_stat_solves = g_stat_p3 = g_stat_rounds = g_stat_calls = 0.0; }
+
 /* BppSolveNormalEqNoGroup (nmf_solver_bpp.hpp:146-219) for the listed columns.
  * X columns are fully overwritten (zeros off the passive set). */
 static int bpp_solve(int k, const double* LHS, const double* RHS, double* X,
@@ -334,6 +339,7 @@ static int bpp_solve(int k, const double* LHS, const double* RHS, double* X,
         int p = 0;
         for (int r = 0; r < k; ++r) { x[r] = 0.0; if (pc[r]) ri[p++] = r; }
         if (p == 0) continue;
+        g_stat_solves += 1.0; g_stat_p3 += (double)p * p * p;
         for (int b = 0; b < p; ++b)
             for (int a = 0; a < p; ++a) AT(Lsub, p, a, b) = AT(LHS, k, ri[a], ri[b]);
         for (int a = 0; a < p; ++a) bsub[a] = AT(RHS, k, ri[a], c);
@@ -385,8 +391,10 @@ int orc_nnls_bpp(int k, int q, const double* LHS, const double* RHS, double* X, 
     }
 
     unsigned iter = 0;
+    g_stat_calls += 1.0;
     while (nno > 0)
     {
+        g_stat_rounds += 1.0;
         if (iter >= MAX_ITER) { rc = ORC_FAILURE; goto done; }
 
         /* UpdatePassiveSet over the non-optimal columns */

@@ -18,6 +18,7 @@
 #include <vector>
 #include <iostream>
 #include <limits>
+#include <chrono>
 
 #include "nmf.hpp"
 #include "nnls.hpp"
@@ -41,6 +42,7 @@ struct TraceSink
     double* Wsnap;        // optional [max_iter][m*k] snapshots (column-major, ld=m)
     double* Hsnap;        // optional [max_iter][k*n]
     int max_iter;
+    double* stamps;       // optional [max_iter] wall-clock seconds at which iteration i's metric was taken
 };
 
 template <typename T, template <typename> class MatrixType>
@@ -59,6 +61,8 @@ public:
         if (sink_ && static_cast<int>(iter) < sink_->max_iter)
         {
             if (sink_->metrics) sink_->metrics[iter] = v;
+            if (sink_->stamps)
+                sink_->stamps[iter] = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
             if (sink_->Wsnap)
             {
                 const size_t m = W.Height(), k = W.Width();
@@ -203,7 +207,7 @@ int ref_nmf_dense_trace(int alg, int prog, int m, int n, int k, double tol, int 
     if (!IsValid(o)) return Result::BAD_PARAM;
     SetMaxThreadCount(o.max_threads);
     DenseMatrix<R> Am(m, n, A, ldA), Wm(m, k, W, ldW), Hm(k, n, H, ldH);
-    TraceSink sink = {metrics, Wsnap, Hsnap, max_iter};
+    TraceSink sink = {metrics, Wsnap, Hsnap, max_iter, nullptr};
     if (metrics) for (int i = 0; i < max_iter; ++i) metrics[i] = std::numeric_limits<double>::quiet_NaN();
     NmfStats st;
     int rc = RunTraced<DenseMatrix>(o, Am, Wm, Hm, st, &sink);
@@ -223,10 +227,30 @@ int ref_nmf_sparse_trace(int alg, int prog, int m, int n, int k, double tol, int
     SetMaxThreadCount(o.max_threads);
     SparseMatrix<R> Am(m, n, nz, col_offsets, row_indices, data);
     DenseMatrix<R> Wm(m, k, W, ldW), Hm(k, n, H, ldH);
-    TraceSink sink = {metrics, Wsnap, Hsnap, max_iter};
+    TraceSink sink = {metrics, Wsnap, Hsnap, max_iter, nullptr};
     if (metrics) for (int i = 0; i < max_iter; ++i) metrics[i] = std::numeric_limits<double>::quiet_NaN();
     NmfStats st;
     int rc = RunTraced<SparseMatrix>(o, Am, Wm, Hm, st, &sink);
+    if (iterations) *iterations = st.iteration_count;
+    return rc;
+}
+
+// Per-iteration wall-clock stamps of a dense solve (bench.py --impl reference): the reference's NmfSolve
+// with its own estimator; stamps[i] is taken right after iteration i's progress update (min_iter = 1).
+int ref_nmf_dense_stamped(int alg, int prog, int m, int n, int k, int max_iter, int max_threads,
+                          double* A, int ldA, double* W, int ldW, double* H, int ldH,
+                          int* iterations, double* stamps, double* t_start)
+{
+    EnsureInit();
+    // tol so small that the stop rule never fires: exactly max_iter iterations are run
+    NmfOptions o = MakeOpts(alg, prog, m, n, k, 1.0e-15, 1, max_iter, 1, max_threads, 0, 0);
+    if (!IsValid(o)) return Result::BAD_PARAM;
+    SetMaxThreadCount(o.max_threads);
+    DenseMatrix<R> Am(m, n, A, ldA), Wm(m, k, W, ldW), Hm(k, n, H, ldH);
+    TraceSink sink = {nullptr, nullptr, nullptr, max_iter, stamps};
+    NmfStats st;
+    if (t_start) *t_start = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    int rc = RunTraced<DenseMatrix>(o, Am, Wm, Hm, st, &sink);
     if (iterations) *iterations = st.iteration_count;
     return rc;
 }

@@ -1,0 +1,87 @@
+// smallk_b200 — the context behind the C ABI: device buffers, the loaded matrix, solver state.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <string>
+#include <vector>
+#include <climits>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "../../include/smallk_b200.h"
+
+namespace smk {
+
+template <typename T>
+struct DevBuf
+{
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    // grow-only allocation; contents are not preserved across a growth
+    void reserve(size_t count)
+    {
+        if (count <= n) return;
+        release();
+        SMK_CUDA(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+        n = count;
+    }
+    void zero(cudaStream_t s) { if (p) SMK_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+};
+
+struct SparseDev
+{
+    int m = 0, n = 0;
+    unsigned int nnz = 0;
+    // CSC as given (duplicates and unsorted rows preserved)
+    DevBuf<unsigned int> colptr, rowidx;
+    DevBuf<double> val;
+    // CSR = CSC of A', built by a stable counting sort (sparse_matrix_ops.hpp:37-126)
+    DevBuf<unsigned int> rowptr, colidx;
+    DevBuf<double> valr;
+};
+
+} // namespace smk
+
+struct smk_ctx
+{
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+
+    // ---- the matrix
+    bool has_dense = false, has_sparse = false;
+    const double* dA = nullptr;     // dense, column-major
+    long long ldA = 0;
+    int m = 0, n = 0;
+    smk::DevBuf<double> A_store;
+    smk::SparseDev S;
+
+    // ---- scratch shared by kernels
+    smk::DevBuf<double> ws;         // split-R partial tiles
+    smk::DevBuf<int> status;        // ST_COUNT ints
+    smk::DevBuf<unsigned int> counter;
+    smk::DevBuf<double> partial;    // 1024 block partials
+    smk::DevBuf<double> acc;        // 8 scalars
+    smk::DevBuf<double> io;         // staging for host<->device transposes
+
+    // ---- solver state (both factors are kept "k x big", column-major: H is k x n, Wt = W' is k x m)
+    bool active = false;
+    smk_nmf_options opts;
+    int steps_done = 0;
+    double pg0 = 0.0;
+    smk::DevBuf<double> H, Wt, gradH, gradWt, WtW, HHt, WtA, HAt, T1, T2, Wprev, norms;
+    float last_ms = 0.f;
+    long long last_launches = 0;
+
+    // ---- multi-GPU
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+};

@@ -1,0 +1,65 @@
+// smallk_b200 — host-side launchers of the sm_100a kernels (internal header).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <string>
+#include <algorithm>
+
+namespace smk {
+
+// device status words shared by the kernels of one solver
+enum { ST_ANY_NONOPT = 0, ST_FAIL_ITER = 1, ST_NORM_EPS = 2, ST_COUNT = 4 };
+
+// ---- gemm_f64.cu ----------------------------------------------------------
+// C (M x N) = A (M x R, col-major) * Bop - D, Bop = B (R x N col-major) if !nt, else B' with B (N x R col-major).
+void gemm_f64(cudaStream_t stream, bool nt, int M, int N, int R,
+              const double* A, long long lda, const double* B, long long ldb,
+              double* C, long long ldc, const double* D, long long ldd,
+              double* workspace, size_t workspace_bytes, int num_sms);
+int gemm_pick_splits(int M, int N, int R, int num_sms, size_t workspace_bytes);
+
+// ---- nnls_bpp.cu ----------------------------------------------------------
+void nnls_bpp(cudaStream_t stream, int k, int q, const double* LHS, long long ldl,
+              const double* RHS, long long ldr, double* X, long long ldx, double* Y, long long ldy,
+              int* status, unsigned int* counter, int outer_iter, int num_sms);
+
+// ---- elementwise.cu -------------------------------------------------------
+// out (cols x rows, ld = ldo) = in' where in is rows x cols (ld = ldi)
+void transpose_f64(cudaStream_t stream, int rows, int cols, const double* in, long long ldi, double* out, long long ldo);
+// X .*= Num ./ (Den + 1e-13)      (nmf_solver_mu.hpp:27-71)
+void mu_update(cudaStream_t stream, long long count, double* X, const double* Num, const double* Den);
+// acc[slot] = sum over entries of G^2 where (G < 0 || X > 0)   (projected_gradient.hpp:125-171)
+// partial: device scratch of at least 1024 doubles. Deterministic two-level reduction.
+void pg_sumsq(cudaStream_t stream, long long count, const double* G, const double* X, double* partial, double* acc_slot, int num_sms);
+// acc[slot] = sum (A - B)^2 (B may be null -> sum A^2)
+void diff_sumsq(cudaStream_t stream, long long count, const double* A, const double* B, double* partial, double* acc_slot, int num_sms);
+
+// ---- factors.cu -----------------------------------------------------------
+// One HALS sweep over the rows of X (k x q): for r = 0..k-1, for every column j
+//   x(r,j) <- max(0, x(r,j) + (R(r,j) - sum_p G(r,p) x(p,j)) / G(r,r)),  NaN -> 0
+// (nmf_solver_hals.hpp:26-61 for H with G = W'W, R = W'A; :64-117 for W' with G = HH', R = HA').
+// normalize_rows = true adds the in-sweep unit-2-norm scaling of row r (= column r of W) and the
+// all-zero -> epsilon rule of :103-115. partial: >= 4096 doubles of scratch.
+void hals_sweep(cudaStream_t stream, int k, int q, double* X, const double* G, const double* R,
+                bool normalize_rows, double* norms, double* partial, int num_sms);
+// Rank-2 solve + optimal active set for X (2 x q): nmf_solver_rank2.hpp:25-318.
+// w_side selects the SystemSolveW / OptimalActiveSetW formulas (same algebra, transposed roles).
+void rank2_update(cudaStream_t stream, int q, double* X, const double* G, const double* B, bool w_side,
+                  int* status, int outer_iter);
+// NormalizeAndScale (normalize.hpp:118-161): rows of Wt scaled to unit norm, rows of H by the norm.
+// If HHt/HAt are given (rank-2, nmf_solver_rank2.hpp:422-441) they are rescaled as well.
+void normalize_and_scale(cudaStream_t stream, int k, int m, int n, double* Wt, double* H, double* norms,
+                         int* status, double* partial, int num_sms, double* HHt = nullptr, double* HAt = nullptr);
+
+// ---- spmm.cu --------------------------------------------------------------
+struct SparseDev;
+// out (k x ncols, ld = ldo) : out(:,j) = sum over the entries (idx, val) of compressed column j of val * B(:, idx)
+// with B k x * column-major. Serves W'A (CSC of A, B = Wt) and H A' (CSR of A, B = H); entries are
+// added in storage order, which is the order the reference adds them (sparse_gemm_ba_impl.hpp:26-140).
+void spmm_gather(cudaStream_t stream, int ncols, const unsigned int* ptr, const unsigned int* idx, const double* val,
+                 int k, const double* B, long long ldb, double alpha, double beta, double* out, long long ldo, int num_sms);
+// Builds rowptr/colidx/valr (CSR = stable transpose) from the CSC arrays already on the device.
+void build_csr(cudaStream_t stream, SparseDev& S);
+
+} // namespace smk

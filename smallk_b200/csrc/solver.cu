@@ -1,0 +1,228 @@
+// smallk_b200 — the NMF solvers as sequences of kernels on one stream.
+//
+// Mirrors the solver functors of the reference (Init + operator()):
+//   Solver_Generic_BPP      common/include/nmf_solver_bpp.hpp:301-383
+//   Solver_Generic_MU       common/include/nmf_solver_mu.hpp:74-169
+//   Solver_Generic_HALS_Da  common/include/nmf_solver_hals.hpp:120-207
+//   Solver_Generic_Rank2    common/include/nmf_solver_rank2.hpp:321-461
+// and the progress estimators of progress_estimator_generic.hpp:30-108.
+//
+// Layout decision: both factors live on the device as "k x big" column-major
+// matrices — H (k x n) as in the reference and Wt = W' (k x m). With that, the
+// W side of every solver is the H side with (A, W, H) -> (A', H', W'): the same
+// GEMM, NNLS and update kernels serve both, the reference's explicit transposed
+// copy of A (nmf_solver_bpp.hpp:319; +8mn bytes) and its per-iteration
+// W <-> Wt transposes (:363-364) disappear, and W is transposed only when it
+// crosses the host boundary.
+#include "context.h"
+#include "solver.h"
+
+namespace smk {
+
+namespace {
+
+void allreduce_sum(smk_ctx* c, double* buf, size_t count)
+{
+    if (c->nranks <= 1) return;
+    ncclResult_t r = ncclAllReduce(buf, buf, count, ncclDouble, ncclSum, c->comm, c->stream);
+    if (r != ncclSuccess) throw std::string("ncclAllReduce: ") + ncclGetErrorString(r);
+}
+
+// ---- the products of one outer iteration ---------------------------------
+// WtA (k x n) = Wt * A
+void prod_WtA(smk_ctx* c)
+{
+    const int k = c->opts.k;
+    if (c->has_dense)
+        gemm_f64(c->stream, false, k, c->n, c->m, c->Wt.p, k, c->dA, c->ldA, c->WtA.p, k, nullptr, 0,
+                 c->ws.p, c->ws.n * sizeof(double), c->num_sms);
+    else
+        spmm_gather(c->stream, c->n, c->S.colptr.p, c->S.rowidx.p, c->S.val.p, k, c->Wt.p, k, 1.0, 0.0, c->WtA.p, k, c->num_sms);
+}
+
+// HAt (k x m) = H * A'   (summed over the column shards when running multi-GPU)
+void prod_HAt(smk_ctx* c)
+{
+    const int k = c->opts.k;
+    if (c->has_dense)
+        gemm_f64(c->stream, true, k, c->m, c->n, c->H.p, k, c->dA, c->ldA, c->HAt.p, k, nullptr, 0,
+                 c->ws.p, c->ws.n * sizeof(double), c->num_sms);
+    else
+        spmm_gather(c->stream, c->m, c->S.rowptr.p, c->S.colidx.p, c->S.valr.p, k, c->H.p, k, 1.0, 0.0, c->HAt.p, k, c->num_sms);
+    allreduce_sum(c, c->HAt.p, static_cast<size_t>(k) * c->m);
+}
+
+// G (k x k) = X * X' for X k x q
+void gram(smk_ctx* c, const double* X, int q, double* G)
+{
+    const int k = c->opts.k;
+    gemm_f64(c->stream, true, k, k, q, X, k, X, k, G, k, nullptr, 0, c->ws.p, c->ws.n * sizeof(double), c->num_sms);
+}
+
+// out (k x q) = G (k x k) * X (k x q) - R   (R may be null)
+void gram_times(smk_ctx* c, const double* G, const double* X, int q, const double* R, double* out)
+{
+    const int k = c->opts.k;
+    gemm_f64(c->stream, false, k, q, k, G, k, X, k, out, k, R, k, nullptr, 0, c->num_sms);
+}
+
+void compute_HHt(smk_ctx* c)
+{
+    gram(c, c->H.p, c->n, c->HHt.p);
+    allreduce_sum(c, c->HHt.p, static_cast<size_t>(c->opts.k) * c->opts.k);
+}
+void compute_WtW(smk_ctx* c) { gram(c, c->Wt.p, c->m, c->WtW.p); }
+
+void run_nnls(smk_ctx* c, const double* LHS, const double* RHS, double* X, double* Y, int q)
+{
+    const int k = c->opts.k;
+    nnls_bpp(c->stream, k, q, LHS, k, RHS, k, X, k, Y, k, c->status.p, c->counter.p, c->steps_done, c->num_sms);
+}
+
+} // namespace
+
+void solver_alloc(smk_ctx* c)
+{
+    const size_t k = c->opts.k, m = c->m, n = c->n;
+    c->H.reserve(k * n); c->Wt.reserve(k * m);
+    c->gradH.reserve(k * n); c->gradWt.reserve(k * m);
+    c->WtW.reserve(k * k); c->HHt.reserve(k * k);
+    c->WtA.reserve(k * n); c->HAt.reserve(k * m);
+    c->norms.reserve(k);
+    if (c->opts.algorithm == SMK_MU || c->opts.algorithm == SMK_HALS) { c->T1.reserve(k * n); c->T2.reserve(k * m); }
+    if (c->opts.prog_est_algorithm == SMK_DELTA_FNORM) c->Wprev.reserve(k * m);
+    // split-R workspace: enough for the gram matrices at 4*SMs splits and for the big products at a few splits
+    size_t want = std::max<size_t>(static_cast<size_t>(4 * c->num_sms) * k * k,
+                                   std::min<size_t>(static_cast<size_t>(32) * k * std::max(m, n), (size_t(768) << 20) / sizeof(double)));
+    c->ws.reserve(want);
+    int init[ST_COUNT] = {0, INT_MAX, 0, 0};
+    SMK_CUDA(cudaMemcpyAsync(c->status.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+}
+
+void solver_init(smk_ctx* c)
+{
+    switch (c->opts.algorithm)
+    {
+    case SMK_BPP:      // nmf_solver_bpp.hpp:310-335
+    case SMK_MU:       // nmf_solver_mu.hpp:93-110
+    case SMK_RANK2:    // nmf_solver_rank2.hpp:333-347
+        compute_WtW(c);
+        prod_WtA(c);
+        break;
+    case SMK_HALS:     // nmf_solver_hals.hpp:141-159
+        compute_HHt(c);
+        prod_HAt(c);
+        break;
+    }
+    if (c->opts.prog_est_algorithm == SMK_DELTA_FNORM)   // ProgEstGenericDeltaW::Init
+        SMK_CUDA(cudaMemcpyAsync(c->Wprev.p, c->Wt.p, sizeof(double) * c->opts.k * c->m, cudaMemcpyDeviceToDevice, c->stream));
+}
+
+void solver_step(smk_ctx* c)
+{
+    const int k = c->opts.k, m = c->m, n = c->n;
+    switch (c->opts.algorithm)
+    {
+    case SMK_BPP:      // nmf_solver_bpp.hpp:342-377
+        run_nnls(c, c->WtW.p, c->WtA.p, c->H.p, c->gradH.p, n);
+        compute_HHt(c);
+        prod_HAt(c);
+        run_nnls(c, c->HHt.p, c->HAt.p, c->Wt.p, c->gradWt.p, m);
+        compute_WtW(c);
+        prod_WtA(c);
+        gram_times(c, c->WtW.p, c->H.p, n, c->WtA.p, c->gradH.p);
+        break;
+    case SMK_MU:       // nmf_solver_mu.hpp:118-163
+        gram_times(c, c->WtW.p, c->H.p, n, nullptr, c->T1.p);
+        mu_update(c->stream, static_cast<long long>(k) * n, c->H.p, c->WtA.p, c->T1.p);
+        compute_HHt(c);
+        prod_HAt(c);
+        gram_times(c, c->HHt.p, c->Wt.p, m, nullptr, c->T2.p);
+        mu_update(c->stream, static_cast<long long>(k) * m, c->Wt.p, c->HAt.p, c->T2.p);
+        prod_WtA(c);
+        compute_WtW(c);
+        gram_times(c, c->HHt.p, c->Wt.p, m, c->HAt.p, c->gradWt.p);
+        gram_times(c, c->WtW.p, c->H.p, n, c->WtA.p, c->gradH.p);
+        break;
+    case SMK_HALS:     // nmf_solver_hals.hpp:166-199
+        hals_sweep(c->stream, k, m, c->Wt.p, c->HHt.p, c->HAt.p, /*normalize=*/true, c->norms.p, c->partial.p, c->num_sms);
+        compute_WtW(c);
+        prod_WtA(c);
+        hals_sweep(c->stream, k, n, c->H.p, c->WtW.p, c->WtA.p, /*normalize=*/false, c->norms.p, c->partial.p, c->num_sms);
+        gram_times(c, c->WtW.p, c->H.p, n, c->WtA.p, c->gradH.p);
+        compute_HHt(c);
+        prod_HAt(c);
+        gram_times(c, c->HHt.p, c->Wt.p, m, c->HAt.p, c->gradWt.p);
+        break;
+    case SMK_RANK2:    // nmf_solver_rank2.hpp:353-455
+        rank2_update(c->stream, n, c->H.p, c->WtW.p, c->WtA.p, false, c->status.p, c->steps_done);
+        compute_HHt(c);
+        prod_HAt(c);
+        rank2_update(c->stream, m, c->Wt.p, c->HHt.p, c->HAt.p, true, c->status.p, c->steps_done);
+        // NormalizeAndScale(W, H, s); HHt, AHt rescaled analytically (:420-441)
+        normalize_and_scale(c->stream, 2, m, n, c->Wt.p, c->H.p, c->norms.p, c->status.p, c->partial.p, c->num_sms,
+                            c->HHt.p, c->HAt.p);
+        gram_times(c, c->HHt.p, c->Wt.p, m, c->HAt.p, c->gradWt.p);
+        compute_WtW(c);
+        prod_WtA(c);
+        gram_times(c, c->WtW.p, c->H.p, n, c->WtA.p, c->gradH.p);
+        break;
+    }
+    c->steps_done += 1;
+}
+
+// ProgressEst::Update for the state after `steps_done` iterations. Synchronises the stream.
+int solver_progress(smk_ctx* c, double* metric)
+{
+    const long long k = c->opts.k;
+    double h[2] = {0.0, 0.0};
+    if (c->opts.prog_est_algorithm == SMK_PG_RATIO)
+    {
+        // projected_gradient.hpp:125-171; the H part is a sum over this rank's columns
+        pg_sumsq(c->stream, k * c->m, c->gradWt.p, c->Wt.p, c->partial.p, c->acc.p + 0, c->num_sms);
+        pg_sumsq(c->stream, k * c->n, c->gradH.p, c->H.p, c->partial.p, c->acc.p + 1, c->num_sms);
+        allreduce_sum(c, c->acc.p + 1, 1);
+        SMK_CUDA(cudaMemcpyAsync(h, c->acc.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        SMK_CUDA(cudaStreamSynchronize(c->stream));
+        const double pg = sqrt(h[0] + h[1]);
+        if (pg != pg) { c->err = "ProjectedGradientNorm: NaN"; return SMK_FAILURE; }
+        if (c->steps_done <= 1) { c->pg0 = pg; *metric = 1.0; }
+        else *metric = pg / c->pg0;
+    }
+    else
+    {
+        // progress_estimator_generic.hpp:58-69
+        diff_sumsq(c->stream, k * c->m, c->Wprev.p, c->Wt.p, c->partial.p, c->acc.p + 0, c->num_sms);
+        diff_sumsq(c->stream, k * c->m, c->Wt.p, nullptr, c->partial.p, c->acc.p + 1, c->num_sms);
+        SMK_CUDA(cudaMemcpyAsync(c->Wprev.p, c->Wt.p, sizeof(double) * k * c->m, cudaMemcpyDeviceToDevice, c->stream));
+        SMK_CUDA(cudaMemcpyAsync(h, c->acc.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        SMK_CUDA(cudaStreamSynchronize(c->stream));
+        *metric = sqrt(h[0]) / sqrt(h[1]);
+    }
+    return SMK_OK;
+}
+
+// NormalizeAndScale(W, H): normalize.hpp:118-138. Returns SMK_FAILURE if a column norm < eps.
+int solver_normalize(smk_ctx* c)
+{
+    const int k = c->opts.k;
+    normalize_and_scale(c->stream, k, c->m, c->n, c->Wt.p, c->H.p, c->norms.p, c->status.p, c->partial.p, c->num_sms);
+    int st[ST_COUNT];
+    SMK_CUDA(cudaMemcpyAsync(st, c->status.p, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+    SMK_CUDA(cudaStreamSynchronize(c->stream));
+    if (st[ST_NORM_EPS]) { c->err = "Normalize: column norm < machine epsilon"; return SMK_FAILURE; }
+    return SMK_OK;
+}
+
+void solver_product(smk_ctx* c, int which) { if (which == 0) prod_WtA(c); else prod_HAt(c); }
+
+// First outer iteration (0-based) in which a kernel reported solver failure, or INT_MAX.
+int solver_fail_iter(smk_ctx* c)
+{
+    int st[ST_COUNT];
+    SMK_CUDA(cudaMemcpyAsync(st, c->status.p, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+    SMK_CUDA(cudaStreamSynchronize(c->stream));
+    return st[ST_FAIL_ITER];
+}
+
+} // namespace smk

@@ -1,0 +1,193 @@
+// smallk_b200 — sparse (CSC) x dense products for the NMF iteration.
+//
+// The reference's four sparse Gemm variants (common/include/sparse_gemm.hpp:26-74,
+// sparse_gemm_ab_impl.hpp, sparse_gemm_ba_impl.hpp) reduce, for the solvers, to two
+// products with a "k x big" dense operand:
+//     W'A  (k x n):  out(:,j) = sum_{(r,a) in column j of A}  a * Wt(:,r)       [B'*A]
+//     H A' (k x m):  out(:,i) = sum_{(c,a) in row i of A}     a * H(:,c)        [A*B' transposed]
+// The first walks the CSC arrays; the second walks a CSR copy of A built once on the
+// device (= the reference's stable Transpose, sparse_matrix_ops.hpp:37-126), so BOTH
+// are gather-reduce kernels: no atomics, each output column written once, and the
+// entries of a compressed column are added in storage order exactly as the reference
+// adds them. Dense columns Wt(:,r) / H(:,c) are contiguous k-vectors, so each gathered
+// operand is one coalesced k*8-byte read.
+#include <cub/cub.cuh>
+#include "context.h"
+
+namespace smk {
+
+namespace {
+
+// L lanes cooperate on one output column, each lane owning KPL rows (row = lane + L*e).
+template <int L, int KPL>
+__global__ void spmm_gather_kernel(int ncols, const unsigned int* __restrict__ ptr, const unsigned int* __restrict__ idx,
+                                   const double* __restrict__ val, int k, const double* __restrict__ B, long long ldb,
+                                   double alpha, double beta, double* __restrict__ out, long long ldo)
+{
+    const int groups_per_block = blockDim.x / L;
+    const int lane = threadIdx.x % L;
+    for (long long j = blockIdx.x * static_cast<long long>(groups_per_block) + threadIdx.x / L; j < ncols;
+         j += static_cast<long long>(gridDim.x) * groups_per_block)
+    {
+        double acc[KPL];
+#pragma unroll
+        for (int e = 0; e < KPL; ++e)
+        {
+            const int r = lane + L * e;
+            double c0 = 0.0;
+            if (beta != 0.0 && r < k) c0 = out[j * ldo + r] * beta;
+            acc[e] = c0;
+        }
+        const unsigned int beg = ptr[j], end = ptr[j + 1];
+        unsigned int o = beg;
+        // 4 entries per trip: issue the index/value loads and the gathers together
+        for (; o + 4 <= end; o += 4)
+        {
+            unsigned int i0 = idx[o], i1 = idx[o + 1], i2 = idx[o + 2], i3 = idx[o + 3];
+            double a0 = alpha * val[o], a1 = alpha * val[o + 1], a2 = alpha * val[o + 2], a3 = alpha * val[o + 3];
+            double b0[KPL], b1[KPL], b2[KPL], b3[KPL];
+#pragma unroll
+            for (int e = 0; e < KPL; ++e)
+            {
+                const int r = lane + L * e;
+                const bool ok = r < k;
+                b0[e] = ok ? B[i0 * ldb + r] : 0.0;
+                b1[e] = ok ? B[i1 * ldb + r] : 0.0;
+                b2[e] = ok ? B[i2 * ldb + r] : 0.0;
+                b3[e] = ok ? B[i3 * ldb + r] : 0.0;
+            }
+#pragma unroll
+            for (int e = 0; e < KPL; ++e)
+            {
+                acc[e] += a0 * b0[e];
+                acc[e] += a1 * b1[e];
+                acc[e] += a2 * b2[e];
+                acc[e] += a3 * b3[e];
+            }
+        }
+        for (; o < end; ++o)
+        {
+            const unsigned int i0 = idx[o];
+            const double a0 = alpha * val[o];
+#pragma unroll
+            for (int e = 0; e < KPL; ++e)
+            {
+                const int r = lane + L * e;
+                if (r < k) acc[e] += a0 * B[i0 * ldb + r];
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < KPL; ++e)
+        {
+            const int r = lane + L * e;
+            if (r < k) out[j * ldo + r] = acc[e];
+        }
+    }
+}
+
+template <int L, int KPL>
+void launch_gather(cudaStream_t stream, int ncols, const unsigned int* ptr, const unsigned int* idx, const double* val,
+                   int k, const double* B, long long ldb, double alpha, double beta, double* out, long long ldo, int num_sms)
+{
+    const int threads = 256;
+    const int gpb = threads / L;
+    int blocks = std::max(1, std::min(ceil_div(ncols, gpb), 16 * num_sms));
+    spmm_gather_kernel<L, KPL><<<blocks, threads, 0, stream>>>(ncols, ptr, idx, val, k, B, ldb, alpha, beta, out, ldo);
+    SMK_LAUNCH_CHECK();
+}
+
+// column index of every stored entry (expands colptr)
+__global__ void expand_cols_kernel(int n, const unsigned int* __restrict__ colptr, unsigned int* __restrict__ colof)
+{
+    for (int j = blockIdx.x; j < n; j += gridDim.x)
+        for (unsigned int o = colptr[j] + threadIdx.x; o < colptr[j + 1]; o += blockDim.x) colof[o] = j;
+}
+
+__global__ void iota_kernel(unsigned int n, unsigned int* __restrict__ v)
+{
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[i] = i;
+}
+
+__global__ void gather_perm_kernel(unsigned int n, const unsigned int* __restrict__ perm, const unsigned int* __restrict__ colof,
+                                   const double* __restrict__ val, unsigned int* __restrict__ colidx, double* __restrict__ valr)
+{
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const unsigned int s = perm[i];
+        colidx[i] = colof[s];
+        valr[i] = val[s];
+    }
+}
+
+// rowptr[r] = first position in the sorted row keys with key >= r
+__global__ void rowptr_kernel(int m, unsigned int nnz, const unsigned int* __restrict__ sorted_rows, unsigned int* __restrict__ rowptr)
+{
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r <= m; r += gridDim.x * blockDim.x)
+    {
+        unsigned int lo = 0, hi = nnz;
+        while (lo < hi)
+        {
+            const unsigned int mid = lo + ((hi - lo) >> 1);
+            if (sorted_rows[mid] < static_cast<unsigned int>(r)) lo = mid + 1; else hi = mid;
+        }
+        rowptr[r] = lo;
+    }
+}
+
+} // namespace
+
+void spmm_gather(cudaStream_t stream, int ncols, const unsigned int* ptr, const unsigned int* idx, const double* val,
+                 int k, const double* B, long long ldb, double alpha, double beta, double* out, long long ldo, int num_sms)
+{
+    if (ncols <= 0) return;
+#define SMK_G(L, KPL) launch_gather<L, KPL>(stream, ncols, ptr, idx, val, k, B, ldb, alpha, beta, out, ldo, num_sms)
+    if (k <= 2) SMK_G(2, 1);
+    else if (k <= 4) SMK_G(4, 1);
+    else if (k <= 8) SMK_G(8, 1);
+    else if (k <= 16) SMK_G(16, 1);
+    else if (k <= 32) SMK_G(32, 1);
+    else if (k <= 64) SMK_G(32, 2);
+    else if (k <= 128) SMK_G(32, 4);
+    else if (k <= 256) SMK_G(32, 8);
+    else throw std::string("spmm: k > 256 is not supported");
+#undef SMK_G
+}
+
+// Stable transpose on the device: a stable radix sort of the entry ids by row index keeps, inside each
+// row, the column-ascending / storage order of the CSC arrays.
+void build_csr(cudaStream_t stream, SparseDev& S)
+{
+    const unsigned int nnz = S.nnz;
+    S.rowptr.reserve(static_cast<size_t>(S.m) + 1);
+    S.colidx.reserve(nnz);
+    S.valr.reserve(nnz);
+    if (nnz == 0)
+    {
+        SMK_CUDA(cudaMemsetAsync(S.rowptr.p, 0, (static_cast<size_t>(S.m) + 1) * sizeof(unsigned int), stream));
+        return;
+    }
+    DevBuf<unsigned int> colof, ids, ids_sorted, rows_sorted;
+    colof.reserve(nnz); ids.reserve(nnz); ids_sorted.reserve(nnz); rows_sorted.reserve(nnz);
+    expand_cols_kernel<<<std::min(S.n, 65535), 128, 0, stream>>>(S.n, S.colptr.p, colof.p);
+    SMK_LAUNCH_CHECK();
+    iota_kernel<<<std::min<unsigned int>((nnz + 255) / 256, 65535u), 256, 0, stream>>>(nnz, ids.p);
+    SMK_LAUNCH_CHECK();
+    int end_bit = 1;
+    while ((1ull << end_bit) < static_cast<unsigned long long>(S.m) && end_bit < 32) ++end_bit;
+    size_t tmp_bytes = 0;
+    SMK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, S.rowidx.p, rows_sorted.p, ids.p, ids_sorted.p,
+                                             static_cast<int>(nnz), 0, end_bit, stream));
+    DevBuf<unsigned char> tmp;
+    tmp.reserve(tmp_bytes);
+    SMK_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, S.rowidx.p, rows_sorted.p, ids.p, ids_sorted.p,
+                                             static_cast<int>(nnz), 0, end_bit, stream));
+    launch_counter() += 4;   // cub's own passes (approximate; not on the iteration path)
+    gather_perm_kernel<<<std::min<unsigned int>((nnz + 255) / 256, 65535u), 256, 0, stream>>>(nnz, ids_sorted.p, colof.p, S.val.p,
+                                                                                              S.colidx.p, S.valr.p);
+    SMK_LAUNCH_CHECK();
+    rowptr_kernel<<<std::min((S.m + 256) / 256, 65535), 256, 0, stream>>>(S.m, nnz, rows_sorted.p, S.rowptr.p);
+    SMK_LAUNCH_CHECK();
+    SMK_CUDA(cudaStreamSynchronize(stream));   // temporaries die here
+}
+
+} // namespace smk

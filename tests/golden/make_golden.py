@@ -1,0 +1,101 @@
+"""Generates tests/golden/*.npz by running the REFERENCE's own code (oracle/_ref/libsmallk_ref.so, i.e. the
+unmodified sources under /root/reference compiled against oracle/shim/El.hpp) on seeded synthetic inputs.
+
+Run in the dev container (where /root/reference exists):  python tests/golden/make_golden.py
+The fixtures travel with the repo; nothing reads /root/reference at test time. Inputs are regenerated from the
+seeds stored in each file by `golden_inputs()` below (shared with the tests), outputs are the reference's.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+# name -> (kind, alg, m, n, k, density, max_iter, tol, min_iter, normalize, seed)
+CASES = {
+    # BASELINE configs[0] / SURVEY C1: nmf CLI defaults otherwise (min_iter 5, PG_RATIO), tol 1e-4
+    "c1_bpp_256_k16":     ("dense", "BPP", 256, 256, 16, None, 400, 1e-4, 5, True, 1),
+    "bpp_300x400_k40":    ("dense", "BPP", 300, 400, 40, None, 25, 1e-12, 1, False, 2),
+    "bpp_400x300_k64":    ("dense", "BPP", 400, 300, 64, None, 15, 1e-12, 1, False, 3),
+    "hals_256_k16":       ("dense", "HALS", 256, 256, 16, None, 60, 1e-12, 1, False, 4),
+    "mu_150x120_k8":      ("dense", "MU", 150, 120, 8, None, 60, 1e-12, 1, True, 5),
+    "rank2_300x200":      ("dense", "RANK2", 300, 200, 2, None, 40, 1e-12, 1, False, 6),
+    "sp_bpp_300x200_k10": ("sparse", "BPP", 300, 200, 10, 0.1, 25, 1e-12, 1, False, 7),
+    "sp_mu_300x200_k10":  ("sparse", "MU", 300, 200, 10, 0.1, 40, 1e-12, 1, False, 8),
+    "sp_rank2_400x300":   ("sparse", "RANK2", 400, 300, 2, 0.05, 40, 1e-12, 1, True, 9),
+    "sp_hals_300x200_k8": ("sparse", "HALS", 300, 200, 8, 0.3, 3, 1e-12, 1, False, 10),
+}
+
+
+def round6(a):
+    """What a matrix looks like after matrixgen wrote it with %.6e and the nmf CLI read it back
+    (common/include/delimited_file.hpp:62-63)."""
+    return np.array([float("%.6e" % v) for v in a.ravel()]).reshape(a.shape)
+
+
+def golden_inputs(name):
+    kind, alg, m, n, k, density, max_iter, tol, min_iter, normalize, seed = CASES[name]
+    rng = np.random.default_rng(1000 + seed)
+    if kind == "dense":
+        A = round6(rng.random((m, n)))
+        sp = None
+    else:
+        import scipy.sparse as sps
+        S = sps.random(m, n, density=density, random_state=np.random.RandomState(seed), format="csc",
+                       data_rvs=np.random.RandomState(seed + 50).random_sample)
+        S.sort_indices()
+        A = None
+        sp = (S.indptr.astype(np.uint32), S.indices.astype(np.uint32), S.data.astype(np.float64))
+    W0 = rng.random((m, k))
+    H0 = rng.random((k, n))
+    return dict(kind=kind, alg=alg, m=m, n=n, k=k, max_iter=max_iter, tol=tol, min_iter=min_iter,
+                normalize=normalize, A=A, sp=sp, W0=W0, H0=H0)
+
+
+def nnls_inputs(seed, k, q):
+    rng = np.random.default_rng(seed)
+    W = rng.random((4 * k, k))
+    A = rng.random((4 * k, q))
+    LHS = W.T @ W
+    RHS = W.T @ A - 0.35 * rng.random((k, q)) * np.abs(W.T @ A).mean()
+    X0 = rng.random((k, q)) * (rng.random((k, q)) > 0.3)
+    return LHS, RHS, X0
+
+
+NNLS_CASES = {"nnls_k16_q64": (21, 16, 64), "nnls_k40_q90": (22, 40, 90), "nnls_k64_q120": (23, 64, 120)}
+
+
+def main():
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    from oracle import Ref
+    ref = Ref()
+    print("reference build BLAS:", ref.blas_backend())
+    for name in CASES:
+        g = golden_inputs(name)
+        kw = dict(alg=g["alg"], tol=g["tol"], min_iter=g["min_iter"], max_iter=g["max_iter"], normalize=g["normalize"],
+                  trace=True, max_threads=2)
+        if g["kind"] == "dense":
+            r = ref.nmf_dense(g["A"], g["W0"], g["H0"], **kw)
+        else:
+            r = ref.nmf_sparse((g["m"], g["n"]), *g["sp"], g["W0"], g["H0"], **kw)
+        assert r["rc"] == 0, (name, r["rc"])
+        it = r["iterations"]
+        # traces hold the un-normalised iterates at the snapshots the estimator saw; keep a few of them
+        keep = sorted(set([0, 1, 2, min(it, g["max_iter"]) - 1]) & set(range(g["max_iter"])))
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), iterations=it, metrics=r["metrics"],
+                            W=r["W"], H=r["H"], snap_iters=np.array(keep),
+                            W_snaps=r["W_trace"][keep], H_snaps=r["H_trace"][keep])
+        print(f"{name}: iterations={it} last metric={r['metrics'][min(it, g['max_iter']) - 1]:.6g}")
+    for name, (seed, k, q) in NNLS_CASES.items():
+        LHS, RHS, X0 = nnls_inputs(seed, k, q)
+        rc, X, Y = ref.nnls_bpp(LHS, RHS, X0)
+        assert rc == 0
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), X=X, Y=Y)
+        print(f"{name}: passive density {np.mean(X > 0):.3f}")
+
+
+if __name__ == "__main__":
+    main()
