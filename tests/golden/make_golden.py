@@ -84,7 +84,8 @@ def main():
         assert r["rc"] == 0, (name, r["rc"])
         it = r["iterations"]
         # traces hold the un-normalised iterates at the snapshots the estimator saw; keep a few of them
-        keep = sorted(set([0, 1, 2, min(it, g["max_iter"]) - 1]) & set(range(g["max_iter"])))
+        seen = np.flatnonzero(~np.isnan(r["metrics"]))       # iterations at which the estimator was called
+        keep = sorted(set(seen[:3].tolist() + [int(seen[-1])]))
         np.savez_compressed(os.path.join(HERE, name + ".npz"), iterations=it, metrics=r["metrics"],
                             W=r["W"], H=r["H"], snap_iters=np.array(keep),
                             W_snaps=r["W_trace"][keep], H_snaps=r["H_trace"][keep])
