@@ -48,7 +48,7 @@ bool options_valid(smk_ctx* c, const smk_nmf_options& o)
 void ensure_scratch(smk_ctx* c)
 {
     c->status.reserve(ST_COUNT);
-    c->counter.reserve(1);
+    c->counter.reserve(2);
     c->partial.reserve(4096 + 512 * 256);
     c->acc.reserve(8);
 }
@@ -431,7 +431,8 @@ int smk_nnls_bpp(smk_ctx* c, int k, int q, const double* LHS, const double* RHS,
         upload_tight(c, X, k, k, q, dX.p);
         int init[ST_COUNT] = {0, INT_MAX, 0, 0};
         SMK_CUDA(cudaMemcpyAsync(c->status.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
-        nnls_bpp(c->stream, k, q, dL.p, k, dR.p, k, dX.p, k, dY.p, k, c->status.p, c->counter.p, 0, c->num_sms);
+        c->deferred.reserve(nnls_deferred_bytes(q));
+        nnls_bpp(c->stream, k, q, dL.p, k, dR.p, k, dX.p, k, dY.p, k, c->status.p, c->counter.p, c->deferred.p, 0, c->num_sms);
         download_tight(c, dX.p, k, q, X, k);
         download_tight(c, dY.p, k, q, Y, k);
         int st[ST_COUNT];

@@ -68,6 +68,7 @@ struct smk_ctx
     smk::DevBuf<double> ws;         // split-R partial tiles
     smk::DevBuf<int> status;        // ST_COUNT ints
     smk::DevBuf<unsigned int> counter;
+    smk::DevBuf<unsigned char> deferred; // BPP columns handed from the fast to the slow NNLS kernel
     smk::DevBuf<double> partial;    // 1024 block partials
     smk::DevBuf<double> acc;        // 8 scalars
     smk::DevBuf<double> io;         // staging for host<->device transposes

@@ -31,7 +31,7 @@ namespace smk {
 
 namespace {
 
-constexpr int BM = 64, BN = 128, BK = 32;
+constexpr int BM = 64, BN = 128, BK = 16;
 constexpr int STAGES = 3;
 constexpr int THREADS = 256;
 constexpr int LDA_S = BM + 4;    // As[BK][LDA_S]
@@ -79,7 +79,7 @@ __device__ __forceinline__ void load_tile(double* s, const double* g, long long 
 }
 
 template <bool NT, int VEC>
-__global__ void __launch_bounds__(THREADS, 1) gemm_skinny_kernel(GemmParams p)
+__global__ void __launch_bounds__(THREADS, 2) gemm_skinny_kernel(GemmParams p)
 {
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x;
@@ -241,7 +241,7 @@ void gemm_f64(cudaStream_t stream, bool nt, int M, int N, int R,
     p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.D = D; p.ldd = ldd;
     p.partial = workspace;
     p.M = M; p.N = N; p.R = R;
-    int splits = (workspace && R > 0) ? gemm_pick_splits(M, N, R, num_sms, workspace_bytes) : 1;
+    int splits = (workspace && R > 0) ? gemm_pick_splits(M, N, R, 2 * num_sms, workspace_bytes) : 1;   // 2 CTAs per SM
     int rchunk = ceil_div(ceil_div(R > 0 ? R : 1, splits), BK) * BK;
     splits = R > 0 ? ceil_div(R, rchunk) : 1;
     p.splits = splits; p.rchunk = rchunk;

@@ -9,7 +9,7 @@
 namespace smk {
 
 // device status words shared by the kernels of one solver
-enum { ST_ANY_NONOPT = 0, ST_FAIL_ITER = 1, ST_NORM_EPS = 2, ST_COUNT = 4 };
+enum { ST_ANY_NONOPT = 0, ST_FAIL_ITER = 1, ST_NORM_EPS = 2, ST_DEFER_COUNT = 3, ST_COUNT = 4 };
 
 // ---- gemm_f64.cu ----------------------------------------------------------
 // C (M x N) = A (M x R, col-major) * Bop - D, Bop = B (R x N col-major) if !nt, else B' with B (N x R col-major).
@@ -22,7 +22,8 @@ int gemm_pick_splits(int M, int N, int R, int num_sms, size_t workspace_bytes);
 // ---- nnls_bpp.cu ----------------------------------------------------------
 void nnls_bpp(cudaStream_t stream, int k, int q, const double* LHS, long long ldl,
               const double* RHS, long long ldr, double* X, long long ldx, double* Y, long long ldy,
-              int* status, unsigned int* counter, int outer_iter, int num_sms);
+              int* status, unsigned int* counter, void* deferred, int outer_iter, int num_sms);
+size_t nnls_deferred_bytes(int q);
 
 // ---- elementwise.cu -------------------------------------------------------
 // out (cols x rows, ld = ldo) = in' where in is rows x cols (ld = ldi)

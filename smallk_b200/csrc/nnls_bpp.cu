@@ -1,55 +1,403 @@
-// smallk_b200 — batched NNLS by block principal pivoting, one warp per column.
+// smallk_b200 — batched NNLS by block principal pivoting (k <= 64), one warp per column.
 //
-// Replaces NnlsBlockpivot + BppSolveNormalEqNoGroup + UpdatePassiveSet + the
-// BitMatrix passes of the reference
+// Replaces NnlsBlockpivot + BppSolveNormalEqNoGroup + UpdatePassiveSet + the BitMatrix passes
+// of the reference
 //   common/include/nnls.hpp:144-244, common/include/nmf_solver_bpp.hpp:146-219,
 //   common/src/nnls.cpp:18-74, common/src/bit_matrix.cpp:432-472,
 //   Elemental cholesky::UVar3Unb + SolveAfter (UVar3.hpp:17-44, SolveAfter.hpp:17-42).
 //
-// The reference runs all right-hand-side columns in lock step: every pivot round
-// gathers the non-optimal columns, solves them, scatters them back and then makes
-// serial BitMatrix passes over all q columns. Columns never exchange data, so here
-// each warp owns one column for its WHOLE pivoting history: the passive set is a
-// 64-bit mask held in a register, the k' x k' normal-equation sub-matrix is
-// gathered from the shared-memory copy of the k x k Gram matrix into a packed
-// upper triangle in shared memory, factored (right-looking upper Cholesky, same
-// recurrence as Elemental's UVar3Unb), solved, and the dual y = LHS*x - rhs is
-// formed — all without leaving the kernel. Columns are handed out through an
-// atomic counter so that long pivoting histories do not unbalance the SMs.
+// The reference runs all right-hand-side columns in lock step: every pivot round gathers the
+// non-optimal columns, solves them (one heap-allocated k' x k' Cholesky per column), scatters them
+// back, then makes serial BitMatrix passes over all q columns. Columns never exchange data, so here
+// a warp owns one column for its WHOLE pivoting history; the passive set is a 64-bit mask in a
+// register and nothing leaves the kernel between rounds. Columns are handed out through an atomic
+// counter so long pivoting histories do not unbalance the SMs.
 //
-// The two places where the reference couples columns are preserved:
-//   * ZeroizeSmallValues(X|Y, 1e-12) is applied to EVERY column iff at least one
-//     column was non-optimal after the initial solve (nnls.hpp:192,226-227):
-//     status[ST_ANY_NONOPT] is raised here and zeroize_if_flag_kernel finishes
-//     the columns that never entered the pivot loop.
-//   * MAX_ITER = 5k pivot rounds, and a non-positive Cholesky pivot, fail the whole
-//     solve (nnls.hpp:195-196, normal_eq.hpp:35-50): status[ST_FAIL_ITER] records
-//     the outer iteration in which that happened.
-// BitMatrix::MaxRowIndex's off-by-one-word defect for k > 32
-// is reproduced in max_row_index_ref() because the backup pivot rule depends on it.
-#include "common.cuh"
-#include "kernels.h"
+// Fast path (nnls_bpp_fast_kernel). With G = LHS (k x k SPD), P the passive set and A its
+// complement, the passive-set normal equations G_PP x_P = b_P can be solved on EITHER index set:
+//     direct      : x_P = G_PP^-1 b_P                                        (size |P|)
+//     complement  : u = G^-1 b,  z = (G^-1)_AA^-1 u_A,  x_P = u_P - (G^-1)_PA z   (size |A|)
+// (block-inverse identity; y_A = -z is the dual). For k <= 64 the smaller of the two never exceeds
+// 32, so every solve is a <= 32 x 32 upper Cholesky held ENTIRELY IN REGISTERS, one matrix column
+// per lane (right-looking, the recurrence of Elemental's UVar3Unb), row j broadcast by shuffles,
+// followed by the two triangular solves (forward in column layout, backward after one
+// shared-memory transpose). G^-1 is formed once per CTA in shared memory (in-place Gauss-Jordan).
+// The residual y_P = (G x - b)_P, which is computed anyway for the dual, is the accuracy check of
+// the complement path: a column whose residual is not at rounding level (ill-conditioned G), or
+// any solve the fast path cannot do (G not invertible), is DEFERRED with its pivoting state to the
+// slow path, which redoes it with the direct method.
+//
+// Slow path (nnls_bpp_slow_kernel): the direct method for any |P| <= 64 with the packed upper
+// triangle in shared memory. Launched after the fast kernel on the deferred list (normally empty).
+//
+// Reference behaviours preserved:
+//   * ZeroizeSmallValues(X|Y, 1e-12) hits EVERY column iff at least one column was non-optimal after
+//     the initial solve (nnls.hpp:192,226-227): status[ST_ANY_NONOPT] + zeroize_if_flag_kernel.
+//   * MAX_ITER = 5k pivot rounds, or a non-positive Cholesky pivot of a passive-set system, fail the
+//     whole solve (nnls.hpp:195-196, normal_eq.hpp:35-50): status[ST_FAIL_ITER] = outer iteration.
+//   * BitMatrix::MaxRowIndex's off-by-one-word defect for k > 32, because the
+//     backup pivot rule depends on it.
+#include "nnls_common.cuh"
 
 namespace smk {
 
 namespace {
 
-constexpr double kZeroThresh = 1.0e-12;    // nnls.hpp:215,226-227
-constexpr int kPbar = 3;                   // nnls.hpp:153
-
 __device__ __forceinline__ int tri(int c) { return (c * (c + 1)) >> 1; }
 
-// BitMatrix::MaxRowIndex as the reference computes it (defect included).
-__device__ __forceinline__ int max_row_index_ref(unsigned long long mask, int k)
+// ===========================================================================
+// register-resident SPD solve, n <= NMAX <= 32, lane c holds column c of the upper triangle
+// ===========================================================================
+// a[i] = M(i, c) for i <= c (c = lane). On return lane c holds x_c.
+// sT: per-warp 32 x 33 doubles (U, row-major with ld 33); sRow: per-warp 2 x 32 doubles (row broadcast).
+// Pivots use one rsqrt per index: r = 1/sqrt(a_jj), U(j,c) = a_jc * r, and the triangular solves multiply by
+// r instead of dividing by U(j,j) (1-2 ulp from the divide form; parity is held to 1e-9, not bitwise).
+template <int NMAX>
+__device__ __forceinline__ bool spd_solve_reg(int n, double (&a)[NMAX], double rhs, double* __restrict__ sT,
+                                              double* __restrict__ sRow, int lane, double& xout)
 {
-    if (mask == 0ull) return 0;
-    const int h = 63 - __clzll(static_cast<long long>(mask));
-    const int full = k >> 5, extra = k & 31;
-    const int w = h >> 5;
-    if (extra > 0 && w == full) return h;
-    return (w > 0) ? h - 32 : h;
+    constexpr unsigned FULL = 0xffffffffu;
+    double rinv = 1.0;      // lane j: 1 / U(j,j)
+    // ---- factor: A = U'U, right-looking (the recurrence of UVar3Unb)
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j)
+    {
+        if (j < n)
+        {
+            const double ajj = __shfl_sync(FULL, a[j], j);
+            if (!(ajj > 0.0)) return false;
+            const double r = rsqrt(ajj);
+            double ujc;
+            if (lane == j) { ujc = ajj * r; rinv = r; }
+            else ujc = a[j] * r;
+            a[j] = ujc;
+            double* row = sRow + (j & 1) * 32;
+            row[lane] = ujc;
+            __syncwarp();
+#pragma unroll
+            for (int h = (j + 1) / 2; h < NMAX / 2; ++h)
+            {
+                const double2 u2 = reinterpret_cast<const double2*>(row)[h];
+                if (2 * h > j && 2 * h <= lane) a[2 * h] = fma(-u2.x, ujc, a[2 * h]);
+                if (2 * h + 1 > j && 2 * h + 1 <= lane) a[2 * h + 1] = fma(-u2.y, ujc, a[2 * h + 1]);
+            }
+        }
+    }
+    // ---- U'y = b, column layout: lane c owns s_c
+    double s = rhs;
+#pragma unroll
+    for (int i = 0; i < NMAX; ++i)
+    {
+        if (i < n)
+        {
+            double yi = s * rinv;                   // meaningful on lane i only
+            yi = __shfl_sync(FULL, yi, i);
+            if (lane == i) s = yi;
+            else if (lane > i) s = fma(-a[i], yi, s);
+        }
+    }
+    // ---- U to shared memory (row-major), then U x = y in row layout: lane r reads U(r, q) as it goes
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < NMAX; ++i)
+        if (i <= lane && lane < n) sT[i * 33 + lane] = a[i];
+    __syncwarp();
+    double x = s;
+    const double* urow = sT + lane * 33;
+#pragma unroll
+    for (int qq = NMAX - 1; qq >= 0; --qq)
+    {
+        if (qq < n)
+        {
+            double xq = x * rinv;                   // meaningful on lane qq only
+            xq = __shfl_sync(FULL, xq, qq);
+            if (lane == qq) x = xq;
+            else if (lane < qq) x = fma(-urow[qq], xq, x);
+        }
+    }
+    __syncwarp();
+    xout = x;
+    return true;
 }
 
+// Gathers M(list,list) from the k x k matrix sM (column-major, ld k) and solves.
+template <int NMAX>
+__device__ __forceinline__ bool gather_solve(const double* __restrict__ sM, int k, const int* __restrict__ list, int n,
+                                             double rhs, double* __restrict__ sT, double* __restrict__ sRow, int lane,
+                                             double& xout)
+{
+    double a[NMAX];
+    const int lc = (lane < n) ? list[lane] * k : 0;
+#pragma unroll
+    for (int i = 0; i < NMAX; ++i) a[i] = (i <= lane && lane < n) ? sM[lc + list[i]] : ((i == lane) ? 1.0 : 0.0);
+    return spd_solve_reg<NMAX>(n, a, rhs, sT, sRow, lane, xout);
+}
+
+__device__ __forceinline__ bool gather_solve_any(const double* __restrict__ sM, int k, const int* __restrict__ list, int n,
+                                                 double rhs, double* __restrict__ sT, double* __restrict__ sRow,
+                                                 int lane, double& xout)
+{
+    if (n <= 8) return gather_solve<8>(sM, k, list, n, rhs, sT, sRow, lane, xout);
+    if (n <= 16) return gather_solve<16>(sM, k, list, n, rhs, sT, sRow, lane, xout);
+    if (n <= 24) return gather_solve<24>(sM, k, list, n, rhs, sT, sRow, lane, xout);
+    return gather_solve<32>(sM, k, list, n, rhs, sT, sRow, lane, xout);
+}
+
+// In-place Gauss-Jordan inversion of the SPD k x k matrix S (shared memory, ld k) by the whole CTA.
+// Returns false (uniformly) if a pivot is not positive; S is then garbage.
+__device__ bool cta_invert_spd(double* __restrict__ S, int k, double* __restrict__ scol, double* __restrict__ srow)
+{
+    for (int j = 0; j < k; ++j)
+    {
+        const double piv = S[j + j * k];
+        if (!(piv > 0.0)) return false;            // uniform: everyone reads the same word after the barrier
+        const double ip = 1.0 / piv;
+        for (int i = threadIdx.x; i < k; i += blockDim.x)
+        {
+            scol[i] = S[i + j * k];
+            srow[i] = S[j + i * k] * ip;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < k * k; e += blockDim.x)
+        {
+            const int i = e % k, c = e / k;
+            double v;
+            if (i == j) v = (c == j) ? ip : srow[c];
+            else if (c == j) v = -scol[i] * ip;
+            else v = S[e] - scol[i] * srow[c];
+            S[e] = v;
+        }
+        __syncthreads();
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// fast kernel
+// ---------------------------------------------------------------------------
+constexpr int kFastWarps = 14;
+
+struct FastSmem
+{
+    // layout in doubles, computed identically on host and device
+    int k;
+    __host__ __device__ size_t g() const { return 0; }
+    __host__ __device__ size_t ginv() const { return static_cast<size_t>(k) * k; }
+    __host__ __device__ size_t rowcol() const { return ginv() + (k > 32 ? static_cast<size_t>(k) * k : 0); }
+    __host__ __device__ size_t warp0() const { return rowcol() + 2 * static_cast<size_t>(k); }
+    __host__ __device__ size_t per_warp() const { return (32 * 33 + 64 + 3 * static_cast<size_t>(k) + 32 + (k + 1) / 2 + 2) & ~static_cast<size_t>(1); }   // even: keeps double2 alignment
+    __host__ __device__ size_t total_bytes(int warps) const { return (warp0() + warps * per_warp()) * sizeof(double) + 16; }
+};
+
+__global__ void __launch_bounds__(kFastWarps * 32, 1)
+nnls_bpp_fast_kernel(int k, int q, const double* __restrict__ LHS, long long ldl,
+                     const double* __restrict__ RHS, long long ldr,
+                     double* __restrict__ X, long long ldx, double* __restrict__ Y, long long ldy,
+                     int* __restrict__ status, unsigned int* __restrict__ counter, int outer_iter,
+                     BppColState* __restrict__ deferred)
+{
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int s_ginv_ok;
+    const FastSmem L{k};
+    double* sG = smem + L.g();
+    double* sGinv = smem + L.ginv();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* wb = smem + L.warp0() + warp * L.per_warp();
+    double* sT = wb;                 // 32 x 33
+    double* sRow = sT + 32 * 33;     // 2 x 32 row broadcast buffers (16-byte aligned: 1056 doubles precede)
+    double* sb = sRow + 64;          // k   rhs column
+    double* su = sb + k;             // k   u = Ginv * b
+    double* sx = su + k;             // k   x column
+    double* sz = sx + k;             // 32  solution of the small system
+    int* list = reinterpret_cast<int*>(sz + 32);   // k ints
+
+    for (int i = threadIdx.x; i < k * k; i += blockDim.x)
+    {
+        const double v = LHS[static_cast<long long>(i / k) * ldl + (i % k)];
+        sG[i] = v;
+        if (k > 32) sGinv[i] = v;
+    }
+    __syncthreads();
+    if (k > 32)
+    {
+        const bool ok = cta_invert_spd(sGinv, k, smem + L.rowcol(), smem + L.rowcol() + k);
+        if (threadIdx.x == 0) s_ginv_ok = ok ? 1 : 0;
+    }
+    else if (threadIdx.x == 0) s_ginv_ok = 0;
+    __syncthreads();
+    const bool ginv_ok = s_ginv_ok != 0;
+
+    const int r0 = lane, r1 = lane + 32;
+    const bool v0 = r0 < k, v1 = r1 < k;
+    const int max_rounds = 5 * k;
+    const unsigned long long kmask = (k >= 64) ? ~0ull : ((1ull << k) - 1ull);
+
+    for (;;)
+    {
+        unsigned int c = 0;
+        if (lane == 0) c = atomicAdd(counter, 1u);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= static_cast<unsigned int>(q)) break;
+
+        const double* rhs = RHS + static_cast<long long>(c) * ldr;
+        double* xcol = X + static_cast<long long>(c) * ldx;
+        double* ycol = Y + static_cast<long long>(c) * ldy;
+
+        const double b0 = v0 ? rhs[r0] : 0.0, b1 = v1 ? rhs[r1] : 0.0;
+        if (v0) sb[r0] = b0;
+        if (v1) sb[r1] = b1;
+        double bmax = fmax(fabs(b0), fabs(b1));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bmax = fmax(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+        unsigned long long pm;
+        {   // warm start: passive = (X > 0)   (nnls.hpp:157)
+            const bool p0 = v0 && (xcol[r0] > 0.0), p1 = v1 && (xcol[r1] > 0.0);
+            pm = static_cast<unsigned long long>(__ballot_sync(0xffffffffu, p0)) |
+                 (static_cast<unsigned long long>(__ballot_sync(0xffffffffu, p1)) << 32);
+        }
+        int P = kPbar, Ninf = k + 1, round = 0;
+        double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0;
+        bool failed = false, defer = false, have_u = false;
+        __syncwarp();
+
+        for (;;)
+        {
+            const int p = __popcll(pm);
+            const bool in0 = (pm >> r0) & 1ull, in1 = v1 && ((pm >> r1) & 1ull);
+            if (p == 0) { x0 = 0.0; x1 = 0.0; }
+            else if (p <= 32)
+            {
+                // ---- direct: G_PP x_P = b_P
+                if (in0) list[__popcll(pm & ((1ull << r0) - 1ull))] = r0;
+                if (in1) list[__popcll(pm & ((1ull << r1) - 1ull))] = r1;
+                __syncwarp();
+                const double rv = (lane < p) ? sb[list[lane]] : 0.0;
+                double z;
+                if (!gather_solve_any(sG, k, list, p, rv, sT, sRow, lane, z)) { failed = true; break; }
+                if (round > 0 && fabs(z) < kZeroThresh) z = 0.0;     // ZeroizeSmallValues(Xsub), nnls.hpp:215
+                if (v0) sx[r0] = 0.0;
+                if (v1) sx[r1] = 0.0;
+                __syncwarp();
+                if (lane < p) sx[list[lane]] = z;
+                __syncwarp();
+                x0 = v0 ? sx[r0] : 0.0;
+                x1 = v1 ? sx[r1] : 0.0;
+            }
+            else
+            {
+                // ---- complement: solve on A = ~P, |A| = k - p < 32
+                if (!ginv_ok) { defer = true; break; }
+                if (!have_u)
+                {
+                    double u0 = 0.0, u1 = 0.0;
+                    for (int cc = 0; cc < k; ++cc)
+                    {
+                        const double bv = sb[cc];
+                        const double* col = sGinv + cc * k;
+                        if (v0) u0 = fma(col[r0], bv, u0);
+                        if (v1) u1 = fma(col[r1], bv, u1);
+                    }
+                    if (v0) su[r0] = u0;
+                    if (v1) su[r1] = u1;
+                    have_u = true;
+                    __syncwarp();
+                }
+                const unsigned long long am = ~pm & kmask;
+                const int na = k - p;
+                if (v0 && !in0) list[__popcll(am & ((1ull << r0) - 1ull))] = r0;
+                if (v1 && !in1) list[__popcll(am & ((1ull << r1) - 1ull))] = r1;
+                __syncwarp();
+                double z = 0.0;
+                if (na > 0)
+                {
+                    const double rv = (lane < na) ? su[list[lane]] : 0.0;
+                    if (!gather_solve_any(sGinv, k, list, na, rv, sT, sRow, lane, z)) { defer = true; break; }
+                    if (lane < na) sz[lane] = z;
+                    __syncwarp();
+                }
+                double a0 = v0 ? su[r0] : 0.0, a1 = v1 ? su[r1] : 0.0;
+                for (int t = 0; t < na; ++t)
+                {
+                    const double zt = sz[t];
+                    const double* col = sGinv + list[t] * k;
+                    if (in0) a0 = fma(-col[r0], zt, a0);
+                    if (in1) a1 = fma(-col[r1], zt, a1);
+                }
+                x0 = in0 ? a0 : 0.0;
+                x1 = in1 ? a1 : 0.0;
+                if (round > 0)
+                {
+                    if (fabs(x0) < kZeroThresh) x0 = 0.0;
+                    if (fabs(x1) < kZeroThresh) x1 = 0.0;
+                }
+                if (v0) sx[r0] = x0;
+                if (v1) sx[r1] = x1;
+                __syncwarp();
+            }
+            // ---- y = LHS * x - rhs over the passive columns (nnls.hpp:168-169, 219-220)
+            double s0 = 0.0, s1 = 0.0;
+            {
+                unsigned long long mm = pm;
+                while (mm)
+                {
+                    const int cc = __ffsll(static_cast<long long>(mm)) - 1;
+                    mm &= mm - 1ull;
+                    const double xv = sx[cc];
+                    const double* col = sG + cc * k;
+                    if (v0) s0 = fma(col[r0], xv, s0);
+                    if (v1) s1 = fma(col[r1], xv, s1);
+                }
+            }
+            y0 = s0 - b0; y1 = s1 - b1;
+            if (p > 32)
+            {
+                // residual of the passive-set equations: must be at rounding level, else redo directly
+                double res = fmax(in0 ? fabs(y0) : 0.0, in1 ? fabs(y1) : 0.0);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) res = fmax(res, __shfl_xor_sync(0xffffffffu, res, o));
+                if (!(res <= 1.0e-11 * bmax)) { defer = true; break; }
+            }
+            if (round > 0)
+            {
+                if (fabs(y0) < kZeroThresh) y0 = 0.0;
+                if (fabs(y1) < kZeroThresh) y1 = 0.0;
+            }
+            const unsigned long long nonopt =
+                static_cast<unsigned long long>(__ballot_sync(0xffffffffu, v0 && !in0 && y0 < 0.0)) |
+                (static_cast<unsigned long long>(__ballot_sync(0xffffffffu, v1 && !in1 && y1 < 0.0)) << 32);
+            const unsigned long long infeas =
+                static_cast<unsigned long long>(__ballot_sync(0xffffffffu, v0 && in0 && x0 < 0.0)) |
+                (static_cast<unsigned long long>(__ballot_sync(0xffffffffu, v1 && in1 && x1 < 0.0)) << 32);
+            const int not_good = __popcll(nonopt) + __popcll(infeas);
+            __syncwarp();
+            if (not_good == 0) break;
+            if (round == 0 && lane == 0) atomicOr(&status[ST_ANY_NONOPT], 1);
+            if (round >= max_rounds) { failed = true; break; }     // nnls.hpp:195-196
+            update_passive_set(pm, P, Ninf, not_good, nonopt, infeas, k);
+            ++round;
+        }
+        if (defer)
+        {
+            if (lane == 0)
+            {
+                const int slot = atomicAdd(&status[ST_DEFER_COUNT], 1);
+                BppColState st;
+                st.pm = pm; st.P = P; st.Ninf = Ninf; st.round = round; st.col = static_cast<int>(c);
+                deferred[slot] = st;
+            }
+            __syncwarp();
+            continue;
+        }
+        if (failed && lane == 0) atomicMin(&status[ST_FAIL_ITER], outer_iter);
+        if (v0) { xcol[r0] = x0; ycol[r0] = y0; }
+        if (v1) { xcol[r1] = x1; ycol[r1] = y1; }
+        __syncwarp();
+    }
+}
+
+// ===========================================================================
+// slow path: direct method, packed upper triangle in shared memory, any |P| <= 64
+// ===========================================================================
 struct WarpScratch
 {
     double* U;     // packed upper triangle, k(k+1)/2
@@ -59,15 +407,12 @@ struct WarpScratch
     int* ri;       // k   passive row list
 };
 
-// Solve LHS[P,P] x_P = b_P for the passive set `pm` (p = popcount rows listed in ri).
-// Returns false on a non-positive pivot. On return vb[0..p) holds x_P.
 __device__ __forceinline__ bool warp_spd_solve(const double* __restrict__ sL, int k, int p,
                                                const WarpScratch& w, int lane)
 {
     double* U = w.U;
     double* vb = w.vb;
     const int* ri = w.ri;
-    // gather
     for (int c = 0; c < p; ++c)
     {
         const int rc = ri[c] * k;
@@ -76,8 +421,6 @@ __device__ __forceinline__ bool warp_spd_solve(const double* __restrict__ sL, in
     }
     for (int i = lane; i < p; i += 32) vb[i] = w.sb[ri[i]];
     __syncwarp();
-
-    // upper Cholesky, right-looking (UVar3Unb)
     for (int j = 0; j < p; ++j)
     {
         const double ajj = U[tri(j) + j];
@@ -95,7 +438,6 @@ __device__ __forceinline__ bool warp_spd_solve(const double* __restrict__ sL, in
         }
         __syncwarp();
     }
-    // U' y = b  (forward, column-update form: same per-entry subtraction order as a dot-form solve)
     for (int i = 0; i < p; ++i)
     {
         const double yi = vb[i] / U[tri(i) + i];
@@ -104,7 +446,6 @@ __device__ __forceinline__ bool warp_spd_solve(const double* __restrict__ sL, in
         for (int c = i + 1 + lane; c < p; c += 32) vb[c] -= U[tri(c) + i] * yi;
         __syncwarp();
     }
-    // U x = y  (backward)
     for (int c = p - 1; c >= 0; --c)
     {
         const int base = tri(c);
@@ -117,14 +458,14 @@ __device__ __forceinline__ bool warp_spd_solve(const double* __restrict__ sL, in
     return true;
 }
 
-// k <= 64. LHS is k x k (ld = ldl), RHS/X/Y are k x q.
-__global__ void nnls_bpp_warp_kernel(int k, int q,
-                                     const double* __restrict__ LHS, long long ldl,
+__global__ void nnls_bpp_slow_kernel(int k, const double* __restrict__ LHS, long long ldl,
                                      const double* __restrict__ RHS, long long ldr,
-                                     double* __restrict__ X, long long ldx,
-                                     double* __restrict__ Y, long long ldy,
-                                     int* __restrict__ status, unsigned int* __restrict__ counter, int outer_iter)
+                                     double* __restrict__ X, long long ldx, double* __restrict__ Y, long long ldy,
+                                     int* __restrict__ status, unsigned int* __restrict__ counter, int outer_iter,
+                                     const BppColState* __restrict__ deferred)
 {
+    const int ndef = status[ST_DEFER_COUNT];
+    if (ndef == 0) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* sL = reinterpret_cast<double*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -145,33 +486,27 @@ __global__ void nnls_bpp_warp_kernel(int k, int q,
 
     for (;;)
     {
-        unsigned int c = 0;
-        if (lane == 0) c = atomicAdd(counter, 1u);
-        c = __shfl_sync(0xffffffffu, c, 0);
-        if (c >= static_cast<unsigned int>(q)) break;
+        unsigned int slot = 0;
+        if (lane == 0) slot = atomicAdd(counter, 1u);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot >= static_cast<unsigned int>(ndef)) break;
+        const BppColState st = deferred[slot];
+        const int c = st.col;
 
         const double* rhs = RHS + static_cast<long long>(c) * ldr;
         double* xcol = X + static_cast<long long>(c) * ldx;
         double* ycol = Y + static_cast<long long>(c) * ldy;
-
         const double b0 = v0 ? rhs[r0] : 0.0, b1 = v1 ? rhs[r1] : 0.0;
         if (v0) w.sb[r0] = b0;
         if (v1) w.sb[r1] = b1;
-        // warm start: passive = (X > 0)   (nnls.hpp:157)
-        unsigned long long pm;
-        {
-            const bool p0 = v0 && (xcol[r0] > 0.0), p1 = v1 && (xcol[r1] > 0.0);
-            pm = static_cast<unsigned long long>(__ballot_sync(0xffffffffu, p0)) |
-                 (static_cast<unsigned long long>(__ballot_sync(0xffffffffu, p1)) << 32);
-        }
-        int P = kPbar, Ninf = k + 1, round = 0;
+        unsigned long long pm = st.pm;
+        int P = st.P, Ninf = st.Ninf, round = st.round;
         double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0;
         bool failed = false;
 
         for (;;)
         {
             const int p = __popcll(pm);
-            // passive row list, ascending
             if (v0 && ((pm >> r0) & 1ull)) w.ri[__popcll(pm & ((1ull << r0) - 1ull))] = r0;
             if (v1 && ((pm >> r1) & 1ull)) w.ri[__popcll(pm & ((1ull << r1) - 1ull))] = r1;
             if (v0) w.sx[r0] = 0.0;
@@ -180,7 +515,6 @@ __global__ void nnls_bpp_warp_kernel(int k, int q,
             if (p > 0)
             {
                 if (!warp_spd_solve(sL, k, p, w, lane)) { failed = true; break; }
-                // ZeroizeSmallValues(Xsub) applies inside the pivot loop only (nnls.hpp:215)
                 for (int i = lane; i < p; i += 32)
                 {
                     double xv = w.vb[i];
@@ -192,7 +526,6 @@ __global__ void nnls_bpp_warp_kernel(int k, int q,
             }
             x0 = v0 ? w.sx[r0] : 0.0;
             x1 = v1 ? w.sx[r1] : 0.0;
-            // y = LHS * x - rhs   (nnls.hpp:168-169, 219-220)
             double s0 = 0.0, s1 = 0.0;
             for (int t = 0; t < p; ++t)
             {
@@ -218,23 +551,8 @@ __global__ void nnls_bpp_warp_kernel(int k, int q,
             __syncwarp();
             if (not_good == 0) break;
             if (round == 0 && lane == 0) atomicOr(&status[ST_ANY_NONOPT], 1);
-            if (round >= max_rounds) { failed = true; break; }     // nnls.hpp:195-196
-            // UpdatePassiveSet (common/src/nnls.cpp:18-74)
-            if (not_good < Ninf)
-            {
-                P = kPbar; Ninf = not_good;
-                pm = (pm | nonopt) & ~infeas;
-            }
-            else if (P >= 1)
-            {
-                P -= 1;
-                pm = (pm | nonopt) & ~infeas;
-            }
-            else
-            {
-                const int ra = max_row_index_ref(nonopt, k), rb = max_row_index_ref(infeas, k);
-                pm ^= (1ull << (ra > rb ? ra : rb));
-            }
+            if (round >= max_rounds) { failed = true; break; }
+            update_passive_set(pm, P, Ninf, not_good, nonopt, infeas, k);
             ++round;
         }
         if (failed && lane == 0) atomicMin(&status[ST_FAIL_ITER], outer_iter);
@@ -244,8 +562,8 @@ __global__ void nnls_bpp_warp_kernel(int k, int q,
     }
 }
 
-// Finishes ZeroizeSmallValues(X), ZeroizeSmallValues(Y) for columns that never
-// entered the pivot loop; a no-op unless some column was non-optimal.
+// Finishes ZeroizeSmallValues(X), ZeroizeSmallValues(Y) for columns that never entered the pivot loop;
+// a no-op unless some column was non-optimal.
 __global__ void zeroize_if_flag_kernel(const int* __restrict__ status, int k, long long q,
                                        double* __restrict__ X, long long ldx, double* __restrict__ Y, long long ldy)
 {
@@ -265,28 +583,43 @@ __global__ void zeroize_if_flag_kernel(const int* __restrict__ status, int k, lo
 
 } // namespace
 
-// status: device int[ST_COUNT]; counter: device unsigned. Both are (re)initialised here.
+size_t nnls_deferred_bytes(int q) { return static_cast<size_t>(q) * sizeof(BppColState); }
+
+// status: device int[ST_COUNT]; counter: device unsigned[2]; deferred: nnls_deferred_bytes(q) bytes.
 void nnls_bpp(cudaStream_t stream, int k, int q, const double* LHS, long long ldl,
               const double* RHS, long long ldr, double* X, long long ldx, double* Y, long long ldy,
-              int* status, unsigned int* counter, int outer_iter, int num_sms)
+              int* status, unsigned int* counter, void* deferred, int outer_iter, int num_sms)
 {
-    if (k > 64) throw std::string("nnls_bpp: k > 64 is not supported by the warp kernel yet");
+    if (k > 64) throw std::string("nnls_bpp: k > 64 is not supported yet");
     if (q <= 0) return;
-    SMK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
+    SMK_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned int), stream));
     SMK_CUDA(cudaMemsetAsync(&status[ST_ANY_NONOPT], 0, sizeof(int), stream));
+    SMK_CUDA(cudaMemsetAsync(&status[ST_DEFER_COUNT], 0, sizeof(int), stream));
+    BppColState* def = static_cast<BppColState*>(deferred);
 
-    const size_t tri_k = static_cast<size_t>(k) * (k + 1) / 2;
-    const size_t per_warp = (tri_k + 3 * k) * sizeof(double) + k * sizeof(int);
-    const size_t fixed = static_cast<size_t>(k) * k * sizeof(double);
-    const size_t budget = 220 * 1024;
-    int warps = static_cast<int>((budget - fixed) / per_warp);
-    warps = std::max(1, std::min(warps, 16));
-    const size_t smem = fixed + warps * per_warp + 16;
-    int blocks_per_sm = std::max(1, std::min<int>(static_cast<int>(budget / smem), 32 / warps > 0 ? 64 / warps : 1));
-    int grid = std::min(num_sms * blocks_per_sm, ceil_div(q, warps));
-    SMK_CUDA(cudaFuncSetAttribute(nnls_bpp_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    nnls_bpp_warp_kernel<<<grid, warps * 32, smem, stream>>>(k, q, LHS, ldl, RHS, ldr, X, ldx, Y, ldy, status, counter, outer_iter);
-    SMK_LAUNCH_CHECK();
+    {
+        const FastSmem L{k};
+        const size_t smem = L.total_bytes(kFastWarps);
+        const int grid = std::min(num_sms, ceil_div(q, kFastWarps));
+        SMK_CUDA(cudaFuncSetAttribute(nnls_bpp_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        nnls_bpp_fast_kernel<<<grid, kFastWarps * 32, smem, stream>>>(k, q, LHS, ldl, RHS, ldr, X, ldx, Y, ldy, status, counter,
+                                                                     outer_iter, def);
+        SMK_LAUNCH_CHECK();
+    }
+    {
+        const size_t tri_k = static_cast<size_t>(k) * (k + 1) / 2;
+        const size_t per_warp = (tri_k + 3 * k) * sizeof(double) + k * sizeof(int);
+        const size_t fixed = static_cast<size_t>(k) * k * sizeof(double);
+        const size_t budget = 220 * 1024;
+        int warps = static_cast<int>((budget - fixed) / per_warp);
+        warps = std::max(1, std::min(warps, 16));
+        const size_t smem = fixed + warps * per_warp + 16;
+        const int grid = std::min(num_sms, ceil_div(q, warps));
+        SMK_CUDA(cudaFuncSetAttribute(nnls_bpp_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        nnls_bpp_slow_kernel<<<grid, warps * 32, smem, stream>>>(k, LHS, ldl, RHS, ldr, X, ldx, Y, ldy, status, counter + 1,
+                                                                outer_iter, def);
+        SMK_LAUNCH_CHECK();
+    }
     const long long total = static_cast<long long>(k) * q;
     int zb = static_cast<int>(std::min<long long>((total + 255) / 256, 8LL * num_sms));
     zeroize_if_flag_kernel<<<zb, 256, 0, stream>>>(status, k, q, X, ldx, Y, ldy);

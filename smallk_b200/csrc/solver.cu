@@ -76,7 +76,7 @@ void compute_WtW(smk_ctx* c) { gram(c, c->Wt.p, c->m, c->WtW.p); }
 void run_nnls(smk_ctx* c, const double* LHS, const double* RHS, double* X, double* Y, int q)
 {
     const int k = c->opts.k;
-    nnls_bpp(c->stream, k, q, LHS, k, RHS, k, X, k, Y, k, c->status.p, c->counter.p, c->steps_done, c->num_sms);
+    nnls_bpp(c->stream, k, q, LHS, k, RHS, k, X, k, Y, k, c->status.p, c->counter.p, c->deferred.p, c->steps_done, c->num_sms);
 }
 
 } // namespace
@@ -89,6 +89,7 @@ void solver_alloc(smk_ctx* c)
     c->WtW.reserve(k * k); c->HHt.reserve(k * k);
     c->WtA.reserve(k * n); c->HAt.reserve(k * m);
     c->norms.reserve(k);
+    c->deferred.reserve(nnls_deferred_bytes(static_cast<int>(std::max(m, n))));
     if (c->opts.algorithm == SMK_MU || c->opts.algorithm == SMK_HALS) { c->T1.reserve(k * n); c->T2.reserve(k * m); }
     if (c->opts.prog_est_algorithm == SMK_DELTA_FNORM) c->Wprev.reserve(k * m);
     // split-R workspace: enough for the gram matrices at 4*SMs splits and for the big products at a few splits

@@ -37,7 +37,7 @@ ctx = sk.Context(0)
 ctx.load_dense_device(A.data_ptr(), m, m, n)
 rng = np.random.default_rng(12)
 W0 = rng.random((m, k)); H0 = rng.random((k, n))
-for alg in ("BPP", "MU", "HALS"):
+for alg in os.environ.get("PROBE_ALGS", "BPP,MU,HALS").split(","):
     opts = sk.make_options(m, n, k, algorithm=alg, tol=1e-12, min_iter=1, max_iter=100, normalize=False)
     t = time.time(); ctx.solver_begin(W0, H0, opts); ctx.synchronize(); out[f"{alg}_begin_s"] = time.time() - t
     times = []
