@@ -31,8 +31,8 @@ namespace smk {
 
 namespace {
 
-constexpr int BM = 64, BN = 128, BK = 16;
-constexpr int STAGES = 3;
+constexpr int BM = 64, BN = 128, BK = 32;
+constexpr int STAGES = 2;
 constexpr int THREADS = 256;
 constexpr int LDA_S = BM + 4;    // As[BK][LDA_S]
 constexpr int LDB_NN = BK + 4;   // Bs[BN][LDB_NN]
