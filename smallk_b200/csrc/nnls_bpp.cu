@@ -77,9 +77,11 @@ __device__ __forceinline__ bool spd_solve_reg(int n, double (&a)[NMAX], double r
 #pragma unroll
             for (int h = (j + 1) / 2; h < NMAX / 2; ++h)
             {
+                // entries a[i] with i > lane lie below the diagonal: never read, so they are updated
+                // unconditionally (garbage in, garbage out) instead of paying a predicate per element
                 const double2 u2 = reinterpret_cast<const double2*>(row)[h];
-                if (2 * h > j && 2 * h <= lane) a[2 * h] = fma(-u2.x, ujc, a[2 * h]);
-                if (2 * h + 1 > j && 2 * h + 1 <= lane) a[2 * h + 1] = fma(-u2.y, ujc, a[2 * h + 1]);
+                if (2 * h > j) a[2 * h] = fma(-u2.x, ujc, a[2 * h]);
+                a[2 * h + 1] = fma(-u2.y, ujc, a[2 * h + 1]);
             }
         }
     }
@@ -184,7 +186,7 @@ struct FastSmem
     __host__ __device__ size_t g() const { return 0; }
     __host__ __device__ size_t ginv() const { return static_cast<size_t>(k) * k; }
     __host__ __device__ size_t rowcol() const { return ginv() + (k > 32 ? static_cast<size_t>(k) * k : 0); }
-    __host__ __device__ size_t warp0() const { return rowcol() + 2 * static_cast<size_t>(k); }
+    __host__ __device__ size_t warp0() const { return (rowcol() + 2 * static_cast<size_t>(k) + 1) & ~static_cast<size_t>(1); }
     __host__ __device__ size_t per_warp() const { return (32 * 33 + 64 + 3 * static_cast<size_t>(k) + 32 + (k + 1) / 2 + 2) & ~static_cast<size_t>(1); }   // even: keeps double2 alignment
     __host__ __device__ size_t total_bytes(int warps) const { return (warp0() + warps * per_warp()) * sizeof(double) + 16; }
 };
@@ -264,7 +266,14 @@ nnls_bpp_fast_kernel(int k, int q, const double* __restrict__ LHS, long long ldl
         {
             const int p = __popcll(pm);
             const bool in0 = (pm >> r0) & 1ull, in1 = v1 && ((pm >> r1) & 1ull);
-            if (p == 0) { x0 = 0.0; x1 = 0.0; }
+            bool quick = false;
+            double zq = 0.0;
+            if (p == 0)
+            {
+                x0 = 0.0; x1 = 0.0;
+                if (v0) sx[r0] = 0.0;
+                if (v1) sx[r1] = 0.0;
+            }
             else if (p <= 32)
             {
                 // ---- direct: G_PP x_P = b_P
@@ -290,6 +299,7 @@ nnls_bpp_fast_kernel(int k, int q, const double* __restrict__ LHS, long long ldl
                 if (!have_u)
                 {
                     double u0 = 0.0, u1 = 0.0;
+#pragma unroll 4
                     for (int cc = 0; cc < k; ++cc)
                     {
                         const double bv = sb[cc];
@@ -333,10 +343,13 @@ nnls_bpp_fast_kernel(int k, int q, const double* __restrict__ LHS, long long ldl
                 if (v0) sx[r0] = x0;
                 if (v1) sx[r1] = x1;
                 __syncwarp();
+                quick = true;
+                zq = z;
             }
-            // ---- y = LHS * x - rhs over the passive columns (nnls.hpp:168-169, 219-220)
-            double s0 = 0.0, s1 = 0.0;
-            {
+            // ---- dual y = LHS * x - rhs (nnls.hpp:168-169, 219-220)
+            // full_y: the product over the passive columns, as the reference forms it.
+            auto full_y = [&](double& o0, double& o1) {
+                double s0 = 0.0, s1 = 0.0;
                 unsigned long long mm = pm;
                 while (mm)
                 {
@@ -347,29 +360,53 @@ nnls_bpp_fast_kernel(int k, int q, const double* __restrict__ LHS, long long ldl
                     if (v0) s0 = fma(col[r0], xv, s0);
                     if (v1) s1 = fma(col[r1], xv, s1);
                 }
-            }
-            y0 = s0 - b0; y1 = s1 - b1;
-            if (p > 32)
+                o0 = s0 - b0; o1 = s1 - b1;
+            };
+            if (quick)
             {
-                // residual of the passive-set equations: must be at rounding level, else redo directly
-                double res = fmax(in0 ? fabs(y0) : 0.0, in1 ? fabs(y1) : 0.0);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) res = fmax(res, __shfl_xor_sync(0xffffffffu, res, o));
-                if (!(res <= 1.0e-11 * bmax)) { defer = true; break; }
+                // complement path: on the active rows y_A = -z, on the passive rows y_P = 0; the pivoting
+                // decisions of this round use that, the product is formed once when the column is accepted
+                if (v0) sT[r0] = 0.0;
+                if (v1) sT[r1] = 0.0;
+                __syncwarp();
+                if (lane < k - p) sT[list[lane]] = -zq;
+                __syncwarp();
+                y0 = v0 ? sT[r0] : 0.0;
+                y1 = v1 ? sT[r1] : 0.0;
+                __syncwarp();
             }
+            else full_y(y0, y1);
             if (round > 0)
             {
                 if (fabs(y0) < kZeroThresh) y0 = 0.0;
                 if (fabs(y1) < kZeroThresh) y1 = 0.0;
             }
-            const unsigned long long nonopt =
+            unsigned long long nonopt =
                 static_cast<unsigned long long>(__ballot_sync(0xffffffffu, v0 && !in0 && y0 < 0.0)) |
                 (static_cast<unsigned long long>(__ballot_sync(0xffffffffu, v1 && !in1 && y1 < 0.0)) << 32);
             const unsigned long long infeas =
                 static_cast<unsigned long long>(__ballot_sync(0xffffffffu, v0 && in0 && x0 < 0.0)) |
                 (static_cast<unsigned long long>(__ballot_sync(0xffffffffu, v1 && in1 && x1 < 0.0)) << 32);
-            const int not_good = __popcll(nonopt) + __popcll(infeas);
+            int not_good = __popcll(nonopt) + __popcll(infeas);
             __syncwarp();
+            if (not_good == 0 && quick)
+            {
+                // acceptance check of the complement path: the true product must (a) leave a rounding-level
+                // residual on the passive rows and (b) agree that the column is optimal; otherwise the
+                // column goes to the direct method (ill-conditioned LHS).
+                full_y(y0, y1);
+                double res = fmax(in0 ? fabs(y0) : 0.0, in1 ? fabs(y1) : 0.0);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) res = fmax(res, __shfl_xor_sync(0xffffffffu, res, o));
+                if (round > 0)
+                {
+                    if (fabs(y0) < kZeroThresh) y0 = 0.0;
+                    if (fabs(y1) < kZeroThresh) y1 = 0.0;
+                }
+                nonopt = static_cast<unsigned long long>(__ballot_sync(0xffffffffu, v0 && !in0 && y0 < 0.0)) |
+                         (static_cast<unsigned long long>(__ballot_sync(0xffffffffu, v1 && !in1 && y1 < 0.0)) << 32);
+                if (!(res <= 1.0e-11 * bmax) || nonopt != 0ull) { defer = true; break; }
+            }
             if (not_good == 0) break;
             if (round == 0 && lane == 0) atomicOr(&status[ST_ANY_NONOPT], 1);
             if (round >= max_rounds) { failed = true; break; }     // nnls.hpp:195-196
