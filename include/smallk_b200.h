@@ -5,7 +5,7 @@
  * common/include/nmf.hpp:77-92 (Nmf, NmfSparse) and the solver-functor concept
  * NmfSolve is templated on (common/include/nmf_solve_generic.hpp:30-40). Each
  * entry point below names the reference interface it stands in for. Host code
- * (smallk_b200/host/*.hpp, the C++ mirror of nmf.hpp / smallk.hpp, and the
+ * (the headers under smallk_b200/host/, the C++ mirror of nmf.hpp / smallk.hpp, and the
  * Python ctypes binding used by tests and bench.py) sits ABOVE this header.
  *
  * Conventions: plain pointers and sizes, no exceptions across the boundary,

@@ -1,0 +1,247 @@
+// smallk_b200 — namespace smallk over host/nmf.hpp. Follows smallk/src/smallk.cpp of the reference:
+// global state (:46-68), setters with clamping (:383-468), LoadMatrix (:205-330), Nmf (:471-650).
+#include "smallk.hpp"
+
+#include <algorithm>
+#include <iostream>
+#include <limits>
+#include <random>
+#include <sstream>
+#include <stdexcept>
+#include <thread>
+
+#include "matrix_io.hpp"
+#include "nmf.hpp"
+
+namespace {
+bool matrix_loaded = false, is_sparse = false;
+unsigned int m = 0, n = 0, k = 0, ldim_a = 0;
+std::vector<double> buf_a, buf_w, buf_h;
+smallk_io::CscMatrix A;
+unsigned int outprecision = 6, max_iter = 5000, min_iter = 5;
+unsigned int max_threads = std::max(2u, std::thread::hardware_concurrency());
+double nmf_tolerance = 0.005;
+std::string outdir;
+std::mt19937 engine;
+std::uniform_real_distribution<double> dist_double;
+const char* DEFAULT_FILENAME_W = "w.csv";
+const char* DEFAULT_FILENAME_H = "h.csv";
+
+// RandomMatrixSequential with center 0.5, radius 0.5 (common/include/matrix_generator.hpp:229-248,
+// random.hpp:154-158). The reference switches to a thread-count-dependent parallel generator for large
+// matrices; this build always uses the sequential stream.
+void RandomMatrix(double* buf, unsigned int ldim, unsigned int height, unsigned int width)
+{
+    for (unsigned int c = 0; c < width; ++c)
+        for (unsigned int r = 0; r < height; ++r)
+            buf[r + static_cast<size_t>(c) * ldim] = 0.5 + 2.0 * 0.5 * dist_double(engine) - 0.5;
+}
+
+std::string EnsureTrailingSep(const std::string& s)
+{
+    if (s.empty() || s.back() == '/') return s;
+    return s + "/";
+}
+} // namespace
+
+namespace smallk
+{
+void Initialize(int& argc, char**& argv) { NmfInitialize(argc, argv); }
+bool IsInitialized() { return Result::INITIALIZED == NmfIsInitialized(); }
+void Finalize() { NmfFinalize(); }
+
+unsigned int GetMajorVersion() { return SMALLK_MAJOR_VERSION; }
+unsigned int GetMinorVersion() { return SMALLK_MINOR_VERSION; }
+unsigned int GetPatchLevel() { return SMALLK_PATCH_LEVEL; }
+std::string GetVersionString()
+{
+    std::ostringstream v;
+    v << SMALLK_MAJOR_VERSION << "." << SMALLK_MINOR_VERSION << "." << SMALLK_PATCH_LEVEL;
+    return v.str();
+}
+
+unsigned int GetOutputPrecision() { return outprecision; }
+void SetOutputPrecision(const unsigned int num_digits)
+{
+    outprecision = num_digits;
+    if (0 == outprecision) outprecision = 1;
+    if (outprecision > static_cast<unsigned int>(std::numeric_limits<double>::max_digits10))
+        outprecision = std::numeric_limits<double>::max_digits10;
+}
+double GetNmfTolerance() { return nmf_tolerance; }
+void SetNmfTolerance(const double tol)
+{
+    if (tol <= 0.0 || tol >= 1.0) throw std::logic_error("smallk::SetNmfTolerance: tolerance must be in the interval (0.0, 1.0)");
+    nmf_tolerance = tol;
+}
+unsigned int GetMaxIter() { return max_iter; }
+void SetMaxIter(const unsigned int v) { max_iter = v; }
+unsigned int GetMinIter() { return min_iter; }
+void SetMinIter(const unsigned int v) { min_iter = v; }
+unsigned int GetMaxThreads() { return max_threads; }
+void SetMaxThreads(const unsigned int v)
+{
+    unsigned int hw = std::max(2u, std::thread::hardware_concurrency());
+    max_threads = std::max(1u, std::min(v, hw));
+}
+void Reset()
+{
+    matrix_loaded = false; is_sparse = false;
+    m = n = k = ldim_a = 0;
+    buf_a.clear(); buf_w.clear(); buf_h.clear();
+    A = smallk_io::CscMatrix();
+    outprecision = 6; max_iter = 5000; min_iter = 5; nmf_tolerance = 0.005;
+    max_threads = std::max(2u, std::thread::hardware_concurrency());
+    outdir.clear();
+    engine.seed();
+}
+void SeedRNG(const int seed) { engine.seed(seed); }
+
+void LoadMatrix(const std::string& filepath)
+{
+    bool ok;
+    if (smallk_io::IsMatrixMarketFile(filepath))
+    {
+        ok = smallk_io::LoadMatrixMarketFile(filepath, A);
+        if (ok) { m = A.height; n = A.width; is_sparse = true; }
+    }
+    else
+    {
+        ok = smallk_io::LoadDelimitedFile(buf_a, m, n, filepath);
+        if (ok) { ldim_a = m; is_sparse = false; }
+    }
+    if (!ok)
+    {
+        std::ostringstream msg;
+        msg << "smallk error (LoadMatrix): load failed for file \"" << filepath << "\"";
+        throw std::runtime_error(msg.str());
+    }
+    matrix_loaded = true;
+}
+
+void LoadMatrix(const double* buffer, const unsigned int ldim, const unsigned int height, const unsigned int width)
+{
+    if (nullptr == buffer) throw std::logic_error("smallk error (LoadMatrix): null buffer");
+    if (ldim < height) throw std::logic_error("smallk error (LoadMatrix): leading dimension too small");
+    // The reference swaps its loop bounds here (smallk.cpp:249-255) and is only right for square inputs;
+    // this copies every column of the height x width matrix.
+    m = height; n = width; ldim_a = height;
+    buf_a.resize(static_cast<size_t>(m) * n);
+    for (unsigned int c = 0; c < n; ++c)
+        for (unsigned int r = 0; r < m; ++r) buf_a[static_cast<size_t>(c) * m + r] = buffer[static_cast<size_t>(c) * ldim + r];
+    is_sparse = false;
+    matrix_loaded = true;
+}
+
+void LoadMatrix(const unsigned int height, const unsigned int width, const unsigned int nz,
+                const std::vector<double>& data, const std::vector<unsigned int>& row_indices,
+                const std::vector<unsigned int>& col_offsets)
+{
+    if (data.size() < nz || row_indices.size() < nz || col_offsets.size() < static_cast<size_t>(width) + 1)
+        throw std::logic_error("smallk error (LoadMatrix): inconsistent sparse arrays");
+    A.height = height; A.width = width;
+    A.data.assign(data.begin(), data.begin() + nz);
+    A.row_indices.assign(row_indices.begin(), row_indices.begin() + nz);
+    A.col_offsets.assign(col_offsets.begin(), col_offsets.begin() + width + 1);
+    m = height; n = width;
+    is_sparse = true;
+    matrix_loaded = true;
+}
+
+bool IsMatrixLoaded() { return matrix_loaded; }
+std::string GetOutputDir() { return outdir; }
+void SetOutputDir(const std::string& d) { outdir = EnsureTrailingSep(d); }
+
+void Nmf(const unsigned int kval, const Algorithm algorithm, const std::string& csv_file_w, const std::string& csv_file_h)
+{
+    using std::cout; using std::cerr; using std::endl;
+    if (!matrix_loaded) throw std::logic_error("smallk error (NMF): no matrix has been loaded.");
+    if (max_iter < min_iter) throw std::logic_error("smallk error (NMF): min_iterations exceeds max_iterations.");
+    if (0 == kval) throw std::logic_error("smallk error (NMF): k must be greater than 0.");
+    const unsigned long long lim = std::numeric_limits<int>::max();
+    if (static_cast<unsigned long long>(m) * kval > lim) throw std::logic_error("smallk error (Nmf): mxk matrix W is too large.");
+    if (static_cast<unsigned long long>(kval) * n > lim) throw std::logic_error("smallk error (Nmf): kxn matrix H is too large.");
+
+    NmfOptions nmf_opts;
+    k = kval;
+    switch (algorithm)
+    {
+    case Algorithm::MU: nmf_opts.algorithm = NmfAlgorithm::MU; break;
+    case Algorithm::HALS: nmf_opts.algorithm = NmfAlgorithm::HALS; break;
+    case Algorithm::RANK2: nmf_opts.algorithm = NmfAlgorithm::RANK2; break;
+    case Algorithm::BPP: nmf_opts.algorithm = NmfAlgorithm::BPP; break;
+    default: throw std::logic_error("smallk error (NMF): unknown NMF algorithm.");
+    }
+    if (NmfAlgorithm::RANK2 == nmf_opts.algorithm) k = 2;
+    const unsigned int ldim_w = m, ldim_h = k;
+    if (buf_w.size() < static_cast<size_t>(m) * k) buf_w.resize(static_cast<size_t>(m) * k);
+    if (buf_h.size() < static_cast<size_t>(k) * n) buf_h.resize(static_cast<size_t>(k) * n);
+
+    bool ok = true;
+    unsigned int height_w = m, width_w = k, height_h = k, width_h = n;
+    cout << "Initializing matrix W..." << endl;
+    if (csv_file_w.empty()) RandomMatrix(&buf_w[0], ldim_w, m, k);
+    else ok = smallk_io::LoadDelimitedFile(buf_w, height_w, width_w, csv_file_w);
+    if (!ok) throw std::runtime_error("smallk error (Nmf): load failed for file \"" + csv_file_w + "\"");
+    if (height_w != m || width_w != k)
+    {
+        cerr << "\tdimensions of matrix W are " << height_w << " x " << width_w << endl;
+        cerr << "\texpected " << m << " x " << k << endl;
+        throw std::logic_error("smallk error (Nmf): non-conformant matrix W.");
+    }
+    cout << "Initializing matrix H..." << endl;
+    if (csv_file_h.empty()) RandomMatrix(&buf_h[0], ldim_h, k, n);
+    else ok = smallk_io::LoadDelimitedFile(buf_h, height_h, width_h, csv_file_h);
+    if (!ok) throw std::runtime_error("smallk error (Nmf): load failed for file \"" + csv_file_h + "\"");
+    if (height_h != k || width_h != n)
+    {
+        cerr << "\tdimensions of matrix H are " << height_h << " x " << width_h << endl;
+        cerr << "\texpected " << k << " x " << n << endl;
+        throw std::logic_error("smallk error (Nmf): non-conformant matrix H.");
+    }
+
+    // smallk.cpp:581-595
+    nmf_opts.prog_est_algorithm = (NmfAlgorithm::MU == nmf_opts.algorithm) ? NmfProgressAlgorithm::DELTA_FNORM
+                                                                            : NmfProgressAlgorithm::PG_RATIO;
+    nmf_opts.tol = nmf_tolerance;
+    nmf_opts.height = m; nmf_opts.width = n; nmf_opts.k = k;
+    nmf_opts.min_iter = min_iter; nmf_opts.max_iter = max_iter;
+    nmf_opts.tolcount = 1;
+    nmf_opts.max_threads = max_threads;
+    nmf_opts.verbose = true;
+    nmf_opts.normalize = true;
+
+    NmfStats stats;
+    Result result;
+    if (is_sparse)
+        result = NmfSparse(nmf_opts, A.height, A.width, A.nnz(), A.col_offsets.data(), A.row_indices.data(), A.data.data(),
+                           &buf_w[0], ldim_w, &buf_h[0], ldim_h, stats);
+    else
+        result = ::Nmf(nmf_opts, &buf_a[0], ldim_a, &buf_w[0], ldim_w, &buf_h[0], ldim_h, stats);
+    cout << "Elapsed wall clock time: " << stats.elapsed_us / 1000.0 << " ms." << endl << endl;
+    if (Result::OK != result) throw std::runtime_error("smallk error (Nmf): NMF solver failure.");
+
+    const std::string outfile_w = outdir + DEFAULT_FILENAME_W, outfile_h = outdir + DEFAULT_FILENAME_H;
+    cout << "Writing output files..." << endl;
+    if (!smallk_io::WriteDelimitedFile(&buf_w[0], ldim_w, m, k, outfile_w, outprecision))
+        throw std::runtime_error("smallk error (Nmf): could not write W result.");
+    if (!smallk_io::WriteDelimitedFile(&buf_h[0], ldim_h, k, n, outfile_h, outprecision))
+        throw std::runtime_error("smallk error (Nmf): could not write H result.");
+}
+
+const double* LockedBufferW(unsigned int& ldim, unsigned int& height, unsigned int& width)
+{
+    ldim = m; height = m; width = k;
+    return buf_w.empty() ? nullptr : &buf_w[0];
+}
+const double* LockedBufferH(unsigned int& ldim, unsigned int& height, unsigned int& width)
+{
+    ldim = k; height = k; width = n;
+    return buf_h.empty() ? nullptr : &buf_h[0];
+}
+
+void HierNmf2(const unsigned int)
+{ throw std::runtime_error("smallk_b200: HierNmf2 (hierclust tree driver) is not part of this build yet; see DESIGN.md"); }
+void HierNmf2WithFlat(const unsigned int)
+{ throw std::runtime_error("smallk_b200: HierNmf2WithFlat is not part of this build yet; see DESIGN.md"); }
+} // namespace smallk

@@ -1,0 +1,59 @@
+// smallk_b200 — the reference's public C++ API (smallk/include/smallk.hpp:34-332), NMF part, implemented on
+// the GPU library. Same namespace, names, default arguments and exception types, so a program using
+// smallk::Initialize / LoadMatrix / Nmf / LockedBufferW/H re-links unchanged.
+// HierNmf2 / HierNmf2WithFlat (hierclust) drive the same rank-2 solver from host-side tree code that
+// is scheduled after the hot path; they throw std::runtime_error until then.
+#pragma once
+
+#include <string>
+#include <vector>
+
+#define SMALLK_MAJOR_VERSION 1
+#define SMALLK_MINOR_VERSION 6
+#define SMALLK_PATCH_LEVEL   2
+
+namespace smallk
+{
+    enum Algorithm { MU, BPP, HALS, RANK2 };
+    enum OutputFormat { XML, JSON };
+
+    void Initialize(int& argc, char**& argv);
+    bool IsInitialized();
+    void Finalize();
+
+    unsigned int GetMajorVersion();
+    unsigned int GetMinorVersion();
+    unsigned int GetPatchLevel();
+    std::string GetVersionString();
+
+    unsigned int GetOutputPrecision();
+    void SetOutputPrecision(const unsigned int num_digits = 6);
+    double GetNmfTolerance();
+    void SetNmfTolerance(const double tol = 0.005);
+    unsigned int GetMaxIter();
+    void SetMaxIter(const unsigned int max_iterations = 5000);
+    unsigned int GetMinIter();
+    void SetMinIter(const unsigned int min_iterations = 5);
+    unsigned int GetMaxThreads();
+    void SetMaxThreads(const unsigned int max_threads);
+    void Reset();
+    void SeedRNG(const int seed);
+
+    void LoadMatrix(const std::string& filepath);
+    void LoadMatrix(const double* buffer, const unsigned int ldim, const unsigned int height, const unsigned int width);
+    void LoadMatrix(const unsigned int height, const unsigned int width, const unsigned int nz,
+                    const std::vector<double>& data, const std::vector<unsigned int>& row_indices,
+                    const std::vector<unsigned int>& col_offsets);
+    bool IsMatrixLoaded();
+
+    std::string GetOutputDir();
+    void SetOutputDir(const std::string& outdir);
+
+    void Nmf(const unsigned int k, const Algorithm algorithm = BPP,
+             const std::string& initfile_w = std::string(""), const std::string& initfile_h = std::string(""));
+    const double* LockedBufferW(unsigned int& ldim, unsigned int& height, unsigned int& width);
+    const double* LockedBufferH(unsigned int& ldim, unsigned int& height, unsigned int& width);
+
+    void HierNmf2(const unsigned int num_clusters);
+    void HierNmf2WithFlat(const unsigned int num_clusters);
+} // namespace smallk
