@@ -64,7 +64,7 @@ def test_smallk_api_hals_sparse_mtx(c1, oracle, tmp_path):
     S = sps.random(m, n, density=0.3, random_state=np.random.RandomState(3), format="coo",
                    data_rvs=np.random.RandomState(4).random_sample)
     with open(tmp_path / "A.mtx", "w") as f:
-        f.write("%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (m, n, S.nnz))
+        f.write("%%%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (m, n, S.nnz))
         for r, c, v in zip(S.row, S.col, S.data):
             f.write("%d %d %.17e\n" % (r + 1, c + 1, v))
     W0 = rng.random((m, k)); H0 = rng.random((k, n)) * 0.1
