@@ -89,6 +89,18 @@ int smk_load_dense_device(smk_ctx* ctx, const double* A_dev, long long ldA, int 
 int smk_load_csc(smk_ctx* ctx, int m, int n, unsigned int nnz,
                  const unsigned int* col_offsets, const unsigned int* row_indices, const double* data);
 
+/* ---- column subsets of the loaded matrix (hierclust) ----
+ * A.SubMatrixColsCompact(Asubset, col_indices, old_to_new_rows, new_to_old_rows):
+ * common/include/sparse_matrix_impl.hpp:479-591 (sparse: the listed columns in list order; rows left without
+ * entries are dropped and the rest renumbered in ascending order) and dense_matrix_impl.hpp:224-285 (dense: all
+ * rows kept). The subset becomes the ACTIVE matrix of the context: smk_nmf / smk_solver_* then factor it, with
+ * opts.height = *new_height and opts.width = count. new_to_old_rows is a host buffer of at least m entries;
+ * *new_height of them are written. The loaded matrix itself stays resident; smk_select_all re-activates it.
+ * Errors as the reference's std::logic_error cases: empty list, index out of range, all-zero submatrix -> SMK_BAD_PARAM. */
+int smk_select_columns(smk_ctx* ctx, const unsigned int* col_indices, int count, int* new_height,
+                       unsigned int* new_to_old_rows);
+int smk_select_all(smk_ctx* ctx);
+
 /* ---- Result Nmf(opts, A, W, H, stats) / NmfSparse(...): common/src/nmf.cpp:173,232 ----
  * W (m x k) and H (k x n) are host buffers: initial guess in, factors out. The matrix must have
  * been loaded with one of the calls above; opts.height/width must match it. */
@@ -117,6 +129,13 @@ int smk_solver_last_step_ms(smk_ctx* ctx, float* ms, long long* kernel_launches)
  * current solver state `reps` times (which: 0 = W'A, 1 = H A') and reports the mean device time per
  * launch from CUDA events on the context's stream. State is left as a solver step would leave it. */
 int smk_solver_time_product(smk_ctx* ctx, int which, int reps, float* mean_ms);
+
+/* bool NnlsHals(A, W, H, tol, verbose, max_iter): common/include/nnls.hpp:249-316 — the flat-clustering step of
+ * HierNmf2WithFlat (hierclust/include/clust_flat_generic.hpp:33-74). W (m x k) is fixed, H (k x n) carries the
+ * initial guess in and the solution out; on success (pg < tol * pg0) W's columns are normalised and H's rows
+ * scaled (normalize.hpp:118-138) and both are copied back. SMK_FAILURE = iteration limit reached. */
+int smk_nnls_hals(smk_ctx* ctx, int k, double* W_host, int ldW, double* H_host, int ldH, double tol, int max_iter,
+                  int* iterations);
 
 /* ---- primitive-level entry points (the linear-algebra seam, SURVEY.md §8b ④), host buffers ----
  * Gemm(orientA, orientB, 1, A, B, 0, C) on DenseMatrix: common/include/dense_matrix_ops.hpp:255-270.

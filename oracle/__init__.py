@@ -191,3 +191,59 @@ class Ref(_NmfMixin):
                                       _d(C), C.shape[0], C.shape[1], max_threads)
         assert rc == 0, rc
         return C
+
+
+_ip = ctypes.POINTER(ctypes.c_int)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+def _hier_outputs(n, num_clusters, maxterms):
+    nodes = 2 * (num_clusters - 1)
+    z = lambda *s: np.zeros(s, dtype=np.int32)
+    return {"assignments": z(n), "parent": z(nodes), "left": z(nodes), "right": z(nodes), "is_left": z(nodes),
+            "doc_count": z(nodes), "terms": z(nodes, maxterms), "priority": np.zeros(nodes), "is_leaf": z(nodes)}
+
+
+def _ref_hierclust(self, A_dense=None, csc=None, shape=None, num_clusters=4, tol=1e-4, min_iter=5, max_iter=5000,
+                   maxterms=5, unbalanced=0.1, trial_allowance=3, flat=False, normalize=False, seed=1, max_threads=1):
+    """Reference HierNMF2 (hierclust/src/clust.cpp) on a dense array or a (colp, rowi, val) CSC triple."""
+    if csc is not None:
+        m, n = shape
+    else:
+        A_dense = _f(A_dense)
+        m, n = A_dense.shape
+    out = _hier_outputs(n, num_clusters, maxterms)
+    n_out = ctypes.c_int(0)
+    stats = np.zeros(2, dtype=np.int32)
+    W = np.zeros((m, num_clusters), order="F")
+    H = np.zeros((num_clusters, n), order="F")
+    fa = np.zeros(n, dtype=np.int32)
+    el = ctypes.c_double(0.0)
+    if csc is not None:
+        colp, rowi, val = csc
+        colp = np.ascontiguousarray(colp, dtype=np.uint32)
+        rowi = np.ascontiguousarray(rowi, dtype=np.uint32)
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        rc = self.lib.ref_hierclust_sparse(
+            m, n, int(colp[-1]), _u(colp), _u(rowi), _d(val), num_clusters, ctypes.c_double(tol), min_iter, max_iter,
+            maxterms, ctypes.c_double(unbalanced), trial_allowance, int(flat), int(normalize), seed, max_threads,
+            _i(out["assignments"]), _i(out["parent"]), _i(out["left"]), _i(out["right"]), _i(out["is_left"]),
+            _i(out["doc_count"]), _i(out["terms"]), _d(out["priority"]), _i(out["is_leaf"]), ctypes.byref(n_out),
+            _d(W), _d(H), _i(stats), _i(fa), ctypes.byref(el))
+    else:
+        rc = self.lib.ref_hierclust_dense(
+            m, n, _d(A_dense), m, num_clusters, ctypes.c_double(tol), min_iter, max_iter,
+            maxterms, ctypes.c_double(unbalanced), trial_allowance, int(flat), int(normalize), seed, max_threads,
+            _i(out["assignments"]), _i(out["parent"]), _i(out["left"]), _i(out["right"]), _i(out["is_left"]),
+            _i(out["doc_count"]), _i(out["terms"]), _d(out["priority"]), _i(out["is_leaf"]), ctypes.byref(n_out),
+            _d(W), _d(H), _i(stats), _i(fa))
+    out.update(rc=rc, n_outliers=n_out.value, nmf_count=int(stats[0]), max_count=int(stats[1]), elapsed_s=el.value)
+    if flat:
+        out.update(W=W, H=H, flat_assignments=fa)
+    return out
+
+
+Ref.hierclust = _ref_hierclust

@@ -28,7 +28,10 @@ EXPORTS = [
     "smk_comm_unique_id", "smk_comm_init", "smk_load_dense", "smk_load_dense_device", "smk_load_csc", "smk_nmf",
     "smk_solver_begin", "smk_solver_step", "smk_solver_progress", "smk_solver_get", "smk_solver_normalize",
     "smk_solver_last_step_ms", "smk_solver_time_product", "smk_gemm", "smk_nnls_bpp", "smk_sparse_gemm",
+    "smk_select_columns", "smk_select_all", "smk_nnls_hals",
 ]
+HOST_LIB_PATH = os.path.join(_HERE, "lib", "libsmallk_host.so")
+HOST_EXPORTS = ["smkh_last_error", "smkh_hierclust_sparse", "smkh_hierclust_dense", "smkh_flatclust", "smkh_compute_priority"]
 
 
 class SmallkError(RuntimeError):
@@ -140,11 +143,11 @@ class Context:
         m, n = A.shape
         self._check(self._lib.smk_load_dense(self._h, _d(A), ctypes.c_longlong(m), m, n))
         self.synchronize()
-        self.shape = (m, n)
+        self.shape = self.full_shape = (m, n)
 
     def load_dense_device(self, ptr, ld, m, n):
         self._check(self._lib.smk_load_dense_device(self._h, ctypes.c_void_p(ptr), ctypes.c_longlong(ld), m, n))
-        self.shape = (m, n)
+        self.shape = self.full_shape = (m, n)
 
     def load_csc(self, shape, col_offsets, row_indices, data):
         colp = np.ascontiguousarray(col_offsets, dtype=np.uint32)
@@ -153,7 +156,31 @@ class Context:
         m, n = shape
         self._check(self._lib.smk_load_csc(self._h, m, n, ctypes.c_uint(int(colp[-1])), colp.ctypes.data_as(_up),
                                            rowi.ctypes.data_as(_up), _d(val)))
-        self.shape = (m, n)
+        self.shape = self.full_shape = (m, n)
+
+    # ---- column subsets (hierclust) -----------------------------------------
+    def select_columns(self, cols):
+        """SubMatrixColsCompact on the device: returns new_to_old_rows (length = new height)."""
+        cols = np.ascontiguousarray(cols, dtype=np.uint32)
+        n2o = np.zeros(self.full_shape[0], dtype=np.uint32)
+        nh = ctypes.c_int(0)
+        self._check(self._lib.smk_select_columns(self._h, cols.ctypes.data_as(_up), len(cols), ctypes.byref(nh),
+                                                 n2o.ctypes.data_as(_up)))
+        self.shape = (nh.value, len(cols))
+        return n2o[:nh.value].copy()
+
+    def select_all(self):
+        self._check(self._lib.smk_select_all(self._h))
+        self.shape = self.full_shape
+
+    def nnls_hals(self, W, H0, tol, max_iter):
+        """NnlsHals (nnls.hpp:249-316): returns (rc, W, H, iterations)."""
+        W = _f(W).copy(order="F")
+        H = _f(H0).copy(order="F")
+        it = ctypes.c_int(0)
+        rc = self._lib.smk_nnls_hals(self._h, H.shape[0], _d(W), W.shape[0], _d(H), H.shape[0], ctypes.c_double(tol),
+                                     int(max_iter), ctypes.byref(it))
+        return rc, W, H, it.value
 
     # ---- Nmf / NmfSparse ---------------------------------------------------
     def nmf(self, W0, H0, options):
@@ -233,3 +260,88 @@ class Context:
         self._check(self._lib.smk_sparse_gemm(self._h, variant, ctypes.c_double(alpha), _d(B), B.shape[0], B.shape[1],
                                               ctypes.c_double(beta), _d(C), C.shape[0], C.shape[1]))
         return C
+
+
+# ---- the C++ host layer (smallk_b200/host/: Clust / ClustSparse / FlatClust*) through its extern "C" veneer ----
+_host = None
+_ip = ctypes.POINTER(ctypes.c_int)
+
+
+def load_host_library():
+    global _host
+    if _host is None:
+        if not os.path.exists(HOST_LIB_PATH):
+            raise SmallkError(NOTINITIALIZED, f"{HOST_LIB_PATH} not built — run `make -C smallk_b200/host`")
+        load_library()
+        _host = ctypes.CDLL(HOST_LIB_PATH)
+        _host.smkh_last_error.restype = ctypes.c_char_p
+        _host.smkh_compute_priority.restype = ctypes.c_double
+    return _host
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+def hierclust(A_dense=None, csc=None, shape=None, num_clusters=4, tol=1e-4, min_iter=5, max_iter=5000, maxterms=5,
+              unbalanced=0.1, trial_allowance=3, flat=False, normalize=False, seed=1, verbose=False):
+    """HierNMF2 through the C++ host driver (host/clust.cpp): Clust for a dense array, ClustSparse for a
+    (col_offsets, row_indices, data) triple. Returns the tree as arrays, like oracle.Ref.hierclust."""
+    lib = load_host_library()
+    if csc is not None:
+        m, n = shape
+    else:
+        A_dense = _f(A_dense)
+        m, n = A_dense.shape
+    nodes = 2 * (num_clusters - 1)
+    z = lambda *s: np.zeros(s, dtype=np.int32)
+    out = {"assignments": z(n), "parent": z(nodes), "left": z(nodes), "right": z(nodes), "is_left": z(nodes),
+           "doc_count": z(nodes), "terms": z(nodes, maxterms), "priority": np.zeros(nodes), "is_leaf": z(nodes)}
+    n_out = ctypes.c_int(0)
+    stats = np.zeros(3, dtype=np.int64)
+    W = np.zeros((m, num_clusters), order="F")
+    H = np.zeros((num_clusters, n), order="F")
+    fa = z(n)
+    el = ctypes.c_double(0.0)
+    tail = (num_clusters, ctypes.c_double(tol), min_iter, max_iter, maxterms, ctypes.c_double(unbalanced), trial_allowance,
+            int(flat), int(normalize), seed, int(verbose), _i(out["assignments"]), _i(out["parent"]), _i(out["left"]),
+            _i(out["right"]), _i(out["is_left"]), _i(out["doc_count"]), _i(out["terms"]), _d(out["priority"]),
+            _i(out["is_leaf"]), ctypes.byref(n_out), _d(W), _d(H), stats.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)),
+            _i(fa), ctypes.byref(el))
+    if csc is not None:
+        colp = np.ascontiguousarray(csc[0], dtype=np.uint32)
+        rowi = np.ascontiguousarray(csc[1], dtype=np.uint32)
+        val = np.ascontiguousarray(csc[2], dtype=np.float64)
+        rc = lib.smkh_hierclust_sparse(m, n, ctypes.c_uint(int(colp[-1])), colp.ctypes.data_as(_up),
+                                       rowi.ctypes.data_as(_up), _d(val), *tail)
+    else:
+        rc = lib.smkh_hierclust_dense(m, n, _d(A_dense), m, *tail)
+    out.update(rc=rc, n_outliers=n_out.value, nmf_count=int(stats[0]), max_count=int(stats[1]),
+               iterations=int(stats[2]), elapsed_s=el.value)
+    if flat:
+        out.update(W=W, H=H, flat_assignments=fa)
+    return out
+
+
+def flatclust(W0, H0, A_dense=None, csc=None, shape=None, algorithm="BPP", tol=0.005, min_iter=5, max_iter=5000, maxterms=5):
+    """FlatClust / FlatClustSparse + ComputeAssignments + TopTerms through the C++ host layer."""
+    lib = load_host_library()
+    W = _f(W0).copy(order="F")
+    H = _f(H0).copy(order="F")
+    m, k = W.shape
+    n = H.shape[1]
+    assign = np.zeros(n, dtype=np.int32)
+    terms = np.zeros((k, maxterms), dtype=np.int32)
+    it = ctypes.c_int(0)
+    if csc is not None:
+        colp = np.ascontiguousarray(csc[0], dtype=np.uint32)
+        rowi = np.ascontiguousarray(csc[1], dtype=np.uint32)
+        val = np.ascontiguousarray(csc[2], dtype=np.float64)
+        rc = lib.smkh_flatclust(ALGORITHMS[algorithm], m, n, k, ctypes.c_double(tol), min_iter, max_iter, maxterms, None, 0,
+                                ctypes.c_uint(int(colp[-1])), colp.ctypes.data_as(_up), rowi.ctypes.data_as(_up), _d(val),
+                                _d(W), _d(H), _i(assign), _i(terms), ctypes.byref(it))
+    else:
+        A = _f(A_dense)
+        rc = lib.smkh_flatclust(ALGORITHMS[algorithm], m, n, k, ctypes.c_double(tol), min_iter, max_iter, maxterms, _d(A), m,
+                                ctypes.c_uint(0), None, None, None, _d(W), _d(H), _i(assign), _i(terms), ctypes.byref(it))
+    return {"rc": rc, "W": W, "H": H, "assignments": assign, "terms": terms, "iterations": it.value}

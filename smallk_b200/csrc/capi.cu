@@ -196,6 +196,7 @@ int smk_load_dense(smk_ctx* c, const double* A, long long ldA, int m, int n)
     if (!c || !A || m <= 0 || n <= 0 || ldA < m) return SMK_BAD_PARAM;
     return guarded(c, [&]() {
         SMK_CUDA(cudaSetDevice(c->device));
+        select_all(c);
         c->A_store.reserve(static_cast<size_t>(m) * n);
         SMK_CUDA(cudaMemcpy2DAsync(c->A_store.p, sizeof(double) * m, A, sizeof(double) * ldA, sizeof(double) * m, n,
                                    cudaMemcpyHostToDevice, c->stream));
@@ -208,6 +209,7 @@ int smk_load_dense(smk_ctx* c, const double* A, long long ldA, int m, int n)
 int smk_load_dense_device(smk_ctx* c, const double* A, long long ldA, int m, int n)
 {
     if (!c || !A || m <= 0 || n <= 0 || ldA < m) return SMK_BAD_PARAM;
+    select_all(c);
     c->dA = A; c->ldA = ldA; c->m = m; c->n = n;
     c->has_dense = true; c->has_sparse = false; c->active = false;
     return SMK_OK;
@@ -218,6 +220,7 @@ int smk_load_csc(smk_ctx* c, int m, int n, unsigned int nnz, const unsigned int*
     if (!c || m <= 0 || n <= 0 || !colp || (nnz && (!rowi || !val))) return SMK_BAD_PARAM;
     return guarded(c, [&]() {
         SMK_CUDA(cudaSetDevice(c->device));
+        select_all(c);
         SparseDev& S = c->S;
         S.m = m; S.n = n; S.nnz = nnz;
         S.colptr.reserve(static_cast<size_t>(n) + 1);
@@ -231,6 +234,54 @@ int smk_load_csc(smk_ctx* c, int m, int n, unsigned int nnz, const unsigned int*
         build_csr(c->stream, S);
         c->m = m; c->n = n;
         c->has_sparse = true; c->has_dense = false; c->active = false;
+        return (int)SMK_OK;
+    });
+}
+
+int smk_select_columns(smk_ctx* c, const unsigned int* cols, int count, int* new_height, unsigned int* new_to_old_rows)
+{
+    if (!c || !new_height || !new_to_old_rows) return SMK_BAD_PARAM;
+    if (!c->has_dense && !c->has_sparse) return fail(c, SMK_BAD_PARAM, "no matrix loaded");
+    if (!cols || count <= 0) return fail(c, SMK_BAD_PARAM, "SubMatrixColsCompact: empty column set");
+    return guarded(c, [&]() {
+        SMK_CUDA(cudaSetDevice(c->device));
+        ensure_scratch(c);
+        *new_height = select_columns(c, cols, count, new_to_old_rows);
+        return (int)SMK_OK;
+    });
+}
+
+int smk_select_all(smk_ctx* c)
+{
+    if (!c) return SMK_BAD_PARAM;
+    select_all(c);
+    return SMK_OK;
+}
+
+int smk_nnls_hals(smk_ctx* c, int k, double* W, int ldW, double* H, int ldH, double tol, int max_iter, int* iterations)
+{
+    if (!c || !W || !H || k <= 0 || max_iter <= 0) return SMK_BAD_PARAM;
+    if (!c->has_dense && !c->has_sparse) return fail(c, SMK_BAD_PARAM, "no matrix loaded");
+    if (ldW < c->m || ldH < k) return fail(c, SMK_BAD_PARAM, "NnlsHals: non-conformant W and H");
+    if (k > 256) return fail(c, SMK_BAD_PARAM, "k > 256 is not supported");
+    return guarded(c, [&]() {
+        SMK_CUDA(cudaSetDevice(c->device));
+        smk_nmf_options o;
+        std::memset(&o, 0, sizeof(o));
+        o.tol = tol; o.algorithm = SMK_HALS; o.prog_est_algorithm = SMK_PG_RATIO;
+        o.height = c->m; o.width = c->n; o.k = k; o.min_iter = 1; o.max_iter = max_iter; o.tolcount = 1;
+        c->opts = o;
+        c->steps_done = 0;
+        ensure_scratch(c);
+        solver_alloc(c);
+        upload_W(c, W, ldW);
+        upload_tight(c, H, ldH, k, c->n, c->H.p);
+        c->active = true;
+        int rc = solver_nnls_hals(c, tol, max_iter, iterations);
+        if (rc != SMK_OK) return rc;
+        download_Wt(c, c->Wt.p, W, ldW);
+        download_tight(c, c->H.p, k, c->n, H, ldH);
+        SMK_CUDA(cudaStreamSynchronize(c->stream));
         return (int)SMK_OK;
     });
 }
@@ -429,7 +480,7 @@ int smk_nnls_bpp(smk_ctx* c, int k, int q, const double* LHS, const double* RHS,
         upload_tight(c, LHS, k, k, k, dL.p);
         upload_tight(c, RHS, k, k, q, dR.p);
         upload_tight(c, X, k, k, q, dX.p);
-        int init[ST_COUNT] = {0, INT_MAX, 0, 0};
+        int init[ST_COUNT] = {0, INT_MAX, 0, 0, 0};
         SMK_CUDA(cudaMemcpyAsync(c->status.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
         c->deferred.reserve(nnls_deferred_bytes(q));
         nnls_bpp(c->stream, k, q, dL.p, k, dR.p, k, dX.p, k, dY.p, k, c->status.p, c->counter.p, c->deferred.p, 0, c->num_sms);
@@ -449,7 +500,7 @@ int smk_sparse_gemm(smk_ctx* c, int variant, double alpha, const double* B, int 
     if (!c || !c->has_sparse || !B || !C || variant < 0 || variant > 3) return SMK_BAD_PARAM;
     return guarded(c, [&]() {
         SMK_CUDA(cudaSetDevice(c->device));
-        const SparseDev& S = c->S;
+        const SparseDev& S = *c->Sa;      // the active matrix (a column subset after smk_select_columns)
         const int m = S.m, n = S.n;
         // reference shape checks: sparse_gemm_ab_impl.hpp / sparse_gemm_ba_impl.hpp
         int k;

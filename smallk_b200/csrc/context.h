@@ -44,6 +44,9 @@ struct SparseDev
     // CSR = CSC of A', built by a stable counting sort (sparse_matrix_ops.hpp:37-126)
     DevBuf<unsigned int> rowptr, colidx;
     DevBuf<double> valr;
+    // build_csr temporaries; kept between calls only for the column-subset matrix, which is rebuilt many times
+    DevBuf<unsigned int> t_colof, t_ids, t_ids_sorted, t_rows_sorted;
+    DevBuf<unsigned char> t_sort;
 };
 
 } // namespace smk
@@ -62,7 +65,18 @@ struct smk_ctx
     long long ldA = 0;
     int m = 0, n = 0;
     smk::DevBuf<double> A_store;
-    smk::SparseDev S;
+    smk::SparseDev S;               // the loaded sparse matrix
+    smk::SparseDev* Sa = &S;        // the ACTIVE sparse matrix: &S, or &Ssub after smk_select_columns
+
+    // ---- column subset (hierclust: SubMatrixColsCompact), see submatrix.cu
+    bool subset_active = false;
+    const double* full_dA = nullptr;
+    long long full_ldA = 0;
+    int full_m = 0, full_n = 0;
+    smk::SparseDev Ssub;
+    smk::DevBuf<double> A_sub;
+    smk::DevBuf<unsigned int> sub_cols, sub_flags, sub_o2n, sub_n2o;
+    smk::DevBuf<unsigned char> sub_scan_tmp;
 
     // ---- scratch shared by kernels
     smk::DevBuf<double> ws;         // split-R partial tiles

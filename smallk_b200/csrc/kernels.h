@@ -9,7 +9,7 @@
 namespace smk {
 
 // device status words shared by the kernels of one solver
-enum { ST_ANY_NONOPT = 0, ST_FAIL_ITER = 1, ST_NORM_EPS = 2, ST_DEFER_COUNT = 3, ST_COUNT = 4 };
+enum { ST_ANY_NONOPT = 0, ST_FAIL_ITER = 1, ST_NORM_EPS = 2, ST_DEFER_COUNT = 3, ST_BAD_INDEX = 4, ST_COUNT = 5 };
 
 // ---- gemm_f64.cu ----------------------------------------------------------
 // C (M x N) = A (M x R, col-major) * Bop - D, Bop = B (R x N col-major) if !nt, else B' with B (N x R col-major).
@@ -61,6 +61,6 @@ struct SparseDev;
 void spmm_gather(cudaStream_t stream, int ncols, const unsigned int* ptr, const unsigned int* idx, const double* val,
                  int k, const double* B, long long ldb, double alpha, double beta, double* out, long long ldo, int num_sms);
 // Builds rowptr/colidx/valr (CSR = stable transpose) from the CSC arrays already on the device.
-void build_csr(cudaStream_t stream, SparseDev& S);
+void build_csr(cudaStream_t stream, SparseDev& S, bool keep_scratch = false);
 
 } // namespace smk

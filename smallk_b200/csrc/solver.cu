@@ -37,7 +37,7 @@ void prod_WtA(smk_ctx* c)
         gemm_f64(c->stream, false, k, c->n, c->m, c->Wt.p, k, c->dA, c->ldA, c->WtA.p, k, nullptr, 0,
                  c->ws.p, c->ws.n * sizeof(double), c->num_sms);
     else
-        spmm_gather(c->stream, c->n, c->S.colptr.p, c->S.rowidx.p, c->S.val.p, k, c->Wt.p, k, 1.0, 0.0, c->WtA.p, k, c->num_sms);
+        spmm_gather(c->stream, c->n, c->Sa->colptr.p, c->Sa->rowidx.p, c->Sa->val.p, k, c->Wt.p, k, 1.0, 0.0, c->WtA.p, k, c->num_sms);
 }
 
 // HAt (k x m) = H * A'   (summed over the column shards when running multi-GPU)
@@ -48,7 +48,7 @@ void prod_HAt(smk_ctx* c)
         gemm_f64(c->stream, true, k, c->m, c->n, c->H.p, k, c->dA, c->ldA, c->HAt.p, k, nullptr, 0,
                  c->ws.p, c->ws.n * sizeof(double), c->num_sms);
     else
-        spmm_gather(c->stream, c->m, c->S.rowptr.p, c->S.colidx.p, c->S.valr.p, k, c->H.p, k, 1.0, 0.0, c->HAt.p, k, c->num_sms);
+        spmm_gather(c->stream, c->m, c->Sa->rowptr.p, c->Sa->colidx.p, c->Sa->valr.p, k, c->H.p, k, 1.0, 0.0, c->HAt.p, k, c->num_sms);
     allreduce_sum(c, c->HAt.p, static_cast<size_t>(k) * c->m);
 }
 
@@ -96,7 +96,7 @@ void solver_alloc(smk_ctx* c)
     size_t want = std::max<size_t>(static_cast<size_t>(4 * c->num_sms) * k * k,
                                    std::min<size_t>(static_cast<size_t>(32) * k * std::max(m, n), (size_t(768) << 20) / sizeof(double)));
     c->ws.reserve(want);
-    int init[ST_COUNT] = {0, INT_MAX, 0, 0};
+    int init[ST_COUNT] = {0, INT_MAX, 0, 0, 0};
     SMK_CUDA(cudaMemcpyAsync(c->status.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
 }
 
@@ -213,6 +213,38 @@ int solver_normalize(smk_ctx* c)
     SMK_CUDA(cudaStreamSynchronize(c->stream));
     if (st[ST_NORM_EPS]) { c->err = "Normalize: column norm < machine epsilon"; return SMK_FAILURE; }
     return SMK_OK;
+}
+
+// NnlsHals (nnls.hpp:249-316): H-only HALS against a fixed W. Expects solver_alloc done with algorithm HALS and
+// Wt, H uploaded. Returns SMK_OK on convergence (W, H normalised), SMK_FAILURE at the iteration limit.
+int solver_nnls_hals(smk_ctx* c, double tol, int max_iter, int* iterations)
+{
+    const int k = c->opts.k, n = c->n;
+    compute_WtW(c);
+    prod_WtA(c);
+    double pg0 = 0.0;
+    int it = 0;
+    for (int i = 0; i < max_iter; ++i)
+    {
+        it = i + 1;
+        hals_sweep(c->stream, k, n, c->H.p, c->WtW.p, c->WtA.p, /*normalize=*/false, c->norms.p, c->partial.p, c->num_sms);
+        gram_times(c, c->WtW.p, c->H.p, n, c->WtA.p, c->gradH.p);
+        pg_sumsq(c->stream, static_cast<long long>(k) * n, c->gradH.p, c->H.p, c->partial.p, c->acc.p, c->num_sms);
+        double h = 0.0;
+        SMK_CUDA(cudaMemcpyAsync(&h, c->acc.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        SMK_CUDA(cudaStreamSynchronize(c->stream));
+        const double pg = sqrt(h);
+        if (pg != pg) { c->err = "ProjectedGradientNorm: NaN"; if (iterations) *iterations = it; return SMK_FAILURE; }
+        if (i == 0) { pg0 = pg; continue; }
+        if (pg < tol * pg0)
+        {
+            if (iterations) *iterations = it;
+            return solver_normalize(c);
+        }
+    }
+    if (iterations) *iterations = it;
+    c->err = "NNLS solver reached iteration limit.";
+    return SMK_FAILURE;
 }
 
 void solver_product(smk_ctx* c, int which) { if (which == 0) prod_WtA(c); else prod_HAt(c); }

@@ -12,5 +12,12 @@ int solver_progress(smk_ctx* c, double* metric);
 int solver_normalize(smk_ctx* c);
 int solver_fail_iter(smk_ctx* c);
 void solver_product(smk_ctx* c, int which);
+int solver_nnls_hals(smk_ctx* c, double tol, int max_iter, int* iterations);
+
+// ---- submatrix.cu: SubMatrixColsCompact on the device (sparse_matrix_impl.hpp:479-591,
+// dense_matrix_impl.hpp:224-285). Makes the listed columns of the loaded matrix the active matrix of the
+// context; returns the new height and writes new_to_old_rows (host, >= m entries).
+int select_columns(smk_ctx* c, const unsigned int* cols_host, int count, unsigned int* new_to_old_host);
+void select_all(smk_ctx* c);
 
 } // namespace smk

@@ -155,7 +155,7 @@ void spmm_gather(cudaStream_t stream, int ncols, const unsigned int* ptr, const 
 
 // Stable transpose on the device: a stable radix sort of the entry ids by row index keeps, inside each
 // row, the column-ascending / storage order of the CSC arrays.
-void build_csr(cudaStream_t stream, SparseDev& S)
+void build_csr(cudaStream_t stream, SparseDev& S, bool keep_scratch)
 {
     const unsigned int nnz = S.nnz;
     S.rowptr.reserve(static_cast<size_t>(S.m) + 1);
@@ -166,28 +166,30 @@ void build_csr(cudaStream_t stream, SparseDev& S)
         SMK_CUDA(cudaMemsetAsync(S.rowptr.p, 0, (static_cast<size_t>(S.m) + 1) * sizeof(unsigned int), stream));
         return;
     }
-    DevBuf<unsigned int> colof, ids, ids_sorted, rows_sorted;
-    colof.reserve(nnz); ids.reserve(nnz); ids_sorted.reserve(nnz); rows_sorted.reserve(nnz);
-    expand_cols_kernel<<<std::min(S.n, 65535), 128, 0, stream>>>(S.n, S.colptr.p, colof.p);
+    S.t_colof.reserve(nnz); S.t_ids.reserve(nnz); S.t_ids_sorted.reserve(nnz); S.t_rows_sorted.reserve(nnz);
+    expand_cols_kernel<<<std::min(S.n, 65535), 128, 0, stream>>>(S.n, S.colptr.p, S.t_colof.p);
     SMK_LAUNCH_CHECK();
-    iota_kernel<<<std::min<unsigned int>((nnz + 255) / 256, 65535u), 256, 0, stream>>>(nnz, ids.p);
+    iota_kernel<<<std::min<unsigned int>((nnz + 255) / 256, 65535u), 256, 0, stream>>>(nnz, S.t_ids.p);
     SMK_LAUNCH_CHECK();
     int end_bit = 1;
     while ((1ull << end_bit) < static_cast<unsigned long long>(S.m) && end_bit < 32) ++end_bit;
     size_t tmp_bytes = 0;
-    SMK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, S.rowidx.p, rows_sorted.p, ids.p, ids_sorted.p,
+    SMK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, S.rowidx.p, S.t_rows_sorted.p, S.t_ids.p, S.t_ids_sorted.p,
                                              static_cast<int>(nnz), 0, end_bit, stream));
-    DevBuf<unsigned char> tmp;
-    tmp.reserve(tmp_bytes);
-    SMK_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, S.rowidx.p, rows_sorted.p, ids.p, ids_sorted.p,
+    S.t_sort.reserve(tmp_bytes);
+    SMK_CUDA(cub::DeviceRadixSort::SortPairs(S.t_sort.p, tmp_bytes, S.rowidx.p, S.t_rows_sorted.p, S.t_ids.p, S.t_ids_sorted.p,
                                              static_cast<int>(nnz), 0, end_bit, stream));
     launch_counter() += 4;   // cub's own passes (approximate; not on the iteration path)
-    gather_perm_kernel<<<std::min<unsigned int>((nnz + 255) / 256, 65535u), 256, 0, stream>>>(nnz, ids_sorted.p, colof.p, S.val.p,
-                                                                                              S.colidx.p, S.valr.p);
+    gather_perm_kernel<<<std::min<unsigned int>((nnz + 255) / 256, 65535u), 256, 0, stream>>>(nnz, S.t_ids_sorted.p, S.t_colof.p,
+                                                                                              S.val.p, S.colidx.p, S.valr.p);
     SMK_LAUNCH_CHECK();
-    rowptr_kernel<<<std::min((S.m + 256) / 256, 65535), 256, 0, stream>>>(S.m, nnz, rows_sorted.p, S.rowptr.p);
+    rowptr_kernel<<<std::min((S.m + 256) / 256, 65535), 256, 0, stream>>>(S.m, nnz, S.t_rows_sorted.p, S.rowptr.p);
     SMK_LAUNCH_CHECK();
-    SMK_CUDA(cudaStreamSynchronize(stream));   // temporaries die here
+    if (!keep_scratch)
+    {
+        SMK_CUDA(cudaStreamSynchronize(stream));
+        S.t_colof.release(); S.t_ids.release(); S.t_ids_sorted.release(); S.t_rows_sorted.release(); S.t_sort.release();
+    }
 }
 
 } // namespace smk

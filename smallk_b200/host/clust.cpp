@@ -1,0 +1,444 @@
+// smallk_b200 host — HierNMF2 driver: Clust / ClustSparse of the reference (hierclust/src/clust.cpp:108-203) and
+// the generic tree-growing code behind them (hierclust/include/clust_hier_generic.hpp:77-517), re-organised
+// around a matrix that lives on the GPU:
+//   * the input matrix is uploaded once (smk_load_csc / smk_load_dense);
+//   * each node's column subset is extracted and row-compacted ON THE DEVICE (smk_select_columns), only the
+//     new->old row map comes back;
+//   * every rank-2 factorization is one smk_nmf call on the active subset;
+//   * labels, the (sparse) scatter of W back to m rows, priorities and tree updates are host work on k = 2 data.
+#include "clust.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <iostream>
+#include <limits>
+#include <sstream>
+#include <stdexcept>
+
+#include "host_internal.hpp"
+#include "matrix_io.hpp"
+
+using std::cerr;
+using std::cout;
+using std::endl;
+
+// --------------------------------------------------------------------------------------------------------------
+// IsValid(ClustOptions): hierclust/src/clust_options.cpp:24-110
+// --------------------------------------------------------------------------------------------------------------
+bool IsValid(const ClustOptions& opts, bool validate_matrix)
+{
+    if (validate_matrix)
+    {
+        if (opts.nmf_opts.height <= 0) { cerr << "error: matrix height must be a positive integer" << endl; return false; }
+        if (opts.nmf_opts.width <= 0) { cerr << "error: matrix width must be a positive integer" << endl; return false; }
+        if (opts.nmf_opts.k <= 0) { cerr << "error: cluster count must be a positive integer" << endl; return false; }
+        if (opts.nmf_opts.k > opts.nmf_opts.width) { cerr << "error: k value cannot exceed the matrix width" << endl; return false; }
+    }
+    if (opts.num_clusters <= 1) { cerr << "error: number of clusters must be >= 2" << endl; return false; }
+    if (opts.nmf_opts.tol <= 0.0 || opts.nmf_opts.tol >= 1.0) { cerr << "error: tolerance must be in the interval (0.0, 1.0)" << endl; return false; }
+    if (opts.nmf_opts.min_iter <= 0) { cerr << "error: miniter must be a positive integer" << endl; return false; }
+    if (opts.nmf_opts.max_iter <= 0) { cerr << "error: maxiter must be a positive integer" << endl; return false; }
+    if (opts.maxterms <= 0) { cerr << "error: maxterms must be a positive integer" << endl; return false; }
+    if (opts.trial_allowance < 0) { cerr << "error: trial_allowance for hierarchical clustering is negative" << endl; return false; }
+    if (opts.unbalanced < 0.0 || opts.unbalanced >= 1.0) { cerr << "error: the unbalanced value should be in the interval [0, 1)" << endl; return false; }
+    if (NmfProgressAlgorithm::PG_RATIO != opts.nmf_opts.prog_est_algorithm && NmfProgressAlgorithm::DELTA_FNORM != opts.nmf_opts.prog_est_algorithm)
+    { cerr << "error: unknown stopping criterion " << endl; return false; }
+    return true;
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// priority score
+// --------------------------------------------------------------------------------------------------------------
+namespace {
+
+// Row indices in decreasing order of v, ties by ascending row (desc_ordered, clust_hier_util.hpp:46-57). The order is
+// total, so any correct sort reproduces it; factor columns are mostly exact zeros below the root, so the rows are
+// split into positive / zero / negative groups and only the two outer groups are sorted.
+void desc_order(const R* v, const int n, std::vector<int>& order)
+{
+    order.resize(n);
+    int npos = 0, nzero = 0;
+    for (int i = 0; i < n; ++i) { if (v[i] > 0) ++npos; else if (v[i] == 0) ++nzero; }
+    int ip = 0, iz = npos, in = npos + nzero;
+    for (int i = 0; i < n; ++i)
+    {
+        if (v[i] > 0) order[ip++] = i;
+        else if (v[i] == 0) order[iz++] = i;
+        else order[in++] = i;                       // negative or NaN (NaN never occurs in a successful factorization)
+    }
+    auto cmp = [v](int a, int b) { return v[a] > v[b] || (v[a] == v[b] && a < b); };
+    std::sort(order.begin(), order.begin() + npos, cmp);
+    std::sort(order.begin() + npos + nzero, order.end(), cmp);
+}
+
+// log(i) and log2(i) of small integers are needed ~4m times per split; tabulated once per matrix height
+struct LogTables
+{
+    std::vector<double> ln, lg2;
+    void ensure(const int n)
+    {
+        if (static_cast<int>(ln.size()) > n + 1) return;
+        const int old = static_cast<int>(ln.size());
+        ln.resize(n + 2); lg2.resize(n + 2);
+        for (int i = old; i < n + 2; ++i) { ln[i] = std::log(static_cast<double>(i)); lg2[i] = std::log2(static_cast<double>(i)); }
+    }
+};
+LogTables g_logs;
+
+// NDCG_part (clust_hier_util.hpp:61-100) numerator: positions i of `test` in order, gain = weight_part at the
+// parent rank of row test[i], discounted by log2(i+1) for i > 0, accumulated left to right.
+R dcg_of(const std::vector<int>& test, const std::vector<int>& rank_parent, const std::vector<R>& weight_part)
+{
+    const int n = static_cast<int>(test.size());
+    R cum = weight_part[rank_parent[test[0]]];
+    for (int i = 1; i < n; ++i)
+    {
+        const R g = weight_part[rank_parent[test[i]]];
+        cum = cum + g / g_logs.lg2[i + 1];
+    }
+    return cum;
+}
+
+} // namespace
+
+R compute_priority(const R* W_parent, const R* W_child, const int n)
+{
+    std::vector<int> ord_p, ord_1, ord_2;
+    int n_part = 0;
+    for (int i = 0; i < n; ++i) if (W_parent[i] != 0) ++n_part;
+    if (n_part <= 1) return R(-3);
+    desc_order(W_parent, n, ord_p);
+    desc_order(W_child, n, ord_1);
+    desc_order(W_child + n, n, ord_2);
+    g_logs.ensure(n);
+    const std::vector<double>& ln = g_logs.ln;
+
+    std::vector<R> weight(n), weight_part(n);
+    for (int i = 0; i < n; ++i) weight[i] = ln[n - i];
+    int first_zero = -1;
+    for (int i = 0; i < n; ++i) if (W_parent[ord_p[i]] == 0) { first_zero = i; break; }
+    if (first_zero > -1) for (int i = first_zero; i < n; ++i) weight[i] = 1;
+    for (int i = 0; i < n_part; ++i) weight_part[i] = ln[n_part - i];
+    for (int i = n_part; i < n; ++i) weight_part[i] = 0;
+
+    // rank of every row in the two child orderings; the worse of the two discounts the row
+    std::vector<int> rank_1(n), rank_2(n), rank_p(n);
+    for (int p = 0; p < n; ++p) { rank_1[ord_1[p]] = p; rank_2[ord_2[p]] = p; rank_p[ord_p[p]] = p; }
+    for (int i = 0; i < n; ++i)
+    {
+        const int row = ord_p[i];
+        const int worst = rank_1[row] < rank_2[row] ? rank_2[row] : rank_1[row];
+        R discount = ln[n - worst];
+        if (discount == 0) discount = ln[2];
+        weight[i] = weight[i] / discount;
+        weight_part[i] = weight_part[i] / discount;
+    }
+
+    const R dcg1 = dcg_of(ord_1, rank_p, weight_part);
+    const R dcg2 = dcg_of(ord_2, rank_p, weight_part);
+    // ideal score: the weights in decreasing order with the same discounting (identical for both children)
+    std::sort(weight.begin(), weight.end(), std::greater<R>());
+    R ideal = weight[0];
+    for (int i = 1; i < n; ++i) ideal = ideal + weight[i] / g_logs.lg2[i + 1];
+    return (dcg1 / ideal) * (dcg2 / ideal);
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// tree growing
+// --------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Factor          // the rank-2 factors of one node: W is m x 2 (ld = m), H is 2 x cols
+{
+    std::vector<R> W, H;
+    unsigned int cols = 0;
+};
+
+struct HierRun
+{
+    smk_ctx* ctx;
+    const ClustOptions& opts;
+    unsigned int m, n;
+    Random& rng;
+    ClustStats& stats;
+    std::vector<unsigned int> new_to_old;      // scratch, m entries
+    std::vector<R> Wsub, Hsub, Winit_full, Hinit_full;
+    int init_counter = 1;                      // Winit_<i>.csv / Hinit_<i>.csv, clust_hier_generic.hpp:586
+
+    HierRun(smk_ctx* c, const ClustOptions& o, Random& r, ClustStats& s)
+        : ctx(c), opts(o), m(o.nmf_opts.height), n(o.nmf_opts.width), rng(r), stats(s), new_to_old(o.nmf_opts.height) {}
+
+    // LoadInitializers, clust_hier_generic.hpp:568-609
+    void load_initializers()
+    {
+        std::ostringstream fw, fh;
+        fw << opts.initdir << "Winit_" << init_counter << ".csv";
+        fh << opts.initdir << "Hinit_" << init_counter << ".csv";
+        unsigned int h = 0, w = 0;
+        if (!smallk_io::LoadDelimitedFile(Winit_full, h, w, fw.str()) || h != m || w != 2)
+            throw std::runtime_error("Load failed for file " + fw.str());
+        if (!smallk_io::LoadDelimitedFile(Hinit_full, h, w, fh.str()) || h != 2 || w != n)
+            throw std::runtime_error("Load failed for file " + fh.str());
+        ++init_counter;
+    }
+
+    // One rank-2 NMF of the active matrix (height x width) from the initial guess in W, H. Throws what the
+    // reference lets escape; returns false where NmfSolve returns false.
+    bool factor(const int height, const int width, R* W, R* H)
+    {
+        NmfOptions o = opts.nmf_opts;
+        o.height = height; o.width = width; o.k = 2; o.algorithm = NmfAlgorithm::RANK2;
+        smk_nmf_options a = NmfToAbi(o);
+        smk_nmf_stats st = {0, 0};
+        const int rc = smk_nmf(ctx, &a, W, height, H, 2, &st);
+        stats.iteration_count += st.iteration_count;
+        if (rc == SMK_OK)
+        {
+            stats.nmf_count += 1;
+            if (st.iteration_count == o.max_iter) stats.max_count += 1;
+            return true;
+        }
+        const std::string err = smk_last_error(ctx);
+        NmfSetLastError(err.c_str());
+        if (rc != SMK_FAILURE) throw std::runtime_error("HierNMF2: " + err);
+        if (err.find("Normalize:") == 0 || err.find("ProjectedGradientNorm") == 0) throw std::runtime_error(err);
+        return false;
+    }
+
+    // clust_hier_generic.hpp:383-517
+    R actual_split(const std::vector<unsigned int>& subset, const R* W_parent, Factor& out, std::vector<unsigned int>& labels)
+    {
+        const size_t cnt = subset.size();
+        out.cols = static_cast<unsigned int>(cnt);
+        out.W.assign(static_cast<size_t>(m) * 2, R(0));
+        out.H.assign(cnt * 2, R(0));
+        if (cnt <= 3) { labels.assign(cnt, 1u); return R(-1); }
+
+        int new_height = 0;
+        const int rc = smk_select_columns(ctx, subset.data(), static_cast<int>(cnt), &new_height, new_to_old.data());
+        if (rc != SMK_OK) throw std::logic_error(smk_last_error(ctx));
+
+        Wsub.resize(static_cast<size_t>(new_height) * 2);
+        Hsub.resize(cnt * 2);
+        bool ok = false;
+        for (int attempt = 0; attempt < 3 && !ok; ++attempt)
+        {
+            if (!opts.initdir.empty())
+            {
+                load_initializers();           // ExtractSubmatrices, clust_hier_generic.hpp:521-544
+                for (int r = 0; r < new_height; ++r)
+                {
+                    Wsub[r] = Winit_full[new_to_old[r]];
+                    Wsub[static_cast<size_t>(new_height) + r] = Winit_full[static_cast<size_t>(m) + new_to_old[r]];
+                }
+                for (size_t c = 0; c < cnt; ++c) { Hsub[2 * c] = Hinit_full[2 * static_cast<size_t>(subset[c])]; Hsub[2 * c + 1] = Hinit_full[2 * static_cast<size_t>(subset[c]) + 1]; }
+            }
+            else
+            {
+                RandomMatrix(Wsub.data(), new_height, new_height, 2, rng, R(0.5), R(0.5));
+                RandomMatrix(Hsub.data(), 2, 2, static_cast<unsigned int>(cnt), rng, R(0.5), R(0.5));
+            }
+            ok = factor(new_height, static_cast<int>(cnt), Wsub.data(), Hsub.data());
+            if (!ok) cout << "\nNode factorization failed, retrying with new initializers..." << endl;
+        }
+        if (!ok) throw std::runtime_error("HierNMF2: node factorization failed after three attempts.");
+
+        bool has_0 = false, has_1 = false;
+        labels.resize(cnt);
+        for (size_t c = 0; c < cnt; ++c)
+        {
+            if (Hsub[2 * c] > Hsub[2 * c + 1]) { labels[c] = 0u; has_0 = true; }
+            else { labels[c] = 1u; has_1 = true; }
+        }
+        for (int r = 0; r < new_height; ++r)
+        {
+            out.W[new_to_old[r]] = Wsub[r];
+            out.W[static_cast<size_t>(m) + new_to_old[r]] = Wsub[static_cast<size_t>(new_height) + r];
+        }
+        out.H = Hsub;
+        return (has_0 && has_1) ? compute_priority(W_parent, out.W.data(), static_cast<int>(m)) : R(-1);
+    }
+
+    // clust_hier_generic.hpp:245-376
+    R trial_split(std::vector<unsigned int>& subset, const R min_priority, const R* W_parent, Factor& out)
+    {
+        const std::vector<unsigned int> backup(subset);
+        std::vector<unsigned int> labels, small, labels_small;
+        Factor tmp;
+        int trial = 0;
+        R priority = R(-2);
+        while (trial < opts.trial_allowance)
+        {
+            priority = actual_split(subset, W_parent, out, labels);
+            if (priority < R(0)) break;
+            int counts[2] = {0, 0};
+            for (unsigned int l : labels) counts[l] += 1;
+            const int smallest = std::min(counts[0], counts[1]);
+            if (!(smallest < opts.unbalanced * labels.size())) break;
+
+            const unsigned int small_label = (smallest == counts[0]) ? 0u : 1u;
+            small.clear();
+            for (size_t q = 0; q < labels.size(); ++q) if (labels[q] == small_label) small.push_back(subset[q]);
+            // priority of the small cluster, with its own topic vector (a column of this split's W) as parent
+            const std::vector<R> w_col(out.W.begin() + static_cast<size_t>(small_label) * m, out.W.begin() + static_cast<size_t>(small_label + 1) * m);
+            const R priority_small = actual_split(small, w_col.data(), tmp, labels_small);
+            if (priority_small < min_priority)
+            {
+                trial += 1;
+                if (trial < opts.trial_allowance)
+                {
+                    cout << "dropping " << small.size() << " items ..." << endl;
+                    std::vector<unsigned int> kept;         // SetDiff(subset, small): both ascending
+                    kept.reserve(subset.size() - small.size());
+                    std::set_difference(subset.begin(), subset.end(), small.begin(), small.end(), std::back_inserter(kept));
+                    subset.swap(kept);
+                }
+            }
+            else break;
+        }
+        if (trial == opts.trial_allowance)
+        {
+            if (opts.verbose) cout << "recycling " << small.size() << " items ..." << endl;
+            subset = backup;
+            std::fill(out.W.begin(), out.W.end(), R(0));
+            out.cols = static_cast<unsigned int>(subset.size());
+            out.H.assign(subset.size() * 2, R(0));
+            priority = R(-2);
+        }
+        return priority;
+    }
+
+    // clust_hier_generic.hpp:77-238
+    bool grow(Tree<R>& tree)
+    {
+        const unsigned int num_clusters = opts.num_clusters;
+        if (num_clusters <= 1) throw std::runtime_error("HierNMF2: number of clusters must be >= 2");
+        const unsigned int node_count = 2 * (num_clusters - 1);
+        tree.Init(num_clusters, node_count, m, n);
+
+        // root: the whole matrix
+        smk_select_all(ctx);
+        Factor root;
+        root.W.resize(static_cast<size_t>(m) * 2); root.H.resize(static_cast<size_t>(n) * 2); root.cols = n;
+        bool ok = false;
+        for (int attempt = 0; attempt < 3 && !ok; ++attempt)
+        {
+            if (!opts.initdir.empty()) { load_initializers(); root.W = Winit_full; root.H = Hinit_full; }
+            else
+            {
+                RandomMatrix(root.W.data(), m, m, 2, rng, R(0.5), R(0.5));
+                RandomMatrix(root.H.data(), 2, 2, n, rng, R(0.5), R(0.5));
+            }
+            ok = factor(static_cast<int>(m), static_cast<int>(n), root.W.data(), root.H.data());
+            if (!ok) cout << "\nRoot node factorization failed, retrying with new initializers..." << endl;
+        }
+        if (!ok) throw std::runtime_error("HierNMF2: root node factorization failed after three attempts");
+
+        std::vector<Factor> node_factor(node_count);
+        R min_priority = std::numeric_limits<R>::infinity(), max_priority = 0;
+        unsigned int split_index = 0;
+        for (unsigned int i = 0; i + 1 < num_clusters; ++i)
+        {
+            if (0 == i) tree.SplitRoot(root.W.data(), root.H.data(), root.cols);
+            else
+            {
+                tree.MinMaxLeafPriorities(min_priority, max_priority, split_index);
+                if (max_priority < R(0)) { cout << "\nHierNMF2: no further factorization possible.\n" << endl; break; }
+                const Factor& f = node_factor[split_index];
+                tree.Split(split_index, f.W.data(), f.H.data(), f.cols);
+            }
+            const unsigned int i0 = tree.LeftChildIndex(), i1 = tree.RightChildIndex();
+            {
+                const std::vector<R> parent(tree.LeftChildTopicVector());
+                tree.SetNodePriority(i0, trial_split(tree.LeftChildDocs(), min_priority, parent.data(), node_factor[i0]));
+            }
+            {
+                const std::vector<R> parent(tree.RightChildTopicVector());
+                tree.SetNodePriority(i1, trial_split(tree.RightChildDocs(), min_priority, parent.data(), node_factor[i1]));
+            }
+            if (opts.verbose) { cout << "[" << (i + 1) << "] "; cout.flush(); }
+            // the factors of a node that has been split are never read again
+            if (i > 0) { Factor().W.swap(node_factor[split_index].W); Factor().H.swap(node_factor[split_index].H); }
+        }
+        smk_select_all(ctx);
+        tree.ComputeTopTerms(opts.maxterms);
+        tree.ComputeAssignments();
+        cout << endl;
+        return true;
+    }
+
+    // ClustFlat, hierclust/include/clust_flat_generic.hpp:33-74
+    bool flat(Tree<R>& tree, R* buf_w, R* buf_h)
+    {
+        const unsigned int k = opts.num_clusters;
+        if (!tree.FlatclustInitW(buf_w, m, m, k)) return false;
+        smk_select_all(ctx);
+        bool ok = false;
+        for (int attempt = 0; attempt < 3 && !ok; ++attempt)
+        {
+            RandomMatrix(buf_h, k, k, n, rng, R(0.5), R(0.5));
+            int iters = 0;
+            const int rc = smk_nnls_hals(ctx, static_cast<int>(k), buf_w, static_cast<int>(m), buf_h, static_cast<int>(k),
+                                         opts.nmf_opts.tol, opts.nmf_opts.max_iter, &iters);
+            if (rc == SMK_OK) ok = true;
+            else
+            {
+                const std::string err = smk_last_error(ctx);
+                if (rc != SMK_FAILURE || err.find("Normalize:") == 0) throw std::runtime_error(err);
+                cerr << err << endl;
+            }
+        }
+        if (!ok) cout << "Flatclust NNLS solver failed after 3 attempts." << endl;
+        return ok;
+    }
+};
+
+Result check_sizes(const ClustOptions& options)
+{
+    if (!NmfContext())
+    {
+        cerr << "clustlib error: nmf_initialize() must be called prior to any clustering routine\n" << endl;
+        return Result::NOTINITIALIZED;
+    }
+    if (!IsValid(options)) return Result::BAD_PARAM;
+    const unsigned long long lim = std::numeric_limits<int>::max();
+    if (2ull * options.nmf_opts.height > lim) { cerr << "W matrix size too large" << endl; return Result::SIZE_TOO_LARGE; }
+    if (2ull * options.nmf_opts.width > lim) { cerr << "H matrix size too large" << endl; return Result::SIZE_TOO_LARGE; }
+    return Result::OK;
+}
+
+Result run(const ClustOptions& options, R* buf_w, R* buf_h, Tree<R>& tree, ClustStats& stats, Random& rng)
+{
+    HierRun job(NmfContext(), options, rng, stats);
+    if (!job.grow(tree)) return Result::FAILURE;
+    if (options.flat && !job.flat(tree, buf_w, buf_h))
+    {
+        cerr << "Flat clustering failed." << endl;
+        return Result::FLATCLUST_FAILURE;
+    }
+    return Result::OK;
+}
+
+} // namespace
+
+Result Clust(const ClustOptions& options, R* buf_a, const int ldim_a, R* buf_w, R* buf_h, Tree<R>& tree, ClustStats& stats,
+             Random& rng)
+{
+    const Result r = check_sizes(options);
+    if (Result::OK != r) return r;
+    if (ldim_a < options.nmf_opts.height) throw std::logic_error("invalid leading dimension for input matrix");
+    const int rc = smk_load_dense(NmfContext(), buf_a, ldim_a, options.nmf_opts.height, options.nmf_opts.width);
+    if (rc != SMK_OK) { NmfSetLastError(smk_last_error(NmfContext())); return NmfFromAbi(rc); }
+    return run(options, buf_w, buf_h, tree, stats, rng);
+}
+
+Result ClustSparse(const ClustOptions& options, const SparseMatrix<R>& A, R* buf_w, R* buf_h, Tree<R>& tree, ClustStats& stats,
+                   Random& rng)
+{
+    const Result r = check_sizes(options);
+    if (Result::OK != r) return r;
+    const int rc = smk_load_csc(NmfContext(), static_cast<int>(A.Height()), static_cast<int>(A.Width()), A.Size(),
+                                A.LockedColBuffer(), A.LockedRowBuffer(), A.LockedDataBuffer());
+    if (rc != SMK_OK) { NmfSetLastError(smk_last_error(NmfContext())); return NmfFromAbi(rc); }
+    return run(options, buf_w, buf_h, tree, stats, rng);
+}

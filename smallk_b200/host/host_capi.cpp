@@ -1,0 +1,156 @@
+// smallk_b200 host — extern "C" veneer over the C++ host interface (Clust/ClustSparse, FlatClust*), for language
+// bindings (the reference ships a Cython binding, pysmallk; here ctypes loads these symbols). Tests call the
+// C++ host layer through this file so that what is checked against the reference is the shipped driver code.
+#include <chrono>
+#include <cstring>
+#include <iostream>
+#include <vector>
+
+#include "clust.hpp"
+#include "flat_clust.hpp"
+
+namespace {
+
+void EnsureInit()
+{
+    if (Result::INITIALIZED != NmfIsInitialized()) { static int argc = 0; NmfInitialize(argc, nullptr); }
+}
+
+ClustOptions MakeOpts(int m, int n, int num_clusters, double tol, int min_iter, int max_iter, int maxterms, double unbalanced,
+                      int trial_allowance, int flat, int normalize, int verbose)
+{
+    ClustOptions o;
+    o.nmf_opts.tol = tol;
+    o.nmf_opts.algorithm = NmfAlgorithm::RANK2;
+    o.nmf_opts.prog_est_algorithm = NmfProgressAlgorithm::PG_RATIO;
+    o.nmf_opts.height = m; o.nmf_opts.width = n; o.nmf_opts.k = 2;
+    o.nmf_opts.min_iter = min_iter; o.nmf_opts.max_iter = max_iter; o.nmf_opts.tolcount = 1;
+    o.nmf_opts.max_threads = 1; o.nmf_opts.verbose = false; o.nmf_opts.normalize = (normalize != 0);
+    o.maxterms = maxterms; o.unbalanced = unbalanced; o.trial_allowance = trial_allowance;
+    o.num_clusters = num_clusters; o.verbose = (verbose != 0); o.flat = (flat != 0);
+    return o;
+}
+
+void ExportTree(Tree<R>& tree, int num_clusters, int maxterms, int n, int* assignments, int* parent, int* left, int* right,
+                int* is_left, int* doc_count, int* terms, double* priority, int* is_leaf, int* n_outliers)
+{
+    const int nodes = 2 * (num_clusters - 1);
+    for (int q = 0; q < nodes; ++q)
+    {
+        const Tree<R>::NodeView v = tree.Node(q);
+        parent[q] = v.parent; left[q] = v.left; right[q] = v.right; is_left[q] = v.is_left_child ? 1 : 0;
+        doc_count[q] = static_cast<int>(v.doc_count);
+        for (int t = 0; t < maxterms; ++t) terms[q * maxterms + t] = (t < static_cast<int>(v.terms->size())) ? (*v.terms)[t] : -1;
+        if (priority) priority[q] = v.is_valid ? v.priority : 0.0;
+        if (is_leaf) is_leaf[q] = v.is_leaf ? 1 : 0;
+    }
+    const std::vector<unsigned int>& a = tree.Assignments();
+    for (int j = 0; j < n; ++j) assignments[j] = (a[j] == Tree<R>::NONE) ? -1 : static_cast<int>(a[j]);
+    if (n_outliers) *n_outliers = static_cast<int>(tree.Outliers().size());
+}
+
+int Finish(Result r, const ClustOptions& o, Tree<R>& tree, ClustStats& cs, int n, int* assignments, int* parent, int* left,
+           int* right, int* is_left, int* doc_count, int* terms, double* priority, int* is_leaf, int* n_outliers,
+           const std::vector<R>& w, const std::vector<R>& h, double* buf_w, double* buf_h, long long* stats, int* flat_assignments)
+{
+    if (stats) { stats[0] = cs.nmf_count; stats[1] = cs.max_count; stats[2] = cs.iteration_count; }
+    if (Result::OK != r) return static_cast<int>(r);
+    ExportTree(tree, o.num_clusters, o.maxterms, n, assignments, parent, left, right, is_left, doc_count, terms, priority, is_leaf, n_outliers);
+    if (o.flat)
+    {
+        if (buf_w) std::memcpy(buf_w, w.data(), sizeof(R) * w.size());
+        if (buf_h) std::memcpy(buf_h, h.data(), sizeof(R) * h.size());
+        if (flat_assignments)
+        {
+            std::vector<unsigned int> fa;
+            ComputeAssignments(fa, h.data(), o.num_clusters, o.num_clusters, n);
+            for (int j = 0; j < n; ++j) flat_assignments[j] = static_cast<int>(fa[j]);
+        }
+    }
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* smkh_last_error() { return NmfLastError(); }
+
+// ClustSparse (hierclust/src/clust.cpp:160). stats[0..2] = nmf_count, max_count, total rank-2 iterations.
+int smkh_hierclust_sparse(int m, int n, unsigned int nz, const unsigned int* col_offsets, const unsigned int* row_indices,
+                          const double* data, int num_clusters, double tol, int min_iter, int max_iter, int maxterms,
+                          double unbalanced, int trial_allowance, int flat, int normalize, int seed, int verbose,
+                          int* assignments, int* parent, int* left, int* right, int* is_left, int* doc_count, int* terms,
+                          double* priority, int* is_leaf, int* n_outliers, double* buf_w, double* buf_h, long long* stats,
+                          int* flat_assignments, double* elapsed_s)
+{
+    try
+    {
+        EnsureInit();
+        ClustOptions o = MakeOpts(m, n, num_clusters, tol, min_iter, max_iter, maxterms, unbalanced, trial_allowance, flat, normalize, verbose);
+        SparseMatrix<R> A(m, n, nz, col_offsets, row_indices, data);
+        Tree<R> tree; ClustStats cs; Random rng; rng.SeedFromInt(seed);
+        std::vector<R> w(static_cast<size_t>(m) * num_clusters), h(static_cast<size_t>(num_clusters) * n);
+        const auto t0 = std::chrono::steady_clock::now();
+        const Result r = ClustSparse(o, A, w.data(), h.data(), tree, cs, rng);
+        if (elapsed_s) *elapsed_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        return Finish(r, o, tree, cs, n, assignments, parent, left, right, is_left, doc_count, terms, priority, is_leaf, n_outliers,
+                      w, h, buf_w, buf_h, stats, flat_assignments);
+    }
+    catch (std::exception& e) { std::cerr << "smkh_hierclust_sparse: " << e.what() << std::endl; return -100; }
+}
+
+// Clust (hierclust/src/clust.cpp:108)
+int smkh_hierclust_dense(int m, int n, double* A, int ldA, int num_clusters, double tol, int min_iter, int max_iter,
+                         int maxterms, double unbalanced, int trial_allowance, int flat, int normalize, int seed, int verbose,
+                         int* assignments, int* parent, int* left, int* right, int* is_left, int* doc_count, int* terms,
+                         double* priority, int* is_leaf, int* n_outliers, double* buf_w, double* buf_h, long long* stats,
+                         int* flat_assignments, double* elapsed_s)
+{
+    try
+    {
+        EnsureInit();
+        ClustOptions o = MakeOpts(m, n, num_clusters, tol, min_iter, max_iter, maxterms, unbalanced, trial_allowance, flat, normalize, verbose);
+        Tree<R> tree; ClustStats cs; Random rng; rng.SeedFromInt(seed);
+        std::vector<R> w(static_cast<size_t>(m) * num_clusters), h(static_cast<size_t>(num_clusters) * n);
+        const auto t0 = std::chrono::steady_clock::now();
+        const Result r = Clust(o, A, ldA, w.data(), h.data(), tree, cs, rng);
+        if (elapsed_s) *elapsed_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        return Finish(r, o, tree, cs, n, assignments, parent, left, right, is_left, doc_count, terms, priority, is_leaf, n_outliers,
+                      w, h, buf_w, buf_h, stats, flat_assignments);
+    }
+    catch (std::exception& e) { std::cerr << "smkh_hierclust_dense: " << e.what() << std::endl; return -100; }
+}
+
+// FlatClust / FlatClustSparse + ComputeAssignments + TopTerms. csc == null pointers -> dense A.
+int smkh_flatclust(int alg, int m, int n, int k, double tol, int min_iter, int max_iter, int maxterms,
+                   double* A, int ldA, unsigned int nz, const unsigned int* col_offsets, const unsigned int* row_indices,
+                   const double* data, double* W, double* H, int* assignments, int* term_indices, int* iterations)
+{
+    try
+    {
+        EnsureInit();
+        NmfOptions o;
+        o.tol = tol; o.algorithm = static_cast<NmfAlgorithm>(alg); o.prog_est_algorithm = NmfProgressAlgorithm::PG_RATIO;
+        o.height = m; o.width = n; o.k = k; o.min_iter = min_iter; o.max_iter = max_iter; o.tolcount = 1;
+        o.max_threads = 1; o.verbose = false; o.normalize = true;
+        NmfStats st;
+        const Result r = A ? FlatClust(o, A, ldA, W, m, H, k, st)
+                           : FlatClustSparse(o, m, n, nz, col_offsets, row_indices, data, W, m, H, k, st);
+        if (iterations) *iterations = st.iteration_count;
+        if (Result::OK != r) return static_cast<int>(r);
+        std::vector<unsigned int> fa;
+        ComputeAssignments(fa, H, k, k, n);
+        for (int j = 0; j < n; ++j) assignments[j] = static_cast<int>(fa[j]);
+        std::vector<int> ti(static_cast<size_t>(maxterms) * k);
+        TopTerms(maxterms, W, m, m, k, ti);
+        for (size_t i = 0; i < ti.size(); ++i) term_indices[i] = ti[i];
+        return 0;
+    }
+    catch (std::exception& e) { std::cerr << "smkh_flatclust: " << e.what() << std::endl; return -100; }
+}
+
+// compute_priority (clust_hier_util.hpp:105-173) on host buffers — unit-testable without a GPU.
+double smkh_compute_priority(const double* W_parent, const double* W_child, int m) { return compute_priority(W_parent, W_child, m); }
+
+} // extern "C"

@@ -8,7 +8,7 @@
 #include <stdexcept>
 #include <string>
 
-#include "../../include/smallk_b200.h"
+#include "host_internal.hpp"
 
 namespace {
 smk_ctx* g_ctx = nullptr;
@@ -100,6 +100,10 @@ void NmfFinalize()
 }
 
 const char* NmfLastError() { return g_err.c_str(); }
+smk_ctx* NmfContext() { return g_ctx; }
+smk_nmf_options NmfToAbi(const NmfOptions& o) { return ToAbi(o); }
+Result NmfFromAbi(int rc) { return FromAbi(rc); }
+void NmfSetLastError(const char* msg) { g_err = msg ? msg : ""; }
 
 bool IsValid(const NmfOptions& opts, bool validate_matrix)
 {

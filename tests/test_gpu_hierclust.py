@@ -1,0 +1,97 @@
+"""HierNMF2 (hierclust) on the GPU: the C++ host driver (smallk_b200/host/clust.cpp) over the CUDA library against
+(1) fixtures produced by the reference's own hierclust code (tests/golden/hier_*.npz) and (2), where the compiled
+reference travelled with the snapshot (oracle/_ref), the reference itself on fresh seeds. Cluster assignments, tree
+topology, document counts and top terms must be identical; priorities (floating point) to 1e-9."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import smallk_b200 as sk
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+sys.path.insert(0, HERE)
+import make_golden_hier as mh      # noqa: E402
+from graphgen import powerlaw_graph  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+EXACT = ["assignments", "parent", "left", "right", "is_left", "doc_count", "is_leaf", "terms"]
+
+
+def check_tree(got, want, name):
+    assert got["rc"] == 0, (name, got["rc"])
+    for key in EXACT:
+        assert np.array_equal(got[key], want[key]), (name, key, got[key], want[key])
+    assert int(got["n_outliers"]) == int(want["n_outliers"])
+    assert int(got["nmf_count"]) == int(want["nmf_count"])
+    assert np.allclose(got["priority"], want["priority"], rtol=1e-9, atol=0), (name, got["priority"], want["priority"])
+
+
+@pytest.mark.parametrize("name", sorted(mh.HIER_CASES))
+def test_hierclust_reproduces_reference_fixture(name):
+    g = mh.hier_inputs(name)
+    z = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    got = sk.hierclust(A_dense=g["A"], csc=g["csc"], shape=g["shape"], num_clusters=g["num_clusters"], seed=g["seed"], **g["extra"])
+    check_tree(got, z, name)
+    if g["extra"].get("flat"):
+        assert np.array_equal(got["flat_assignments"], z["flat_assignments"])
+        assert np.linalg.norm(got["H"] - z["H"]) <= 1e-7 * np.linalg.norm(z["H"])
+        assert np.linalg.norm(got["W"] - z["W"]) <= 1e-9 * np.linalg.norm(z["W"])
+
+
+def test_hierclust_matches_live_reference_on_fresh_seeds():
+    from oracle import Ref
+    if not Ref.available():
+        pytest.skip("oracle/_ref not built on this machine")
+    ref = Ref()
+    for n, deg, gseed, clusters, seed in ((2500, 9, 77, 7, 21), (1200, 16, 78, 5, 22), (4000, 8, 79, 10, 23)):
+        csc = powerlaw_graph(n, deg, gseed)
+        want = ref.hierclust(csc=csc, shape=(n, n), num_clusters=clusters, seed=seed, max_threads=1)
+        got = sk.hierclust(csc=csc, shape=(n, n), num_clusters=clusters, seed=seed)
+        check_tree(got, want, f"graph{n}")
+
+
+def test_select_columns_is_submatrix_cols_compact(gpu):
+    """Device SubMatrixColsCompact: the active subset behaves as A(:, cols) with empty rows removed."""
+    import scipy.sparse as sps
+    rng = np.random.default_rng(5)
+    m, n = 500, 300
+    S = sps.random(m, n, density=0.01, random_state=np.random.RandomState(1), format="csc",
+                   data_rvs=np.random.RandomState(2).random_sample)
+    S.sort_indices()
+    gpu.load_csc((m, n), S.indptr, S.indices, S.data)
+    cols = np.sort(rng.choice(n, size=40, replace=False)).astype(np.uint32)
+    n2o = gpu.select_columns(cols)
+    sub = S[:, cols].toarray()
+    keep = np.nonzero(np.abs(sub).sum(axis=1) > 0)[0]
+    assert np.array_equal(n2o, keep)
+    sub = sub[keep]
+    k = 3
+    B = rng.random((len(cols), k))
+    C = gpu.sparse_gemm(0, 1.0, B, 0.0, np.zeros((len(keep), k)))            # A_sub * B
+    assert np.allclose(C, sub @ B, rtol=1e-12, atol=1e-14)
+    Bt = rng.random((len(keep), k))
+    C2 = gpu.sparse_gemm(3, 1.0, Bt, 0.0, np.zeros((k, len(cols))))          # B' * A_sub
+    assert np.allclose(C2, Bt.T @ sub, rtol=1e-12, atol=1e-14)
+    gpu.select_all()
+    C3 = gpu.sparse_gemm(0, 1.0, rng.random((n, k)), 0.0, np.zeros((m, k)))
+    assert C3.shape == (m, k)
+    with pytest.raises(sk.SmallkError):
+        gpu.select_columns(np.array([n + 5], dtype=np.uint32))
+    gpu.select_all()
+
+
+def test_nnls_hals_matches_reference_fixture_shape(gpu, oracle):
+    """smk_nnls_hals (NnlsHals, nnls.hpp:249-316): converges and leaves unit-norm W columns, nonnegative H."""
+    rng = np.random.default_rng(9)
+    m, n, k = 200, 150, 6
+    Wt = rng.random((m, k)); Ht = rng.random((k, n)) * (rng.random((k, n)) < 0.4)
+    A = Wt @ Ht
+    gpu.load_dense(A)
+    rc, W, H, it = gpu.nnls_hals(Wt, rng.random((k, n)), 1e-6, 5000)
+    assert rc == 0 and it > 1
+    assert np.allclose(np.linalg.norm(W, axis=0), 1.0, rtol=1e-12)
+    assert H.min() >= 0.0
+    assert np.linalg.norm(W @ H - A) <= 1e-4 * np.linalg.norm(A)
