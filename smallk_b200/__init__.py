@@ -31,7 +31,8 @@ EXPORTS = [
     "smk_select_columns", "smk_select_all", "smk_nnls_hals",
 ]
 HOST_LIB_PATH = os.path.join(_HERE, "lib", "libsmallk_host.so")
-HOST_EXPORTS = ["smkh_last_error", "smkh_hierclust_sparse", "smkh_hierclust_dense", "smkh_flatclust", "smkh_compute_priority"]
+HOST_EXPORTS = ["smkh_last_error", "smkh_hierclust_sparse", "smkh_hierclust_dense", "smkh_flatclust", "smkh_compute_priority",
+                "smkh_last_hier_profile"]
 
 
 class SmallkError(RuntimeError):
@@ -316,8 +317,11 @@ def hierclust(A_dense=None, csc=None, shape=None, num_clusters=4, tol=1e-4, min_
                                        rowi.ctypes.data_as(_up), _d(val), *tail)
     else:
         rc = lib.smkh_hierclust_dense(m, n, _d(A_dense), m, *tail)
+    prof = np.zeros(5)
+    lib.smkh_last_hier_profile(_d(prof))
     out.update(rc=rc, n_outliers=n_out.value, nmf_count=int(stats[0]), max_count=int(stats[1]),
-               iterations=int(stats[2]), elapsed_s=el.value)
+               iterations=int(stats[2]), elapsed_s=el.value,
+               profile=dict(zip(("extract_s", "init_s", "factor_s", "priority_s", "terms_s"), prof.tolist())))
     if flat:
         out.update(W=W, H=H, flat_assignments=fa)
     return out

@@ -482,7 +482,7 @@ int smk_nnls_bpp(smk_ctx* c, int k, int q, const double* LHS, const double* RHS,
         upload_tight(c, X, k, k, q, dX.p);
         int init[ST_COUNT] = {0, INT_MAX, 0, 0, 0};
         SMK_CUDA(cudaMemcpyAsync(c->status.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
-        c->deferred.reserve(nnls_deferred_bytes(q));
+        c->deferred.reserve(nnls_deferred_bytes(q, k, c->num_sms));
         nnls_bpp(c->stream, k, q, dL.p, k, dR.p, k, dX.p, k, dY.p, k, c->status.p, c->counter.p, c->deferred.p, 0, c->num_sms);
         download_tight(c, dX.p, k, q, X, k);
         download_tight(c, dY.p, k, q, Y, k);

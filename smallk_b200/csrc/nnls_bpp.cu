@@ -620,18 +620,35 @@ __global__ void zeroize_if_flag_kernel(const int* __restrict__ status, int k, lo
 
 } // namespace
 
-size_t nnls_deferred_bytes(int q) { return static_cast<size_t>(q) * sizeof(BppColState); }
+size_t nnls_wide_scratch_bytes(int k, int num_sms);
+void nnls_bpp_wide(cudaStream_t stream, int k, int q, const double* LHS, long long ldl, const double* RHS, long long ldr,
+                   double* X, long long ldx, double* Y, long long ldy, int* status, unsigned int* counter, void* scratch,
+                   int outer_iter, int num_sms);
+
+// bytes of the `deferred` buffer nnls_bpp needs: the fast->slow hand-over list (k <= 64) or the wide kernel's scratch
+size_t nnls_deferred_bytes(int q, int k, int num_sms)
+{
+    return std::max(static_cast<size_t>(q) * sizeof(BppColState), nnls_wide_scratch_bytes(k, num_sms));
+}
 
 // status: device int[ST_COUNT]; counter: device unsigned[2]; deferred: nnls_deferred_bytes(q) bytes.
 void nnls_bpp(cudaStream_t stream, int k, int q, const double* LHS, long long ldl,
               const double* RHS, long long ldr, double* X, long long ldx, double* Y, long long ldy,
               int* status, unsigned int* counter, void* deferred, int outer_iter, int num_sms)
 {
-    if (k > 64) throw std::string("nnls_bpp: k > 64 is not supported yet");
     if (q <= 0) return;
     SMK_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned int), stream));
     SMK_CUDA(cudaMemsetAsync(&status[ST_ANY_NONOPT], 0, sizeof(int), stream));
     SMK_CUDA(cudaMemsetAsync(&status[ST_DEFER_COUNT], 0, sizeof(int), stream));
+    if (k > 64)
+    {
+        nnls_bpp_wide(stream, k, q, LHS, ldl, RHS, ldr, X, ldx, Y, ldy, status, counter, deferred, outer_iter, num_sms);
+        const long long total = static_cast<long long>(k) * q;
+        const int zb = static_cast<int>(std::min<long long>((total + 255) / 256, 8LL * num_sms));
+        zeroize_if_flag_kernel<<<zb, 256, 0, stream>>>(status, k, q, X, ldx, Y, ldy);
+        SMK_LAUNCH_CHECK();
+        return;
+    }
     BppColState* def = static_cast<BppColState*>(deferred);
 
     {

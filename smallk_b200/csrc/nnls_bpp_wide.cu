@@ -1,0 +1,387 @@
+// smallk_b200 — batched NNLS by block principal pivoting for 64 < k <= 256: one CTA per right-hand side.
+//
+// Same contract and reference behaviours as nnls_bpp.cu (NnlsBlockpivot, nnls.hpp:144-244; BppSolveNormalEqNoGroup,
+// nmf_solver_bpp.hpp:146-219; UpdatePassiveSet, nnls.cpp:18-74; MaxRowIndex defect, bit_matrix.cpp:432-472), for
+// the ranks where a passive-set system no longer fits a warp's registers (flatclust BPP at k = 256).
+//
+// A CTA of 256 threads owns one column for its whole pivoting history; thread t owns row t. The passive set is a
+// 256-bit mask (eight ballot words in shared memory). Each pivot round solves G_PP x_P = b_P by an upper Cholesky
+// factorization held as a PACKED triangle in shared memory (<= 128 x 128: 66 KB, three CTAs per SM):
+//     |P| <= 128 : direct, G_PP gathered from the L2-resident G;
+//     |P| >  128 : on the complement A = ~P (|A| < 128) with the block-inverse identity
+//                  u = G^-1 b,  z = (G^-1)_AA^-1 u_A,  x_P = u_P - (G^-1)_PA z,
+//                  G^-1 formed once per call by invert_spd_kernel. The true residual (G x - b)_P is the acceptance
+//                  test; a column that fails it (ill-conditioned G), or any solve when G^-1 could not be formed,
+//                  falls back to the direct method with the packed triangle in a per-CTA global scratch (L2).
+// The dual y = G x - b is always formed as the full product, as the reference does (nnls.hpp:168-169, 219-220).
+#include "nnls_common.cuh"
+
+namespace smk {
+
+namespace {
+
+constexpr int kWideThreads = 256;
+constexpr int kWideNmax = 128;
+
+__device__ __forceinline__ int tri(int c) { return (c * (c + 1)) >> 1; }
+
+// In-place Gauss-Jordan inversion of the SPD k x k matrix in global memory (one CTA). ok[0] = 1 on success.
+__global__ void __launch_bounds__(1024, 1)
+invert_spd_kernel(int k, const double* __restrict__ G, long long ldg, double* __restrict__ Ginv, int* __restrict__ ok)
+{
+    __shared__ double scol[256], srow[256];
+    __shared__ int s_ok;
+    for (int e = threadIdx.x; e < k * k; e += blockDim.x) Ginv[e] = G[static_cast<long long>(e / k) * ldg + (e % k)];
+    if (threadIdx.x == 0) s_ok = 1;
+    __syncthreads();
+    for (int j = 0; j < k; ++j)
+    {
+        const double piv = Ginv[j + j * k];
+        if (!(piv > 0.0)) { if (threadIdx.x == 0) s_ok = 0; break; }     // uniform
+        const double ip = 1.0 / piv;
+        for (int i = threadIdx.x; i < k; i += blockDim.x) { scol[i] = Ginv[i + j * k]; srow[i] = Ginv[j + i * k] * ip; }
+        __syncthreads();
+        for (int e = threadIdx.x; e < k * k; e += blockDim.x)
+        {
+            const int i = e % k, c = e / k;
+            double v;
+            if (i == j) v = (c == j) ? ip : srow[c];
+            else if (c == j) v = -scol[i] * ip;
+            else v = Ginv[e] - scol[i] * srow[c];
+            Ginv[e] = v;
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) ok[0] = s_ok;
+}
+
+// Solves (U'U) x = vb for the SPD matrix whose upper triangle is packed by columns in M (element (i,c), i <= c, at
+// tri(c) + i); x overwrites vb. Whole CTA; M may live in shared or global memory. Right-looking factorization with
+// the recurrence of Elemental's UVar3Unb (sqrt, divide), then both triangular solves by warp 0.
+// Returns false (uniformly) on a non-positive pivot.
+__device__ bool cta_spd_solve_packed(double* M, double* __restrict__ vb, int n, double* __restrict__ rowj)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    for (int j = 0; j < n; ++j)
+    {
+        const double ajj = M[tri(j) + j];
+        if (!(ajj > 0.0)) return false;
+        const double d = sqrt(ajj);
+        __syncthreads();                                   // everyone has read the pivot
+        for (int c = j + tid; c < n; c += blockDim.x)
+        {
+            const double v = (c == j) ? d : M[tri(c) + j] / d;
+            M[tri(c) + j] = v;
+            rowj[c] = v;
+        }
+        __syncthreads();
+        for (int c = j + 1 + warp; c < n; c += nwarps)
+        {
+            const double ujc = rowj[c];
+            double* col = M + tri(c);
+            for (int i = j + 1 + lane; i <= c; i += 32) col[i] = fma(-rowj[i], ujc, col[i]);
+        }
+        __syncthreads();
+    }
+    if (warp == 0)
+    {
+        // U'y = b, right-looking over rows
+        for (int i = 0; i < n; ++i)
+        {
+            const double yi = vb[i] / M[tri(i) + i];
+            __syncwarp();
+            if (lane == 0) vb[i] = yi;
+            for (int c = i + 1 + lane; c < n; c += 32) vb[c] = fma(-M[tri(c) + i], yi, vb[c]);
+            __syncwarp();
+        }
+        // U x = y, right-looking over columns (column c of the packed triangle is contiguous)
+        for (int c = n - 1; c >= 0; --c)
+        {
+            const double* col = M + tri(c);
+            const double xc = vb[c] / col[c];
+            __syncwarp();
+            if (lane == 0) vb[c] = xc;
+            for (int i = lane; i < c; i += 32) vb[i] = fma(-col[i], xc, vb[i]);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    return true;
+}
+
+// BitMatrix::MaxRowIndex as the reference computes it (defect included) on a multi-word column mask.
+__device__ __forceinline__ int max_row_index_ref_words(const unsigned int* w, int k)
+{
+    const int nw = (k + 31) >> 5;
+    int h = -1;
+    for (int q = nw - 1; q >= 0; --q)
+        if (w[q]) { h = q * 32 + 31 - __clz(static_cast<int>(w[q])); break; }
+    if (h < 0) return 0;
+    const int full = k >> 5, extra = k & 31;
+    const int wd = h >> 5;
+    if (extra > 0 && wd == full) return h;
+    return (wd > 0) ? h - 32 : h;
+}
+
+struct WideSmem
+{
+    int k;
+    __host__ __device__ size_t tri_doubles() const { return static_cast<size_t>(kWideNmax) * (kWideNmax + 1) / 2; }
+    __host__ __device__ size_t total_bytes() const
+    {
+        // U | rowj[128] | vb[128] | sb[256] | sx[256] | su[256] | list[256] shorts | words[64]   (75,008 bytes: 3 CTAs per SM)
+        return (tri_doubles() + 2 * kWideNmax + 3 * 256) * sizeof(double) + 256 * sizeof(unsigned short) + 64 * sizeof(unsigned int);
+    }
+};
+
+__global__ void __launch_bounds__(kWideThreads)
+nnls_bpp_wide_kernel(int k, int q, const double* __restrict__ G, long long ldg, const double* __restrict__ Ginv,
+                     const int* __restrict__ ginv_flag, const double* __restrict__ RHS, long long ldr,
+                     double* __restrict__ X, long long ldx, double* __restrict__ Y, long long ldy,
+                     int* __restrict__ status, unsigned int* __restrict__ counter, int outer_iter,
+                     double* __restrict__ gscratch, size_t gscratch_stride)
+{
+    extern __shared__ __align__(16) double smem[];
+    const WideSmem L{k};
+    double* sU = smem;
+    double* s_rowj = sU + L.tri_doubles();
+    double* s_vb = s_rowj + kWideNmax;
+    double* sb = s_vb + kWideNmax;
+    double* sx = sb + 256;
+    double* su = sx + 256;
+    unsigned short* list = reinterpret_cast<unsigned short*>(su + 256);
+    unsigned int* words = reinterpret_cast<unsigned int*>(list + 256);   // [0..7] passive, [8..15] nonopt, [16..23] infeas, [24] column
+    // direct method on more than 128 rows: packed triangle, right-hand side and row buffer in this CTA's global scratch
+    double* gU = gscratch + static_cast<size_t>(blockIdx.x) * gscratch_stride;
+    double* g_vb = gU + (static_cast<size_t>(k) * (k + 1) / 2);
+    double* g_rowj = g_vb + 256;
+    double* rowj = s_rowj;      // also the 8-entry scratch of the CTA-wide max reductions
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const bool valid = t < k;
+    const int nw = (k + 31) >> 5;
+    const bool ginv_ok = ginv_flag[0] != 0;
+    const int max_rounds = 5 * k;
+
+    for (;;)
+    {
+        __syncthreads();
+        if (t == 0) words[24] = atomicAdd(counter, 1u);
+        __syncthreads();
+        const unsigned int c = words[24];
+        if (c >= static_cast<unsigned int>(q)) break;
+
+        const double* rhs = RHS + static_cast<long long>(c) * ldr;
+        double* xcol = X + static_cast<long long>(c) * ldx;
+        double* ycol = Y + static_cast<long long>(c) * ldy;
+        const double b = valid ? rhs[t] : 0.0;
+        sb[t] = b;
+        {   // warm start: passive = (X > 0)   (nnls.hpp:157)
+            const unsigned int w = __ballot_sync(0xffffffffu, valid && xcol[t] > 0.0);
+            if (lane == 0) words[warp] = w;
+        }
+        double bmax = fabs(b);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bmax = fmax(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+        if (lane == 0) rowj[warp] = bmax;
+        __syncthreads();
+        bmax = 0.0;
+        for (int w = 0; w < 8; ++w) bmax = fmax(bmax, rowj[w]);
+        __syncthreads();
+
+        int P = kPbar, Ninf = k + 1, round = 0;
+        double x = 0.0, y = 0.0;
+        bool failed = false, have_u = false;
+
+        for (;;)
+        {
+            // ---- position of this row inside the passive list / the complement list
+            int p = 0, before = 0;
+            for (int w = 0; w < nw; ++w)
+            {
+                const int pc = __popc(words[w]);
+                p += pc;
+                if (w < warp) before += pc;
+            }
+            const unsigned int myword = words[warp];
+            const bool in = valid && ((myword >> lane) & 1u);
+            const int pos_in = before + __popc(myword & ((1u << lane) - 1u));
+            const int pos_out = t - pos_in;                 // rows t' < t that are not passive (t < k)
+            bool use_complement = (p > kWideNmax) && ginv_ok;
+            bool solved = false;
+
+            if (p == 0) { x = 0.0; solved = true; }
+            while (!solved)
+            {
+                if (p <= kWideNmax || !use_complement)
+                {
+                    // ---- direct: G_PP x_P = b_P
+                    const bool small = p <= kWideNmax;
+                    double* M = small ? sU : gU;
+                    double* vb = small ? s_vb : g_vb;
+                    __syncthreads();
+                    if (in) list[pos_in] = t;
+                    __syncthreads();
+                    for (int cc = warp; cc < p; cc += (kWideThreads >> 5))
+                    {
+                        const double* gcol = G + static_cast<long long>(list[cc]) * ldg;
+                        double* col = M + tri(cc);
+                        for (int i = lane; i <= cc; i += 32) col[i] = gcol[list[i]];
+                    }
+                    if (t < p) vb[t] = sb[list[t]];
+                    __syncthreads();
+                    if (!cta_spd_solve_packed(M, vb, p, small ? s_rowj : g_rowj)) { failed = true; break; }
+                    x = in ? vb[pos_in] : 0.0;
+                    solved = true;
+                }
+                else
+                {
+                    // ---- complement: solve on A = ~P, |A| = k - p < 128
+                    const int na = k - p;
+                    if (!have_u)
+                    {
+                        double u = 0.0;
+                        if (valid)
+                            for (int cc = 0; cc < k; ++cc) u = fma(Ginv[static_cast<long long>(cc) * k + t], sb[cc], u);
+                        su[t] = u;
+                        have_u = true;
+                    }
+                    __syncthreads();
+                    if (valid && !in) list[pos_out] = t;
+                    __syncthreads();
+                    for (int cc = warp; cc < na; cc += (kWideThreads >> 5))
+                    {
+                        const double* gcol = Ginv + static_cast<long long>(list[cc]) * k;
+                        double* col = sU + tri(cc);
+                        for (int i = lane; i <= cc; i += 32) col[i] = gcol[list[i]];
+                    }
+                    if (t < na) s_vb[t] = su[list[t]];
+                    __syncthreads();
+                    if (na > 0 && !cta_spd_solve_packed(sU, s_vb, na, s_rowj)) { use_complement = false; continue; }
+                    double a = su[t];
+                    if (in)
+                        for (int e = 0; e < na; ++e) a = fma(-Ginv[static_cast<long long>(list[e]) * k + t], s_vb[e], a);
+                    x = in ? a : 0.0;
+                    solved = true;
+                }
+            }
+            if (failed) break;
+            if (round > 0 && fabs(x) < kZeroThresh) x = 0.0;         // ZeroizeSmallValues(Xsub), nnls.hpp:215
+            __syncthreads();
+            sx[t] = x;
+            if (in) list[pos_in] = t;                                  // passive list for the product (the complement path overwrote it)
+            __syncthreads();
+            // ---- dual y = G x - b over the passive columns (nnls.hpp:168-169, 219-220)
+            double s = 0.0;
+            if (valid)
+                for (int e = 0; e < p; ++e)
+                {
+                    const int cc = list[e];
+                    s = fma(G[static_cast<long long>(cc) * ldg + t], sx[cc], s);
+                }
+            y = s - b;
+            if (use_complement && p > kWideNmax)
+            {
+                // acceptance of the complement path: rounding-level residual on the passive rows
+                double res = in ? fabs(y) : 0.0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) res = fmax(res, __shfl_xor_sync(0xffffffffu, res, o));
+                __syncthreads();
+                if (lane == 0) rowj[warp] = res;
+                __syncthreads();
+                res = 0.0;
+                for (int w = 0; w < 8; ++w) res = fmax(res, rowj[w]);
+                if (!(res <= 1.0e-11 * bmax))
+                {
+                    // redo this round with the direct method in global scratch (uniform decision)
+                    __syncthreads();
+                    double* M = gU;
+                    for (int cc = warp; cc < p; cc += (kWideThreads >> 5))
+                    {
+                        const double* gcol = G + static_cast<long long>(list[cc]) * ldg;
+                        double* col = M + tri(cc);
+                        for (int i = lane; i <= cc; i += 32) col[i] = gcol[list[i]];
+                    }
+                    if (t < p) g_vb[t] = sb[list[t]];
+                    __syncthreads();
+                    if (!cta_spd_solve_packed(M, g_vb, p, g_rowj)) { failed = true; break; }
+                    x = in ? g_vb[pos_in] : 0.0;
+                    if (round > 0 && fabs(x) < kZeroThresh) x = 0.0;
+                    __syncthreads();
+                    sx[t] = x;
+                    __syncthreads();
+                    s = 0.0;
+                    if (valid)
+                        for (int e = 0; e < p; ++e)
+                        {
+                            const int cc = list[e];
+                            s = fma(G[static_cast<long long>(cc) * ldg + t], sx[cc], s);
+                        }
+                    y = s - b;
+                }
+            }
+            if (round > 0 && fabs(y) < kZeroThresh) y = 0.0;
+            // ---- nonopt = (Y < 0) & ~P, infeas = (X < 0) & P   (nnls.hpp:42-140)
+            const unsigned int wn = __ballot_sync(0xffffffffu, valid && !in && y < 0.0);
+            const unsigned int wi = __ballot_sync(0xffffffffu, in && x < 0.0);
+            __syncthreads();
+            if (lane == 0) { words[8 + warp] = wn; words[16 + warp] = wi; }
+            __syncthreads();
+            int not_good = 0;
+            for (int w = 0; w < nw; ++w) not_good += __popc(words[8 + w]) + __popc(words[16 + w]);
+            if (not_good == 0) break;
+            if (round == 0 && t == 0) atomicOr(&status[ST_ANY_NONOPT], 1);
+            if (round >= max_rounds) { failed = true; break; }        // nnls.hpp:195-196
+            // ---- UpdatePassiveSet (nnls.cpp:18-74)
+            __syncthreads();
+            if (not_good < Ninf || P >= 1)
+            {
+                if (not_good < Ninf) { P = kPbar; Ninf = not_good; } else P -= 1;
+                if (t < nw) words[t] = (words[t] | words[8 + t]) & ~words[16 + t];
+            }
+            else if (t == 0)
+            {
+                const int ra = max_row_index_ref_words(words + 8, k), rb = max_row_index_ref_words(words + 16, k);
+                const int r = ra > rb ? ra : rb;
+                words[r >> 5] ^= (1u << (r & 31));
+            }
+            __syncthreads();
+            ++round;
+        }
+        if (failed && t == 0) atomicMin(&status[ST_FAIL_ITER], outer_iter);
+        if (valid) { xcol[t] = x; ycol[t] = y; }
+    }
+}
+
+} // namespace
+
+size_t nnls_wide_scratch_bytes(int k, int num_sms)
+{
+    if (k <= 64) return 0;
+    const size_t tri_k = static_cast<size_t>(k) * (k + 1) / 2;
+    return (static_cast<size_t>(k) * k + static_cast<size_t>(3 * num_sms) * (tri_k + 512)) * sizeof(double) + 64;
+}
+
+// scratch layout: [Ginv k*k doubles][per-CTA packed triangles][flag int]
+void nnls_bpp_wide(cudaStream_t stream, int k, int q, const double* LHS, long long ldl, const double* RHS, long long ldr,
+                   double* X, long long ldx, double* Y, long long ldy, int* status, unsigned int* counter, void* scratch,
+                   int outer_iter, int num_sms)
+{
+    if (k > 256) throw std::string("nnls_bpp: k > 256 is not supported");
+    const size_t tri_k = static_cast<size_t>(k) * (k + 1) / 2;
+    double* Ginv = static_cast<double*>(scratch);
+    double* gscr = Ginv + static_cast<size_t>(k) * k;
+    const int grid = std::min(3 * num_sms, q);
+    int* flag = reinterpret_cast<int*>(gscr + static_cast<size_t>(3 * num_sms) * (tri_k + 512));
+    invert_spd_kernel<<<1, 1024, 0, stream>>>(k, LHS, ldl, Ginv, flag);
+    SMK_LAUNCH_CHECK();
+    const WideSmem L{k};
+    const size_t smem = L.total_bytes();
+    SMK_CUDA(cudaFuncSetAttribute(nnls_bpp_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    nnls_bpp_wide_kernel<<<grid, kWideThreads, smem, stream>>>(k, q, LHS, ldl, Ginv, flag, RHS, ldr, X, ldx, Y, ldy, status,
+                                                              counter, outer_iter, gscr, tri_k + 512);
+    SMK_LAUNCH_CHECK();
+}
+
+} // namespace smk

@@ -89,7 +89,7 @@ void solver_alloc(smk_ctx* c)
     c->WtW.reserve(k * k); c->HHt.reserve(k * k);
     c->WtA.reserve(k * n); c->HAt.reserve(k * m);
     c->norms.reserve(k);
-    c->deferred.reserve(nnls_deferred_bytes(static_cast<int>(std::max(m, n))));
+    c->deferred.reserve(nnls_deferred_bytes(static_cast<int>(std::max(m, n)), c->opts.k, c->num_sms));
     if (c->opts.algorithm == SMK_MU || c->opts.algorithm == SMK_HALS) { c->T1.reserve(k * n); c->T2.reserve(k * m); }
     if (c->opts.prog_est_algorithm == SMK_DELTA_FNORM) c->Wprev.reserve(k * m);
     // split-R workspace: enough for the gram matrices at 4*SMs splits and for the big products at a few splits

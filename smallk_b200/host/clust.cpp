@@ -9,6 +9,7 @@
 #include "clust.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <iostream>
 #include <limits>
@@ -148,6 +149,14 @@ R compute_priority(const R* W_parent, const R* W_child, const int n)
 // --------------------------------------------------------------------------------------------------------------
 namespace {
 
+struct Stopwatch
+{
+    double& acc;
+    std::chrono::steady_clock::time_point t0;
+    explicit Stopwatch(double& a) : acc(a), t0(std::chrono::steady_clock::now()) {}
+    ~Stopwatch() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 struct Factor          // the rank-2 factors of one node: W is m x 2 (ld = m), H is 2 x cols
 {
     std::vector<R> W, H;
@@ -190,7 +199,8 @@ struct HierRun
         o.height = height; o.width = width; o.k = 2; o.algorithm = NmfAlgorithm::RANK2;
         smk_nmf_options a = NmfToAbi(o);
         smk_nmf_stats st = {0, 0};
-        const int rc = smk_nmf(ctx, &a, W, height, H, 2, &st);
+        int rc;
+        { Stopwatch sw(stats.t_factor); rc = smk_nmf(ctx, &a, W, height, H, 2, &st); }
         stats.iteration_count += st.iteration_count;
         if (rc == SMK_OK)
         {
@@ -215,8 +225,11 @@ struct HierRun
         if (cnt <= 3) { labels.assign(cnt, 1u); return R(-1); }
 
         int new_height = 0;
-        const int rc = smk_select_columns(ctx, subset.data(), static_cast<int>(cnt), &new_height, new_to_old.data());
-        if (rc != SMK_OK) throw std::logic_error(smk_last_error(ctx));
+        {
+            Stopwatch sw(stats.t_extract);
+            const int rc = smk_select_columns(ctx, subset.data(), static_cast<int>(cnt), &new_height, new_to_old.data());
+            if (rc != SMK_OK) throw std::logic_error(smk_last_error(ctx));
+        }
 
         Wsub.resize(static_cast<size_t>(new_height) * 2);
         Hsub.resize(cnt * 2);
@@ -235,6 +248,7 @@ struct HierRun
             }
             else
             {
+                Stopwatch sw(stats.t_init);
                 RandomMatrix(Wsub.data(), new_height, new_height, 2, rng, R(0.5), R(0.5));
                 RandomMatrix(Hsub.data(), 2, 2, static_cast<unsigned int>(cnt), rng, R(0.5), R(0.5));
             }
@@ -256,7 +270,9 @@ struct HierRun
             out.W[static_cast<size_t>(m) + new_to_old[r]] = Wsub[static_cast<size_t>(new_height) + r];
         }
         out.H = Hsub;
-        return (has_0 && has_1) ? compute_priority(W_parent, out.W.data(), static_cast<int>(m)) : R(-1);
+        if (!(has_0 && has_1)) return R(-1);
+        Stopwatch sw(stats.t_priority);
+        return compute_priority(W_parent, out.W.data(), static_cast<int>(m));
     }
 
     // clust_hier_generic.hpp:245-376
@@ -361,7 +377,7 @@ struct HierRun
             if (i > 0) { Factor().W.swap(node_factor[split_index].W); Factor().H.swap(node_factor[split_index].H); }
         }
         smk_select_all(ctx);
-        tree.ComputeTopTerms(opts.maxterms);
+        { Stopwatch sw(stats.t_terms); tree.ComputeTopTerms(opts.maxterms); }
         tree.ComputeAssignments();
         cout << endl;
         return true;

@@ -11,6 +11,8 @@
 
 namespace {
 
+double g_profile[5] = {0, 0, 0, 0, 0};
+
 void EnsureInit()
 {
     if (Result::INITIALIZED != NmfIsInitialized()) { static int argc = 0; NmfInitialize(argc, nullptr); }
@@ -54,6 +56,7 @@ int Finish(Result r, const ClustOptions& o, Tree<R>& tree, ClustStats& cs, int n
            const std::vector<R>& w, const std::vector<R>& h, double* buf_w, double* buf_h, long long* stats, int* flat_assignments)
 {
     if (stats) { stats[0] = cs.nmf_count; stats[1] = cs.max_count; stats[2] = cs.iteration_count; }
+    g_profile[0] = cs.t_extract; g_profile[1] = cs.t_init; g_profile[2] = cs.t_factor; g_profile[3] = cs.t_priority; g_profile[4] = cs.t_terms;
     if (Result::OK != r) return static_cast<int>(r);
     ExportTree(tree, o.num_clusters, o.maxterms, n, assignments, parent, left, right, is_left, doc_count, terms, priority, is_leaf, n_outliers);
     if (o.flat)
@@ -75,6 +78,9 @@ int Finish(Result r, const ClustOptions& o, Tree<R>& tree, ClustStats& cs, int n
 extern "C" {
 
 const char* smkh_last_error() { return NmfLastError(); }
+
+// seconds spent by the last smkh_hierclust_* call in: subset extraction, initialisers, smk_nmf, priority scores, top terms
+void smkh_last_hier_profile(double* out5) { for (int i = 0; i < 5; ++i) out5[i] = g_profile[i]; }
 
 // ClustSparse (hierclust/src/clust.cpp:160). stats[0..2] = nmf_count, max_count, total rank-2 iterations.
 int smkh_hierclust_sparse(int m, int n, unsigned int nz, const unsigned int* col_offsets, const unsigned int* row_indices,

@@ -27,6 +27,10 @@ CASES = {
     "sp_mu_300x200_k10":  ("sparse", "MU", 300, 200, 10, 0.1, 40, 1e-12, 1, False, 8),
     "sp_rank2_400x300":   ("sparse", "RANK2", 400, 300, 2, 0.05, 40, 1e-12, 1, True, 9),
     "sp_hals_300x200_k8": ("sparse", "HALS", 300, 200, 8, 0.3, 3, 1e-12, 1, False, 10),
+    # k > 64: the one-CTA-per-column NNLS kernel (SURVEY C5 is k = 256)
+    "bpp_500x420_k96":    ("dense", "BPP", 500, 420, 96, None, 10, 1e-12, 1, False, 11),
+    "bpp_420x400_k160":   ("dense", "BPP", 420, 400, 160, None, 6, 1e-12, 1, False, 12),
+    "sp_bpp_900x800_k72": ("sparse", "BPP", 900, 800, 72, 0.15, 8, 1e-12, 1, False, 13),
 }
 
 
@@ -55,17 +59,28 @@ def golden_inputs(name):
                 normalize=normalize, A=A, sp=sp, W0=W0, H0=H0)
 
 
-def nnls_inputs(seed, k, q):
+def nnls_inputs(seed, k, q, shift=0.35):
+    """shift sets how much of the unconstrained solution is negative: 0.35 leaves ~10 % of the entries passive,
+    0.01 leaves most of them passive (|P| > k/2: the complement path of the GPU kernels)."""
     rng = np.random.default_rng(seed)
     W = rng.random((4 * k, k))
     A = rng.random((4 * k, q))
     LHS = W.T @ W
-    RHS = W.T @ A - 0.35 * rng.random((k, q)) * np.abs(W.T @ A).mean()
+    if shift < 0:
+        # planted mostly-positive solution: |P| is close to (1 + shift) * k, X0 is a cold start
+        Xt = rng.random((k, q)) * (rng.random((k, q)) > -shift)
+        RHS = LHS @ Xt - 1e-3 * rng.random((k, q)) * np.abs(LHS @ Xt).mean()
+        X0 = rng.random((k, q)) * (rng.random((k, q)) > 0.5)
+        return LHS, RHS, X0
+    RHS = W.T @ A - shift * rng.random((k, q)) * np.abs(W.T @ A).mean()
     X0 = rng.random((k, q)) * (rng.random((k, q)) > 0.3)
     return LHS, RHS, X0
 
 
-NNLS_CASES = {"nnls_k16_q64": (21, 16, 64), "nnls_k40_q90": (22, 40, 90), "nnls_k64_q120": (23, 64, 120)}
+NNLS_CASES = {"nnls_k16_q64": (21, 16, 64), "nnls_k40_q90": (22, 40, 90), "nnls_k64_q120": (23, 64, 120),
+              "nnls_k100_q150": (24, 100, 150), "nnls_k200_q90": (25, 200, 90), "nnls_k256_q64": (26, 256, 64),
+              "nnls_k60_q100_dense": (27, 60, 100, -0.15), "nnls_k200_q80_dense": (28, 200, 80, -0.2),
+              "nnls_k256_q60_dense": (29, 256, 60, -0.1), "nnls_k250_q40_half": (30, 250, 40, -0.5)}
 
 
 def main():
@@ -73,7 +88,10 @@ def main():
     from oracle import Ref
     ref = Ref()
     print("reference build BLAS:", ref.blas_backend())
+    only = set(sys.argv[1:])
     for name in CASES:
+        if only and name not in only:
+            continue
         g = golden_inputs(name)
         kw = dict(alg=g["alg"], tol=g["tol"], min_iter=g["min_iter"], max_iter=g["max_iter"], normalize=g["normalize"],
                   trace=True, max_threads=2)
@@ -90,8 +108,10 @@ def main():
                             W=r["W"], H=r["H"], snap_iters=np.array(keep),
                             W_snaps=r["W_trace"][keep], H_snaps=r["H_trace"][keep])
         print(f"{name}: iterations={it} last metric={r['metrics'][min(it, g['max_iter']) - 1]:.6g}")
-    for name, (seed, k, q) in NNLS_CASES.items():
-        LHS, RHS, X0 = nnls_inputs(seed, k, q)
+    for name, args in NNLS_CASES.items():
+        if only and name not in only:
+            continue
+        LHS, RHS, X0 = nnls_inputs(*args)
         rc, X, Y = ref.nnls_bpp(LHS, RHS, X0)
         assert rc == 0
         np.savez_compressed(os.path.join(HERE, name + ".npz"), X=X, Y=Y)

@@ -53,7 +53,8 @@ def _nnls_problem(k, q, seed, m=None):
     return LHS, RHS, X0
 
 
-@pytest.mark.parametrize("k,q,seed", [(16, 256, 1), (5, 37, 2), (32, 500, 3), (33, 300, 4), (64, 700, 5), (48, 1, 6)])
+@pytest.mark.parametrize("k,q,seed", [(16, 256, 1), (5, 37, 2), (32, 500, 3), (33, 300, 4), (64, 700, 5), (48, 1, 6),
+                                      (65, 300, 7), (100, 500, 8), (129, 200, 9), (200, 333, 10), (256, 450, 11)])
 def test_nnls_bpp_matches_oracle(gpu, oracle, k, q, seed):
     LHS, RHS, X0 = _nnls_problem(k, q, seed)
     rc, Xo, Yo = oracle.nnls_bpp(LHS, RHS, X0)
@@ -66,6 +67,22 @@ def test_nnls_bpp_matches_oracle(gpu, oracle, k, q, seed):
     # KKT: x >= 0, y >= 0 on the active set, complementary
     assert X.min() >= 0.0
     assert Y[X == 0].min() >= -1e-9 if (X == 0).any() else True
+
+
+@pytest.mark.parametrize("k,q,frac,seed", [(70, 200, 0.1, 1), (128, 150, 0.5, 2), (200, 120, 0.15, 3), (256, 300, 0.05, 4),
+                                           (256, 100, 0.5, 5), (250, 80, 0.45, 6)])
+def test_nnls_bpp_wide_mostly_passive_matches_oracle(gpu, oracle, k, q, frac, seed):
+    """k > 64 with large passive sets: |P| > 128 takes the complement path of nnls_bpp_wide_kernel."""
+    import sys as _s, os as _o
+    _s.path.insert(0, _o.path.join(_o.path.dirname(_o.path.abspath(__file__)), "golden"))
+    import make_golden as mg
+    LHS, RHS, X0 = mg.nnls_inputs(100 + seed, k, q, -frac)
+    rc, Xo, Yo = oracle.nnls_bpp(LHS, RHS, X0)
+    assert rc == 0
+    X, Y = gpu.nnls_bpp(LHS, RHS, X0)
+    assert np.array_equal(X > 0, Xo > 0)
+    assert rel(X, Xo) < 1e-9
+    assert np.abs(Y - Yo).max() <= 1e-8 * max(1.0, np.abs(Yo).max())
 
 
 def test_nnls_bpp_all_optimal_after_first_solve_keeps_tiny_values(gpu, oracle):
@@ -88,8 +105,9 @@ def test_nnls_bpp_all_optimal_after_first_solve_keeps_tiny_values(gpu, oracle):
     assert rel(X2, Xo2) < 1e-12
 
 
-def test_nnls_bpp_non_hpd_fails(gpu):
-    k, q = 6, 10
+@pytest.mark.parametrize("k", [6, 100])
+def test_nnls_bpp_non_hpd_fails(gpu, k):
+    q = 10
     LHS = -np.eye(k)
     with pytest.raises(sk.SmallkError) as e:
         gpu.nnls_bpp(LHS, np.ones((k, q)), np.ones((k, q)))
@@ -114,6 +132,8 @@ def _trace_gpu(ctx, W0, H0, opts, iters):
     ("BPP", 256, 256, 16, 30),        # C1 shape
     ("BPP", 300, 400, 40, 20),
     ("BPP", 500, 333, 64, 12),
+    ("BPP", 400, 450, 100, 8),        # k > 64: one CTA per column
+    ("BPP", 600, 520, 256, 5),
     ("MU", 150, 120, 8, 30),
     ("HALS", 200, 300, 12, 30),
     ("HALS", 260, 200, 40, 15),       # 2 rows per lane

@@ -45,8 +45,8 @@ def test_oracle_reproduces_reference_fixture(oracle, name):
 
 @pytest.mark.parametrize("name", sorted(mg.NNLS_CASES))
 def test_oracle_nnls_reproduces_reference_fixture(oracle, name):
-    seed, k, q = mg.NNLS_CASES[name]
-    LHS, RHS, X0 = mg.nnls_inputs(seed, k, q)
+    LHS, RHS, X0 = mg.nnls_inputs(*mg.NNLS_CASES[name])
+    k, q = RHS.shape
     z = np.load(os.path.join(GOLD, name + ".npz"))
     rc, X, Y = oracle.nnls_bpp(LHS, RHS, X0)
     assert rc == 0
@@ -99,8 +99,8 @@ def test_oracle_sparse_gemm_matches_reference(oracle, variant):
 @needs_ref
 def test_oracle_nnls_matches_reference_live(oracle):
     ref = Ref()
-    for seed, k, q in [(31, 8, 40), (32, 33, 70), (33, 64, 50)]:
-        LHS, RHS, X0 = mg.nnls_inputs(seed, k, q)
+    for args in [(31, 8, 40), (32, 33, 70), (33, 64, 50), (34, 100, 30), (35, 200, 20, -0.5), (36, 130, 25, -0.1)]:
+        LHS, RHS, X0 = mg.nnls_inputs(*args)
         rc1, X1, Y1 = oracle.nnls_bpp(LHS, RHS, X0)
         rc2, X2, Y2 = ref.nnls_bpp(LHS, RHS, X0, max_threads=2)
         assert rc1 == rc2 == 0
