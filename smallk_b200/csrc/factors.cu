@@ -48,10 +48,10 @@ __global__ void hals_sweep_cols_kernel(int k, int q, double* __restrict__ X, con
         for (int e = 0; e < KPL; ++e) { const int p = lane + 32 * e; x[e] = (p < k) ? xcol[p] : 0.0; }
         for (int r = 0; r < k; ++r)
         {
-            const double* grow = G + r;      // G(r,p) = G[r + p*k]
+            const double* gcol = G + static_cast<long long>(r) * k;      // G is symmetric: row r is read as column r (coalesced)
             double s = 0.0;
 #pragma unroll
-            for (int e = 0; e < KPL; ++e) { const int p = lane + 32 * e; if (p < k) s += __ldg(grow + static_cast<long long>(p) * k) * x[e]; }
+            for (int e = 0; e < KPL; ++e) { const int p = lane + 32 * e; if (p < k) s += __ldg(gcol + p) * x[e]; }
             s = warp_sum(s);
             const double grr = __ldg(G + r + static_cast<long long>(r) * k);
             const double rr = __ldg(rcol + r);
@@ -132,7 +132,7 @@ __global__ void hals_sweep_row_kernel(int k, int q, int r, double* __restrict__ 
                 double xv = xcol[p];
                 if (p == r - 1) { xv = (fill_prev ? DBL_EPSILON : xv) * inv_prev; xcol[p] = xv; }
                 if (p == r) xr = xv;
-                s += __ldg(G + r + static_cast<long long>(p) * k) * xv;
+                s += __ldg(G + static_cast<long long>(r) * k + p) * xv;
             }
         }
         s = warp_sum(s);
@@ -150,6 +150,140 @@ __global__ void hals_sweep_row_kernel(int k, int q, int r, double* __restrict__ 
     if (threadIdx.x == 0)
     {
         double* pc = partial + (r & 1) * 2 * kSweepBlocks;
+        pc[blockIdx.x] = sumsq;
+        pc[kSweepBlocks + blockIdx.x] = zeros;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// HALS, W side, blocked: the same k dependent steps, but the k-long dot products are not re-read from memory at
+// every step. Columns are taken in blocks of kHalsB. For a block [c0, c0+B):
+//   phase A (hals_block_outer_kernel): Q(l, j) = sum over p OUTSIDE the block of X(p,j) G(p,c0+l) - R(c0+l,j)
+//            — one pass over X per block (k/B passes per sweep instead of k), FMA-pipe GEMM from a shared-memory tile;
+//   phase B (hals_block_step_kernel), B dependent steps: step l needs only the block's own B entries of each column
+//            and Q(l, j):  x <- max(0, x - (Q + sum_{p in block} X(p,j) G(p,c)) / G(c,c)),  NaN -> 0,
+//            then the grid-wide unit-norm scaling of row c is applied by the NEXT kernel (as in hals_sweep_row_kernel).
+// Traffic per sweep and column of X: k*k/B + k*(B+3) doubles instead of k*k.
+// ---------------------------------------------------------------------------
+constexpr int kHalsB = 16;
+constexpr int kHalsTJ = 64;      // columns of X per shared-memory tile in phase A
+
+// norm of row `prev` from the block partials of the step that produced it; returns 1/norm and whether the row is refilled with eps
+__device__ __forceinline__ double finish_prev_row(const double* __restrict__ partial, int prev, int nblocks_prev, int q,
+                                                  double* __restrict__ norms, double* red, bool& fill_prev)
+{
+    const double* pp = partial + (prev & 1) * 2 * kSweepBlocks;
+    double s = 0.0, z = 0.0;
+    for (int i = threadIdx.x; i < nblocks_prev; i += blockDim.x) { s += pp[i]; z += pp[kSweepBlocks + i]; }
+    s = block_sum_f(s, red);
+    z = block_sum_f(z, red);
+    double norm;
+    fill_prev = (z == static_cast<double>(q));
+    if (fill_prev) norm = DBL_EPSILON * sqrt(static_cast<double>(q));
+    else norm = sqrt(s);
+    if (blockIdx.x == 0 && threadIdx.x == 0) norms[prev] = norm;
+    return 1.0 / norm;
+}
+
+__global__ void __launch_bounds__(256)
+hals_block_outer_kernel(int k, int q, int c0, double* __restrict__ X, const double* __restrict__ G, const double* __restrict__ R,
+                        double* __restrict__ Q, const double* __restrict__ partial, int nblocks_prev, double* __restrict__ norms)
+{
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double red[32];
+    const int ldt = k + 1;
+    double* sX = sm;                                   // [kHalsTJ][k + 1]
+    double* sG = sm + static_cast<size_t>(kHalsTJ) * ldt;   // [k][kHalsB], rows of the block zeroed
+    const int nb = min(kHalsB, k - c0);
+    bool fill_prev = false;
+    double inv_prev = 1.0;
+    if (c0 > 0) inv_prev = finish_prev_row(partial, c0 - 1, nblocks_prev, q, norms, red, fill_prev);
+    for (int e = threadIdx.x; e < k * kHalsB; e += blockDim.x)
+    {
+        const int p = e / kHalsB, l = e % kHalsB;
+        const bool inside = (p >= c0 && p < c0 + nb);
+        sG[e] = (l < nb && !inside) ? G[static_cast<long long>(c0 + l) * k + p] : 0.0;
+    }
+    const int jl = threadIdx.x & (kHalsTJ - 1), lg = threadIdx.x / kHalsTJ;     // 4 groups of 4 block columns
+    for (long long j0 = static_cast<long long>(blockIdx.x) * kHalsTJ; j0 < q; j0 += static_cast<long long>(gridDim.x) * kHalsTJ)
+    {
+        __syncthreads();
+        const int nj = static_cast<int>(min(static_cast<long long>(kHalsTJ), q - j0));
+        double* src = X + j0 * k;
+        for (int e = threadIdx.x; e < nj * k; e += blockDim.x)
+        {
+            const int jj = e / k, p = e - jj * k;
+            double v = src[e];
+            if (c0 > 0 && p == c0 - 1) { v = (fill_prev ? DBL_EPSILON : v) * inv_prev; src[e] = v; }
+            sX[jj * ldt + p] = v;
+        }
+        __syncthreads();
+        if (jl < nj)
+        {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            const double* xr = sX + jl * ldt;
+            const double* gp = sG + lg * 4;
+#pragma unroll 4
+            for (int p = 0; p < k; ++p)
+            {
+                const double xv = xr[p];
+                const double2 g01 = *reinterpret_cast<const double2*>(gp + p * kHalsB);
+                const double2 g23 = *reinterpret_cast<const double2*>(gp + p * kHalsB + 2);
+                a0 = fma(xv, g01.x, a0); a1 = fma(xv, g01.y, a1); a2 = fma(xv, g23.x, a2); a3 = fma(xv, g23.y, a3);
+            }
+            const long long j = j0 + jl;
+            const int l0 = lg * 4;
+            const double* rj = R + j * k + c0;
+            if (l0 + 0 < nb) Q[static_cast<long long>(l0 + 0) * q + j] = a0 - rj[l0 + 0];
+            if (l0 + 1 < nb) Q[static_cast<long long>(l0 + 1) * q + j] = a1 - rj[l0 + 1];
+            if (l0 + 2 < nb) Q[static_cast<long long>(l0 + 2) * q + j] = a2 - rj[l0 + 2];
+            if (l0 + 3 < nb) Q[static_cast<long long>(l0 + 3) * q + j] = a3 - rj[l0 + 3];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+hals_block_step_kernel(int k, int q, int c0, int l, double* __restrict__ X, const double* __restrict__ G,
+                       const double* __restrict__ Q, double* __restrict__ partial, int nblocks_prev, double* __restrict__ norms)
+{
+    __shared__ double red[32];
+    __shared__ double sg[kHalsB];
+    const int nb = min(kHalsB, k - c0);
+    const int c = c0 + l;
+    bool fill_prev = false;
+    double inv_prev = 1.0;
+    if (l > 0) inv_prev = finish_prev_row(partial, c - 1, nblocks_prev, q, norms, red, fill_prev);
+    if (threadIdx.x < kHalsB) sg[threadIdx.x] = (threadIdx.x < nb) ? G[static_cast<long long>(c) * k + c0 + threadIdx.x] : 0.0;
+    __syncthreads();
+    const double gcc = sg[l];
+    const double* ql = Q + static_cast<long long>(l) * q;
+    double sumsq = 0.0, zeros = 0.0;
+    for (long long j = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; j < q;
+         j += static_cast<long long>(gridDim.x) * blockDim.x)
+    {
+        double* xj = X + j * k + c0;
+        double dot = 0.0, xc = 0.0;
+#pragma unroll
+        for (int t = 0; t < kHalsB; ++t)
+        {
+            if (t < nb)
+            {
+                double v = xj[t];
+                if (l > 0 && t == l - 1) { v = (fill_prev ? DBL_EPSILON : v) * inv_prev; xj[t] = v; }
+                if (t == l) xc = v;
+                dot = fma(v, sg[t], dot);
+            }
+        }
+        double w = xc - (ql[j] + dot) / gcc;
+        if (isnan(w) || w < 0.0) { w = 0.0; zeros += 1.0; }
+        xj[l] = w;
+        sumsq += w * w;
+    }
+    sumsq = block_sum_f(sumsq, red);
+    zeros = block_sum_f(zeros, red);
+    if (threadIdx.x == 0)
+    {
+        double* pc = partial + (c & 1) * 2 * kSweepBlocks;
         pc[blockIdx.x] = sumsq;
         pc[kSweepBlocks + blockIdx.x] = zeros;
     }
@@ -300,11 +434,40 @@ int ew_blocks(long long total, int num_sms) { return static_cast<int>(std::max<l
 
 } // namespace
 
+size_t hals_sweep_scratch_doubles(int q) { return static_cast<size_t>(kHalsB) * q; }
+
 void hals_sweep(cudaStream_t stream, int k, int q, double* X, const double* G, const double* R,
-                bool normalize_rows, double* norms, double* partial, int num_sms)
+                bool normalize_rows, double* norms, double* partial, int num_sms, double* scratch)
 {
     if (q <= 0) return;
     const int threads = 256, wpb = threads / 32;
+    if (normalize_rows && scratch && k >= 8)
+    {
+        // blocked sweep (see hals_block_outer_kernel)
+        const size_t smem = (static_cast<size_t>(kHalsTJ) * (k + 1) + static_cast<size_t>(k) * kHalsB) * sizeof(double);
+        SMK_CUDA(cudaFuncSetAttribute(hals_block_outer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        const int per_sm = std::max(1, static_cast<int>((220 * 1024) / (smem + 1024)));
+        const int outer_blocks = std::max(1, std::min(ceil_div(q, kHalsTJ), per_sm * num_sms));
+        const int step_blocks = std::max(1, std::min(std::min(ceil_div(q, threads), 4 * num_sms), kSweepBlocks));
+        for (int c0 = 0; c0 < k; c0 += kHalsB)
+        {
+            hals_block_outer_kernel<<<outer_blocks, threads, smem, stream>>>(k, q, c0, X, G, R, scratch, partial, step_blocks, norms);
+            SMK_LAUNCH_CHECK();
+            const int nb = std::min(kHalsB, k - c0);
+            for (int l = 0; l < nb; ++l)
+            {
+                hals_block_step_kernel<<<step_blocks, threads, 0, stream>>>(k, q, c0, l, X, G, scratch, partial, step_blocks, norms);
+                SMK_LAUNCH_CHECK();
+            }
+        }
+        // the scaling of the last row (the r == k pass of the unblocked kernel)
+        dispatch_kpl(k, [&](auto kpl) {
+            constexpr int KPL = decltype(kpl)::value;
+            hals_sweep_row_kernel<KPL><<<step_blocks, threads, 0, stream>>>(k, q, k, X, G, R, partial, step_blocks, norms);
+            SMK_LAUNCH_CHECK();
+        });
+        return;
+    }
     dispatch_kpl(k, [&](auto kpl) {
         constexpr int KPL = decltype(kpl)::value;
         if (!normalize_rows)

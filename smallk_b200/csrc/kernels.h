@@ -42,8 +42,11 @@ void diff_sumsq(cudaStream_t stream, long long count, const double* A, const dou
 // (nmf_solver_hals.hpp:26-61 for H with G = W'W, R = W'A; :64-117 for W' with G = HH', R = HA').
 // normalize_rows = true adds the in-sweep unit-2-norm scaling of row r (= column r of W) and the
 // all-zero -> epsilon rule of :103-115. partial: >= 4096 doubles of scratch.
+// scratch (optional, hals_sweep_scratch_doubles(q) doubles) enables the blocked W-side sweep, which reads X k/16
+// times per sweep instead of k times.
 void hals_sweep(cudaStream_t stream, int k, int q, double* X, const double* G, const double* R,
-                bool normalize_rows, double* norms, double* partial, int num_sms);
+                bool normalize_rows, double* norms, double* partial, int num_sms, double* scratch = nullptr);
+size_t hals_sweep_scratch_doubles(int q);
 // Rank-2 solve + optimal active set for X (2 x q): nmf_solver_rank2.hpp:25-318.
 // w_side selects the SystemSolveW / OptimalActiveSetW formulas (same algebra, transposed roles).
 void rank2_update(cudaStream_t stream, int q, double* X, const double* G, const double* B, bool w_side,

@@ -90,7 +90,8 @@ void solver_alloc(smk_ctx* c)
     c->WtA.reserve(k * n); c->HAt.reserve(k * m);
     c->norms.reserve(k);
     c->deferred.reserve(nnls_deferred_bytes(static_cast<int>(std::max(m, n)), c->opts.k, c->num_sms));
-    if (c->opts.algorithm == SMK_MU || c->opts.algorithm == SMK_HALS) { c->T1.reserve(k * n); c->T2.reserve(k * m); }
+    if (c->opts.algorithm == SMK_MU) { c->T1.reserve(k * n); c->T2.reserve(k * m); }
+    if (c->opts.algorithm == SMK_HALS) c->T2.reserve(std::max(k * m, hals_sweep_scratch_doubles(static_cast<int>(m))));
     if (c->opts.prog_est_algorithm == SMK_DELTA_FNORM) c->Wprev.reserve(k * m);
     // split-R workspace: enough for the gram matrices at 4*SMs splits and for the big products at a few splits
     size_t want = std::max<size_t>(static_cast<size_t>(4 * c->num_sms) * k * k,
@@ -146,7 +147,7 @@ void solver_step(smk_ctx* c)
         gram_times(c, c->WtW.p, c->H.p, n, c->WtA.p, c->gradH.p);
         break;
     case SMK_HALS:     // nmf_solver_hals.hpp:166-199
-        hals_sweep(c->stream, k, m, c->Wt.p, c->HHt.p, c->HAt.p, /*normalize=*/true, c->norms.p, c->partial.p, c->num_sms);
+        hals_sweep(c->stream, k, m, c->Wt.p, c->HHt.p, c->HAt.p, /*normalize=*/true, c->norms.p, c->partial.p, c->num_sms, c->T2.p);
         compute_WtW(c);
         prod_WtA(c);
         hals_sweep(c->stream, k, n, c->H.p, c->WtW.p, c->WtA.p, /*normalize=*/false, c->norms.p, c->partial.p, c->num_sms);

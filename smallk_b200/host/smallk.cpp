@@ -10,6 +10,9 @@
 #include <stdexcept>
 #include <thread>
 
+#include "clust.hpp"
+#include "flat_clust.hpp"
+#include "flat_clust_output.hpp"
 #include "matrix_io.hpp"
 #include "nmf.hpp"
 
@@ -22,8 +25,12 @@ unsigned int outprecision = 6, max_iter = 5000, min_iter = 5;
 unsigned int max_threads = std::max(2u, std::thread::hardware_concurrency());
 double nmf_tolerance = 0.005;
 std::string outdir;
-std::mt19937 engine;
-std::uniform_real_distribution<double> dist_double;
+Random rng;                 // one stream for Nmf and HierNmf2, as in the reference (smallk.cpp:47)
+bool dict_loaded = false;
+std::vector<std::string> dictionary;
+unsigned int maxterms = 5;
+double hier_nmf2_tolerance = 0.0001;
+smallk::OutputFormat clustfile_format = smallk::JSON;
 const char* DEFAULT_FILENAME_W = "w.csv";
 const char* DEFAULT_FILENAME_H = "h.csv";
 
@@ -32,9 +39,7 @@ const char* DEFAULT_FILENAME_H = "h.csv";
 // matrices; this build always uses the sequential stream.
 void RandomMatrix(double* buf, unsigned int ldim, unsigned int height, unsigned int width)
 {
-    for (unsigned int c = 0; c < width; ++c)
-        for (unsigned int r = 0; r < height; ++r)
-            buf[r + static_cast<size_t>(c) * ldim] = 0.5 + 2.0 * 0.5 * dist_double(engine) - 0.5;
+    ::RandomMatrix(buf, ldim, height, width, rng, 0.5, 0.5);
 }
 
 std::string EnsureTrailingSep(const std::string& s)
@@ -93,9 +98,35 @@ void Reset()
     outprecision = 6; max_iter = 5000; min_iter = 5; nmf_tolerance = 0.005;
     max_threads = std::max(2u, std::thread::hardware_concurrency());
     outdir.clear();
-    engine.seed();
+    dict_loaded = false; dictionary.clear();
+    maxterms = 5; hier_nmf2_tolerance = 0.0001; clustfile_format = JSON;
+    rng.SetDefaultState();
 }
-void SeedRNG(const int seed) { engine.seed(seed); }
+void SeedRNG(const int seed) { rng.SeedFromInt(seed); }
+
+// smallk.cpp:652-735
+void LoadDictionary(const std::string& filepath)
+{
+    dict_loaded = false;
+    if (!LoadStringsFromFile(filepath, dictionary))
+        throw std::runtime_error("smallk error (LoadDictionary): load failed for file \"" + filepath + "\"");
+    dict_loaded = true;
+}
+void LoadDictionary(const std::vector<std::string>& terms)
+{
+    dictionary.assign(terms.begin(), terms.end());
+    dict_loaded = true;
+}
+unsigned int GetMaxTerms() { return maxterms; }
+void SetMaxTerms(const unsigned int max_terms) { maxterms = max_terms ? max_terms : 1; }
+OutputFormat GetOutputFormat() { return clustfile_format; }
+void SetOutputFormat(const OutputFormat format) { clustfile_format = format; }
+double GetHierNmf2Tolerance() { return hier_nmf2_tolerance; }
+void SetHierNmf2Tolerance(const double tol)
+{
+    if (tol <= 0.0 || tol >= 1.0) throw std::logic_error("smallk error (SetHierNmf2Tolerance): tolerance must be in the interval (0.0, 1.0)");
+    hier_nmf2_tolerance = tol;
+}
 
 void LoadMatrix(const std::string& filepath)
 {
@@ -240,8 +271,66 @@ const double* LockedBufferH(unsigned int& ldim, unsigned int& height, unsigned i
     return buf_h.empty() ? nullptr : &buf_h[0];
 }
 
-void HierNmf2(const unsigned int)
-{ throw std::runtime_error("smallk_b200: HierNmf2 (hierclust tree driver) is not part of this build yet; see DESIGN.md"); }
-void HierNmf2WithFlat(const unsigned int)
-{ throw std::runtime_error("smallk_b200: HierNmf2WithFlat is not part of this build yet; see DESIGN.md"); }
+// smallk.cpp:737-856: HierNMF2 on the loaded matrix; writes assignments_N.csv and tree_N.{xml,json} (and, with the
+// flat step, assignments_flat_N.csv, assignments_fuzzy_N.csv, clusters_N.*) into the output directory.
+static void HierNmf2Internal(const bool generate_flat, const unsigned int num_clusters)
+{
+    using std::cout; using std::cerr; using std::endl;
+    if (!matrix_loaded) throw std::logic_error("smallk error (HierNmf2): no matrix has been loaded.");
+    if (!dict_loaded) throw std::logic_error("smallk error (HierNmf2): no dictionary has been loaded.");
+    if (0 == num_clusters) throw std::logic_error("smallk error (HierNmf2): num_clusters must be greater than 0.");
+    const unsigned long long lim = std::numeric_limits<int>::max();
+    if (2ull * m > lim) throw std::logic_error("smallk error (HierNmf2): matrix height too large.");
+    if (2ull * n > lim) throw std::logic_error("smallk error (HierNmf2): matrix width too large.");
+    if (dictionary.size() < m) throw std::logic_error("smallk error (HierNmf2): dictionary has fewer terms than the matrix has rows.");
+
+    ClustOptions o;
+    o.nmf_opts.tol = hier_nmf2_tolerance;
+    o.nmf_opts.algorithm = NmfAlgorithm::RANK2;
+    o.nmf_opts.prog_est_algorithm = NmfProgressAlgorithm::PG_RATIO;
+    o.nmf_opts.height = m; o.nmf_opts.width = n; o.nmf_opts.k = 2;
+    o.nmf_opts.min_iter = min_iter; o.nmf_opts.max_iter = max_iter; o.nmf_opts.tolcount = 1;
+    o.nmf_opts.max_threads = max_threads; o.nmf_opts.verbose = false;
+    o.nmf_opts.normalize = true;                 // smallk.cpp:766 (the hierclust CLI passes false)
+    o.maxterms = maxterms; o.unbalanced = 0.1; o.trial_allowance = 3;
+    o.num_clusters = num_clusters; o.verbose = true; o.flat = generate_flat;
+
+    const FileFormat format = (XML == clustfile_format) ? FileFormat::XML : FileFormat::JSON;
+    std::ostringstream an, tn;
+    an << "assignments_" << num_clusters;
+    tn << "tree_" << num_clusters;
+    const std::string assignfile = outdir + AppendExtension(an.str(), FileFormat::CSV);
+    const std::string treefile = outdir + AppendExtension(tn.str(), format);
+
+    Tree<R> tree;
+    ClustStats stats;
+    std::vector<R> flat_w(static_cast<size_t>(m) * num_clusters), flat_h(static_cast<size_t>(num_clusters) * n);
+    Result result;
+    if (is_sparse)
+    {
+        SparseMatrix<R> S(A.height, A.width, A.nnz(), A.col_offsets.data(), A.row_indices.data(), A.data.data());
+        result = ClustSparse(o, S, flat_w.data(), flat_h.data(), tree, stats, rng);
+    }
+    else result = Clust(o, &buf_a[0], ldim_a, flat_w.data(), flat_h.data(), tree, stats, rng);
+    if (Result::OK != result) throw std::runtime_error("smallk error (HierNMF2): HierNMF2 fatal error.");
+    cout << (stats.nmf_count - stats.max_count) << "/" << stats.nmf_count << " factorizations converged." << endl << endl;
+    cout << "Writing output files..." << endl;
+    if (!tree.WriteAssignments(assignfile)) cerr << "\terror writing assignments file" << endl;
+    IHierclustWriter* writer = CreateHierclustWriter(format);
+    if (!tree.WriteTree(writer, treefile, dictionary)) cerr << "\terror writing hierarchical results file" << endl;
+    delete writer;
+    if (generate_flat)
+    {
+        std::vector<float> probabilities;
+        std::vector<unsigned int> assignments_flat;
+        std::vector<int> term_indices(static_cast<size_t>(maxterms) * num_clusters);
+        ComputeFuzzyAssignments(probabilities, flat_h.data(), num_clusters, num_clusters, n);
+        ComputeAssignments(assignments_flat, flat_h.data(), num_clusters, num_clusters, n);
+        TopTerms(static_cast<int>(maxterms), flat_w.data(), m, m, num_clusters, term_indices);
+        FlatClustWriteResults(outdir, assignments_flat, probabilities, dictionary, term_indices, format, maxterms, n, num_clusters);
+    }
+}
+
+void HierNmf2(const unsigned int num_clusters) { HierNmf2Internal(false, num_clusters); }
+void HierNmf2WithFlat(const unsigned int num_clusters) { HierNmf2Internal(true, num_clusters); }
 } // namespace smallk

@@ -1,8 +1,7 @@
 // smallk_b200 — the reference's public C++ API (smallk/include/smallk.hpp:34-332), NMF part, implemented on
 // the GPU library. Same namespace, names, default arguments and exception types, so a program using
 // smallk::Initialize / LoadMatrix / Nmf / LockedBufferW/H re-links unchanged.
-// HierNmf2 / HierNmf2WithFlat (hierclust) drive the same rank-2 solver from host-side tree code that
-// is scheduled after the hot path; they throw std::runtime_error until then.
+// HierNmf2 / HierNmf2WithFlat drive the rank-2 solver from the host-side tree code of host/clust.cpp.
 #pragma once
 
 #include <string>
@@ -53,6 +52,15 @@ namespace smallk
              const std::string& initfile_w = std::string(""), const std::string& initfile_h = std::string(""));
     const double* LockedBufferW(unsigned int& ldim, unsigned int& height, unsigned int& width);
     const double* LockedBufferH(unsigned int& ldim, unsigned int& height, unsigned int& width);
+
+    void LoadDictionary(const std::string& filepath);
+    void LoadDictionary(const std::vector<std::string>& terms);
+    unsigned int GetMaxTerms();
+    void SetMaxTerms(const unsigned int max_terms = 5);
+    OutputFormat GetOutputFormat();
+    void SetOutputFormat(const OutputFormat format = JSON);
+    double GetHierNmf2Tolerance();
+    void SetHierNmf2Tolerance(const double tol = 0.0001);
 
     void HierNmf2(const unsigned int num_clusters);
     void HierNmf2WithFlat(const unsigned int num_clusters);
