@@ -232,6 +232,8 @@ int smk_load_csc(smk_ctx* c, int m, int n, unsigned int nnz, const unsigned int*
             SMK_CUDA(cudaMemcpyAsync(S.val.p, val, sizeof(double) * nnz, cudaMemcpyHostToDevice, c->stream));
         }
         build_csr(c->stream, S);
+        build_segments(c->stream, n, S.colptr.p, S.seg_cols, c->num_sms);
+        build_segments(c->stream, m, S.rowptr.p, S.seg_rows, c->num_sms);
         c->m = m; c->n = n;
         c->has_sparse = true; c->has_dense = false; c->active = false;
         return (int)SMK_OK;
@@ -534,10 +536,11 @@ int smk_sparse_gemm(smk_ctx* c, int variant, double alpha, const double* B, int 
             if (beta != 0.0) transpose_f64(c->stream, Ch, Cw, dC.p, Ch, dCt.p, Cw);
             Ck = dCt.p;
         }
+        c->spmm_partial.reserve(static_cast<size_t>(std::max(S.seg_cols.nslots, S.seg_rows.nslots)) * k + 1);
         if (variant <= 1)   // C = A*op(B): rows of A -> CSR walk, output k x m
-            spmm_gather(c->stream, m, S.rowptr.p, S.colidx.p, S.valr.p, k, Bk, k, alpha, beta, Ck, k, c->num_sms);
+            spmm_gather_seg(c->stream, m, S.seg_rows, S.colidx.p, S.valr.p, k, Bk, k, alpha, beta, Ck, k, c->spmm_partial.p, c->num_sms);
         else                // C = op(B)*A: columns of A -> CSC walk, output k x n
-            spmm_gather(c->stream, n, S.colptr.p, S.rowidx.p, S.val.p, k, Bk, k, alpha, beta, Ck, k, c->num_sms);
+            spmm_gather_seg(c->stream, n, S.seg_cols, S.rowidx.p, S.val.p, k, Bk, k, alpha, beta, Ck, k, c->spmm_partial.p, c->num_sms);
         if (!c_is_kmajor) transpose_f64(c->stream, Cw, Ch, dCt.p, Cw, dC.p, Ch);
         download_tight(c, dC.p, Ch, Cw, C, Ch);
         SMK_CUDA(cudaStreamSynchronize(c->stream));

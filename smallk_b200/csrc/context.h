@@ -34,6 +34,18 @@ struct DevBuf
     void zero(cudaStream_t s) { if (p) SMK_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
 };
 
+// Work decomposition of a compressed matrix for the gather SpMM: every compressed column is cut into segments of at
+// most kSpmmSeg stored entries, so that one heavy column (a popular term, a hub node) cannot serialise the kernel.
+struct SegTable
+{
+    int nseg = 0, nslots = 0, nmulti = 0;
+    DevBuf<unsigned int> col, beg, end, slot;   // per segment: its column, entry range, partial slot (0xFFFFFFFF: writes the output directly)
+    DevBuf<unsigned int> first_slot;            // per column (+1): first partial slot
+    DevBuf<unsigned int> multi_col;             // the columns that have more than one segment
+    DevBuf<unsigned int> t_cnt, t_first, t_mpos; // build temporaries (kept: the column-subset matrix is rebuilt many times)
+    DevBuf<unsigned char> t_scan;
+};
+
 struct SparseDev
 {
     int m = 0, n = 0;
@@ -47,6 +59,7 @@ struct SparseDev
     // build_csr temporaries; kept between calls only for the column-subset matrix, which is rebuilt many times
     DevBuf<unsigned int> t_colof, t_ids, t_ids_sorted, t_rows_sorted;
     DevBuf<unsigned char> t_sort;
+    SegTable seg_cols, seg_rows;                // segments of the CSC columns / of the CSR rows
 };
 
 } // namespace smk
@@ -86,6 +99,7 @@ struct smk_ctx
     smk::DevBuf<double> partial;    // 1024 block partials
     smk::DevBuf<double> acc;        // 8 scalars
     smk::DevBuf<double> io;         // staging for host<->device transposes
+    smk::DevBuf<double> spmm_partial; // partial sums of the segmented SpMM (columns with more than one segment)
 
     // ---- solver state (both factors are kept "k x big", column-major: H is k x n, Wt = W' is k x m)
     bool active = false;

@@ -9,7 +9,7 @@ namespace smk {
 namespace {
 
 constexpr int kMaxKPL = 8;          // rows per lane: k <= 256
-constexpr int kSweepBlocks = 1024;  // upper bound on the grid of the per-row sweep kernels
+constexpr int kSweepBlocks = 2048;  // upper bound on the grid of the per-row sweep kernels
 
 __device__ __forceinline__ double block_sum_f(double v, double* red)
 {
@@ -159,14 +159,13 @@ __global__ void hals_sweep_row_kernel(int k, int q, int r, double* __restrict__ 
 // HALS, W side, blocked: the same k dependent steps, but the k-long dot products are not re-read from memory at
 // every step. Columns are taken in blocks of kHalsB. For a block [c0, c0+B):
 //   phase A (hals_block_outer_kernel): Q(l, j) = sum over p OUTSIDE the block of X(p,j) G(p,c0+l) - R(c0+l,j)
-//            — one pass over X per block (k/B passes per sweep instead of k), FMA-pipe GEMM from a shared-memory tile;
+//            — one pass over X per block (k/B passes per sweep instead of k), a 16 x k x q GEMM on the FP64 tensor pipe;
 //   phase B (hals_block_step_kernel), B dependent steps: step l needs only the block's own B entries of each column
 //            and Q(l, j):  x <- max(0, x - (Q + sum_{p in block} X(p,j) G(p,c)) / G(c,c)),  NaN -> 0,
 //            then the grid-wide unit-norm scaling of row c is applied by the NEXT kernel (as in hals_sweep_row_kernel).
 // Traffic per sweep and column of X: k*k/B + k*(B+3) doubles instead of k*k.
 // ---------------------------------------------------------------------------
 constexpr int kHalsB = 16;
-constexpr int kHalsTJ = 64;      // columns of X per shared-memory tile in phase A
 
 // norm of row `prev` from the block partials of the step that produced it; returns 1/norm and whether the row is refilled with eps
 __device__ __forceinline__ double finish_prev_row(const double* __restrict__ partial, int prev, int nblocks_prev, int q,
@@ -185,59 +184,65 @@ __device__ __forceinline__ double finish_prev_row(const double* __restrict__ par
     return 1.0 / norm;
 }
 
+// Phase A on the FP64 tensor pipe: D (16 block columns x 8 columns of X) = GmT (16 x k) * X (k x 8), two DMMA.8x8x4 per
+// four rows of X. One warp per 8 columns of X; the B fragments come straight from global memory (each lane reads
+// X(4s + (lane & 3), j0 + (lane >> 2)): eight fully used 32-byte sectors per warp load, no shared-memory tile, no
+// barriers), the A fragments of the masked Gram block sit in shared memory in fragment order.
 __global__ void __launch_bounds__(256)
 hals_block_outer_kernel(int k, int q, int c0, double* __restrict__ X, const double* __restrict__ G, const double* __restrict__ R,
                         double* __restrict__ Q, const double* __restrict__ partial, int nblocks_prev, double* __restrict__ norms)
 {
-    extern __shared__ __align__(16) double sm[];
+    extern __shared__ __align__(16) double sA[];       // [ksteps][2 m-tiles][32 lanes]
     __shared__ double red[32];
-    const int ldt = k + 1;
-    double* sX = sm;                                   // [kHalsTJ][k + 1]
-    double* sG = sm + static_cast<size_t>(kHalsTJ) * ldt;   // [k][kHalsB], rows of the block zeroed
+    const int ksteps = (k + 3) >> 2;
     const int nb = min(kHalsB, k - c0);
     bool fill_prev = false;
     double inv_prev = 1.0;
     if (c0 > 0) inv_prev = finish_prev_row(partial, c0 - 1, nblocks_prev, q, norms, red, fill_prev);
-    for (int e = threadIdx.x; e < k * kHalsB; e += blockDim.x)
+    for (int e = threadIdx.x; e < ksteps * 64; e += blockDim.x)
     {
-        const int p = e / kHalsB, l = e % kHalsB;
+        const int ln = e & 31, mt = (e >> 5) & 1, st = e >> 6;
+        const int row = mt * 8 + (ln >> 2), p = 4 * st + (ln & 3);
         const bool inside = (p >= c0 && p < c0 + nb);
-        sG[e] = (l < nb && !inside) ? G[static_cast<long long>(c0 + l) * k + p] : 0.0;
+        sA[e] = (row < nb && p < k && !inside) ? G[static_cast<long long>(c0 + row) * k + p] : 0.0;
     }
-    const int jl = threadIdx.x & (kHalsTJ - 1), lg = threadIdx.x / kHalsTJ;     // 4 groups of 4 block columns
-    for (long long j0 = static_cast<long long>(blockIdx.x) * kHalsTJ; j0 < q; j0 += static_cast<long long>(gridDim.x) * kHalsTJ)
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int n = lane >> 2, kk = lane & 3;
+    const int prev = c0 - 1;
+    for (long long j0 = (static_cast<long long>(blockIdx.x) * wpb + warp) * 8; j0 < q; j0 += static_cast<long long>(gridDim.x) * wpb * 8)
     {
-        __syncthreads();
-        const int nj = static_cast<int>(min(static_cast<long long>(kHalsTJ), q - j0));
-        double* src = X + j0 * k;
-        for (int e = threadIdx.x; e < nj * k; e += blockDim.x)
+        const long long j = j0 + n;
+        const bool livecol = j < q;
+        const double* xcol = X + (livecol ? j : static_cast<long long>(q) - 1) * k;
+        double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+#pragma unroll 8
+        for (int st = 0; st < ksteps; ++st)
         {
-            const int jj = e / k, p = e - jj * k;
-            double v = src[e];
-            if (c0 > 0 && p == c0 - 1) { v = (fill_prev ? DBL_EPSILON : v) * inv_prev; src[e] = v; }
-            sX[jj * ldt + p] = v;
+            const int p = 4 * st + kk;
+            double b = xcol[min(p, k - 1)];
+            if (p >= k || !livecol) b = 0.0;
+            if (p == prev) b = (fill_prev ? DBL_EPSILON : b) * inv_prev;      // row c0-1 is finished on the fly (stored below)
+            const double a0 = sA[(st * 2) * 32 + lane], a1 = sA[(st * 2 + 1) * 32 + lane];
+            dmma884(c00, c01, a0, b);
+            dmma884(c10, c11, a1, b);
         }
-        __syncthreads();
-        if (jl < nj)
+        const int row = lane >> 2, col = 2 * (lane & 3);
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc)
         {
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            const double* xr = sX + jl * ldt;
-            const double* gp = sG + lg * 4;
-#pragma unroll 4
-            for (int p = 0; p < k; ++p)
+            const long long jj = j0 + col + cc;
+            if (jj < q)
             {
-                const double xv = xr[p];
-                const double2 g01 = *reinterpret_cast<const double2*>(gp + p * kHalsB);
-                const double2 g23 = *reinterpret_cast<const double2*>(gp + p * kHalsB + 2);
-                a0 = fma(xv, g01.x, a0); a1 = fma(xv, g01.y, a1); a2 = fma(xv, g23.x, a2); a3 = fma(xv, g23.y, a3);
+                const double* rj = R + jj * k + c0;
+                if (row < nb) Q[static_cast<long long>(row) * q + jj] = (cc ? c01 : c00) - rj[row];
+                if (row + 8 < nb) Q[static_cast<long long>(row + 8) * q + jj] = (cc ? c11 : c10) - rj[row + 8];
             }
-            const long long j = j0 + jl;
-            const int l0 = lg * 4;
-            const double* rj = R + j * k + c0;
-            if (l0 + 0 < nb) Q[static_cast<long long>(l0 + 0) * q + j] = a0 - rj[l0 + 0];
-            if (l0 + 1 < nb) Q[static_cast<long long>(l0 + 1) * q + j] = a1 - rj[l0 + 1];
-            if (l0 + 2 < nb) Q[static_cast<long long>(l0 + 2) * q + j] = a2 - rj[l0 + 2];
-            if (l0 + 3 < nb) Q[static_cast<long long>(l0 + 3) * q + j] = a3 - rj[l0 + 3];
+        }
+        if (c0 > 0 && lane < 8 && j0 + lane < q)
+        {
+            double* px = X + (j0 + lane) * k + prev;
+            *px = (fill_prev ? DBL_EPSILON : *px) * inv_prev;
         }
     }
 }
@@ -258,26 +263,54 @@ hals_block_step_kernel(int k, int q, int c0, int l, double* __restrict__ X, cons
     const double gcc = sg[l];
     const double* ql = Q + static_cast<long long>(l) * q;
     double sumsq = 0.0, zeros = 0.0;
-    for (long long j = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; j < q;
-         j += static_cast<long long>(gridDim.x) * blockDim.x)
+    // half a warp per column of X: lane t holds entry c0 + t (one 128-byte read per column), the block's dot product is a
+    // 4-step shuffle reduction inside the half-warp
+    const int t = threadIdx.x & (kHalsB - 1);
+    const long long halves = (static_cast<long long>(gridDim.x) * blockDim.x) / kHalsB;
+    const long long h = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) / kHalsB;
+    constexpr int U = 4;                                 // columns in flight per half-warp
+    for (long long base = 0; base < q; base += U * halves)
     {
-        double* xj = X + j * k + c0;
-        double dot = 0.0, xc = 0.0;
+        double v[U], dot[U], qv[U];
+        bool live[U];
+        const int tc = min(t, nb - 1);
+        // branch-free loads from clamped addresses: all 2U loads of a trip are in flight together
 #pragma unroll
-        for (int t = 0; t < kHalsB; ++t)
+        for (int u = 0; u < U; ++u)
         {
-            if (t < nb)
+            const long long j = base + u * halves + h;
+            live[u] = j < q;
+            const long long jc = live[u] ? j : q - 1;
+            v[u] = X[jc * k + c0 + tc];
+            qv[u] = ql[jc];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            if (!(live[u] && t < nb)) v[u] = 0.0;
+            if (l > 0 && t == l - 1 && live[u])
             {
-                double v = xj[t];
-                if (l > 0 && t == l - 1) { v = (fill_prev ? DBL_EPSILON : v) * inv_prev; xj[t] = v; }
-                if (t == l) xc = v;
-                dot = fma(v, sg[t], dot);
+                v[u] = (fill_prev ? DBL_EPSILON : v[u]) * inv_prev;
+                X[(base + u * halves + h) * k + c0 + t] = v[u];
+            }
+            dot[u] = v[u] * sg[t];
+        }
+#pragma unroll
+        for (int o = kHalsB / 2; o > 0; o >>= 1)
+#pragma unroll
+            for (int u = 0; u < U; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], o);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            if (live[u] && t == l)
+            {
+                const long long j = base + u * halves + h;
+                double w = v[u] - (qv[u] + dot[u]) / gcc;
+                if (isnan(w) || w < 0.0) { w = 0.0; zeros += 1.0; }
+                X[j * k + c0 + l] = w;
+                sumsq += w * w;
             }
         }
-        double w = xc - (ql[j] + dot) / gcc;
-        if (isnan(w) || w < 0.0) { w = 0.0; zeros += 1.0; }
-        xj[l] = w;
-        sumsq += w * w;
     }
     sumsq = block_sum_f(sumsq, red);
     zeros = block_sum_f(zeros, red);
@@ -444,11 +477,10 @@ void hals_sweep(cudaStream_t stream, int k, int q, double* X, const double* G, c
     if (normalize_rows && scratch && k >= 8)
     {
         // blocked sweep (see hals_block_outer_kernel)
-        const size_t smem = (static_cast<size_t>(kHalsTJ) * (k + 1) + static_cast<size_t>(k) * kHalsB) * sizeof(double);
+        const size_t smem = static_cast<size_t>((k + 3) / 4) * 64 * sizeof(double);
         SMK_CUDA(cudaFuncSetAttribute(hals_block_outer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        const int per_sm = std::max(1, static_cast<int>((220 * 1024) / (smem + 1024)));
-        const int outer_blocks = std::max(1, std::min(ceil_div(q, kHalsTJ), per_sm * num_sms));
-        const int step_blocks = std::max(1, std::min(std::min(ceil_div(q, threads), 4 * num_sms), kSweepBlocks));
+        const int outer_blocks = std::max(1, std::min(ceil_div(q, 64), 8 * num_sms));
+        const int step_blocks = std::max(1, std::min(std::min(ceil_div(static_cast<long long>(q) * kHalsB, threads), 8 * num_sms), kSweepBlocks));
         for (int c0 = 0; c0 < k; c0 += kHalsB)
         {
             hals_block_outer_kernel<<<outer_blocks, threads, smem, stream>>>(k, q, c0, X, G, R, scratch, partial, step_blocks, norms);

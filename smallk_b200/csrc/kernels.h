@@ -63,6 +63,16 @@ struct SparseDev;
 // added in storage order, which is the order the reference adds them (sparse_gemm_ba_impl.hpp:26-140).
 void spmm_gather(cudaStream_t stream, int ncols, const unsigned int* ptr, const unsigned int* idx, const double* val,
                  int k, const double* B, long long ldb, double alpha, double beta, double* out, long long ldo, int num_sms);
+struct SegTable;
+constexpr int kSpmmSeg = 512;
+// Segment table of a compressed matrix (ncols compressed columns, offsets ptr[ncols + 1]); synchronises the stream.
+void build_segments(cudaStream_t stream, int ncols, const unsigned int* ptr, SegTable& T, int num_sms);
+// Same product as spmm_gather, one work item per segment; columns cut into several segments are summed from
+// per-segment partials in segment order (deterministic; differs from the one-pass order at rounding level only).
+// partial: at least T.nslots * k doubles.
+void spmm_gather_seg(cudaStream_t stream, int ncols, const SegTable& T, const unsigned int* idx, const double* val,
+                     int k, const double* B, long long ldb, double alpha, double beta, double* out, long long ldo,
+                     double* partial, int num_sms);
 // Builds rowptr/colidx/valr (CSR = stable transpose) from the CSC arrays already on the device.
 void build_csr(cudaStream_t stream, SparseDev& S, bool keep_scratch = false);
 

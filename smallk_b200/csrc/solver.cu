@@ -37,7 +37,8 @@ void prod_WtA(smk_ctx* c)
         gemm_f64(c->stream, false, k, c->n, c->m, c->Wt.p, k, c->dA, c->ldA, c->WtA.p, k, nullptr, 0,
                  c->ws.p, c->ws.n * sizeof(double), c->num_sms);
     else
-        spmm_gather(c->stream, c->n, c->Sa->colptr.p, c->Sa->rowidx.p, c->Sa->val.p, k, c->Wt.p, k, 1.0, 0.0, c->WtA.p, k, c->num_sms);
+        spmm_gather_seg(c->stream, c->n, c->Sa->seg_cols, c->Sa->rowidx.p, c->Sa->val.p, k, c->Wt.p, k, 1.0, 0.0, c->WtA.p, k,
+                        c->spmm_partial.p, c->num_sms);
 }
 
 // HAt (k x m) = H * A'   (summed over the column shards when running multi-GPU)
@@ -48,7 +49,8 @@ void prod_HAt(smk_ctx* c)
         gemm_f64(c->stream, true, k, c->m, c->n, c->H.p, k, c->dA, c->ldA, c->HAt.p, k, nullptr, 0,
                  c->ws.p, c->ws.n * sizeof(double), c->num_sms);
     else
-        spmm_gather(c->stream, c->m, c->Sa->rowptr.p, c->Sa->colidx.p, c->Sa->valr.p, k, c->H.p, k, 1.0, 0.0, c->HAt.p, k, c->num_sms);
+        spmm_gather_seg(c->stream, c->m, c->Sa->seg_rows, c->Sa->colidx.p, c->Sa->valr.p, k, c->H.p, k, 1.0, 0.0, c->HAt.p, k,
+                        c->spmm_partial.p, c->num_sms);
     allreduce_sum(c, c->HAt.p, static_cast<size_t>(k) * c->m);
 }
 
@@ -89,6 +91,7 @@ void solver_alloc(smk_ctx* c)
     c->WtW.reserve(k * k); c->HHt.reserve(k * k);
     c->WtA.reserve(k * n); c->HAt.reserve(k * m);
     c->norms.reserve(k);
+    if (c->has_sparse) c->spmm_partial.reserve(static_cast<size_t>(std::max(c->Sa->seg_cols.nslots, c->Sa->seg_rows.nslots)) * k + 1);
     c->deferred.reserve(nnls_deferred_bytes(static_cast<int>(std::max(m, n)), c->opts.k, c->num_sms));
     if (c->opts.algorithm == SMK_MU) { c->T1.reserve(k * n); c->T2.reserve(k * m); }
     if (c->opts.algorithm == SMK_HALS) c->T2.reserve(std::max(k * m, hals_sweep_scratch_doubles(static_cast<int>(m))));

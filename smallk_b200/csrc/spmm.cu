@@ -134,6 +134,149 @@ __global__ void rowptr_kernel(int m, unsigned int nnz, const unsigned int* __res
     }
 }
 
+// ---------------------------------------------------------------------------
+// segmented variant: one group of L lanes per SEGMENT (<= kSpmmSeg stored entries of one compressed column)
+// ---------------------------------------------------------------------------
+__global__ void seg_count_kernel(int ncols, const unsigned int* __restrict__ ptr, unsigned int* __restrict__ cnt,
+                                 unsigned int* __restrict__ mcnt, unsigned int* __restrict__ flag)
+{
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j <= ncols; j += gridDim.x * blockDim.x)
+    {
+        unsigned int c = 0;
+        if (j < ncols) { const unsigned int len = ptr[j + 1] - ptr[j]; c = len == 0 ? 1u : (len + kSpmmSeg - 1) / kSpmmSeg; }
+        cnt[j] = c;
+        mcnt[j] = c > 1 ? c : 0u;
+        flag[j] = c > 1 ? 1u : 0u;
+    }
+}
+
+// one warp per column fills the records of its segments
+__global__ void seg_fill_kernel(int ncols, const unsigned int* __restrict__ ptr, const unsigned int* __restrict__ first,
+                                const unsigned int* __restrict__ first_slot, const unsigned int* __restrict__ mpos,
+                                unsigned int* __restrict__ scol, unsigned int* __restrict__ sbeg, unsigned int* __restrict__ send,
+                                unsigned int* __restrict__ sslot, unsigned int* __restrict__ multi_col)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < ncols; j += warps)
+    {
+        const unsigned int f = first[j], cnt = first[j + 1] - f, b0 = ptr[j], e0 = ptr[j + 1];
+        for (unsigned int sg = lane; sg < cnt; sg += 32)
+        {
+            const unsigned int b = b0 + sg * kSpmmSeg;
+            scol[f + sg] = j;
+            sbeg[f + sg] = b;
+            send[f + sg] = min(e0, b + kSpmmSeg);
+            sslot[f + sg] = cnt > 1 ? first_slot[j] + sg : 0xFFFFFFFFu;
+        }
+        if (cnt > 1 && lane == 0) multi_col[mpos[j]] = j;
+    }
+}
+
+template <int L, int KPL>
+__global__ void spmm_seg_kernel(int nseg, const unsigned int* __restrict__ scol, const unsigned int* __restrict__ sbeg,
+                                const unsigned int* __restrict__ send, const unsigned int* __restrict__ sslot,
+                                const unsigned int* __restrict__ idx, const double* __restrict__ val, int k,
+                                const double* __restrict__ B, long long ldb, double alpha, double beta,
+                                double* __restrict__ out, long long ldo, double* __restrict__ partial)
+{
+    const int groups_per_block = blockDim.x / L;
+    const int lane = threadIdx.x % L;
+    for (long long it = blockIdx.x * static_cast<long long>(groups_per_block) + threadIdx.x / L; it < nseg;
+         it += static_cast<long long>(gridDim.x) * groups_per_block)
+    {
+        const unsigned int j = scol[it], slot = sslot[it];
+        const bool direct = slot == 0xFFFFFFFFu;
+        double acc[KPL];
+#pragma unroll
+        for (int e = 0; e < KPL; ++e)
+        {
+            const int r = lane + L * e;
+            acc[e] = (direct && beta != 0.0 && r < k) ? out[j * ldo + r] * beta : 0.0;
+        }
+        const unsigned int end = send[it];
+        unsigned int o = sbeg[it];
+        for (; o + 4 <= end; o += 4)
+        {
+            const unsigned int i0 = idx[o], i1 = idx[o + 1], i2 = idx[o + 2], i3 = idx[o + 3];
+            const double a0 = alpha * val[o], a1 = alpha * val[o + 1], a2 = alpha * val[o + 2], a3 = alpha * val[o + 3];
+            double b0[KPL], b1[KPL], b2[KPL], b3[KPL];
+#pragma unroll
+            for (int e = 0; e < KPL; ++e)
+            {
+                const int r = lane + L * e;
+                const bool ok = r < k;
+                b0[e] = ok ? B[i0 * ldb + r] : 0.0;
+                b1[e] = ok ? B[i1 * ldb + r] : 0.0;
+                b2[e] = ok ? B[i2 * ldb + r] : 0.0;
+                b3[e] = ok ? B[i3 * ldb + r] : 0.0;
+            }
+#pragma unroll
+            for (int e = 0; e < KPL; ++e)
+            {
+                acc[e] += a0 * b0[e];
+                acc[e] += a1 * b1[e];
+                acc[e] += a2 * b2[e];
+                acc[e] += a3 * b3[e];
+            }
+        }
+        for (; o < end; ++o)
+        {
+            const unsigned int i0 = idx[o];
+            const double a0 = alpha * val[o];
+#pragma unroll
+            for (int e = 0; e < KPL; ++e)
+            {
+                const int r = lane + L * e;
+                if (r < k) acc[e] += a0 * B[i0 * ldb + r];
+            }
+        }
+        double* dst = direct ? out + j * ldo : partial + static_cast<long long>(slot) * k;
+#pragma unroll
+        for (int e = 0; e < KPL; ++e)
+        {
+            const int r = lane + L * e;
+            if (r < k) dst[r] = acc[e];
+        }
+    }
+}
+
+// out(:, j) = beta * out(:, j) + sum of the partials of column j, in segment order
+__global__ void spmm_combine_kernel(int nmulti, const unsigned int* __restrict__ multi_col, const unsigned int* __restrict__ first_slot,
+                                    int k, double beta, const double* __restrict__ partial, double* __restrict__ out, long long ldo)
+{
+    for (int i = blockIdx.x; i < nmulti; i += gridDim.x)
+    {
+        const unsigned int j = multi_col[i];
+        const unsigned int s0 = first_slot[j], s1 = first_slot[j + 1];
+        for (int r = threadIdx.x; r < k; r += blockDim.x)
+        {
+            double acc = (beta != 0.0) ? out[j * ldo + r] * beta : 0.0;
+            unsigned int sl = s0;
+            for (; sl + 4 <= s1; sl += 4)
+            {
+                const double p0 = partial[static_cast<long long>(sl) * k + r], p1 = partial[static_cast<long long>(sl + 1) * k + r];
+                const double p2 = partial[static_cast<long long>(sl + 2) * k + r], p3 = partial[static_cast<long long>(sl + 3) * k + r];
+                acc += p0; acc += p1; acc += p2; acc += p3;
+            }
+            for (; sl < s1; ++sl) acc += partial[static_cast<long long>(sl) * k + r];
+            out[j * ldo + r] = acc;
+        }
+    }
+}
+
+template <int L, int KPL>
+void launch_seg(cudaStream_t stream, const SegTable& T, const unsigned int* idx, const double* val, int k, const double* B,
+                long long ldb, double alpha, double beta, double* out, long long ldo, double* partial, int num_sms)
+{
+    const int threads = 256;
+    const int gpb = threads / L;
+    const int blocks = std::max(1, std::min(ceil_div(T.nseg, gpb), 32 * num_sms));
+    spmm_seg_kernel<L, KPL><<<blocks, threads, 0, stream>>>(T.nseg, T.col.p, T.beg.p, T.end.p, T.slot.p, idx, val, k, B, ldb,
+                                                           alpha, beta, out, ldo, partial);
+    SMK_LAUNCH_CHECK();
+}
+
 } // namespace
 
 void spmm_gather(cudaStream_t stream, int ncols, const unsigned int* ptr, const unsigned int* idx, const double* val,
@@ -151,6 +294,61 @@ void spmm_gather(cudaStream_t stream, int ncols, const unsigned int* ptr, const 
     else if (k <= 256) SMK_G(32, 8);
     else throw std::string("spmm: k > 256 is not supported");
 #undef SMK_G
+}
+
+void spmm_gather_seg(cudaStream_t stream, int ncols, const SegTable& T, const unsigned int* idx, const double* val,
+                     int k, const double* B, long long ldb, double alpha, double beta, double* out, long long ldo,
+                     double* partial, int num_sms)
+{
+    if (ncols <= 0 || T.nseg <= 0) return;
+#define SMK_S(L, KPL) launch_seg<L, KPL>(stream, T, idx, val, k, B, ldb, alpha, beta, out, ldo, partial, num_sms)
+    if (k <= 2) SMK_S(2, 1);
+    else if (k <= 4) SMK_S(4, 1);
+    else if (k <= 8) SMK_S(8, 1);
+    else if (k <= 16) SMK_S(16, 1);
+    else if (k <= 32) SMK_S(32, 1);
+    else if (k <= 64) SMK_S(32, 2);
+    else if (k <= 128) SMK_S(32, 4);
+    else if (k <= 256) SMK_S(32, 8);
+    else throw std::string("spmm: k > 256 is not supported");
+#undef SMK_S
+    if (T.nmulti > 0)
+    {
+        const int threads = k <= 32 ? 32 : (k <= 64 ? 64 : 128);
+        spmm_combine_kernel<<<std::min(T.nmulti, 16 * num_sms), threads, 0, stream>>>(T.nmulti, T.multi_col.p, T.first_slot.p, k, beta,
+                                                                                     partial, out, ldo);
+        SMK_LAUNCH_CHECK();
+    }
+}
+
+void build_segments(cudaStream_t stream, int ncols, const unsigned int* ptr, SegTable& T, int num_sms)
+{
+    const size_t n1 = static_cast<size_t>(ncols) + 1;
+    T.t_cnt.reserve(3 * n1);                // cnt | mcnt | flag
+    T.t_first.reserve(n1); T.first_slot.reserve(n1); T.t_mpos.reserve(n1);
+    unsigned int* cnt = T.t_cnt.p; unsigned int* mcnt = cnt + n1; unsigned int* flag = mcnt + n1;
+    const int blocks = std::max(1, std::min(ceil_div(static_cast<long long>(n1), 256), 8 * num_sms));
+    seg_count_kernel<<<blocks, 256, 0, stream>>>(ncols, ptr, cnt, mcnt, flag);
+    SMK_LAUNCH_CHECK();
+    size_t bytes = 0;
+    SMK_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, cnt, T.t_first.p, static_cast<int>(n1), stream));
+    T.t_scan.reserve(bytes);
+    SMK_CUDA(cub::DeviceScan::ExclusiveSum(T.t_scan.p, bytes, cnt, T.t_first.p, static_cast<int>(n1), stream));
+    SMK_CUDA(cub::DeviceScan::ExclusiveSum(T.t_scan.p, bytes, mcnt, T.first_slot.p, static_cast<int>(n1), stream));
+    SMK_CUDA(cub::DeviceScan::ExclusiveSum(T.t_scan.p, bytes, flag, T.t_mpos.p, static_cast<int>(n1), stream));
+    launch_counter() += 6;
+    unsigned int h[3] = {0, 0, 0};
+    SMK_CUDA(cudaMemcpyAsync(&h[0], T.t_first.p + ncols, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+    SMK_CUDA(cudaMemcpyAsync(&h[1], T.first_slot.p + ncols, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+    SMK_CUDA(cudaMemcpyAsync(&h[2], T.t_mpos.p + ncols, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+    SMK_CUDA(cudaStreamSynchronize(stream));
+    T.nseg = static_cast<int>(h[0]); T.nslots = static_cast<int>(h[1]); T.nmulti = static_cast<int>(h[2]);
+    T.col.reserve(T.nseg); T.beg.reserve(T.nseg); T.end.reserve(T.nseg); T.slot.reserve(T.nseg);
+    T.multi_col.reserve(std::max(1, T.nmulti));
+    const int fblocks = std::max(1, std::min(ceil_div(ncols, 8), 8 * num_sms));
+    seg_fill_kernel<<<fblocks, 256, 0, stream>>>(ncols, ptr, T.t_first.p, T.first_slot.p, T.t_mpos.p, T.col.p, T.beg.p, T.end.p,
+                                                 T.slot.p, T.multi_col.p);
+    SMK_LAUNCH_CHECK();
 }
 
 // Stable transpose on the device: a stable radix sort of the entry ids by row index keeps, inside each

@@ -163,7 +163,8 @@ int select_columns(smk_ctx* c, const unsigned int* cols_host, int count, unsigne
     U.t_colof.reserve(F.nnz); U.t_ids.reserve(F.nnz); U.t_ids_sorted.reserve(F.nnz); U.t_rows_sorted.reserve(F.nnz);
     U.colidx.reserve(F.nnz); U.valr.reserve(F.nnz); U.rowptr.reserve(static_cast<size_t>(m) + 1);
     build_csr(s, U, /*keep_scratch=*/true);
-    SMK_CUDA(cudaStreamSynchronize(s));
+    build_segments(s, U.n, U.colptr.p, U.seg_cols, c->num_sms);
+    build_segments(s, U.m, U.rowptr.p, U.seg_rows, c->num_sms);
     c->Sa = &U; c->m = U.m; c->n = count;
     c->subset_active = true; c->active = false;
     return U.m;

@@ -49,7 +49,9 @@ def c3(m=1000000, n=200000, per_col=500, k=128, iters=5):
     H0 = np.asfortranarray(np.random.default_rng(23).random((k, n))) * (2.0 / k)
     opts = sk.make_options(m, n, k, algorithm="HALS", tol=1e-15, min_iter=1, max_iter=100, normalize=False)
     ctx.solver_begin(W0, H0, opts)
-    ctx.solver_step(2)
+    ctx.solver_step(1)
+    ctx.solver_progress()
+    ctx.solver_step(1)
     times = []
     for _ in range(iters):
         ctx.solver_step(1)
