@@ -137,6 +137,14 @@ int smk_solver_time_product(smk_ctx* ctx, int which, int reps, float* mean_ms);
 int smk_nnls_hals(smk_ctx* ctx, int k, double* W_host, int ldW, double* H_host, int ldH, double tol, int max_iter,
                   int* iterations);
 
+/* ---- ordering primitives for the host-side tree code of hierclust ----
+ * desc_ordered(values) of hierclust/include/clust_hier_util.hpp:46-57: the permutation that lists the indices by
+ * decreasing value, ties by increasing index (a stable descending radix sort on the device; -0.0 is treated as 0.0,
+ * NaN is not supported). order_host receives n ints. */
+int smk_argsort_desc(smk_ctx* ctx, const double* values_host, int n, int* order_host);
+/* std::sort(v.begin(), v.end(), std::greater<double>()) on a host array (NDCG ideal scores, clust_hier_util.hpp:86). */
+int smk_sort_desc(smk_ctx* ctx, double* values_host, int n);
+
 /* ---- primitive-level entry points (the linear-algebra seam, SURVEY.md §8b ④), host buffers ----
  * Gemm(orientA, orientB, 1, A, B, 0, C) on DenseMatrix: common/include/dense_matrix_ops.hpp:255-270.
  * C (M x N) = op(A) * op(B); transA/transB are 0 (NORMAL) or 1 (TRANSPOSE). */

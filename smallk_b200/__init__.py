@@ -28,7 +28,7 @@ EXPORTS = [
     "smk_comm_unique_id", "smk_comm_init", "smk_load_dense", "smk_load_dense_device", "smk_load_csc", "smk_nmf",
     "smk_solver_begin", "smk_solver_step", "smk_solver_progress", "smk_solver_get", "smk_solver_normalize",
     "smk_solver_last_step_ms", "smk_solver_time_product", "smk_gemm", "smk_nnls_bpp", "smk_sparse_gemm",
-    "smk_select_columns", "smk_select_all", "smk_nnls_hals",
+    "smk_select_columns", "smk_select_all", "smk_nnls_hals", "smk_argsort_desc", "smk_sort_desc",
 ]
 HOST_LIB_PATH = os.path.join(_HERE, "lib", "libsmallk_host.so")
 HOST_EXPORTS = ["smkh_last_error", "smkh_hierclust_sparse", "smkh_hierclust_dense", "smkh_flatclust", "smkh_compute_priority",

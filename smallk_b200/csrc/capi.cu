@@ -260,6 +260,20 @@ int smk_select_all(smk_ctx* c)
     return SMK_OK;
 }
 
+int smk_argsort_desc(smk_ctx* c, const double* values, int n, int* order)
+{
+    if (!c || !values || !order || n < 0) return SMK_BAD_PARAM;
+    if (n == 0) return SMK_OK;
+    return guarded(c, [&]() { SMK_CUDA(cudaSetDevice(c->device)); device_sort_desc(c, values, n, order, nullptr); return (int)SMK_OK; });
+}
+
+int smk_sort_desc(smk_ctx* c, double* values, int n)
+{
+    if (!c || !values || n < 0) return SMK_BAD_PARAM;
+    if (n == 0) return SMK_OK;
+    return guarded(c, [&]() { SMK_CUDA(cudaSetDevice(c->device)); device_sort_desc(c, values, n, nullptr, values); return (int)SMK_OK; });
+}
+
 int smk_nnls_hals(smk_ctx* c, int k, double* W, int ldW, double* H, int ldH, double tol, int max_iter, int* iterations)
 {
     if (!c || !W || !H || k <= 0 || max_iter <= 0) return SMK_BAD_PARAM;

@@ -99,6 +99,9 @@ struct smk_ctx
     smk::DevBuf<double> partial;    // 1024 block partials
     smk::DevBuf<double> acc;        // 8 scalars
     smk::DevBuf<double> io;         // staging for host<->device transposes
+    smk::DevBuf<double> sort_keys, sort_keys_out;       // smk_argsort_desc / smk_sort_desc
+    smk::DevBuf<int> sort_vals, sort_vals_out;
+    smk::DevBuf<unsigned char> sort_tmp;
     smk::DevBuf<double> spmm_partial; // partial sums of the segmented SpMM (columns with more than one segment)
 
     // ---- solver state (both factors are kept "k x big", column-major: H is k x n, Wt = W' is k x m)

@@ -163,7 +163,8 @@ __global__ void hals_sweep_row_kernel(int k, int q, int r, double* __restrict__ 
 //   phase B (hals_block_step_kernel), B dependent steps: step l needs only the block's own B entries of each column
 //            and Q(l, j):  x <- max(0, x - (Q + sum_{p in block} X(p,j) G(p,c)) / G(c,c)),  NaN -> 0,
 //            then the grid-wide unit-norm scaling of row c is applied by the NEXT kernel (as in hals_sweep_row_kernel).
-// Traffic per sweep and column of X: k*k/B + k*(B+3) doubles instead of k*k.
+// Traffic per sweep and column of X: k*k/B + k*(B+3) doubles instead of k*k, all of it streamed (the B steps of a
+// block run on a compact q x B copy of the block, not on 128-byte pieces of 8k-byte-strided columns).
 // ---------------------------------------------------------------------------
 constexpr int kHalsB = 16;
 
@@ -188,9 +189,12 @@ __device__ __forceinline__ double finish_prev_row(const double* __restrict__ par
 // four rows of X. One warp per 8 columns of X; the B fragments come straight from global memory (each lane reads
 // X(4s + (lane & 3), j0 + (lane >> 2)): eight fully used 32-byte sectors per warp load, no shared-memory tile, no
 // barriers), the A fragments of the masked Gram block sit in shared memory in fragment order.
+// The block's own entries are copied to a COMPACT buffer Xb (q x 16) on which the B step kernels then stream at full
+// bandwidth; the previous block's finished entries are taken from its compact buffer and written back to X here.
 __global__ void __launch_bounds__(256)
 hals_block_outer_kernel(int k, int q, int c0, double* __restrict__ X, const double* __restrict__ G, const double* __restrict__ R,
-                        double* __restrict__ Q, const double* __restrict__ partial, int nblocks_prev, double* __restrict__ norms)
+                        double* __restrict__ Q, double* __restrict__ Xb_cur, const double* __restrict__ Xb_prev,
+                        const double* __restrict__ partial, int nblocks_prev, double* __restrict__ norms)
 {
     extern __shared__ __align__(16) double sA[];       // [ksteps][2 m-tiles][32 lanes]
     __shared__ double red[32];
@@ -209,24 +213,54 @@ hals_block_outer_kernel(int k, int q, int c0, double* __restrict__ X, const doub
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int n = lane >> 2, kk = lane & 3;
-    const int prev = c0 - 1;
+    constexpr int BS = kHalsB / 4;                      // k-steps per block
+    const int st_cur = c0 >> 2;                         // first k-step of this block
+    const int st_prev = st_cur - BS;                    // first k-step of the previous block (c0 > 0)
     for (long long j0 = (static_cast<long long>(blockIdx.x) * wpb + warp) * 8; j0 < q; j0 += static_cast<long long>(gridDim.x) * wpb * 8)
     {
         const long long j = j0 + n;
         const bool livecol = j < q;
-        const double* xcol = X + (livecol ? j : static_cast<long long>(q) - 1) * k;
+        const long long jc = livecol ? j : static_cast<long long>(q) - 1;
+        const double* xcol = X + jc * k;
         double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
-#pragma unroll 8
-        for (int st = 0; st < ksteps; ++st)
-        {
+        double wb[BS], cur[BS];
+        // rows before the previous block, and rows after this block: read from X
+        auto plain = [&](int st) {
             const int p = 4 * st + kk;
             double b = xcol[min(p, k - 1)];
             if (p >= k || !livecol) b = 0.0;
-            if (p == prev) b = (fill_prev ? DBL_EPSILON : b) * inv_prev;      // row c0-1 is finished on the fly (stored below)
             const double a0 = sA[(st * 2) * 32 + lane], a1 = sA[(st * 2 + 1) * 32 + lane];
             dmma884(c00, c01, a0, b);
             dmma884(c10, c11, a1, b);
+        };
+#pragma unroll 8
+        for (int st = 0; st < max(st_prev, 0); ++st) plain(st);
+        if (c0 > 0)
+        {
+            // the previous block: finished values from its compact buffer (row c0-1 still needs its scaling)
+#pragma unroll
+            for (int u = 0; u < BS; ++u)
+            {
+                const int st = st_prev + u, t = 4 * u + kk;
+                double b = Xb_prev[jc * kHalsB + t];
+                if (t == kHalsB - 1) b = (fill_prev ? DBL_EPSILON : b) * inv_prev;
+                wb[u] = b;
+                if (!livecol) b = 0.0;
+                const double a0 = sA[(st * 2) * 32 + lane], a1 = sA[(st * 2 + 1) * 32 + lane];
+                dmma884(c00, c01, a0, b);
+                dmma884(c10, c11, a1, b);
+            }
         }
+        // this block: no contribution (masked), entries go to the compact buffer
+#pragma unroll
+        for (int u = 0; u < BS; ++u)
+        {
+            const int p = c0 + 4 * u + kk;
+            cur[u] = xcol[min(p, k - 1)];
+        }
+#pragma unroll 8
+        for (int st = st_cur + BS; st < ksteps; ++st) plain(st);
+
         const int row = lane >> 2, col = 2 * (lane & 3);
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc)
@@ -239,16 +273,22 @@ hals_block_outer_kernel(int k, int q, int c0, double* __restrict__ X, const doub
                 if (row + 8 < nb) Q[static_cast<long long>(row + 8) * q + jj] = (cc ? c11 : c10) - rj[row + 8];
             }
         }
-        if (c0 > 0 && lane < 8 && j0 + lane < q)
+        if (livecol)
         {
-            double* px = X + (j0 + lane) * k + prev;
-            *px = (fill_prev ? DBL_EPSILON : *px) * inv_prev;
+#pragma unroll
+            for (int u = 0; u < BS; ++u)
+            {
+                const int t = 4 * u + kk;
+                if (c0 > 0) X[j * k + (c0 - kHalsB) + t] = wb[u];
+                Xb_cur[j * kHalsB + t] = (t < nb) ? cur[u] : 0.0;
+            }
         }
     }
 }
 
+// One step of phase B on the compact block buffer Xb (q x 16): half a warp per column of X.
 __global__ void __launch_bounds__(256)
-hals_block_step_kernel(int k, int q, int c0, int l, double* __restrict__ X, const double* __restrict__ G,
+hals_block_step_kernel(int k, int q, int c0, int l, double* __restrict__ Xb, const double* __restrict__ G,
                        const double* __restrict__ Q, double* __restrict__ partial, int nblocks_prev, double* __restrict__ norms)
 {
     __shared__ double red[32];
@@ -263,8 +303,6 @@ hals_block_step_kernel(int k, int q, int c0, int l, double* __restrict__ X, cons
     const double gcc = sg[l];
     const double* ql = Q + static_cast<long long>(l) * q;
     double sumsq = 0.0, zeros = 0.0;
-    // half a warp per column of X: lane t holds entry c0 + t (one 128-byte read per column), the block's dot product is a
-    // 4-step shuffle reduction inside the half-warp
     const int t = threadIdx.x & (kHalsB - 1);
     const long long halves = (static_cast<long long>(gridDim.x) * blockDim.x) / kHalsB;
     const long long h = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) / kHalsB;
@@ -273,7 +311,6 @@ hals_block_step_kernel(int k, int q, int c0, int l, double* __restrict__ X, cons
     {
         double v[U], dot[U], qv[U];
         bool live[U];
-        const int tc = min(t, nb - 1);
         // branch-free loads from clamped addresses: all 2U loads of a trip are in flight together
 #pragma unroll
         for (int u = 0; u < U; ++u)
@@ -281,17 +318,17 @@ hals_block_step_kernel(int k, int q, int c0, int l, double* __restrict__ X, cons
             const long long j = base + u * halves + h;
             live[u] = j < q;
             const long long jc = live[u] ? j : q - 1;
-            v[u] = X[jc * k + c0 + tc];
+            v[u] = Xb[jc * kHalsB + t];
             qv[u] = ql[jc];
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
         {
-            if (!(live[u] && t < nb)) v[u] = 0.0;
+            if (!live[u]) v[u] = 0.0;
             if (l > 0 && t == l - 1 && live[u])
             {
                 v[u] = (fill_prev ? DBL_EPSILON : v[u]) * inv_prev;
-                X[(base + u * halves + h) * k + c0 + t] = v[u];
+                Xb[(base + u * halves + h) * kHalsB + t] = v[u];
             }
             dot[u] = v[u] * sg[t];
         }
@@ -307,7 +344,7 @@ hals_block_step_kernel(int k, int q, int c0, int l, double* __restrict__ X, cons
                 const long long j = base + u * halves + h;
                 double w = v[u] - (qv[u] + dot[u]) / gcc;
                 if (isnan(w) || w < 0.0) { w = 0.0; zeros += 1.0; }
-                X[j * k + c0 + l] = w;
+                Xb[j * kHalsB + l] = w;
                 sumsq += w * w;
             }
         }
@@ -319,6 +356,30 @@ hals_block_step_kernel(int k, int q, int c0, int l, double* __restrict__ X, cons
         double* pc = partial + (c & 1) * 2 * kSweepBlocks;
         pc[blockIdx.x] = sumsq;
         pc[kSweepBlocks + blockIdx.x] = zeros;
+    }
+}
+
+// End of the sweep: the last block goes back to X, its last row (row k-1) scaled to unit norm.
+__global__ void __launch_bounds__(256)
+hals_block_writeback_kernel(int k, int q, int c0, double* __restrict__ X, const double* __restrict__ Xb,
+                            const double* __restrict__ partial, int nblocks_prev, double* __restrict__ norms)
+{
+    __shared__ double red[32];
+    const int nb = k - c0;
+    bool fill_prev = false;
+    const double inv_prev = finish_prev_row(partial, k - 1, nblocks_prev, q, norms, red, fill_prev);
+    const long long total = static_cast<long long>(q) * kHalsB;
+    for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x)
+    {
+        const long long j = e / kHalsB;
+        const int t = static_cast<int>(e % kHalsB);
+        if (t < nb)
+        {
+            double v = Xb[e];
+            if (t == nb - 1) v = (fill_prev ? DBL_EPSILON : v) * inv_prev;
+            X[j * k + c0 + t] = v;
+        }
     }
 }
 
@@ -467,7 +528,7 @@ int ew_blocks(long long total, int num_sms) { return static_cast<int>(std::max<l
 
 } // namespace
 
-size_t hals_sweep_scratch_doubles(int q) { return static_cast<size_t>(kHalsB) * q; }
+size_t hals_sweep_scratch_doubles(int q) { return 3 * static_cast<size_t>(kHalsB) * q; }   // Q + two compact block buffers
 
 void hals_sweep(cudaStream_t stream, int k, int q, double* X, const double* G, const double* R,
                 bool normalize_rows, double* norms, double* partial, int num_sms, double* scratch)
@@ -481,23 +542,24 @@ void hals_sweep(cudaStream_t stream, int k, int q, double* X, const double* G, c
         SMK_CUDA(cudaFuncSetAttribute(hals_block_outer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         const int outer_blocks = std::max(1, std::min(ceil_div(q, 64), 8 * num_sms));
         const int step_blocks = std::max(1, std::min(std::min(ceil_div(static_cast<long long>(q) * kHalsB, threads), 8 * num_sms), kSweepBlocks));
-        for (int c0 = 0; c0 < k; c0 += kHalsB)
+        double* Qs = scratch;
+        double* Xb[2] = {scratch + static_cast<size_t>(kHalsB) * q, scratch + 2 * static_cast<size_t>(kHalsB) * q};
+        int cur = 0, c_last = 0;
+        for (int c0 = 0; c0 < k; c0 += kHalsB, cur ^= 1)
         {
-            hals_block_outer_kernel<<<outer_blocks, threads, smem, stream>>>(k, q, c0, X, G, R, scratch, partial, step_blocks, norms);
+            hals_block_outer_kernel<<<outer_blocks, threads, smem, stream>>>(k, q, c0, X, G, R, Qs, Xb[cur], c0 > 0 ? Xb[cur ^ 1] : nullptr,
+                                                                            partial, step_blocks, norms);
             SMK_LAUNCH_CHECK();
             const int nb = std::min(kHalsB, k - c0);
             for (int l = 0; l < nb; ++l)
             {
-                hals_block_step_kernel<<<step_blocks, threads, 0, stream>>>(k, q, c0, l, X, G, scratch, partial, step_blocks, norms);
+                hals_block_step_kernel<<<step_blocks, threads, 0, stream>>>(k, q, c0, l, Xb[cur], G, Qs, partial, step_blocks, norms);
                 SMK_LAUNCH_CHECK();
             }
+            c_last = c0;
         }
-        // the scaling of the last row (the r == k pass of the unblocked kernel)
-        dispatch_kpl(k, [&](auto kpl) {
-            constexpr int KPL = decltype(kpl)::value;
-            hals_sweep_row_kernel<KPL><<<step_blocks, threads, 0, stream>>>(k, q, k, X, G, R, partial, step_blocks, norms);
-            SMK_LAUNCH_CHECK();
-        });
+        hals_block_writeback_kernel<<<step_blocks, threads, 0, stream>>>(k, q, c_last, X, Xb[cur ^ 1], partial, step_blocks, norms);
+        SMK_LAUNCH_CHECK();
         return;
     }
     dispatch_kpl(k, [&](auto kpl) {

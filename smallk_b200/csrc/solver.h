@@ -20,4 +20,7 @@ int solver_nnls_hals(smk_ctx* c, double tol, int max_iter, int* iterations);
 int select_columns(smk_ctx* c, const unsigned int* cols_host, int count, unsigned int* new_to_old_host);
 void select_all(smk_ctx* c);
 
+// ---- sort.cu: stable descending sort of a host array on the device; exactly one of order_host / sorted_host is set
+void device_sort_desc(smk_ctx* c, const double* host_in, int n, int* order_host, double* sorted_host);
+
 } // namespace smk

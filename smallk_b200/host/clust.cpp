@@ -50,12 +50,18 @@ bool IsValid(const ClustOptions& opts, bool validate_matrix)
 // --------------------------------------------------------------------------------------------------------------
 // priority score
 // --------------------------------------------------------------------------------------------------------------
+R compute_priority_on(smk_ctx* ctx, const R* W_parent, const R* W_child, int n);
+
 namespace {
 
 // Row indices in decreasing order of v, ties by ascending row (desc_ordered, clust_hier_util.hpp:46-57). The order is
 // total, so any correct sort reproduces it; factor columns are mostly exact zeros below the root, so the rows are
 // split into positive / zero / negative groups and only the two outer groups are sorted.
-void desc_order(const R* v, const int n, std::vector<int>& order)
+// Sorts of more than this many keys go to the GPU (smk_argsort_desc / smk_sort_desc: one stable radix sort instead of
+// an O(n log n) comparison sort on one host core); shorter ones are not worth the round trip.
+const int kDeviceSortMin = 8192;
+
+void desc_order(const R* v, const int n, std::vector<int>& order, smk_ctx* ctx)
 {
     order.resize(n);
     int npos = 0, nzero = 0;
@@ -68,7 +74,18 @@ void desc_order(const R* v, const int n, std::vector<int>& order)
         else order[in++] = i;                       // negative or NaN (NaN never occurs in a successful factorization)
     }
     auto cmp = [v](int a, int b) { return v[a] > v[b] || (v[a] == v[b] && a < b); };
-    std::sort(order.begin(), order.begin() + npos, cmp);
+    if (ctx && npos >= kDeviceSortMin)
+    {
+        // positives in index order -> stable descending sort keeps the index tie-break
+        std::vector<R> keys(npos);
+        std::vector<int> perm(npos);
+        for (int i = 0; i < npos; ++i) keys[i] = v[order[i]];
+        if (smk_argsort_desc(ctx, keys.data(), npos, perm.data()) != SMK_OK) throw std::runtime_error(smk_last_error(ctx));
+        std::vector<int> sorted(npos);
+        for (int i = 0; i < npos; ++i) sorted[i] = order[perm[i]];
+        std::copy(sorted.begin(), sorted.end(), order.begin());
+    }
+    else std::sort(order.begin(), order.begin() + npos, cmp);
     std::sort(order.begin() + npos + nzero, order.end(), cmp);
 }
 
@@ -102,15 +119,17 @@ R dcg_of(const std::vector<int>& test, const std::vector<int>& rank_parent, cons
 
 } // namespace
 
-R compute_priority(const R* W_parent, const R* W_child, const int n)
+R compute_priority(const R* W_parent, const R* W_child, const int n) { return compute_priority_on(nullptr, W_parent, W_child, n); }
+
+R compute_priority_on(smk_ctx* ctx, const R* W_parent, const R* W_child, const int n)
 {
     std::vector<int> ord_p, ord_1, ord_2;
     int n_part = 0;
     for (int i = 0; i < n; ++i) if (W_parent[i] != 0) ++n_part;
     if (n_part <= 1) return R(-3);
-    desc_order(W_parent, n, ord_p);
-    desc_order(W_child, n, ord_1);
-    desc_order(W_child + n, n, ord_2);
+    desc_order(W_parent, n, ord_p, ctx);
+    desc_order(W_child, n, ord_1, ctx);
+    desc_order(W_child + n, n, ord_2, ctx);
     g_logs.ensure(n);
     const std::vector<double>& ln = g_logs.ln;
 
@@ -138,7 +157,11 @@ R compute_priority(const R* W_parent, const R* W_child, const int n)
     const R dcg1 = dcg_of(ord_1, rank_p, weight_part);
     const R dcg2 = dcg_of(ord_2, rank_p, weight_part);
     // ideal score: the weights in decreasing order with the same discounting (identical for both children)
-    std::sort(weight.begin(), weight.end(), std::greater<R>());
+    if (ctx && n >= kDeviceSortMin)
+    {
+        if (smk_sort_desc(ctx, weight.data(), n) != SMK_OK) throw std::runtime_error(smk_last_error(ctx));
+    }
+    else std::sort(weight.begin(), weight.end(), std::greater<R>());
     R ideal = weight[0];
     for (int i = 1; i < n; ++i) ideal = ideal + weight[i] / g_logs.lg2[i + 1];
     return (dcg1 / ideal) * (dcg2 / ideal);
@@ -272,7 +295,7 @@ struct HierRun
         out.H = Hsub;
         if (!(has_0 && has_1)) return R(-1);
         Stopwatch sw(stats.t_priority);
-        return compute_priority(W_parent, out.W.data(), static_cast<int>(m));
+        return compute_priority_on(ctx, W_parent, out.W.data(), static_cast<int>(m));
     }
 
     // clust_hier_generic.hpp:245-376

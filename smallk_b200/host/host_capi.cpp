@@ -8,6 +8,9 @@
 
 #include "clust.hpp"
 #include "flat_clust.hpp"
+#include "host_internal.hpp"
+
+R compute_priority_on(smk_ctx* ctx, const R* W_parent, const R* W_child, int n);
 
 namespace {
 
@@ -158,5 +161,11 @@ int smkh_flatclust(int alg, int m, int n, int k, double tol, int min_iter, int m
 
 // compute_priority (clust_hier_util.hpp:105-173) on host buffers — unit-testable without a GPU.
 double smkh_compute_priority(const double* W_parent, const double* W_child, int m) { return compute_priority(W_parent, W_child, m); }
+// the same with the large sorts on the GPU (what the tree driver uses): must give the identical value
+double smkh_compute_priority_gpu(const double* W_parent, const double* W_child, int m)
+{
+    EnsureInit();
+    return compute_priority_on(NmfContext(), W_parent, W_child, m);
+}
 
 } // extern "C"

@@ -47,3 +47,43 @@ def topic_matrix(m, n, topics, seed, terms_per_doc=25):
     S = sps.csc_matrix((vals, (rows, cols)), shape=(m, n))
     S.sum_duplicates(); S.sort_indices()
     return S
+
+
+def community_graph(n, edges, communities, seed, p_in=0.85, exponent=2.5):
+    """Degree-corrected planted-partition graph: power-law expected degrees, `communities` groups of power-law sizes, a
+    fraction p_in of the edges inside a group. Undirected, no self loops, no isolated nodes; returns the full symmetric
+    CSC pattern (values 1.0, rows ascending) — what LoadMatrixMarketFile makes of a `pattern symmetric` file."""
+    rng = np.random.default_rng(seed)
+    w = (np.arange(1, n + 1, dtype=np.float64)) ** (-1.0 / (exponent - 1.0))
+    w = w[rng.permutation(n)]
+    sizes = (np.arange(1, communities + 1, dtype=np.float64)) ** (-0.7)
+    comm = rng.choice(communities, size=n, p=sizes / sizes.sum())
+    order = np.argsort(comm, kind="stable")
+    start = np.searchsorted(comm[order], np.arange(communities + 1))
+    cw = np.concatenate([[0.0], np.cumsum(w[order])])          # cumulative weights in community order
+    tot = cw[-1]
+    u = order[np.minimum(np.searchsorted(cw, rng.random(edges) * tot, side="right") - 1, n - 1)]
+    inside = rng.random(edges) < p_in
+    cu = comm[u]
+    lo, hi = cw[start[cu]], cw[start[cu + 1]]
+    r = rng.random(edges)
+    target = np.where(inside, lo + r * (hi - lo), r * tot)
+    v = order[np.minimum(np.searchsorted(cw, target, side="right") - 1, n - 1)]
+    keep = u != v
+    u, v = u[keep], v[keep]
+    deg = np.bincount(np.concatenate([u, v]), minlength=n)
+    iso = np.nonzero(deg == 0)[0]
+    if len(iso):
+        # attach isolated nodes to a member of their own community
+        ci = comm[iso]
+        t = order[np.minimum(start[ci] + (rng.random(len(iso)) * (start[ci + 1] - start[ci])).astype(np.int64), n - 1)]
+        t = np.where(t == iso, (t + 1) % n, t)
+        u = np.concatenate([u, iso]); v = np.concatenate([v, t])
+    a, b = np.minimum(u, v).astype(np.int64), np.maximum(u, v).astype(np.int64)
+    e = np.unique(a * n + b)
+    a, b = e // n, e % n
+    rows = np.concatenate([a, b]); cols = np.concatenate([b, a])
+    o = np.lexsort((rows, cols))
+    rows, cols = rows[o], cols[o]
+    colp = np.concatenate([[0], np.cumsum(np.bincount(cols, minlength=n))]).astype(np.uint32)
+    return colp, rows.astype(np.uint32), np.ones(len(rows))

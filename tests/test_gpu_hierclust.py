@@ -95,3 +95,19 @@ def test_nnls_hals_matches_reference_fixture_shape(gpu, oracle):
     assert np.allclose(np.linalg.norm(W, axis=0), 1.0, rtol=1e-12)
     assert H.min() >= 0.0
     assert np.linalg.norm(W @ H - A) <= 1e-4 * np.linalg.norm(A)
+
+
+def test_priority_score_with_device_sorts_is_bit_identical():
+    """compute_priority with the large sorts on the GPU (smk_argsort_desc / smk_sort_desc) == the host evaluation."""
+    import ctypes
+    lib = sk.load_host_library()
+    lib.smkh_compute_priority_gpu.restype = ctypes.c_double
+    dp = ctypes.POINTER(ctypes.c_double)
+    rng = np.random.default_rng(3)
+    for m, dens in ((20000, 0.9), (50000, 0.3), (30000, 1.0)):
+        P = rng.random(m) * (rng.random(m) < dens)
+        C = np.asfortranarray(rng.random((m, 2)) * (rng.random((m, 2)) < dens))
+        C[: m // 3, 0] = np.round(C[: m // 3, 0], 2)        # ties
+        a = lib.smkh_compute_priority(P.ctypes.data_as(dp), C.ctypes.data_as(dp), m)
+        b = lib.smkh_compute_priority_gpu(P.ctypes.data_as(dp), C.ctypes.data_as(dp), m)
+        assert a == b, (m, a, b)

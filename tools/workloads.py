@@ -7,11 +7,13 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from graphgen import powerlaw_graph   # noqa: E402,F401
+from graphgen import community_graph, powerlaw_graph   # noqa: E402,F401
 
 
-def c4_graph(n=320000, edges=2000000, seed=31):
-    return powerlaw_graph(n, 2.0 * edges / n, seed)
+def c4_graph(n=320000, edges=2000000, seed=31, communities=100):
+    """DBLP-scale co-authorship-like graph: power-law degrees with planted communities (a graph without community
+    structure gives HierNMF2 nothing to split: it stops after a handful of factorizations)."""
+    return community_graph(n, edges, communities, seed)
 
 
 def c3_tfidf_csc(m=1000000, n=200000, nnz_per_col=500, seed=21, device="cuda"):
