@@ -202,8 +202,8 @@ def main():
     m = n = args.size
     k = K_RANK
     # column block of this rank (contiguous, balanced)
-    c0 = (n * rank) // world
-    c1 = (n * (rank + 1)) // world
+    from smallk_b200.sharding import column_block
+    c0, c1 = column_block(n, rank, world)
     n_loc = c1 - c0
 
     ctx = sk.Context(local_rank)

@@ -500,6 +500,7 @@ int smk_nnls_bpp(smk_ctx* c, int k, int q, const double* LHS, const double* RHS,
         SMK_CUDA(cudaMemcpyAsync(c->status.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
         c->deferred.reserve(nnls_deferred_bytes(q, k, c->num_sms));
         nnls_bpp(c->stream, k, q, dL.p, k, dR.p, k, dX.p, k, dY.p, k, c->status.p, c->counter.p, c->deferred.p, 0, c->num_sms);
+        nnls_bpp_finish(c->stream, k, q, dX.p, k, dY.p, k, c->status.p, c->num_sms);
         download_tight(c, dX.p, k, q, X, k);
         download_tight(c, dY.p, k, q, Y, k);
         int st[ST_COUNT];

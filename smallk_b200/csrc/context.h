@@ -116,4 +116,10 @@ struct smk_ctx
     // ---- multi-GPU
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
+    // W-side row sharding (BPP, MU): rank g owns rows [g*m_loc, min(m, (g+1)*m_loc)) of W; k x m buffers are padded to
+    // k x (m_loc * nranks) so that reduce-scatter / all-gather move equal pieces. m_loc == m when nranks == 1.
+    int m_loc = 0;
+    bool w_sharded = false;
+    int w_row0() const { return rank * m_loc; }
+    int w_rows() const { const int r = m - rank * m_loc; return r < 0 ? 0 : (r < m_loc ? r : m_loc); }
 };

@@ -24,6 +24,7 @@ void nnls_bpp(cudaStream_t stream, int k, int q, const double* LHS, long long ld
               const double* RHS, long long ldr, double* X, long long ldx, double* Y, long long ldy,
               int* status, unsigned int* counter, void* deferred, int outer_iter, int num_sms);
 size_t nnls_deferred_bytes(int q, int k, int num_sms);
+void nnls_bpp_finish(cudaStream_t stream, int k, int q, double* X, long long ldx, double* Y, long long ldy, int* status, int num_sms);
 
 // ---- elementwise.cu -------------------------------------------------------
 // out (cols x rows, ld = ldo) = in' where in is rows x cols (ld = ldi)

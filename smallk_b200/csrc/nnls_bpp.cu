@@ -636,17 +636,13 @@ void nnls_bpp(cudaStream_t stream, int k, int q, const double* LHS, long long ld
               const double* RHS, long long ldr, double* X, long long ldx, double* Y, long long ldy,
               int* status, unsigned int* counter, void* deferred, int outer_iter, int num_sms)
 {
-    if (q <= 0) return;
     SMK_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned int), stream));
     SMK_CUDA(cudaMemsetAsync(&status[ST_ANY_NONOPT], 0, sizeof(int), stream));
     SMK_CUDA(cudaMemsetAsync(&status[ST_DEFER_COUNT], 0, sizeof(int), stream));
+    if (q <= 0) return;          // a rank may own no rows; the flags above are still reset for the reduction that follows
     if (k > 64)
     {
         nnls_bpp_wide(stream, k, q, LHS, ldl, RHS, ldr, X, ldx, Y, ldy, status, counter, deferred, outer_iter, num_sms);
-        const long long total = static_cast<long long>(k) * q;
-        const int zb = static_cast<int>(std::min<long long>((total + 255) / 256, 8LL * num_sms));
-        zeroize_if_flag_kernel<<<zb, 256, 0, stream>>>(status, k, q, X, ldx, Y, ldy);
-        SMK_LAUNCH_CHECK();
         return;
     }
     BppColState* def = static_cast<BppColState*>(deferred);
@@ -674,8 +670,16 @@ void nnls_bpp(cudaStream_t stream, int k, int q, const double* LHS, long long ld
                                                                 outer_iter, def);
         SMK_LAUNCH_CHECK();
     }
+}
+
+// Second half of NnlsBlockpivot's cross-column coupling (nnls.hpp:192,226-227): X and Y are zeroized everywhere iff
+// SOME column was non-optimal after its first solve. Kept separate from nnls_bpp so that a multi-GPU caller can
+// OR-reduce status[ST_ANY_NONOPT] over the ranks in between.
+void nnls_bpp_finish(cudaStream_t stream, int k, int q, double* X, long long ldx, double* Y, long long ldy, int* status, int num_sms)
+{
+    if (q <= 0) return;
     const long long total = static_cast<long long>(k) * q;
-    int zb = static_cast<int>(std::min<long long>((total + 255) / 256, 8LL * num_sms));
+    const int zb = static_cast<int>(std::min<long long>((total + 255) / 256, 8LL * num_sms));
     zeroize_if_flag_kernel<<<zb, 256, 0, stream>>>(status, k, q, X, ldx, Y, ldy);
     SMK_LAUNCH_CHECK();
 }

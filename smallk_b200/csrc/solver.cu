@@ -28,6 +28,11 @@ void allreduce_sum(smk_ctx* c, double* buf, size_t count)
     if (r != ncclSuccess) throw std::string("ncclAllReduce: ") + ncclGetErrorString(r);
 }
 
+void nccl_check(ncclResult_t r, const char* what)
+{
+    if (r != ncclSuccess) throw std::string(what) + ": " + ncclGetErrorString(r);
+}
+
 // ---- the products of one outer iteration ---------------------------------
 // WtA (k x n) = Wt * A
 void prod_WtA(smk_ctx* c)
@@ -51,7 +56,22 @@ void prod_HAt(smk_ctx* c)
     else
         spmm_gather_seg(c->stream, c->m, c->Sa->seg_rows, c->Sa->colidx.p, c->Sa->valr.p, k, c->H.p, k, 1.0, 0.0, c->HAt.p, k,
                         c->spmm_partial.p, c->num_sms);
-    allreduce_sum(c, c->HAt.p, static_cast<size_t>(k) * c->m);
+    if (c->nranks <= 1) return;
+    if (c->w_sharded)
+    {
+        // row-sharded W update: every rank receives the sum of its own k x m_loc slice only
+        const size_t piece = static_cast<size_t>(k) * c->m_loc;
+        nccl_check(ncclReduceScatter(c->HAt.p, c->HAt.p + c->rank * piece, piece, ncclDouble, ncclSum, c->comm, c->stream), "ncclReduceScatter");
+    }
+    else allreduce_sum(c, c->HAt.p, static_cast<size_t>(k) * c->m);
+}
+
+// after a row-sharded W update: every rank's slice of Wt to every rank
+void gather_Wt(smk_ctx* c)
+{
+    if (c->nranks <= 1 || !c->w_sharded) return;
+    const size_t piece = static_cast<size_t>(c->opts.k) * c->m_loc;
+    nccl_check(ncclAllGather(c->Wt.p + c->rank * piece, c->Wt.p, piece, ncclDouble, c->comm, c->stream), "ncclAllGather");
 }
 
 // G (k x k) = X * X' for X k x q
@@ -79,21 +99,34 @@ void run_nnls(smk_ctx* c, const double* LHS, const double* RHS, double* X, doubl
 {
     const int k = c->opts.k;
     nnls_bpp(c->stream, k, q, LHS, k, RHS, k, X, k, Y, k, c->status.p, c->counter.p, c->deferred.p, c->steps_done, c->num_sms);
+    // "zeroize everything iff any column was non-optimal" couples the column shards: one int, OR-reduced
+    if (c->nranks > 1)
+        nccl_check(ncclAllReduce(c->status.p + ST_ANY_NONOPT, c->status.p + ST_ANY_NONOPT, 1, ncclInt, ncclMax, c->comm, c->stream), "ncclAllReduce");
+    nnls_bpp_finish(c->stream, k, q, X, k, Y, k, c->status.p, c->num_sms);
 }
 
 } // namespace
 
 void solver_alloc(smk_ctx* c)
 {
-    const size_t k = c->opts.k, m = c->m, n = c->n;
+    const size_t k = c->opts.k, n = c->n;
+    c->w_sharded = c->nranks > 1 && (c->opts.algorithm == SMK_BPP || c->opts.algorithm == SMK_MU);
+    c->m_loc = c->w_sharded ? (c->m + c->nranks - 1) / c->nranks : c->m;
+    const size_t m = c->w_sharded ? static_cast<size_t>(c->m_loc) * c->nranks : c->m;     // padded
     c->H.reserve(k * n); c->Wt.reserve(k * m);
     c->gradH.reserve(k * n); c->gradWt.reserve(k * m);
     c->WtW.reserve(k * k); c->HHt.reserve(k * k);
     c->WtA.reserve(k * n); c->HAt.reserve(k * m);
+    if (c->w_sharded)
+    {
+        SMK_CUDA(cudaMemsetAsync(c->Wt.p, 0, k * m * sizeof(double), c->stream));
+        SMK_CUDA(cudaMemsetAsync(c->HAt.p, 0, k * m * sizeof(double), c->stream));
+        SMK_CUDA(cudaMemsetAsync(c->gradWt.p, 0, k * m * sizeof(double), c->stream));
+    }
     c->norms.reserve(k);
     if (c->has_sparse) c->spmm_partial.reserve(static_cast<size_t>(std::max(c->Sa->seg_cols.nslots, c->Sa->seg_rows.nslots)) * k + 1);
     c->deferred.reserve(nnls_deferred_bytes(static_cast<int>(std::max(m, n)), c->opts.k, c->num_sms));
-    if (c->opts.algorithm == SMK_MU) { c->T1.reserve(k * n); c->T2.reserve(k * m); }
+    if (c->opts.algorithm == SMK_MU) { c->T1.reserve(k * n); c->T2.reserve(k * m); }    // m is the padded row count here
     if (c->opts.algorithm == SMK_HALS) c->T2.reserve(std::max(k * m, hals_sweep_scratch_doubles(static_cast<int>(m))));
     if (c->opts.prog_est_algorithm == SMK_DELTA_FNORM) c->Wprev.reserve(k * m);
     // split-R workspace: enough for the gram matrices at 4*SMs splits and for the big products at a few splits
@@ -132,7 +165,11 @@ void solver_step(smk_ctx* c)
         run_nnls(c, c->WtW.p, c->WtA.p, c->H.p, c->gradH.p, n);
         compute_HHt(c);
         prod_HAt(c);
-        run_nnls(c, c->HHt.p, c->HAt.p, c->Wt.p, c->gradWt.p, m);
+        {
+            const size_t off = static_cast<size_t>(k) * c->w_row0();      // 0 unless the W update is row-sharded
+            run_nnls(c, c->HHt.p, c->HAt.p + off, c->Wt.p + off, c->gradWt.p + off, c->w_rows());
+            gather_Wt(c);
+        }
         compute_WtW(c);
         prod_WtA(c);
         gram_times(c, c->WtW.p, c->H.p, n, c->WtA.p, c->gradH.p);
@@ -142,11 +179,19 @@ void solver_step(smk_ctx* c)
         mu_update(c->stream, static_cast<long long>(k) * n, c->H.p, c->WtA.p, c->T1.p);
         compute_HHt(c);
         prod_HAt(c);
-        gram_times(c, c->HHt.p, c->Wt.p, m, nullptr, c->T2.p);
-        mu_update(c->stream, static_cast<long long>(k) * m, c->Wt.p, c->HAt.p, c->T2.p);
-        prod_WtA(c);
-        compute_WtW(c);
-        gram_times(c, c->HHt.p, c->Wt.p, m, c->HAt.p, c->gradWt.p);
+        {
+            const size_t off = static_cast<size_t>(k) * c->w_row0();
+            const int rows = c->w_rows();
+            if (rows > 0)
+            {
+                gram_times(c, c->HHt.p, c->Wt.p + off, rows, nullptr, c->T2.p + off);
+                mu_update(c->stream, static_cast<long long>(k) * rows, c->Wt.p + off, c->HAt.p + off, c->T2.p + off);
+            }
+            gather_Wt(c);
+            prod_WtA(c);
+            compute_WtW(c);
+            if (rows > 0) gram_times(c, c->HHt.p, c->Wt.p + off, rows, c->HAt.p + off, c->gradWt.p + off);
+        }
         gram_times(c, c->WtW.p, c->H.p, n, c->WtA.p, c->gradH.p);
         break;
     case SMK_HALS:     // nmf_solver_hals.hpp:166-199
@@ -184,9 +229,14 @@ int solver_progress(smk_ctx* c, double* metric)
     if (c->opts.prog_est_algorithm == SMK_PG_RATIO)
     {
         // projected_gradient.hpp:125-171; the H part is a sum over this rank's columns
-        pg_sumsq(c->stream, k * c->m, c->gradWt.p, c->Wt.p, c->partial.p, c->acc.p + 0, c->num_sms);
+        // the W part is a sum over this rank's rows when the W update is row-sharded, else every rank has all of it
+        const long long woff = c->w_sharded ? k * c->w_row0() : 0;
+        const long long wrows = c->w_sharded ? c->w_rows() : c->m;
+        if (wrows > 0) pg_sumsq(c->stream, k * wrows, c->gradWt.p + woff, c->Wt.p + woff, c->partial.p, c->acc.p + 0, c->num_sms);
+        else SMK_CUDA(cudaMemsetAsync(c->acc.p, 0, sizeof(double), c->stream));
         pg_sumsq(c->stream, k * c->n, c->gradH.p, c->H.p, c->partial.p, c->acc.p + 1, c->num_sms);
-        allreduce_sum(c, c->acc.p + 1, 1);
+        if (c->w_sharded) allreduce_sum(c, c->acc.p, 2);
+        else allreduce_sum(c, c->acc.p + 1, 1);
         SMK_CUDA(cudaMemcpyAsync(h, c->acc.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         SMK_CUDA(cudaStreamSynchronize(c->stream));
         const double pg = sqrt(h[0] + h[1]);
@@ -257,6 +307,8 @@ void solver_product(smk_ctx* c, int which) { if (which == 0) prod_WtA(c); else p
 int solver_fail_iter(smk_ctx* c)
 {
     int st[ST_COUNT];
+    if (c->nranks > 1)      // all ranks must take the same exit
+        nccl_check(ncclAllReduce(c->status.p + ST_FAIL_ITER, c->status.p + ST_FAIL_ITER, 1, ncclInt, ncclMin, c->comm, c->stream), "ncclAllReduce");
     SMK_CUDA(cudaMemcpyAsync(st, c->status.p, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
     SMK_CUDA(cudaStreamSynchronize(c->stream));
     return st[ST_FAIL_ITER];

@@ -1,0 +1,71 @@
+"""Launched by tests/test_gpu_multi.py under torch.distributed.run, one rank per GPU: column-sharded NMF through the CUDA
+library (NCCL inside) against the single-process CPU oracle. Every rank checks the full W and its own block of H."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import smallk_b200 as sk                                     # noqa: E402
+from smallk_b200.sharding import column_block              # noqa: E402
+from oracle import Oracle                                     # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = sk.Context(local)
+    uid = [ctx.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx.comm_init(rank, world, uid[0])
+    orc = Oracle()
+    failures = []
+    cases = [("BPP", 301, 257, 24, 8, False), ("BPP", 420, 390, 100, 5, False), ("MU", 203, 190, 9, 12, False),
+             ("HALS", 230, 200, 12, 10, False), ("RANK2", 250, 240, 2, 12, False), ("BPP", 300, 280, 16, 8, True)]
+    for alg, m, n, k, iters, sparse in cases:
+        rng = np.random.default_rng(m * 7 + n)
+        A = rng.random((m, n))
+        if sparse:
+            A *= rng.random((m, n)) < 0.2
+        W0 = rng.random((m, k)); H0 = rng.random((k, n))
+        if alg == "HALS":
+            H0 *= 2.0 / k
+        c0, c1 = column_block(n, rank, world)
+        if sparse:
+            import scipy.sparse as sps
+            S = sps.csc_matrix(A[:, c0:c1]); S.sort_indices()
+            ctx.load_csc((m, c1 - c0), S.indptr, S.indices, S.data)
+            Sf = sps.csc_matrix(A); Sf.sort_indices()
+            o = orc.nmf_sparse((m, n), Sf.indptr.astype(np.uint32), Sf.indices.astype(np.uint32), Sf.data, W0, H0, alg=alg, tol=1e-12,
+                               min_iter=1, max_iter=iters, trace=True)
+        else:
+            ctx.load_dense(np.asfortranarray(A[:, c0:c1]))
+            o = orc.nmf_dense(A, W0, H0, alg=alg, tol=1e-12, min_iter=1, max_iter=iters, trace=True)
+        opts = sk.make_options(m, c1 - c0, k, algorithm=alg, tol=1e-12, min_iter=1, max_iter=iters, normalize=False)
+        ctx.solver_begin(W0, np.asfortranarray(H0[:, c0:c1]), opts)
+        tol = 1e-6 if alg == "HALS" else 1e-9
+        for it in range(iters):
+            ctx.solver_step(1)
+            metric = ctx.solver_progress()
+            W, H = ctx.solver_get()
+            rw = np.linalg.norm(W - o["W_trace"][it]) / np.linalg.norm(o["W_trace"][it])
+            rh = np.linalg.norm(H - o["H_trace"][it][:, c0:c1]) / np.linalg.norm(o["H_trace"][it][:, c0:c1])
+            rm = abs(metric - o["metrics"][it]) / abs(o["metrics"][it])
+            if not (rw < tol and rh < tol and rm < max(tol, 1e-8)):
+                failures.append((alg, m, n, k, sparse, it, rw, rh, rm))
+                break
+    ctx.close()
+    t = torch.tensor([len(failures)], device="cuda")
+    dist.all_reduce(t)
+    if rank == 0:
+        print("MULTI_GPU_RESULT", "OK" if int(t.item()) == 0 else "FAIL", failures, flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if not failures else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,114 @@
+"""world_size-2 runs of the column-sharded NMF exchange pattern on CPU (gloo): the partition helpers of
+smallk_b200/sharding.py plus the collective sequence the CUDA library issues over NCCL (csrc/solver.cu) reproduce the
+single-process CPU oracle. The per-shard arithmetic is the oracle's (tests may use it); what is under test is the
+sharding: column blocks of A/H, all-reduce of H*H', row-sliced reduction of H*A', all-gather of W, summed progress metric."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from smallk_b200.sharding import column_block, row_slice      # noqa: E402
+
+WORLD = 2
+
+
+def _allreduce(a):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    dist.all_reduce(t)
+    return t.numpy()
+
+
+def _allgather_rows(W_slice_padded):
+    t = torch.from_numpy(np.ascontiguousarray(W_slice_padded))
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return np.concatenate([o.numpy() for o in out], axis=0)
+
+
+def _pg_sq(G, X):
+    mask = (G < 0) | (X > 0)
+    return float((G[mask] ** 2).sum())
+
+
+def _worker(rank, port, alg, m, n, k, iters, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    try:
+        from oracle import Oracle
+        orc = Oracle()
+        rng = np.random.default_rng(77)
+        A = rng.random((m, n)); W = rng.random((m, k)); Hfull = rng.random((k, n))
+        c0, c1 = column_block(n, rank, WORLD)
+        r0, rows, m_loc = row_slice(m, rank, WORLD)
+        Al, H = A[:, c0:c1], Hfull[:, c0:c1].copy()
+        WtW = W.T @ W; WtA = W.T @ Al
+        metrics = []
+        for it in range(iters):
+            if alg == "MU":
+                H *= WtA / (WtW @ H + 1e-13)
+            else:
+                rc, H, _ = orc.nnls_bpp(WtW, WtA, H)
+                assert rc == 0
+            HHt = _allreduce(H @ H.T)                                   # k x k all-reduce
+            AHt = _allreduce(Al @ H.T)[r0:r0 + rows]                    # reduce-scatter == all-reduce + own row slice
+            Wl = W[r0:r0 + rows]
+            if alg == "MU":
+                Wl = Wl * (AHt / (Wl @ HHt + 1e-13))
+            else:
+                rc, Wlt, _ = orc.nnls_bpp(HHt, AHt.T.copy(), Wl.T.copy())
+                assert rc == 0
+                Wl = Wlt.T
+            gradWl = Wl @ HHt - AHt
+            pad = np.zeros((m_loc, k)); pad[:rows] = Wl
+            W = _allgather_rows(pad)[:m]                                # all-gather of the padded slices
+            WtW = W.T @ W; WtA = W.T @ Al
+            gradH = WtW @ H - WtA
+            pg2 = _allreduce(np.array([_pg_sq(gradWl, Wl), _pg_sq(gradH, H)]))   # two partial sums, one all-reduce
+            metrics.append(float(np.sqrt(pg2.sum())))
+        Hall = [torch.empty((k, column_block(n, r, WORLD)[1] - column_block(n, r, WORLD)[0]), dtype=torch.float64) for r in range(WORLD)]
+        dist.all_gather(Hall, torch.from_numpy(np.ascontiguousarray(H))) if n % WORLD == 0 else None
+        if rank == 0:
+            q.put((W, np.concatenate([h.numpy() for h in Hall], axis=1) if n % WORLD == 0 else None, metrics))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("alg,m,n,k", [("MU", 61, 40, 5), ("BPP", 50, 36, 6)])
+def test_column_sharded_exchange_matches_single_process_oracle(alg, m, n, k):
+    from oracle import Oracle
+    iters = 6
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, port, alg, m, n, k, iters, q)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    W, H, metrics = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(77)
+    A = rng.random((m, n)); W0 = rng.random((m, k)); H0 = rng.random((k, n))
+    o = Oracle().nmf_dense(A, W0, H0, alg=alg, tol=1e-12, min_iter=1, max_iter=iters, normalize=False, trace=True)
+    assert np.linalg.norm(W - o["W"]) <= 1e-9 * np.linalg.norm(o["W"])
+    assert np.linalg.norm(H - o["H"]) <= 1e-9 * np.linalg.norm(o["H"])
+    ratios = np.array(metrics[1:]) / metrics[0]
+    assert np.allclose(ratios, o["metrics"][1:iters], rtol=1e-8)
+
+
+def test_partition_helpers_cover_everything_once():
+    for n, world in ((20000, 8), (7, 4), (5, 8), (33, 2)):
+        blocks = [column_block(n, r, world) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+        slices = [row_slice(n, r, world) for r in range(world)]
+        assert sum(s[1] for s in slices) == n
+        assert len({s[2] for s in slices}) == 1 and slices[0][2] * world >= n
+        assert all(s[0] == r * s[2] for r, s in enumerate(slices))
