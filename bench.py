@@ -44,28 +44,37 @@ def flops_per_iter(m, n, k):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
-
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons during the timed region, sampled in-process through NVML every 5 ms
+    (the nvidia-smi CLI takes longer per call than a short timed region lasts)."""
 
     def __init__(self, index):
-        self.index = index
-        self.rows = []
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        # NVML indexes physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v for v in vis.split(",") if v.strip().isdigit()]
+        phys = int(ids[index]) if index < len(ids) else index
+        self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        self.sm, self.reasons, self.power = [], set(), []
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
+        nv = self.nv
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.rows.append(parts)
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for name, bit in names:
+                    if bits & int(bit):
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.005)
 
     def start(self):
         self._t.start()
@@ -73,15 +82,13 @@ class ClockSampler:
     def stop(self):
         self._stop.set()
         self._t.join(timeout=3)
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+        try:
+            mx = float(self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "power_w_max": max(self.power) if self.power else None, "how": "NVML in-process, 5 ms period"}
 
 
 def measured_fp64_peak():
@@ -173,7 +180,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="smallk_b200")
     ap.add_argument("--size", type=int, default=20000, help="m = n of the dense workload (20000 = BASELINE C2)")
@@ -242,8 +249,9 @@ def main():
         ctx.solver_step(1)
         metric_trace.append(ctx.solver_progress())
 
-    sampler = ClockSampler(local_rank)
+    sampler = None
     if rank == 0:
+        sampler = ClockSampler(local_rank)
         sampler.start()
     launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -256,7 +264,7 @@ def main():
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if sampler is not None else None
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
