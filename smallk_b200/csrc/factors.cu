@@ -157,58 +157,82 @@ __global__ void hals_sweep_row_kernel(int k, int q, int r, double* __restrict__ 
 
 // ---------------------------------------------------------------------------
 // HALS, W side, blocked: the same k dependent steps, but the k-long dot products are not re-read from memory at
-// every step. Columns are taken in blocks of kHalsB. For a block [c0, c0+B):
-//   phase A (hals_block_outer_kernel): Q(l, j) = sum over p OUTSIDE the block of X(p,j) G(p,c0+l) - R(c0+l,j)
-//            — one pass over X per block (k/B passes per sweep instead of k), a 16 x k x q GEMM on the FP64 tensor pipe;
-//   phase B (hals_block_step_kernel), B dependent steps: step l needs only the block's own B entries of each column
-//            and Q(l, j):  x <- max(0, x - (Q + sum_{p in block} X(p,j) G(p,c)) / G(c,c)),  NaN -> 0,
-//            then the grid-wide unit-norm scaling of row c is applied by the NEXT kernel (as in hals_sweep_row_kernel).
-// Traffic per sweep and column of X: k*k/B + k*(B+3) doubles instead of k*k, all of it streamed (the B steps of a
-// block run on a compact q x B copy of the block, not on 128-byte pieces of 8k-byte-strided columns).
+// every step. Columns of W (rows of X = Wt) are taken in blocks of kHalsB. For a block [c0, c0+B):
+//   phase A (hals_block_outer_kernel): for row l of the block
+//            Q(l, j) = sum over p NOT in [c0, c0+l) of X(p,j) G(p,c0+l) - R(c0+l,j)
+//            i.e. everything the update of row c0+l needs except the rows of this block that are updated before it
+//            (the triangular mask keeps the block's own not-yet-updated rows, whose old values are still in X) —
+//            one pass over X per block (k/B passes per sweep instead of k), a 16 x k x q GEMM on the FP64 tensor pipe;
+//   phase B (hals_block_step_kernel<L>), B dependent steps on a COMPACT row-major copy Xb (B x q) of the block:
+//            x_l <- max(0, x_l - (Q(l,j) + sum_{t<l} Xb(t,j) G(c0+t,c)) / G(c,c)),  NaN -> 0,
+//            one thread per column of X, every load a fully coalesced 8-byte-per-lane stream; step l reads l + 2
+//            rows and writes 2 (its own row and the unit-norm scaling of row l-1, which needs the grid-wide norm
+//            of the previous step). The block that finishes last reduces the per-block partial sums in fixed order
+//            and publishes 1/norm for the next launch (deterministic; no second reduction pass per launch).
+// Traffic per sweep and column of X: k*k/B + k*(B/2 + 4) doubles instead of k*k.
 // ---------------------------------------------------------------------------
 constexpr int kHalsB = 16;
 
-// norm of row `prev` from the block partials of the step that produced it; returns 1/norm and whether the row is refilled with eps
-__device__ __forceinline__ double finish_prev_row(const double* __restrict__ partial, int prev, int nblocks_prev, int q,
-                                                  double* __restrict__ norms, double* red, bool& fill_prev)
+// rowinfo[2*c] = 1 / norm of row c, rowinfo[2*c+1] = 1.0 when the whole row was clamped (refill with eps)
+__device__ __forceinline__ void publish_row_norm(double sumsq, double zeros, int c, int q, double* __restrict__ partial,
+                                                 double* __restrict__ rowinfo, unsigned int* __restrict__ ticket,
+                                                 double* __restrict__ norms, double* red)
 {
-    const double* pp = partial + (prev & 1) * 2 * kSweepBlocks;
+    __shared__ bool s_last;
+    sumsq = block_sum_f(sumsq, red);
+    zeros = block_sum_f(zeros, red);
+    if (threadIdx.x == 0)
+    {
+        partial[blockIdx.x] = sumsq;
+        partial[kSweepBlocks + blockIdx.x] = zeros;
+        __threadfence();
+        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
     double s = 0.0, z = 0.0;
-    for (int i = threadIdx.x; i < nblocks_prev; i += blockDim.x) { s += pp[i]; z += pp[kSweepBlocks + i]; }
+    for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += blockDim.x)
+    {
+        s += __ldcg(partial + i);
+        z += __ldcg(partial + kSweepBlocks + i);
+    }
     s = block_sum_f(s, red);
     z = block_sum_f(z, red);
-    double norm;
-    fill_prev = (z == static_cast<double>(q));
-    if (fill_prev) norm = DBL_EPSILON * sqrt(static_cast<double>(q));
-    else norm = sqrt(s);
-    if (blockIdx.x == 0 && threadIdx.x == 0) norms[prev] = norm;
-    return 1.0 / norm;
+    if (threadIdx.x == 0)
+    {
+        const bool fill = (z == static_cast<double>(q));
+        const double norm = fill ? DBL_EPSILON * sqrt(static_cast<double>(q)) : sqrt(s);
+        norms[c] = norm;
+        rowinfo[2 * c] = 1.0 / norm;
+        rowinfo[2 * c + 1] = fill ? 1.0 : 0.0;
+        *ticket = 0u;
+    }
 }
 
-// Phase A on the FP64 tensor pipe: D (16 block columns x 8 columns of X) = GmT (16 x k) * X (k x 8), two DMMA.8x8x4 per
+// Phase A on the FP64 tensor pipe: D (16 block rows x 8 columns of X) = GmT (16 x k) * X (k x 8), two DMMA.8x8x4 per
 // four rows of X. One warp per 8 columns of X; the B fragments come straight from global memory (each lane reads
 // X(4s + (lane & 3), j0 + (lane >> 2)): eight fully used 32-byte sectors per warp load, no shared-memory tile, no
 // barriers), the A fragments of the masked Gram block sit in shared memory in fragment order.
-// The block's own entries are copied to a COMPACT buffer Xb (q x 16) on which the B step kernels then stream at full
-// bandwidth; the previous block's finished entries are taken from its compact buffer and written back to X here.
+// The block's own entries are copied to the compact buffer Xb_cur (16 x q); the previous block's finished entries are
+// taken from its compact buffer and written back to X here.
 __global__ void __launch_bounds__(256)
 hals_block_outer_kernel(int k, int q, int c0, double* __restrict__ X, const double* __restrict__ G, const double* __restrict__ R,
                         double* __restrict__ Q, double* __restrict__ Xb_cur, const double* __restrict__ Xb_prev,
-                        const double* __restrict__ partial, int nblocks_prev, double* __restrict__ norms)
+                        const double* __restrict__ rowinfo)
 {
     extern __shared__ __align__(16) double sA[];       // [ksteps][2 m-tiles][32 lanes]
-    __shared__ double red[32];
     const int ksteps = (k + 3) >> 2;
     const int nb = min(kHalsB, k - c0);
     bool fill_prev = false;
     double inv_prev = 1.0;
-    if (c0 > 0) inv_prev = finish_prev_row(partial, c0 - 1, nblocks_prev, q, norms, red, fill_prev);
+    if (c0 > 0) { inv_prev = rowinfo[2 * (c0 - 1)]; fill_prev = rowinfo[2 * (c0 - 1) + 1] != 0.0; }
     for (int e = threadIdx.x; e < ksteps * 64; e += blockDim.x)
     {
         const int ln = e & 31, mt = (e >> 5) & 1, st = e >> 6;
         const int row = mt * 8 + (ln >> 2), p = 4 * st + (ln & 3);
-        const bool inside = (p >= c0 && p < c0 + nb);
-        sA[e] = (row < nb && p < k && !inside) ? G[static_cast<long long>(c0 + row) * k + p] : 0.0;
+        const bool updated_before = (p >= c0 && p < c0 + row);      // rows of this block updated before row c0+row
+        sA[e] = (row < nb && p < k && !updated_before) ? G[static_cast<long long>(c0 + row) * k + p] : 0.0;
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -224,14 +248,17 @@ hals_block_outer_kernel(int k, int q, int c0, double* __restrict__ X, const doub
         const double* xcol = X + jc * k;
         double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
         double wb[BS], cur[BS];
+        auto mma_step = [&](int st, double b) {
+            const double a0 = sA[(st * 2) * 32 + lane], a1 = sA[(st * 2 + 1) * 32 + lane];
+            dmma884(c00, c01, a0, b);
+            dmma884(c10, c11, a1, b);
+        };
         // rows before the previous block, and rows after this block: read from X
         auto plain = [&](int st) {
             const int p = 4 * st + kk;
             double b = xcol[min(p, k - 1)];
             if (p >= k || !livecol) b = 0.0;
-            const double a0 = sA[(st * 2) * 32 + lane], a1 = sA[(st * 2 + 1) * 32 + lane];
-            dmma884(c00, c01, a0, b);
-            dmma884(c10, c11, a1, b);
+            mma_step(st, b);
         };
 #pragma unroll 8
         for (int st = 0; st < max(st_prev, 0); ++st) plain(st);
@@ -241,22 +268,24 @@ hals_block_outer_kernel(int k, int q, int c0, double* __restrict__ X, const doub
 #pragma unroll
             for (int u = 0; u < BS; ++u)
             {
-                const int st = st_prev + u, t = 4 * u + kk;
-                double b = Xb_prev[jc * kHalsB + t];
+                const int t = 4 * u + kk;
+                double b = Xb_prev[static_cast<long long>(t) * q + jc];
                 if (t == kHalsB - 1) b = (fill_prev ? DBL_EPSILON : b) * inv_prev;
                 wb[u] = b;
                 if (!livecol) b = 0.0;
-                const double a0 = sA[(st * 2) * 32 + lane], a1 = sA[(st * 2 + 1) * 32 + lane];
-                dmma884(c00, c01, a0, b);
-                dmma884(c10, c11, a1, b);
+                mma_step(st_prev + u, b);
             }
         }
-        // this block: no contribution (masked), entries go to the compact buffer
+        // this block: old values (triangular mask in sA), and a copy to the compact buffer
 #pragma unroll
         for (int u = 0; u < BS; ++u)
         {
             const int p = c0 + 4 * u + kk;
-            cur[u] = xcol[min(p, k - 1)];
+            double b = xcol[min(p, k - 1)];
+            if (p >= k) b = 0.0;
+            cur[u] = b;
+            if (!livecol) b = 0.0;
+            if (st_cur + u < ksteps) mma_step(st_cur + u, b);
         }
 #pragma unroll 8
         for (int st = st_cur + BS; st < ksteps; ++st) plain(st);
@@ -280,94 +309,67 @@ hals_block_outer_kernel(int k, int q, int c0, double* __restrict__ X, const doub
             {
                 const int t = 4 * u + kk;
                 if (c0 > 0) X[j * k + (c0 - kHalsB) + t] = wb[u];
-                Xb_cur[j * kHalsB + t] = (t < nb) ? cur[u] : 0.0;
+                Xb_cur[static_cast<long long>(t) * q + j] = cur[u];
             }
         }
     }
 }
 
-// One step of phase B on the compact block buffer Xb (q x 16): half a warp per column of X.
+// Step L of phase B on the compact block buffer Xb (16 x q, row-major): one thread per column of X.
+template <int L>
 __global__ void __launch_bounds__(256)
-hals_block_step_kernel(int k, int q, int c0, int l, double* __restrict__ Xb, const double* __restrict__ G,
-                       const double* __restrict__ Q, double* __restrict__ partial, int nblocks_prev, double* __restrict__ norms)
+hals_block_step_kernel(int k, int q, int c0, double* __restrict__ Xb, const double* __restrict__ G, const double* __restrict__ Q,
+                       double* __restrict__ partial, double* __restrict__ rowinfo, unsigned int* __restrict__ ticket,
+                       double* __restrict__ norms)
 {
     __shared__ double red[32];
     __shared__ double sg[kHalsB];
-    const int nb = min(kHalsB, k - c0);
-    const int c = c0 + l;
+    const int c = c0 + L;
+    if (threadIdx.x < kHalsB) sg[threadIdx.x] = (threadIdx.x < L) ? G[static_cast<long long>(c) * k + c0 + threadIdx.x] : 0.0;
+    __syncthreads();
     bool fill_prev = false;
     double inv_prev = 1.0;
-    if (l > 0) inv_prev = finish_prev_row(partial, c - 1, nblocks_prev, q, norms, red, fill_prev);
-    if (threadIdx.x < kHalsB) sg[threadIdx.x] = (threadIdx.x < nb) ? G[static_cast<long long>(c) * k + c0 + threadIdx.x] : 0.0;
-    __syncthreads();
-    const double gcc = sg[l];
-    const double* ql = Q + static_cast<long long>(l) * q;
+    if (L > 0) { inv_prev = rowinfo[2 * (c - 1)]; fill_prev = rowinfo[2 * (c - 1) + 1] != 0.0; }
+    const double gcc = G[static_cast<long long>(c) * k + c];
+    double g[L > 0 ? L : 1];
+#pragma unroll
+    for (int t = 0; t < L; ++t) g[t] = sg[t];
+    const double* ql = Q + static_cast<long long>(L) * q;
+    double* xl = Xb + static_cast<long long>(L) * q;
     double sumsq = 0.0, zeros = 0.0;
-    const int t = threadIdx.x & (kHalsB - 1);
-    const long long halves = (static_cast<long long>(gridDim.x) * blockDim.x) / kHalsB;
-    const long long h = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) / kHalsB;
-    constexpr int U = 4;                                 // columns in flight per half-warp
-    for (long long base = 0; base < q; base += U * halves)
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long j = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; j < q; j += stride)
     {
-        double v[U], dot[U], qv[U];
-        bool live[U];
-        // branch-free loads from clamped addresses: all 2U loads of a trip are in flight together
+        double y[L > 0 ? L : 1];
 #pragma unroll
-        for (int u = 0; u < U; ++u)
+        for (int t = 0; t < L; ++t) y[t] = Xb[static_cast<long long>(t) * q + j];
+        const double x = xl[j];
+        const double qv = __ldcs(ql + j);
+        if (L > 0)
         {
-            const long long j = base + u * halves + h;
-            live[u] = j < q;
-            const long long jc = live[u] ? j : q - 1;
-            v[u] = Xb[jc * kHalsB + t];
-            qv[u] = ql[jc];
+            y[L > 0 ? L - 1 : 0] = (fill_prev ? DBL_EPSILON : y[L > 0 ? L - 1 : 0]) * inv_prev;
+            Xb[static_cast<long long>(L > 0 ? L - 1 : 0) * q + j] = y[L > 0 ? L - 1 : 0];
         }
+        double dot = 0.0;
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-        {
-            if (!live[u]) v[u] = 0.0;
-            if (l > 0 && t == l - 1 && live[u])
-            {
-                v[u] = (fill_prev ? DBL_EPSILON : v[u]) * inv_prev;
-                Xb[(base + u * halves + h) * kHalsB + t] = v[u];
-            }
-            dot[u] = v[u] * sg[t];
-        }
-#pragma unroll
-        for (int o = kHalsB / 2; o > 0; o >>= 1)
-#pragma unroll
-            for (int u = 0; u < U; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], o);
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-        {
-            if (live[u] && t == l)
-            {
-                const long long j = base + u * halves + h;
-                double w = v[u] - (qv[u] + dot[u]) / gcc;
-                if (isnan(w) || w < 0.0) { w = 0.0; zeros += 1.0; }
-                Xb[j * kHalsB + l] = w;
-                sumsq += w * w;
-            }
-        }
+        for (int t = 0; t < L; ++t) dot += g[t] * y[t];
+        double w = x - (qv + dot) / gcc;
+        if (isnan(w) || w < 0.0) { w = 0.0; zeros += 1.0; }
+        xl[j] = w;
+        sumsq += w * w;
     }
-    sumsq = block_sum_f(sumsq, red);
-    zeros = block_sum_f(zeros, red);
-    if (threadIdx.x == 0)
-    {
-        double* pc = partial + (c & 1) * 2 * kSweepBlocks;
-        pc[blockIdx.x] = sumsq;
-        pc[kSweepBlocks + blockIdx.x] = zeros;
-    }
+    publish_row_norm(sumsq, zeros, c, q, partial, rowinfo, ticket, norms, red);
 }
 
 // End of the sweep: the last block goes back to X, its last row (row k-1) scaled to unit norm.
 __global__ void __launch_bounds__(256)
 hals_block_writeback_kernel(int k, int q, int c0, double* __restrict__ X, const double* __restrict__ Xb,
-                            const double* __restrict__ partial, int nblocks_prev, double* __restrict__ norms)
+                            const double* __restrict__ rowinfo)
 {
-    __shared__ double red[32];
     const int nb = k - c0;
-    bool fill_prev = false;
-    const double inv_prev = finish_prev_row(partial, k - 1, nblocks_prev, q, norms, red, fill_prev);
+    const double inv_prev = rowinfo[2 * (k - 1)];
+    const bool fill_prev = rowinfo[2 * (k - 1) + 1] != 0.0;
+    // thread e: column j = e / 16, entry t = e % 16: the writes to X are 128-byte pieces, the reads 8 rows of Xb
     const long long total = static_cast<long long>(q) * kHalsB;
     for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
          e += static_cast<long long>(gridDim.x) * blockDim.x)
@@ -376,9 +378,134 @@ hals_block_writeback_kernel(int k, int q, int c0, double* __restrict__ X, const 
         const int t = static_cast<int>(e % kHalsB);
         if (t < nb)
         {
-            double v = Xb[e];
+            double v = Xb[static_cast<long long>(t) * q + j];
             if (t == nb - 1) v = (fill_prev ? DBL_EPSILON : v) * inv_prev;
             X[j * k + c0 + t] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// HALS, H side, fused and blocked: no coupling between the columns of X, so a whole sweep of a column is done in ONE
+// pass, by the same blocking as the W side. A warp owns 8 columns of X in shared memory (k x 8 tile, XOR-swizzled so
+// the DMMA B fragments are conflict-free). For each block of 16 rows:
+//   phase A: D (16 x 8) = masked GmT (16 x k) * tile (k x 8) on the FP64 tensor pipe (two DMMA.8x8x4 per four rows),
+//            A fragments of the block's Gram slab in shared memory (one slab per CTA and block, triangular mask as on
+//            the W side);
+//   phase B: lanes 0..7 run the 16 dependent steps of their column in registers,
+//            x_l <- max(0, x_l - (D_l - R_l + sum_{t<l} x_t G(c0+t,c)) / G(c,c)),  NaN -> 0.
+// X is read once and written once; G slabs come from L2 (k*k*8 bytes per 64 columns).
+// ---------------------------------------------------------------------------
+constexpr int kColsWarps = 8;
+
+__device__ __forceinline__ int xs_index(int p, int n) { return p * 8 + (n ^ (((p >> 1) & 1) << 2)); }
+
+__global__ void __launch_bounds__(kColsWarps * 32)
+hals_cols_fused_kernel(int k, int q, double* __restrict__ X, const double* __restrict__ G, const double* __restrict__ R)
+{
+    extern __shared__ __align__(16) double smem[];
+    const int ksteps = (k + 3) >> 2;
+    const int kpad = ksteps * 4;
+    double* sA = smem;                                   // [ksteps][2][32]
+    double* gd = sA + ksteps * 64;                       // [16][16] diagonal block G(c0+t, c0+l) at t*16+l
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* xs = gd + 256 + warp * (kpad * 8 + 256);     // [kpad][8] swizzled
+    double* qs = xs + kpad * 8;                          // [16][8]  D
+    double* rs = qs + 128;                               // [16][8]  R
+    const int n = lane >> 2, kk = lane & 3;
+    const long long nchunks = (static_cast<long long>(q) + 8 * kColsWarps - 1) / (8 * kColsWarps);
+    for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x)
+    {
+        const long long j0 = (ch * kColsWarps + warp) * 8;
+        const bool livewarp = j0 < q;
+        // tile load: lane -> column (lane & 7), rows p0 + (lane >> 3)
+        {
+            const long long j = j0 + (lane & 7);
+            const bool live = j < q;
+            const double* xcol = X + (live ? j : 0) * k;
+#pragma unroll 8
+            for (int p0 = 0; p0 < kpad; p0 += 4)
+            {
+                const int p = p0 + (lane >> 3);
+                xs[xs_index(p, lane & 7)] = (live && p < k) ? xcol[p] : 0.0;
+            }
+        }
+        for (int c0 = 0; c0 < k; c0 += kHalsB)
+        {
+            const int nb = min(kHalsB, k - c0);
+            __syncthreads();                             // previous slab no longer in use; tiles visible
+            for (int e = threadIdx.x; e < ksteps * 64; e += blockDim.x)
+            {
+                const int ln = e & 31, mt = (e >> 5) & 1, st = e >> 6;
+                const int row = mt * 8 + (ln >> 2), p = 4 * st + (ln & 3);
+                const bool updated_before = (p >= c0 && p < c0 + row);
+                sA[e] = (row < nb && p < k && !updated_before) ? G[static_cast<long long>(c0 + row) * k + p] : 0.0;
+            }
+            if (threadIdx.x < 256)
+            {
+                const int t = threadIdx.x >> 4, l = threadIdx.x & 15;
+                gd[threadIdx.x] = (t < nb && l < nb) ? G[static_cast<long long>(c0 + l) * k + c0 + t] : (t == l ? 1.0 : 0.0);
+            }
+            // R tile of this block: 8 columns x 16 rows
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+            {
+                const int e = lane + 32 * i, col = e >> 4, row = e & 15;
+                const long long j = j0 + col;
+                rs[row * 8 + col] = (j < q && row < nb) ? R[j * k + c0 + row] : 0.0;
+            }
+            __syncthreads();
+            if (!livewarp) continue;
+            double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+#pragma unroll 8
+            for (int st = 0; st < ksteps; ++st)
+            {
+                const double b = xs[xs_index(4 * st + kk, n)];
+                const double a0 = sA[(st * 2) * 32 + lane], a1 = sA[(st * 2 + 1) * 32 + lane];
+                dmma884(c00, c01, a0, b);
+                dmma884(c10, c11, a1, b);
+            }
+            {
+                const int row = lane >> 2, col = 2 * (lane & 3);
+                qs[row * 8 + col] = c00; qs[row * 8 + col + 1] = c01;
+                qs[(row + 8) * 8 + col] = c10; qs[(row + 8) * 8 + col + 1] = c11;
+            }
+            __syncwarp();
+            if (lane < 8)
+            {
+                double y[kHalsB];
+#pragma unroll
+                for (int l = 0; l < kHalsB; ++l)
+                {
+                    if (l < nb)
+                    {
+                        const int xi = xs_index(c0 + l, lane);
+                        double dot = qs[l * 8 + lane] - rs[l * 8 + lane];
+#pragma unroll
+                        for (int t = 0; t < l; ++t) dot += gd[t * 16 + l] * y[t];
+                        double w = xs[xi] - dot / gd[l * 16 + l];
+                        if (isnan(w) || w < 0.0) w = 0.0;
+                        y[l] = w;
+                        xs[xi] = w;
+                    }
+                    else y[l] = 0.0;
+                }
+            }
+            __syncwarp();
+        }
+        // tile store
+        {
+            const long long j = j0 + (lane & 7);
+            if (j < q)
+            {
+                double* xcol = X + j * k;
+#pragma unroll 8
+                for (int p0 = 0; p0 < kpad; p0 += 4)
+                {
+                    const int p = p0 + (lane >> 3);
+                    if (p < k) xcol[p] = xs[xs_index(p, lane & 7)];
+                }
+            }
         }
     }
 }
@@ -528,43 +655,75 @@ int ew_blocks(long long total, int num_sms) { return static_cast<int>(std::max<l
 
 } // namespace
 
-size_t hals_sweep_scratch_doubles(int q) { return 3 * static_cast<size_t>(kHalsB) * q; }   // Q + two compact block buffers
+// Q + two compact block buffers + the per-row norm records (2 x 256) + the finish ticket
+size_t hals_sweep_scratch_doubles(int q) { return 3 * static_cast<size_t>(kHalsB) * q + 2 * 256 + 8; }
+
+namespace {
+template <int L>
+void launch_block_step(cudaStream_t stream, int blocks, int k, int q, int c0, double* Xb, const double* G, const double* Q,
+                       double* partial, double* rowinfo, unsigned int* ticket, double* norms)
+{
+    hals_block_step_kernel<L><<<blocks, 256, 0, stream>>>(k, q, c0, Xb, G, Q, partial, rowinfo, ticket, norms);
+    SMK_LAUNCH_CHECK();
+}
+} // namespace
 
 void hals_sweep(cudaStream_t stream, int k, int q, double* X, const double* G, const double* R,
                 bool normalize_rows, double* norms, double* partial, int num_sms, double* scratch)
 {
     if (q <= 0) return;
     const int threads = 256, wpb = threads / 32;
-    if (normalize_rows && scratch && k >= 8)
+    const char* dbg = getenv("SMK_HALS_DEBUG");
+    const int dbgv = dbg ? atoi(dbg) : 0;
+    if (normalize_rows && scratch && k >= 8 && !(dbgv & 1))
     {
         // blocked sweep (see hals_block_outer_kernel)
         const size_t smem = static_cast<size_t>((k + 3) / 4) * 64 * sizeof(double);
         SMK_CUDA(cudaFuncSetAttribute(hals_block_outer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         const int outer_blocks = std::max(1, std::min(ceil_div(q, 64), 8 * num_sms));
-        const int step_blocks = std::max(1, std::min(std::min(ceil_div(static_cast<long long>(q) * kHalsB, threads), 8 * num_sms), kSweepBlocks));
+        const int step_blocks = std::max(1, std::min(std::min(ceil_div(q, threads), 8 * num_sms), kSweepBlocks));
         double* Qs = scratch;
         double* Xb[2] = {scratch + static_cast<size_t>(kHalsB) * q, scratch + 2 * static_cast<size_t>(kHalsB) * q};
+        double* rowinfo = scratch + 3 * static_cast<size_t>(kHalsB) * q;
+        unsigned int* ticket = reinterpret_cast<unsigned int*>(rowinfo + 2 * 256);
+        SMK_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), stream));
         int cur = 0, c_last = 0;
         for (int c0 = 0; c0 < k; c0 += kHalsB, cur ^= 1)
         {
             hals_block_outer_kernel<<<outer_blocks, threads, smem, stream>>>(k, q, c0, X, G, R, Qs, Xb[cur], c0 > 0 ? Xb[cur ^ 1] : nullptr,
-                                                                            partial, step_blocks, norms);
+                                                                            rowinfo);
             SMK_LAUNCH_CHECK();
             const int nb = std::min(kHalsB, k - c0);
             for (int l = 0; l < nb; ++l)
             {
-                hals_block_step_kernel<<<step_blocks, threads, 0, stream>>>(k, q, c0, l, Xb[cur], G, Qs, partial, step_blocks, norms);
-                SMK_LAUNCH_CHECK();
+#define SMK_STEP(L) case L: launch_block_step<L>(stream, step_blocks, k, q, c0, Xb[cur], G, Qs, partial, rowinfo, ticket, norms); break;
+                switch (l)
+                {
+                    SMK_STEP(0) SMK_STEP(1) SMK_STEP(2) SMK_STEP(3) SMK_STEP(4) SMK_STEP(5) SMK_STEP(6) SMK_STEP(7)
+                    SMK_STEP(8) SMK_STEP(9) SMK_STEP(10) SMK_STEP(11) SMK_STEP(12) SMK_STEP(13) SMK_STEP(14) SMK_STEP(15)
+                }
+#undef SMK_STEP
             }
             c_last = c0;
         }
-        hals_block_writeback_kernel<<<step_blocks, threads, 0, stream>>>(k, q, c_last, X, Xb[cur ^ 1], partial, step_blocks, norms);
+        const int wb_blocks = std::max(1, std::min(ceil_div(static_cast<long long>(q) * kHalsB, threads), 8 * num_sms));
+        hals_block_writeback_kernel<<<wb_blocks, threads, 0, stream>>>(k, q, c_last, X, Xb[cur ^ 1], rowinfo);
         SMK_LAUNCH_CHECK();
         return;
     }
     dispatch_kpl(k, [&](auto kpl) {
         constexpr int KPL = decltype(kpl)::value;
-        if (!normalize_rows)
+        if (!normalize_rows && k >= 8 && !(dbgv & 2))
+        {
+            const int kpad = ((k + 3) / 4) * 4;
+            const size_t smem = (static_cast<size_t>(kpad) * 16 + 256 + kColsWarps * (static_cast<size_t>(kpad) * 8 + 256)) * sizeof(double);
+            SMK_CUDA(cudaFuncSetAttribute(hals_cols_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            const int per_sm = smem <= 112 * 1024 ? 2 : 1;
+            const int blocks = std::max(1, std::min(ceil_div(q, 8 * kColsWarps), per_sm * num_sms));
+            hals_cols_fused_kernel<<<blocks, kColsWarps * 32, smem, stream>>>(k, q, X, G, R);
+            SMK_LAUNCH_CHECK();
+        }
+        else if (!normalize_rows)
         {
             int blocks = std::max(1, std::min(ceil_div(q, wpb), 8 * num_sms));
             hals_sweep_cols_kernel<KPL><<<blocks, threads, 0, stream>>>(k, q, X, G, R);

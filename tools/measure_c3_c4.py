@@ -46,7 +46,8 @@ def c3(m=1000000, n=200000, per_col=500, k=128, iters=5):
     ctx.synchronize()
     load_s = time.time() - t
     W0 = np.asfortranarray(np.random.default_rng(22).random((m, k)))
-    H0 = np.asfortranarray(np.random.default_rng(23).random((k, n))) * (2.0 / k)
+    # H0 scaled so that mean(W0*H0) = mean(A): from W0*H0 >> A, HALS clamps whole factors to zero in its first sweep
+    H0 = np.asfortranarray(np.random.default_rng(23).random((k, n))) * (float(val.sum()) / m / n / (0.25 * k))
     opts = sk.make_options(m, n, k, algorithm="HALS", tol=1e-15, min_iter=1, max_iter=100, normalize=False)
     ctx.solver_begin(W0, H0, opts)
     ctx.solver_step(1)
