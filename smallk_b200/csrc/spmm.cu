@@ -241,6 +241,93 @@ __global__ void spmm_seg_kernel(int nseg, const unsigned int* __restrict__ scol,
     }
 }
 
+// Wide-k variant of spmm_seg_kernel (k even, 64 <= k <= 256): one warp per segment, lane l owns the double2 pieces
+// (2l, 2l+1) + 64v of the k-vector, v < NV, so a gathered operand B(:, i) is NV 512-byte LDG.128 wavefronts.
+// The (index, value) pairs of a segment are read 32 at a time, one pair per lane (two coalesced loads instead of 64
+// broadcast loads), and handed round by shuffles; U gathered operands (U * NV LDG.128 per lane, U KB per warp) are in
+// flight before the first FMA consumes one. The gathers are what the kernel waits for: at 8 KB in flight per warp
+// and 16 warps per SM the memory system, not the issue rate, sets the pace. The entries are still added in storage
+// order, one fused multiply-add per entry and output element, as in the scalar kernel.
+template <int NV, int U>
+__global__ void __launch_bounds__(256, 2)
+spmm_seg_wide_kernel(int nseg, const unsigned int* __restrict__ scol, const unsigned int* __restrict__ sbeg,
+                     const unsigned int* __restrict__ send, const unsigned int* __restrict__ sslot,
+                     const unsigned int* __restrict__ idx, const double* __restrict__ val, int k,
+                     const double* __restrict__ B, long long ldb, double alpha, double beta,
+                     double* __restrict__ out, long long ldo, double* __restrict__ partial)
+{
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    bool live[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) live[v] = 2 * lane + 64 * v < k;
+    for (long long it = blockIdx.x * static_cast<long long>(wpb) + (threadIdx.x >> 5); it < nseg;
+         it += static_cast<long long>(gridDim.x) * wpb)
+    {
+        const unsigned int j = scol[it], slot = sslot[it];
+        const bool direct = slot == 0xFFFFFFFFu;
+        double2 acc[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+        {
+            acc[v] = make_double2(0.0, 0.0);
+            if (direct && beta != 0.0 && live[v])
+            {
+                const double2 c0 = *reinterpret_cast<const double2*>(out + j * ldo + 2 * lane + 64 * v);
+                acc[v] = make_double2(c0.x * beta, c0.y * beta);
+            }
+        }
+        const unsigned int end = send[it];
+        unsigned int o = sbeg[it];
+        unsigned int nxt_i = 0; double nxt_a = 0.0;
+        if (o + lane < end) { nxt_i = idx[o + lane]; nxt_a = alpha * val[o + lane]; }
+        while (o < end)
+        {
+            const int cnt = min(32u, end - o);
+            const unsigned int my_i = nxt_i; const double my_a = nxt_a;
+            o += 32;
+            if (o + lane < end) { nxt_i = idx[o + lane]; nxt_a = alpha * val[o + lane]; }      // next batch, behind the gathers
+            int t = 0;
+            for (; t + U <= cnt; t += U)
+            {
+                double2 b[U][NV];
+                double a[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                {
+                    const unsigned int iu = __shfl_sync(0xffffffffu, my_i, t + u);
+                    a[u] = __shfl_sync(0xffffffffu, my_a, t + u);
+                    const double* bcol = B + iu * ldb + 2 * lane;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v)
+                        b[u][v] = live[v] ? __ldg(reinterpret_cast<const double2*>(bcol + 64 * v)) : make_double2(0.0, 0.0);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) { acc[v].x += a[u] * b[u][v].x; acc[v].y += a[u] * b[u][v].y; }
+            }
+            for (; t < cnt; ++t)
+            {
+                const unsigned int iu = __shfl_sync(0xffffffffu, my_i, t);
+                const double au = __shfl_sync(0xffffffffu, my_a, t);
+                const double* bcol = B + iu * ldb + 2 * lane;
+#pragma unroll
+                for (int v = 0; v < NV; ++v)
+                    if (live[v])
+                    {
+                        const double2 bv = __ldg(reinterpret_cast<const double2*>(bcol + 64 * v));
+                        acc[v].x += au * bv.x; acc[v].y += au * bv.y;
+                    }
+            }
+        }
+        double* dst = direct ? out + j * ldo : partial + static_cast<long long>(slot) * k;
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+            if (live[v]) *reinterpret_cast<double2*>(dst + 2 * lane + 64 * v) = acc[v];
+    }
+}
+
 // out(:, j) = beta * out(:, j) + sum of the partials of column j, in segment order
 __global__ void spmm_combine_kernel(int nmulti, const unsigned int* __restrict__ multi_col, const unsigned int* __restrict__ first_slot,
                                     int k, double beta, const double* __restrict__ partial, double* __restrict__ out, long long ldo)
@@ -301,6 +388,22 @@ void spmm_gather_seg(cudaStream_t stream, int ncols, const SegTable& T, const un
                      double* partial, int num_sms)
 {
     if (ncols <= 0 || T.nseg <= 0) return;
+    const bool aligned16 = ((reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(partial)) & 15) == 0;
+    if (k >= 64 && k <= 256 && (k & 1) == 0 && (ldb & 1) == 0 && (ldo & 1) == 0 && aligned16)
+    {
+        const int wpb = 8;
+        const int blocks = std::max(1, std::min(ceil_div(T.nseg, wpb), 2 * num_sms * 8));
+#define SMK_W(NV, U) spmm_seg_wide_kernel<NV, U><<<blocks, 32 * wpb, 0, stream>>>(T.nseg, T.col.p, T.beg.p, T.end.p, T.slot.p, idx, val, k, \
+                                                                             B, ldb, alpha, beta, out, ldo, partial)
+        if (k <= 64) SMK_W(1, 8);
+        else if (k <= 128) SMK_W(2, 8);
+        else if (k <= 192) SMK_W(3, 4);
+        else SMK_W(4, 4);
+#undef SMK_W
+        SMK_LAUNCH_CHECK();
+    }
+    else
+    {
 #define SMK_S(L, KPL) launch_seg<L, KPL>(stream, T, idx, val, k, B, ldb, alpha, beta, out, ldo, partial, num_sms)
     if (k <= 2) SMK_S(2, 1);
     else if (k <= 4) SMK_S(4, 1);
@@ -312,6 +415,7 @@ void spmm_gather_seg(cudaStream_t stream, int ncols, const SegTable& T, const un
     else if (k <= 256) SMK_S(32, 8);
     else throw std::string("spmm: k > 256 is not supported");
 #undef SMK_S
+    }
     if (T.nmulti > 0)
     {
         const int threads = k <= 32 ? 32 : (k <= 64 ? 64 : 128);
