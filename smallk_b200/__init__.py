@@ -28,7 +28,7 @@ EXPORTS = [
     "smk_comm_unique_id", "smk_comm_init", "smk_load_dense", "smk_load_dense_device", "smk_load_csc", "smk_nmf",
     "smk_solver_begin", "smk_solver_step", "smk_solver_progress", "smk_solver_get", "smk_solver_normalize",
     "smk_solver_last_step_ms", "smk_solver_time_product", "smk_gemm", "smk_nnls_bpp", "smk_sparse_gemm",
-    "smk_select_columns", "smk_select_all", "smk_nnls_hals", "smk_argsort_desc", "smk_sort_desc",
+    "smk_select_columns", "smk_select_all", "smk_nnls_hals", "smk_argsort_desc", "smk_sort_desc", "smk_spmm_tier_info",
 ]
 HOST_LIB_PATH = os.path.join(_HERE, "lib", "libsmallk_host.so")
 HOST_EXPORTS = ["smkh_last_error", "smkh_hierclust_sparse", "smkh_hierclust_dense", "smkh_flatclust", "smkh_compute_priority",
@@ -254,6 +254,12 @@ class Context:
         k, q = RHS.shape
         self._check(self._lib.smk_nnls_bpp(self._h, k, q, _d(LHS), _d(RHS), _d(X), _d(Y)))
         return X, Y
+
+    def spmm_tier_info(self, which):
+        """(on, smem_rows, share) of the residency classes of product `which` (0 = W'A, 1 = H A')."""
+        on, rows, share = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_double(0.0)
+        self._check(self._lib.smk_spmm_tier_info(self._h, which, ctypes.byref(on), ctypes.byref(rows), ctypes.byref(share)))
+        return bool(on.value), rows.value, share.value
 
     def sparse_gemm(self, variant, alpha, B, beta, C):
         B = _f(B)

@@ -43,7 +43,7 @@ void prod_WtA(smk_ctx* c)
                  c->ws.p, c->ws.n * sizeof(double), c->num_sms);
     else
         spmm_gather_seg(c->stream, c->n, c->Sa->seg_cols, c->Sa->rowidx.p, c->Sa->val.p, k, c->Wt.p, k, 1.0, 0.0, c->WtA.p, k,
-                        c->spmm_partial.p, c->num_sms);
+                        c->spmm_partial.p, c->num_sms, c->m);
 }
 
 // HAt (k x m) = H * A'   (summed over the column shards when running multi-GPU)
@@ -55,7 +55,7 @@ void prod_HAt(smk_ctx* c)
                  c->ws.p, c->ws.n * sizeof(double), c->num_sms);
     else
         spmm_gather_seg(c->stream, c->m, c->Sa->seg_rows, c->Sa->colidx.p, c->Sa->valr.p, k, c->H.p, k, 1.0, 0.0, c->HAt.p, k,
-                        c->spmm_partial.p, c->num_sms);
+                        c->spmm_partial.p, c->num_sms, c->n);
     if (c->nranks <= 1) return;
     if (c->w_sharded)
     {
@@ -124,6 +124,15 @@ void solver_alloc(smk_ctx* c)
         SMK_CUDA(cudaMemsetAsync(c->gradWt.p, 0, k * m * sizeof(double), c->stream));
     }
     c->norms.reserve(k);
+    if (c->has_sparse && c->Sa == &c->S)
+    {
+        // residency classes of the SpMM gathers (k-dependent; only for operands far larger than L2, see spmm.cu)
+        SparseDev& S = c->S;
+        if (!(S.seg_cols.tiers_on && S.seg_cols.tier_k == c->opts.k))
+            build_gather_tiers(c->stream, S.seg_cols, S.m, S.rowptr.p, S.rowidx.p, S.nnz, c->opts.k, c->num_sms);
+        if (!(S.seg_rows.tiers_on && S.seg_rows.tier_k == c->opts.k))
+            build_gather_tiers(c->stream, S.seg_rows, S.n, S.colptr.p, S.colidx.p, S.nnz, c->opts.k, c->num_sms);
+    }
     if (c->has_sparse) c->spmm_partial.reserve(static_cast<size_t>(std::max(c->Sa->seg_cols.nslots, c->Sa->seg_rows.nslots)) * k + 1);
     c->deferred.reserve(nnls_deferred_bytes(static_cast<int>(std::max(m, n)), c->opts.k, c->num_sms));
     if (c->opts.algorithm == SMK_MU) { c->T1.reserve(k * n); c->T2.reserve(k * m); }    // m is the padded row count here

@@ -12,6 +12,8 @@
 // adds them. Dense columns Wt(:,r) / H(:,c) are contiguous k-vectors, so each gathered
 // operand is one coalesced k*8-byte read.
 #include <cub/cub.cuh>
+#include <vector>
+#include <cstdlib>
 #include "context.h"
 
 namespace smk {
@@ -328,6 +330,204 @@ spmm_seg_wide_kernel(int nseg, const unsigned int* __restrict__ scol, const unsi
     }
 }
 
+// ---------------------------------------------------------------------------
+// Tiered variant (k % 4 == 0, 64 <= k <= 256, fewer than 2^30 gathered vectors): 256-bit gathers + residency classes.
+//
+// A gather SpMM moves k*8 bytes of the dense operand per stored entry (C3: 1 KB x 7.7e7 = 79 GB per product), ~60x the
+// compulsory HBM bytes, so what bounds it is where those bytes come from. Term frequencies are Zipf-like: a few
+// hundred rows of A take a quarter of the entries and a few percent of the rows take three quarters, while the
+// operand as a whole (C3: Wt = 1 GB) is far larger than L2 and the long tail of cold rows keeps flushing the
+// popular ones out of it. The two top bits of a private copy of the index array therefore carry a residency class
+// per entry, chosen once per matrix from the degree of the gathered vector (build_gather_tiers):
+//     10 | slot : the vector is one of the `smem_rows` most popular ones and is served from shared memory, which
+//                 every CTA fills once (conflict-free LDS.128 pairs; no L2 traffic at all for these entries),
+//     01 | id   : popular enough to be kept in L2   -> LDG.E.EL.ELL2.256  (L1 and L2 evict_last),
+//     11 | id   : cold tail, touched and dropped    -> LDG.E.NA.EFL2.256  (L1 no_allocate, L2 evict_first),
+//     00 | id   : no tiers built (small or unskewed operand): plain LDG.E.256.
+// Lane l owns the four consecutive doubles 4l..4l+3 (+128v) of the k-vector, so one gathered operand is NV 256-bit
+// loads per lane (sm_100 LDG.256) instead of 2 NV LDG.128. Entries are still added in storage order, one fused
+// multiply-add per entry and output element: results are those of the kernels above.
+// ---------------------------------------------------------------------------
+struct d4 { double x, y, z, w; };
+
+__device__ __forceinline__ d4 ldg256(const double* p)
+{
+    d4 r;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ d4 ldg256_keep(const double* p)
+{
+    d4 r;
+    asm("ld.global.nc.L1::evict_last.L2::evict_last.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ d4 ldg256_drop(const double* p)
+{
+    d4 r;
+    asm("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+
+constexpr int kTierSmemBytes = 200 * 1024;                    // shared-memory tier per CTA (one 512-thread CTA per SM)
+constexpr size_t kTierKeepBytes = size_t(48) << 20;           // L2-resident tier: well under half of the 126 MB L2
+constexpr size_t kTierMinOperandBytes = size_t(96) << 20;     // smaller operands live in L2 without help
+constexpr unsigned int kTierSmem = 0x80000000u, kTierKeep = 0x40000000u, kTierDrop = 0xC0000000u, kTierMask = 0xC0000000u;
+
+// one gathered operand piece, by residency class (the class is warp-uniform: no divergence)
+__device__ __forceinline__ d4 tier_load(unsigned int code, const double* __restrict__ B, long long ldb, const double* sh, int k, int off, int q)
+{
+    const unsigned int cls = code & kTierMask;
+    if (cls == kTierSmem)
+    {
+        const double* row = sh + static_cast<size_t>(code & ~kTierMask) * k;
+        const double2 lo = *reinterpret_cast<const double2*>(row + 2 * q);
+        const double2 hi = *reinterpret_cast<const double2*>(row + (k >> 1) + 2 * q);
+        d4 r; r.x = lo.x; r.y = lo.y; r.z = hi.x; r.w = hi.y;
+        return r;
+    }
+    const double* p = B + static_cast<long long>(code & ~kTierMask) * ldb + off;
+    if (cls == kTierDrop) return ldg256_drop(p);
+    if (cls == kTierKeep) return ldg256_keep(p);
+    return ldg256(p);
+}
+
+template <int NV, int U>
+__global__ void __launch_bounds__(512, 1)
+spmm_seg_tier_kernel(int nseg, const unsigned int* __restrict__ scol, const unsigned int* __restrict__ sbeg,
+                     const unsigned int* __restrict__ send, const unsigned int* __restrict__ sslot,
+                     const unsigned int* __restrict__ idx, const double* __restrict__ val, int k,
+                     const double* __restrict__ B, long long ldb, double alpha, double beta,
+                     double* __restrict__ out, long long ldo, double* __restrict__ partial,
+                     int smem_rows, const unsigned int* __restrict__ smem_ids)
+{
+    extern __shared__ __align__(16) double tier_sh[];
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5;
+    bool live[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) live[v] = 4 * lane + 128 * v < k;
+    // shared-memory tier: row s = operand vector smem_ids[s]; the piece (lane, v) is stored as two double2 halves,
+    // k/2 doubles apart, at double2 index q = 32v + lane, so both LDS.128 of a warp are contiguous
+    for (int s = warp; s < smem_rows; s += wpb)
+    {
+        const double* src = B + static_cast<long long>(smem_ids[s]) * ldb;
+        double* row = tier_sh + static_cast<size_t>(s) * k;
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+            if (live[v])
+            {
+                const d4 x = ldg256_keep(src + 4 * lane + 128 * v);
+                const int q = 32 * v + lane;
+                *reinterpret_cast<double2*>(row + 2 * q) = make_double2(x.x, x.y);
+                *reinterpret_cast<double2*>(row + (k >> 1) + 2 * q) = make_double2(x.z, x.w);
+            }
+    }
+    __syncthreads();
+
+    for (long long it = blockIdx.x * static_cast<long long>(wpb) + warp; it < nseg; it += static_cast<long long>(gridDim.x) * wpb)
+    {
+        const unsigned int j = scol[it], slot = sslot[it];
+        const bool direct = slot == 0xFFFFFFFFu;
+        d4 acc[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+        {
+            acc[v].x = acc[v].y = acc[v].z = acc[v].w = 0.0;
+            if (direct && beta != 0.0 && live[v])
+            {
+                const double* c0 = out + j * ldo + 4 * lane + 128 * v;     // plain loads: out is written by this kernel
+                const double2 lo = *reinterpret_cast<const double2*>(c0), hi = *reinterpret_cast<const double2*>(c0 + 2);
+                acc[v].x = lo.x * beta; acc[v].y = lo.y * beta; acc[v].z = hi.x * beta; acc[v].w = hi.y * beta;
+            }
+        }
+        const unsigned int end = send[it];
+        unsigned int o = sbeg[it];
+        unsigned int nxt_i = 0; double nxt_a = 0.0;
+        if (o + lane < end) { nxt_i = __ldcs(idx + o + lane); nxt_a = alpha * __ldcs(val + o + lane); }
+        while (o < end)
+        {
+            const int cnt = min(32u, end - o);
+            const unsigned int my_i = nxt_i; const double my_a = nxt_a;
+            o += 32;
+            if (o + lane < end) { nxt_i = __ldcs(idx + o + lane); nxt_a = alpha * __ldcs(val + o + lane); }
+            int t = 0;
+            for (; t + U <= cnt; t += U)
+            {
+                d4 b[U][NV];
+                double a[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                {
+                    const unsigned int code = __shfl_sync(0xffffffffu, my_i, t + u);
+                    a[u] = __shfl_sync(0xffffffffu, my_a, t + u);
+#pragma unroll
+                    for (int v = 0; v < NV; ++v)
+                    {
+                        if (live[v]) b[u][v] = tier_load(code, B, ldb, tier_sh, k, 4 * lane + 128 * v, 32 * v + lane);
+                        else { b[u][v].x = b[u][v].y = b[u][v].z = b[u][v].w = 0.0; }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int v = 0; v < NV; ++v)
+                    {
+                        acc[v].x += a[u] * b[u][v].x; acc[v].y += a[u] * b[u][v].y;
+                        acc[v].z += a[u] * b[u][v].z; acc[v].w += a[u] * b[u][v].w;
+                    }
+            }
+            for (; t < cnt; ++t)
+            {
+                const unsigned int code = __shfl_sync(0xffffffffu, my_i, t);
+                const double au = __shfl_sync(0xffffffffu, my_a, t);
+#pragma unroll
+                for (int v = 0; v < NV; ++v)
+                    if (live[v])
+                    {
+                        const d4 bv = tier_load(code, B, ldb, tier_sh, k, 4 * lane + 128 * v, 32 * v + lane);
+                        acc[v].x += au * bv.x; acc[v].y += au * bv.y; acc[v].z += au * bv.z; acc[v].w += au * bv.w;
+                    }
+            }
+        }
+        double* dst = direct ? out + j * ldo : partial + static_cast<long long>(slot) * k;
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+            if (live[v])
+            {
+                double* p = dst + 4 * lane + 128 * v;
+                *reinterpret_cast<double2*>(p) = make_double2(acc[v].x, acc[v].y);
+                *reinterpret_cast<double2*>(p + 2) = make_double2(acc[v].z, acc[v].w);
+            }
+    }
+}
+
+// residency class of every gatherable vector from its rank in decreasing degree order
+__global__ void tier_code_kernel(int count, const unsigned int* __restrict__ ids_by_degree, int smem_rows, int keep_rows,
+                                 unsigned int* __restrict__ code, unsigned int* __restrict__ smem_ids)
+{
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < count; r += gridDim.x * blockDim.x)
+    {
+        const unsigned int id = ids_by_degree[r];
+        unsigned int c;
+        if (r < smem_rows) { c = kTierSmem | static_cast<unsigned int>(r); smem_ids[r] = id; }
+        else if (r < smem_rows + keep_rows) c = kTierKeep | id;
+        else c = kTierDrop | id;
+        code[id] = c;
+    }
+}
+
+__global__ void tier_degree_kernel(int count, const unsigned int* __restrict__ ptr, unsigned int* __restrict__ deg, unsigned int* __restrict__ ids)
+{
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < count; r += gridDim.x * blockDim.x) { deg[r] = ptr[r + 1] - ptr[r]; ids[r] = r; }
+}
+
+__global__ void tier_apply_kernel(unsigned int nnz, const unsigned int* __restrict__ idx, const unsigned int* __restrict__ code, unsigned int* __restrict__ out)
+{
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += gridDim.x * blockDim.x) out[i] = code[idx[i]];
+}
+
 // out(:, j) = beta * out(:, j) + sum of the partials of column j, in segment order
 __global__ void spmm_combine_kernel(int nmulti, const unsigned int* __restrict__ multi_col, const unsigned int* __restrict__ first_slot,
                                     int k, double beta, const double* __restrict__ partial, double* __restrict__ out, long long ldo)
@@ -385,11 +585,31 @@ void spmm_gather(cudaStream_t stream, int ncols, const unsigned int* ptr, const 
 
 void spmm_gather_seg(cudaStream_t stream, int ncols, const SegTable& T, const unsigned int* idx, const double* val,
                      int k, const double* B, long long ldb, double alpha, double beta, double* out, long long ldo,
-                     double* partial, int num_sms)
+                     double* partial, int num_sms, int ngather)
 {
     if (ncols <= 0 || T.nseg <= 0) return;
-    const bool aligned16 = ((reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(partial)) & 15) == 0;
-    if (k >= 64 && k <= 256 && (k & 1) == 0 && (ldb & 1) == 0 && (ldo & 1) == 0 && aligned16)
+    const uintptr_t addr_bits = reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(partial);
+    const bool aligned16 = (addr_bits & 15) == 0;
+    if (k >= 96 && k <= 256 && (k & 3) == 0 && (ldb & 3) == 0 && (ldo & 3) == 0 && (addr_bits & 31) == 0 && ngather > 0 && ngather < (1 << 30))
+    {
+        const bool tiers = T.tiers_on && T.tier_k == k;
+        const int smem_rows = tiers ? T.tier_smem_rows : 0;
+        const size_t smem_bytes = static_cast<size_t>(smem_rows) * k * sizeof(double);
+        const unsigned int* use_idx = tiers ? T.tier_idx.p : idx;
+        const int blocks = std::max(1, std::min(ceil_div(T.nseg, 16), num_sms));
+#define SMK_T(NV, U)                                                                                                                  \
+        do {                                                                                                                          \
+            static bool attr_set = false;                                                                                             \
+            if (!attr_set) { SMK_CUDA(cudaFuncSetAttribute(spmm_seg_tier_kernel<NV, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTierSmemBytes)); attr_set = true; } \
+            spmm_seg_tier_kernel<NV, U><<<blocks, 512, smem_bytes, stream>>>(T.nseg, T.col.p, T.beg.p, T.end.p, T.slot.p, use_idx, val, k, B, ldb, \
+                                                                             alpha, beta, out, ldo, partial, smem_rows, T.tier_smem_ids.p);      \
+        } while (0)
+        if (k <= 128) SMK_T(1, 8);
+        else SMK_T(2, 4);
+#undef SMK_T
+        SMK_LAUNCH_CHECK();
+    }
+    else if (k >= 64 && k <= 256 && (k & 1) == 0 && (ldb & 1) == 0 && (ldo & 1) == 0 && aligned16)
     {
         const int wpb = 8;
         const int blocks = std::max(1, std::min(ceil_div(T.nseg, wpb), 2 * num_sms * 8));
@@ -425,8 +645,58 @@ void spmm_gather_seg(cudaStream_t stream, int ncols, const SegTable& T, const un
     }
 }
 
+// Residency classes for the gathers of one orientation (see spmm_seg_tier_kernel). count = number of gatherable
+// vectors, degree_ptr = offsets of the OTHER orientation (degree of vector r = degree_ptr[r+1] - degree_ptr[r]).
+// Built only when the operand is much larger than L2 and the degrees are skewed enough for a static choice to beat
+// L2's own replacement: the two resident tiers must cover at least twice the share of the stored entries that the same
+// number of average vectors would. Synchronises the stream.
+void build_gather_tiers(cudaStream_t stream, SegTable& T, int count, const unsigned int* degree_ptr, const unsigned int* idx,
+                        unsigned int nnz, int k, int num_sms)
+{
+    T.tiers_on = false;
+    if (k < 96 || k > 256 || (k & 3) || count <= 0 || count >= (1 << 30) || nnz == 0) return;
+    // tuning / test knobs: SMK_SPMM_TIERS=0 turns the classes off; the two *_KB values shrink the thresholds so that
+    // small test matrices exercise all four classes
+    if (const char* e = getenv("SMK_SPMM_TIERS")) if (atoi(e) == 0) return;
+    size_t min_operand = kTierMinOperandBytes, keep_bytes = kTierKeepBytes;
+    if (const char* e = getenv("SMK_SPMM_TIER_MIN_KB")) min_operand = static_cast<size_t>(atoll(e)) << 10;
+    if (const char* e = getenv("SMK_SPMM_TIER_KEEP_KB")) keep_bytes = static_cast<size_t>(atoll(e)) << 10;
+    const size_t vec_bytes = static_cast<size_t>(k) * sizeof(double);
+    if (static_cast<size_t>(count) * vec_bytes <= min_operand) return;
+    const int smem_rows = static_cast<int>(std::min<size_t>(count, kTierSmemBytes / vec_bytes));
+    const int keep_rows = static_cast<int>(std::min<size_t>(count - smem_rows, keep_bytes / vec_bytes));
+    DevBuf<unsigned int> deg, ids, deg_s, ids_s, code;
+    DevBuf<unsigned char> tmp;
+    deg.reserve(count); ids.reserve(count); deg_s.reserve(count); ids_s.reserve(count);
+    const int blocks = std::max(1, std::min(ceil_div(count, 256), 8 * num_sms));
+    tier_degree_kernel<<<blocks, 256, 0, stream>>>(count, degree_ptr, deg.p, ids.p);
+    SMK_LAUNCH_CHECK();
+    size_t bytes = 0;
+    SMK_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, deg.p, deg_s.p, ids.p, ids_s.p, count, 0, 32, stream));
+    tmp.reserve(bytes);
+    SMK_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp.p, bytes, deg.p, deg_s.p, ids.p, ids_s.p, count, 0, 32, stream));
+    launch_counter() += 4;
+    std::vector<unsigned int> top(static_cast<size_t>(smem_rows) + keep_rows);
+    SMK_CUDA(cudaMemcpyAsync(top.data(), deg_s.p, top.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+    SMK_CUDA(cudaStreamSynchronize(stream));
+    double covered = 0.0;
+    for (unsigned int d : top) covered += d;
+    const double share = covered / nnz, uniform_share = static_cast<double>(top.size()) / count;
+    if (share < 2.0 * uniform_share) return;
+    code.reserve(count);
+    T.tier_idx.reserve(nnz);
+    T.tier_smem_ids.reserve(std::max(1, smem_rows));
+    tier_code_kernel<<<blocks, 256, 0, stream>>>(count, ids_s.p, smem_rows, keep_rows, code.p, T.tier_smem_ids.p);
+    SMK_LAUNCH_CHECK();
+    tier_apply_kernel<<<std::min<unsigned int>((nnz + 255) / 256, 64u * num_sms), 256, 0, stream>>>(nnz, idx, code.p, T.tier_idx.p);
+    SMK_LAUNCH_CHECK();
+    SMK_CUDA(cudaStreamSynchronize(stream));
+    T.tiers_on = true; T.tier_k = k; T.tier_smem_rows = smem_rows; T.tier_share = share;
+}
+
 void build_segments(cudaStream_t stream, int ncols, const unsigned int* ptr, SegTable& T, int num_sms)
 {
+    T.tiers_on = false;                      // residency classes belong to the matrix the table was built for
     const size_t n1 = static_cast<size_t>(ncols) + 1;
     T.t_cnt.reserve(3 * n1);                // cnt | mcnt | flag
     T.t_first.reserve(n1); T.first_slot.reserve(n1); T.t_mpos.reserve(n1);

@@ -207,6 +207,58 @@ def test_sparse_gemm_matches_oracle(gpu, oracle, variant, k):
         assert rel(got, want) < REL_PRIM
 
 
+def _zipf_csc(m, n, per_col, seed):
+    """Rows drawn log-uniformly (Zipf, s = 1) as in the C3 generator: a few rows take most of the entries."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    rows = np.minimum((m ** rng.random((n, per_col))).astype(np.int64) - 1, m - 1).clip(0)
+    cols = np.repeat(np.arange(n), per_col)
+    S = sp.csc_matrix((rng.random(n * per_col) + 0.1, (rows.ravel(), cols)), shape=(m, n))     # duplicates summed
+    S.sort_indices()
+    return S
+
+
+@pytest.mark.parametrize("k", [96, 128, 200, 256])
+def test_sparse_gemm_with_residency_classes_matches_oracle(gpu, oracle, k, monkeypatch):
+    """The tiered SpMM (shared-memory rows, L2-kept rows, dropped tail) against the oracle: thresholds shrunk through the
+    library's test knobs so that a 4000 x 500 matrix uses all classes."""
+    monkeypatch.setenv("SMK_SPMM_TIER_MIN_KB", "0")
+    monkeypatch.setenv("SMK_SPMM_TIER_KEEP_KB", str(300 * k * 8 // 1024))
+    m, n = 4000, 500
+    S = _zipf_csc(m, n, 60, 17)
+    rng = np.random.default_rng(k)
+    gpu.load_csc((m, n), S.indptr, S.indices, S.data)
+    for variant in (2, 3, 0, 1):
+        shapeB = {0: (n, k), 1: (k, n), 2: (k, m), 3: (m, k)}[variant]
+        shapeC = (m, k) if variant < 2 else (k, n)
+        B = rng.random(shapeB); C = rng.random(shapeC)
+        for alpha, beta in [(1.0, 0.0), (0.7, -1.3)]:
+            got = gpu.sparse_gemm(variant, alpha, B, beta, C)
+            want = oracle.sparse_gemm(variant, alpha, (m, n), S.indptr, S.indices, S.data, B, beta, C)
+            assert rel(got, want) < REL_PRIM
+    on, smem_rows, share = gpu.spmm_tier_info(0)
+    assert on and smem_rows == 200 * 1024 // (8 * k) and share > 0.5       # the row gathers are skewed: classes in use
+    assert not gpu.spmm_tier_info(1)[0]                                      # the column gathers are not: plain loads
+
+
+def test_sparse_hals_with_residency_classes_matches_oracle(gpu, oracle, monkeypatch):
+    monkeypatch.setenv("SMK_SPMM_TIER_MIN_KB", "0")
+    monkeypatch.setenv("SMK_SPMM_TIER_KEEP_KB", "200")
+    m, n, k, iters = 3000, 400, 128, 6
+    S = _zipf_csc(m, n, 80, 5)
+    rng = np.random.default_rng(6)
+    W0 = rng.random((m, k)); H0 = rng.random((k, n)) * (S.sum() / m / n / (0.25 * k))
+    o = oracle.nmf_sparse((m, n), S.indptr, S.indices, S.data, W0, H0, alg="HALS", tol=1e-12, min_iter=1, max_iter=iters, trace=True)
+    assert o["rc"] == 0
+    gpu.load_csc((m, n), S.indptr, S.indices, S.data)
+    opts = sk.make_options(m, n, k, algorithm="HALS", tol=1e-12, min_iter=1, max_iter=iters, normalize=False)
+    metrics, Ws, Hs = _trace_gpu(gpu, W0, H0, opts, iters)
+    assert gpu.spmm_tier_info(0)[0]
+    for i in range(iters):
+        assert rel(Ws[i], o["W_trace"][i]) < REL_FACTOR, (i, rel(Ws[i], o["W_trace"][i]))
+        assert rel(Hs[i], o["H_trace"][i]) < REL_FACTOR, (i, rel(Hs[i], o["H_trace"][i]))
+
+
 @pytest.mark.parametrize("alg,k,iters", [("BPP", 10, 20), ("MU", 10, 30), ("RANK2", 2, 30), ("HALS", 10, 12)])
 def test_sparse_trace_matches_oracle(gpu, oracle, alg, k, iters):
     m, n = 300, 200
