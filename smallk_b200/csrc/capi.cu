@@ -49,6 +49,7 @@ void ensure_scratch(smk_ctx* c)
 {
     c->status.reserve(ST_COUNT);
     c->counter.reserve(2);
+    if (!c->ticket.p) { c->ticket.reserve(4); SMK_CUDA(cudaMemsetAsync(c->ticket.p, 0, 4 * sizeof(unsigned int), c->stream)); }
     c->partial.reserve(4096 + 512 * 256);
     c->acc.reserve(8);
 }

@@ -101,6 +101,7 @@ struct smk_ctx
     smk::DevBuf<double> ws;         // split-R partial tiles
     smk::DevBuf<int> status;        // ST_COUNT ints
     smk::DevBuf<unsigned int> counter;
+    smk::DevBuf<unsigned int> ticket;   // arrival tickets of the fused rank-2 kernels (self-resetting; zeroed once)
     smk::DevBuf<unsigned char> deferred; // BPP columns handed from the fast to the slow NNLS kernel
     smk::DevBuf<double> partial;    // 1024 block partials
     smk::DevBuf<double> acc;        // 8 scalars
@@ -116,6 +117,9 @@ struct smk_ctx
     int steps_done = 0;
     double pg0 = 0.0;
     smk::DevBuf<double> H, Wt, gradH, gradWt, WtW, HHt, WtA, HAt, T1, T2, Wprev, norms;
+    bool pg_ready = false;          // the last solver_step left both projected-gradient sums in acc[0..1] (fused rank-2)
+    bool status_cached = false;     // status_host holds the status words as of the last solver_progress
+    int status_host[smk::ST_COUNT] = {0, INT_MAX, 0, 0, 0};
     float last_ms = 0.f;
     long long last_launches = 0;
 

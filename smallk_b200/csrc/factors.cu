@@ -3,6 +3,7 @@
 #include <cfloat>
 #include "common.cuh"
 #include "kernels.h"
+#include "rank2_math.cuh"
 
 namespace smk {
 
@@ -216,7 +217,8 @@ __device__ __forceinline__ void publish_row_norm(double sumsq, double zeros, int
 // barriers), the A fragments of the masked Gram block sit in shared memory in fragment order.
 // The block's own entries are copied to the compact buffer Xb_cur (16 x q); the previous block's finished entries are
 // taken from its compact buffer and written back to X here.
-__global__ void __launch_bounds__(256)
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
 hals_block_outer_kernel(int k, int q, int c0, double* __restrict__ X, const double* __restrict__ G, const double* __restrict__ R,
                         double* __restrict__ Q, double* __restrict__ Xb_cur, const double* __restrict__ Xb_prev,
                         const double* __restrict__ rowinfo)
@@ -516,61 +518,18 @@ hals_cols_fused_kernel(int k, int q, double* __restrict__ X, const double* __res
 __global__ void rank2_update_kernel(int q, double* __restrict__ X, const double* __restrict__ G,
                                     const double* __restrict__ B, int w_side, int* __restrict__ status, int outer_iter)
 {
-    // G is 2 x 2 column-major: G[0]=(0,0) G[1]=(1,0) G[2]=(0,1) G[3]=(1,1)
-    const double a00 = G[0], a10 = G[1], a01 = G[2], a11 = G[3];
-    const double eps = DBL_EPSILON;
-    bool fail = (fabs(a00) < eps) && (fabs(a01) < eps);
-    double t = 0.0, a2 = 1.0, b2 = 0.0, d2 = 1.0;
-    const bool cosine = fabs(a00) >= fabs(a01);
-    if (!fail)
-    {
-        if (!w_side)
-        {   // SystemSolveH, nmf_solver_rank2.hpp:81-131
-            if (cosine) { t = -a10 / a00; a2 = a00 - t * a10; b2 = a01 - t * a11; d2 = a11 + t * a01; }
-            else        { t = -a00 / a10; a2 = -a10 + t * a00; b2 = -a11 + t * a01; d2 = a01 + t * a11; }
-        }
-        else
-        {   // SystemSolveW, nmf_solver_rank2.hpp:157-211
-            if (cosine) { t = a01 / a00; a2 = a00 + t * a01; b2 = a10 + t * a11; d2 = a11 - t * a10; }
-            else        { t = a00 / a01; a2 = -a01 - t * a00; b2 = -a11 - t * a10; d2 = a10 - t * a11; }
-        }
-        if (fabs(d2 / a2) < eps) fail = true;
-    }
-    if (fail)
+    Rank2Solve sol;
+    sol.init(G, w_side != 0);
+    if (sol.fail)
     {
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicMin(&status[ST_FAIL_ITER], outer_iter);
         return;
     }
-    const double inv_a2 = 1.0 / a2, inv_d2 = 1.0 / d2;
-    // OptimalActiveSet{H,W}: :218-318
-    const double inv00 = 1.0 / a00, inv11 = 1.0 / a11, sq00 = sqrt(a00), sq11 = sqrt(a11);
-
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < q;
          i += static_cast<long long>(gridDim.x) * blockDim.x)
     {
         const double2 bb = *reinterpret_cast<const double2*>(B + 2 * i);
-        const double b0 = bb.x, b1 = bb.y;
-        double e2, f2;
-        if (!w_side)
-        {
-            if (cosine) { e2 = b0 - t * b1;  f2 = b1 + t * b0; }
-            else        { e2 = -b1 + t * b0; f2 = b0 + t * b1; }
-        }
-        else
-        {
-            if (cosine) { e2 = b0 + t * b1;  f2 = b1 - t * b0; }
-            else        { e2 = -b1 - t * b0; f2 = b0 - t * b1; }
-        }
-        double x1 = f2 * inv_d2;
-        double x0 = (e2 - b2 * x1) * inv_a2;
-        if (x0 <= 0.0 || x1 <= 0.0)
-        {
-            double v1 = b0 * inv00, v2 = b1 * inv11;
-            const double vv1 = v1 * sq00, vv2 = v2 * sq11;
-            if (vv1 >= vv2) v2 = 0.0; else v1 = 0.0;
-            x0 = v1; x1 = v2;
-        }
-        *reinterpret_cast<double2*>(X + 2 * i) = make_double2(x0, x1);
+        *reinterpret_cast<double2*>(X + 2 * i) = sol.apply(bb.x, bb.y);
     }
 }
 
@@ -679,7 +638,10 @@ void hals_sweep(cudaStream_t stream, int k, int q, double* X, const double* G, c
     {
         // blocked sweep (see hals_block_outer_kernel)
         const size_t smem = static_cast<size_t>((k + 3) / 4) * 64 * sizeof(double);
-        SMK_CUDA(cudaFuncSetAttribute(hals_block_outer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        // resident CTAs per SM the outer pass is compiled for (register budget 65536 / (256 * MINB)); SMK_HALS_OUTER_OCC overrides
+        static const int outer_occ = [] { const char* e = getenv("SMK_HALS_OUTER_OCC"); const int v = e ? atoi(e) : 3; return v == 3 ? 3 : (v == 1 ? 1 : 2); }();      // 3: C3 step 25.2 -> 24.3 ms
+        auto outer_kernel = outer_occ == 3 ? hals_block_outer_kernel<3> : (outer_occ == 1 ? hals_block_outer_kernel<1> : hals_block_outer_kernel<2>);
+        SMK_CUDA(cudaFuncSetAttribute(outer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         const int outer_blocks = std::max(1, std::min(ceil_div(q, 64), 8 * num_sms));
         const int step_blocks = std::max(1, std::min(std::min(ceil_div(q, threads), 8 * num_sms), kSweepBlocks));
         double* Qs = scratch;
@@ -690,7 +652,7 @@ void hals_sweep(cudaStream_t stream, int k, int q, double* X, const double* G, c
         int cur = 0, c_last = 0;
         for (int c0 = 0; c0 < k; c0 += kHalsB, cur ^= 1)
         {
-            hals_block_outer_kernel<<<outer_blocks, threads, smem, stream>>>(k, q, c0, X, G, R, Qs, Xb[cur], c0 > 0 ? Xb[cur ^ 1] : nullptr,
+            outer_kernel<<<outer_blocks, threads, smem, stream>>>(k, q, c0, X, G, R, Qs, Xb[cur], c0 > 0 ? Xb[cur ^ 1] : nullptr,
                                                                             rowinfo);
             SMK_LAUNCH_CHECK();
             const int nb = std::min(kHalsB, k - c0);

@@ -14,12 +14,20 @@
 // copy of A (nmf_solver_bpp.hpp:319; +8mn bytes) and its per-iteration
 // W <-> Wt transposes (:363-364) disappear, and W is transposed only when it
 // crosses the host boundary.
+#include <cstdlib>
 #include "context.h"
 #include "solver.h"
 
 namespace smk {
 
 namespace {
+
+// SMK_RANK2_FUSED=0 keeps the generic kernel sequence for sparse rank-2 (A/B measurements, parity diagnostics)
+bool rank2_fused_enabled()
+{
+    const char* e = getenv("SMK_RANK2_FUSED");
+    return !(e && atoi(e) == 0);
+}
 
 void allreduce_sum(smk_ctx* c, double* buf, size_t count)
 {
@@ -136,6 +144,7 @@ void solver_alloc(smk_ctx* c)
     if (c->has_sparse) c->spmm_partial.reserve(static_cast<size_t>(std::max(c->Sa->seg_cols.nslots, c->Sa->seg_rows.nslots)) * k + 1);
     c->deferred.reserve(nnls_deferred_bytes(static_cast<int>(std::max(m, n)), c->opts.k, c->num_sms));
     if (c->opts.algorithm == SMK_MU) { c->T1.reserve(k * n); c->T2.reserve(k * m); }    // m is the padded row count here
+    if (c->opts.algorithm == SMK_RANK2 && c->has_sparse && c->nranks <= 1) c->T2.reserve(k * m);   // unnormalised W of the fused iteration
     if (c->opts.algorithm == SMK_HALS) c->T2.reserve(std::max(k * m, hals_sweep_scratch_doubles(static_cast<int>(m))));
     if (c->opts.prog_est_algorithm == SMK_DELTA_FNORM) c->Wprev.reserve(k * m);
     // split-R workspace: enough for the gram matrices at 4*SMs splits and for the big products at a few splits
@@ -168,6 +177,8 @@ void solver_init(smk_ctx* c)
 void solver_step(smk_ctx* c)
 {
     const int k = c->opts.k, m = c->m, n = c->n;
+    c->pg_ready = false;
+    c->status_cached = false;
     switch (c->opts.algorithm)
     {
     case SMK_BPP:      // nmf_solver_bpp.hpp:342-377
@@ -214,6 +225,13 @@ void solver_step(smk_ctx* c)
         gram_times(c, c->HHt.p, c->Wt.p, m, c->HAt.p, c->gradWt.p);
         break;
     case SMK_RANK2:    // nmf_solver_rank2.hpp:353-455
+        if (c->has_sparse && c->nranks <= 1 && rank2_fused_enabled())
+        {
+            rank2_fused_step(c, c->T2.p);     // the same iteration in three kernels, projected-gradient sums included
+            c->steps_done += 1;
+            c->pg_ready = true;
+            return;
+        }
         rank2_update(c->stream, n, c->H.p, c->WtW.p, c->WtA.p, false, c->status.p, c->steps_done);
         compute_HHt(c);
         prod_HAt(c);
@@ -241,13 +259,19 @@ int solver_progress(smk_ctx* c, double* metric)
         // the W part is a sum over this rank's rows when the W update is row-sharded, else every rank has all of it
         const long long woff = c->w_sharded ? k * c->w_row0() : 0;
         const long long wrows = c->w_sharded ? c->w_rows() : c->m;
-        if (wrows > 0) pg_sumsq(c->stream, k * wrows, c->gradWt.p + woff, c->Wt.p + woff, c->partial.p, c->acc.p + 0, c->num_sms);
-        else SMK_CUDA(cudaMemsetAsync(c->acc.p, 0, sizeof(double), c->stream));
-        pg_sumsq(c->stream, k * c->n, c->gradH.p, c->H.p, c->partial.p, c->acc.p + 1, c->num_sms);
-        if (c->w_sharded) allreduce_sum(c, c->acc.p, 2);
-        else allreduce_sum(c, c->acc.p + 1, 1);
+        if (!c->pg_ready)
+        {
+            if (wrows > 0) pg_sumsq(c->stream, k * wrows, c->gradWt.p + woff, c->Wt.p + woff, c->partial.p, c->acc.p + 0, c->num_sms);
+            else SMK_CUDA(cudaMemsetAsync(c->acc.p, 0, sizeof(double), c->stream));
+            pg_sumsq(c->stream, k * c->n, c->gradH.p, c->H.p, c->partial.p, c->acc.p + 1, c->num_sms);
+            if (c->w_sharded) allreduce_sum(c, c->acc.p, 2);
+            else allreduce_sum(c, c->acc.p + 1, 1);
+        }
         SMK_CUDA(cudaMemcpyAsync(h, c->acc.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if (c->nranks <= 1)     // the status words ride on the same synchronisation (solver_fail_iter reads them next)
+            SMK_CUDA(cudaMemcpyAsync(c->status_host, c->status.p, sizeof(c->status_host), cudaMemcpyDeviceToHost, c->stream));
         SMK_CUDA(cudaStreamSynchronize(c->stream));
+        c->status_cached = c->nranks <= 1;
         const double pg = sqrt(h[0] + h[1]);
         if (pg != pg) { c->err = "ProjectedGradientNorm: NaN"; return SMK_FAILURE; }
         if (c->steps_done <= 1) { c->pg0 = pg; *metric = 1.0; }
@@ -315,6 +339,7 @@ void solver_product(smk_ctx* c, int which) { if (which == 0) prod_WtA(c); else p
 // First outer iteration (0-based) in which a kernel reported solver failure, or INT_MAX.
 int solver_fail_iter(smk_ctx* c)
 {
+    if (c->status_cached) return c->status_host[ST_FAIL_ITER];
     int st[ST_COUNT];
     if (c->nranks > 1)      // all ranks must take the same exit
         nccl_check(ncclAllReduce(c->status.p + ST_FAIL_ITER, c->status.p + ST_FAIL_ITER, 1, ncclInt, ncclMin, c->comm, c->stream), "ncclAllReduce");

@@ -12,6 +12,8 @@ int solver_progress(smk_ctx* c, double* metric);
 int solver_normalize(smk_ctx* c);
 int solver_fail_iter(smk_ctx* c);
 void solver_product(smk_ctx* c, int which);
+// rank2_fused.cu: one Rank2 iteration on the active sparse matrix in three kernels (Wu: 2 * m doubles of scratch)
+void rank2_fused_step(smk_ctx* c, double* Wu);
 int solver_nnls_hals(smk_ctx* c, double tol, int max_iter, int* iterations);
 
 // ---- submatrix.cu: SubMatrixColsCompact on the device (sparse_matrix_impl.hpp:479-591,

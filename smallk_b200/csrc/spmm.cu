@@ -372,6 +372,7 @@ __device__ __forceinline__ d4 ldg256_drop(const double* p)
 constexpr int kTierSmemBytes = 200 * 1024;                    // shared-memory tier per CTA (one 512-thread CTA per SM)
 constexpr size_t kTierKeepBytes = size_t(48) << 20;           // L2-resident tier: well under half of the 126 MB L2
 constexpr size_t kTierMinOperandBytes = size_t(96) << 20;     // smaller operands live in L2 without help
+constexpr size_t kSlabMaxBytes = size_t(64) << 20;            // a 32-row operand slab of at most this size is gathered from L2
 constexpr unsigned int kTierSmem = 0x80000000u, kTierKeep = 0x40000000u, kTierDrop = 0xC0000000u, kTierMask = 0xC0000000u;
 
 // one gathered operand piece, by residency class (the class is warp-uniform: no divergence)
@@ -503,6 +504,75 @@ spmm_seg_tier_kernel(int nseg, const unsigned int* __restrict__ scol, const unsi
     }
 }
 
+// ---------------------------------------------------------------------------
+// k-slab variant: an operand that is larger than L2 but whose 32-row slab fits (C3: H = 205 MB, slab 51 MB) is gathered
+// one slab per launch, so every gather after the first touch of a vector is an L2 hit; A's index/value arrays are
+// streamed once per slab (12 bytes per entry, against the 256 bytes the entry gathers). 8 lanes own a segment (lane g
+// the doubles koff + 4g .. 4g+3 of the k-vector: one LDG.E.256 per lane and entry), four segments per warp; the
+// (index, value) pairs are read 8 at a time and handed round inside the group. Entries are added in storage order
+// with one fused multiply-add per entry and output element: bit for bit the sums of the kernels above.
+// ---------------------------------------------------------------------------
+constexpr int kSlab = 32;
+
+__global__ void __launch_bounds__(256, 2)
+spmm_seg_slab_kernel(int nseg, const unsigned int* __restrict__ scol, const unsigned int* __restrict__ sbeg,
+                     const unsigned int* __restrict__ send, const unsigned int* __restrict__ sslot,
+                     const unsigned int* __restrict__ idx, const double* __restrict__ val, int k, int koff,
+                     const double* __restrict__ B, long long ldb, double alpha, double beta,
+                     double* __restrict__ out, long long ldo, double* __restrict__ partial)
+{
+    const int lane = threadIdx.x & 31, g = lane & 7;
+    const unsigned int mask = 0xFFu << (lane & ~7);
+    const long long ngroups = static_cast<long long>(gridDim.x) * (blockDim.x >> 3);
+    const int off = koff + 4 * g;
+    for (long long it = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3; it < nseg; it += ngroups)
+    {
+        const unsigned int j = scol[it], slot = sslot[it];
+        const bool direct = slot == 0xFFFFFFFFu;
+        d4 acc; acc.x = acc.y = acc.z = acc.w = 0.0;
+        if (direct && beta != 0.0)
+        {
+            const double* c0 = out + j * ldo + off;
+            const double2 lo = *reinterpret_cast<const double2*>(c0), hi = *reinterpret_cast<const double2*>(c0 + 2);
+            acc.x = lo.x * beta; acc.y = lo.y * beta; acc.z = hi.x * beta; acc.w = hi.y * beta;
+        }
+        const unsigned int end = send[it];
+        unsigned int o = sbeg[it];
+        unsigned int nxt_i = 0; double nxt_a = 0.0;
+        if (o + g < end) { nxt_i = __ldcs(idx + o + g); nxt_a = alpha * __ldcs(val + o + g); }
+        while (o < end)
+        {
+            const int cnt = min(8u, end - o);
+            const unsigned int my_i = nxt_i; const double my_a = nxt_a;
+            o += 8;
+            nxt_i = 0; nxt_a = 0.0;
+            if (o + g < end) { nxt_i = __ldcs(idx + o + g); nxt_a = alpha * __ldcs(val + o + g); }
+            d4 b[8];
+            double a[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+            {
+                const unsigned int iu = __shfl_sync(mask, my_i, t, 8);
+                a[t] = __shfl_sync(mask, my_a, t, 8);
+                if (t < cnt) b[t] = ldg256(B + iu * ldb + off);
+                else { b[t].x = b[t].y = b[t].z = b[t].w = 0.0; }
+            }
+            if (cnt == 8)
+            {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) { acc.x += a[t] * b[t].x; acc.y += a[t] * b[t].y; acc.z += a[t] * b[t].z; acc.w += a[t] * b[t].w; }
+            }
+            else
+            {
+                for (int t = 0; t < cnt; ++t) { acc.x += a[t] * b[t].x; acc.y += a[t] * b[t].y; acc.z += a[t] * b[t].z; acc.w += a[t] * b[t].w; }
+            }
+        }
+        double* p = (direct ? out + j * ldo : partial + static_cast<long long>(slot) * k) + off;
+        *reinterpret_cast<double2*>(p) = make_double2(acc.x, acc.y);
+        *reinterpret_cast<double2*>(p + 2) = make_double2(acc.z, acc.w);
+    }
+}
+
 // residency class of every gatherable vector from its rank in decreasing degree order
 __global__ void tier_code_kernel(int count, const unsigned int* __restrict__ ids_by_degree, int smem_rows, int keep_rows,
                                  unsigned int* __restrict__ code, unsigned int* __restrict__ smem_ids)
@@ -590,9 +660,25 @@ void spmm_gather_seg(cudaStream_t stream, int ncols, const SegTable& T, const un
     if (ncols <= 0 || T.nseg <= 0) return;
     const uintptr_t addr_bits = reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(partial);
     const bool aligned16 = (addr_bits & 15) == 0;
-    if (k >= 96 && k <= 256 && (k & 3) == 0 && (ldb & 3) == 0 && (ldo & 3) == 0 && (addr_bits & 31) == 0 && ngather > 0 && ngather < (1 << 30))
+    const bool wide256 = k >= 64 && k <= 256 && (ldb & 3) == 0 && (ldo & 3) == 0 && (addr_bits & 31) == 0 && ngather > 0 && ngather < (1 << 30);
+    const bool tiers = T.tiers_on && T.tier_k == k;
+    static const bool slab_enabled = [] { const char* e = getenv("SMK_SPMM_SLAB"); return !(e && atoi(e) == 0); }();
+    // operand larger than L2 can keep, 32-row slab small enough to stay: one launch per slab
+    const size_t operand_bytes = static_cast<size_t>(ngather > 0 ? ngather : 0) * k * sizeof(double);
+    if (wide256 && !tiers && slab_enabled && (k % kSlab) == 0 && operand_bytes > kTierMinOperandBytes &&
+        static_cast<size_t>(ngather) * kSlab * sizeof(double) <= kSlabMaxBytes)
     {
-        const bool tiers = T.tiers_on && T.tier_k == k;
+        const int groups_per_block = 256 / 8;
+        const int blocks = std::max(1, std::min(ceil_div(T.nseg, groups_per_block), 2 * num_sms));
+        for (int koff = 0; koff < k; koff += kSlab)
+        {
+            spmm_seg_slab_kernel<<<blocks, 256, 0, stream>>>(T.nseg, T.col.p, T.beg.p, T.end.p, T.slot.p, idx, val, k, koff, B, ldb,
+                                                             alpha, beta, out, ldo, partial);
+            SMK_LAUNCH_CHECK();
+        }
+    }
+    else if (wide256 && k >= 96 && (k & 3) == 0)
+    {
         const int smem_rows = tiers ? T.tier_smem_rows : 0;
         const size_t smem_bytes = static_cast<size_t>(smem_rows) * k * sizeof(double);
         const unsigned int* use_idx = tiers ? T.tier_idx.p : idx;

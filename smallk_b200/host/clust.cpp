@@ -51,6 +51,7 @@ bool IsValid(const ClustOptions& opts, bool validate_matrix)
 // priority score
 // --------------------------------------------------------------------------------------------------------------
 R compute_priority_on(smk_ctx* ctx, const R* W_parent, const R* W_child, int n);
+R compute_priority_plain(smk_ctx* ctx, const R* W_parent, const R* W_child, int n);
 
 namespace {
 
@@ -121,7 +122,9 @@ R dcg_of(const std::vector<int>& test, const std::vector<int>& rank_parent, cons
 
 R compute_priority(const R* W_parent, const R* W_child, const int n) { return compute_priority_on(nullptr, W_parent, W_child, n); }
 
-R compute_priority_on(smk_ctx* ctx, const R* W_parent, const R* W_child, const int n)
+// The straightforward evaluation: every step of clust_hier_util.hpp:105-173 on full-length arrays. Used when a factor
+// has a negative or NaN entry (never after a successful factorization) and as the yardstick of the streaming version.
+R compute_priority_plain(smk_ctx* ctx, const R* W_parent, const R* W_child, const int n)
 {
     std::vector<int> ord_p, ord_1, ord_2;
     int n_part = 0;
@@ -164,6 +167,149 @@ R compute_priority_on(smk_ctx* ctx, const R* W_parent, const R* W_child, const i
     else std::sort(weight.begin(), weight.end(), std::greater<R>());
     R ideal = weight[0];
     for (int i = 1; i < n; ++i) ideal = ideal + weight[i] / g_logs.lg2[i + 1];
+    return (dcg1 / ideal) * (dcg2 / ideal);
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// The same score without the full-length random-access passes. Below the root a node's factors are zero in all
+// but the node's own rows, while every vector is m long, so the plain evaluation spends its time ranking, gathering
+// and sorting zeros. What the score needs, and how each piece is obtained with the reference's exact arithmetic:
+//   * desc_ordered of a non-negative vector = its positive entries sorted (ties by row), then its zero rows in row
+//     order: a zero row's rank is (number of positives) + (number of zero rows before it), a running count;
+//   * the DCG sums add weight_part[rank_parent[row]] / log2(position + 1) over the positions of a child ordering, and
+//     weight_part is exactly 0 beyond the parent's positive rows: cum + 0 == cum, so only parent-positive rows are
+//     visited, in increasing position — child-positive rows in sorted order, then child-zero rows in row order;
+//   * the ideal sum needs the weights sorted in decreasing order. A row that is zero in the parent and in both
+//     children has weight 1 / log(n - max(rank_1, rank_2)), both ranks running counts: these weights are already
+//     non-decreasing in the row index, so they are merged, from the last row down, with the sorted weights of the
+//     other rows. Equal weights are interchangeable in the sum, so the merge equals std::sort + loop bit for bit.
+// --------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct PriorityScratch
+{
+    std::vector<int> pos_p, pos_1, pos_2, pz_1, pz_2, other, rank_p, rank_1, rank_2, perm, tmp_i;
+    std::vector<R> keys, wfull, wpart, wsort;
+};
+PriorityScratch g_ps;
+
+// rows[0..cnt) (ascending row order) sorted by decreasing v[row], ties by ascending row
+void sort_rows_desc(const R* v, std::vector<int>& rows, smk_ctx* ctx)
+{
+    const int cnt = static_cast<int>(rows.size());
+    if (ctx && cnt >= kDeviceSortMin)
+    {
+        g_ps.keys.resize(cnt); g_ps.perm.resize(cnt); g_ps.tmp_i.resize(cnt);
+        for (int i = 0; i < cnt; ++i) g_ps.keys[i] = v[rows[i]];
+        if (smk_argsort_desc(ctx, g_ps.keys.data(), cnt, g_ps.perm.data()) != SMK_OK) throw std::runtime_error(smk_last_error(ctx));
+        for (int i = 0; i < cnt; ++i) g_ps.tmp_i[i] = rows[g_ps.perm[i]];
+        rows.swap(g_ps.tmp_i);
+    }
+    else std::sort(rows.begin(), rows.end(), [v](int a, int b) { return v[a] > v[b] || (v[a] == v[b] && a < b); });
+}
+
+} // namespace
+
+R compute_priority_on(smk_ctx* ctx, const R* W_parent, const R* W_child, const int n)
+{
+    const R* P = W_parent; const R* C1 = W_child; const R* C2 = W_child + n;
+    // pass 0: counts; anything but non-negative finite entries goes the plain way
+    int np = 0, n1 = 0, n2 = 0;
+    bool regular = true;
+    for (int i = 0; i < n; ++i)
+    {
+        const R p = P[i], a = C1[i], b = C2[i];
+        if (!(p >= 0) || !(a >= 0) || !(b >= 0)) { regular = false; break; }
+        np += p > 0; n1 += a > 0; n2 += b > 0;
+    }
+    if (!regular) return compute_priority_plain(ctx, W_parent, W_child, n);
+    const int n_part = np;
+    if (n_part <= 1) return R(-3);
+    g_logs.ensure(n);
+    const std::vector<double>& ln = g_logs.ln;
+    const std::vector<double>& lg2 = g_logs.lg2;
+    auto discount_of = [&](const int worst) { const R d = ln[n - worst]; return d == 0 ? ln[2] : d; };
+
+    PriorityScratch& S = g_ps;
+    S.pos_p.clear(); S.pos_1.clear(); S.pos_2.clear(); S.pz_1.clear(); S.pz_2.clear(); S.other.clear();
+    if (static_cast<int>(S.rank_p.size()) < n) { S.rank_p.resize(n); S.rank_1.resize(n); S.rank_2.resize(n); }
+    // pass A: positive rows of each vector; ranks of the zero rows that will be looked up
+    int z1 = 0, z2 = 0;
+    for (int i = 0; i < n; ++i)
+    {
+        const bool p = P[i] > 0, a = C1[i] > 0, b = C2[i] > 0;
+        if (p) S.pos_p.push_back(i);
+        if (a) S.pos_1.push_back(i); else { if (p || b) S.rank_1[i] = n1 + z1; if (p) S.pz_1.push_back(i); ++z1; }
+        if (b) S.pos_2.push_back(i); else { if (p || a) S.rank_2[i] = n2 + z2; if (p) S.pz_2.push_back(i); ++z2; }
+        if (!p && (a || b)) S.other.push_back(i);
+    }
+    sort_rows_desc(P, S.pos_p, ctx);
+    sort_rows_desc(C1, S.pos_1, ctx);
+    sort_rows_desc(C2, S.pos_2, ctx);
+    for (int q = 0; q < np; ++q) S.rank_p[S.pos_p[q]] = q;
+    for (int q = 0; q < n1; ++q) S.rank_1[S.pos_1[q]] = q;
+    for (int q = 0; q < n2; ++q) S.rank_2[S.pos_2[q]] = q;
+
+    // weights of the parent-positive rows (positions 0..np-1 of the parent ordering), then of the rows that are zero in
+    // the parent but positive in a child (weight 1 / discount, like every position from first_zero on)
+    S.wfull.resize(static_cast<size_t>(np) + S.other.size()); S.wpart.resize(np);
+    for (int i = 0; i < np; ++i)
+    {
+        const int row = S.pos_p[i];
+        const R d = discount_of(std::max(S.rank_1[row], S.rank_2[row]));
+        S.wfull[i] = ln[n - i] / d;
+        S.wpart[i] = ln[n_part - i] / d;
+    }
+    for (size_t u = 0; u < S.other.size(); ++u)
+    {
+        const int row = S.other[u];
+        S.wfull[np + u] = R(1) / discount_of(std::max(S.rank_1[row], S.rank_2[row]));
+    }
+
+    // DCG of a child ordering: its positive rows in sorted order, then the parent-positive rows among its zero rows
+    auto dcg = [&](const std::vector<int>& pos, const std::vector<int>& pz, const std::vector<int>& rank_c, const R* Pv) {
+        R cum = 0;
+        const int cnt = static_cast<int>(pos.size());
+        for (int q = 0; q < cnt; ++q)
+        {
+            const int row = pos[q];
+            if (!(Pv[row] > 0)) continue;                    // weight_part is 0 there
+            const R g = S.wpart[S.rank_p[row]];
+            cum = q == 0 ? g : cum + g / lg2[q + 1];
+        }
+        for (const int row : pz)
+        {
+            const int q = rank_c[row];
+            const R g = S.wpart[S.rank_p[row]];
+            cum = q == 0 ? g : cum + g / lg2[q + 1];
+        }
+        return cum;
+    };
+    const R dcg1 = dcg(S.pos_1, S.pz_1, S.rank_1, P);
+    const R dcg2 = dcg(S.pos_2, S.pz_2, S.rank_2, P);
+
+    // ideal score: sorted irregular weights merged with the all-zero rows' weights, last row first
+    const int nw = static_cast<int>(S.wfull.size());
+    if (ctx && nw >= kDeviceSortMin)
+    {
+        if (smk_sort_desc(ctx, S.wfull.data(), nw) != SMK_OK) throw std::runtime_error(smk_last_error(ctx));
+    }
+    else std::sort(S.wfull.begin(), S.wfull.end(), std::greater<R>());
+    R ideal = 0;
+    int pos = 0, head = 0;
+    auto take = [&](const R w) { ideal = pos == 0 ? w : ideal + w / lg2[pos + 1]; ++pos; };
+    int zb1 = n - n1, zb2 = n - n2;                              // zero rows of each child not yet passed, counting from the end
+    for (int row = n - 1; row >= 0; --row)
+    {
+        const bool a0 = !(C1[row] > 0), b0 = !(C2[row] > 0);
+        if (a0) --zb1;
+        if (b0) --zb2;
+        if (!(a0 && b0) || P[row] > 0) continue;
+        const R w = R(1) / discount_of(std::max(n1 + zb1, n2 + zb2));
+        while (head < nw && S.wfull[head] >= w) take(S.wfull[head++]);
+        take(w);
+    }
+    while (head < nw) take(S.wfull[head++]);
     return (dcg1 / ideal) * (dcg2 / ideal);
 }
 

@@ -11,6 +11,7 @@
 #include "host_internal.hpp"
 
 R compute_priority_on(smk_ctx* ctx, const R* W_parent, const R* W_child, int n);
+R compute_priority_plain(smk_ctx* ctx, const R* W_parent, const R* W_child, int n);
 
 namespace {
 
@@ -161,6 +162,8 @@ int smkh_flatclust(int alg, int m, int n, int k, double tol, int min_iter, int m
 
 // compute_priority (clust_hier_util.hpp:105-173) on host buffers — unit-testable without a GPU.
 double smkh_compute_priority(const double* W_parent, const double* W_child, int m) { return compute_priority(W_parent, W_child, m); }
+// the full-length evaluation the streaming one is checked against
+double smkh_compute_priority_plain(const double* W_parent, const double* W_child, int m) { return compute_priority_plain(nullptr, W_parent, W_child, m); }
 // the same with the large sorts on the GPU (what the tree driver uses): must give the identical value
 double smkh_compute_priority_gpu(const double* W_parent, const double* W_child, int m)
 {
