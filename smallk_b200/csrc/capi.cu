@@ -49,6 +49,7 @@ void ensure_scratch(smk_ctx* c)
 {
     c->status.reserve(ST_COUNT);
     c->counter.reserve(2);
+    if (!c->pinned) SMK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->pinned), 16 * sizeof(double), cudaHostAllocDefault));
     if (!c->ticket.p) { c->ticket.reserve(4); SMK_CUDA(cudaMemsetAsync(c->ticket.p, 0, 4 * sizeof(unsigned int), c->stream)); }
     c->partial.reserve(4096 + 512 * 256);
     c->acc.reserve(8);
@@ -145,6 +146,7 @@ void smk_destroy(smk_ctx* c)
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->pinned) cudaFreeHost(c->pinned);
     delete c;
 }
 

@@ -120,6 +120,7 @@ struct smk_ctx
     bool pg_ready = false;          // the last solver_step left both projected-gradient sums in acc[0..1] (fused rank-2)
     bool status_cached = false;     // status_host holds the status words as of the last solver_progress
     int status_host[smk::ST_COUNT] = {0, INT_MAX, 0, 0, 0};
+    double* pinned = nullptr;       // 16 doubles of page-locked host memory: per-iteration readbacks (PG sums, status words)
     float last_ms = 0.f;
     long long last_launches = 0;
 

@@ -17,10 +17,11 @@
 //                                  block partials of both projected-gradient sums (projected_gradient.hpp:125-171),
 //                                  which the last block adds up for ProgressEst::Update
 //
-// A compressed row / column is walked by 8 lanes that load 8 entries at a time and add them in storage order (the
-// order of the reference and of the generic SpMM: hierclust's priority score ranks the entries of W, so rounding-level
-// reordering shows up in it); those with more than kSpmmSeg entries (hubs: the multi-segment list of the segment
-// table) get a whole CTA, one group per kSpmmSeg-entry segment, segment sums added in order. The Gram / norm / PG
+// A compressed row / column is walked by 4 lanes (up to 64 entries) or a warp (up to kSpmmSeg) that load a batch of
+// entries at a time and add them in storage order (the order of the reference and of the generic SpMM: hierclust's
+// priority score ranks the entries of W, so rounding-level reordering shows up in it); those with more than kSpmmSeg
+// entries (hubs: the multi-segment list of the segment table; the generic SpMM segments them too, so no order to keep)
+// get a whole CTA, entries strided over its threads and a fixed tree. The Gram / norm / PG
 // reductions are fixed-shape trees over a grid whose size depends only on the matrix: reproducible run to run. The state left behind (H, Wt, WtW, HHt, WtA, HAt, gradH,
 // gradWt) is what the generic sequence leaves.
 #include <cfloat>
@@ -33,8 +34,6 @@ namespace smk {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kGroup = 8;                       // lanes per compressed row / column
-constexpr int kGroupsPerBlock = kThreads / kGroup;
 
 // sum over the block, returned to thread 0 (fixed shape: xor butterfly inside the warp, warps added in order)
 __device__ __forceinline__ double block_sum0(double v, double* red)
@@ -50,99 +49,182 @@ __device__ __forceinline__ double block_sum0(double v, double* red)
     return s;
 }
 
-// true in exactly one block: the one that arrives last. The ticket resets itself for the next launch.
+// true in exactly one block: the one that arrives last. Called after thread 0 has written this block's partials (they
+// are the only data other blocks of this launch read, so thread 0 alone fences). The ticket resets itself.
 __device__ __forceinline__ bool last_block(unsigned int* ticket, bool* flag)
 {
-    __threadfence();
-    __syncthreads();
     if (threadIdx.x == 0)
     {
+        __threadfence();
         const unsigned int t = atomicAdd(ticket, 1u);
         *flag = (t == gridDim.x - 1);
-        if (*flag) *ticket = 0u;
+        if (*flag) { *ticket = 0u; __threadfence(); }
     }
     __syncthreads();
-    if (*flag) __threadfence();
     return *flag;
 }
 
-// total of column c of the per-block partials (ncomp per block), by the calling block; valid in thread 0
-__device__ __forceinline__ double partial_total(const double* __restrict__ partial, int nblocks, int ncomp, int c, double* red)
+// three sums over the block at once, returned to thread 0 (same fixed shape as block_sum0, one barrier pair)
+__device__ __forceinline__ void block_sum3(double& a, double& b, double& c, double* red3)
 {
-    double s = 0.0;
-    for (int b = threadIdx.x; b < nblocks; b += kThreads) s += __ldcg(partial + static_cast<size_t>(b) * ncomp + c);
-    return block_sum0(s, red);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+    __syncthreads();
+    if (lane == 0) { red3[warp] = a; red3[8 + warp] = b; red3[16 + warp] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        a = 0.0; b = 0.0; c = 0.0;
+        for (int w = 0; w < (kThreads >> 5); ++w) { a += red3[w]; b += red3[8 + w]; c += red3[16 + w]; }
+    }
+}
+
+// totals of the per-block partials (ncomp <= 3 per block), by the calling block; valid in thread 0
+__device__ __forceinline__ void partial_totals(const double* __restrict__ partial, int nblocks, int ncomp, double& t0, double& t1, double& t2,
+                                               double* red3)
+{
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += kThreads)
+    {
+        const double* p = partial + static_cast<size_t>(i) * ncomp;
+        a += __ldcg(p); b += __ldcg(p + 1);
+        if (ncomp > 2) c += __ldcg(p + 2);
+    }
+    block_sum3(a, b, c, red3);
+    t0 = a; t1 = b; t2 = c;
 }
 
 // Sum over the stored entries [beg, end) of val * (X(:, idx) .* f), added ONE AFTER THE OTHER in storage order with a
 // single accumulator per component — the order of the reference's loops (sparse_gemm_ab_impl.hpp / _ba_impl.hpp) and
-// of the generic SpMM — while the loads run 8 wide: lane g of the group fetches entry o + g (coalesced index / value
-// reads, one gather each, the next batch already in flight), then all lanes replay the batch in order from shuffles.
-// Every lane of the group returns the same sum. The groups of a warp run different trip counts: each names only its
-// own lanes in the shuffles.
+// of the generic SpMM — while the loads run kGroup wide: lane g of the group fetches entry o + g (coalesced index /
+// value reads two batches ahead, the gather they feed one batch ahead), parks value and operand in the warp's
+// shared-memory stage (sv: 32 doubles, sx: 32 double2), and every lane of the group replays the batch in order from
+// broadcast reads: one LDS.64 + one LDS.128 + two DFMA per entry (handing the entries round by shuffles cost ~10
+// instructions per entry and made the kernels issue-bound). Every lane of the group returns the same sum. The groups
+// of a warp run different trip counts: each synchronises only its own lanes.
+template <int kGroup>
 __device__ __forceinline__ double2 walk_in_order(const unsigned int* __restrict__ idx, const double* __restrict__ val,
                                                  const double* __restrict__ X, unsigned int beg, unsigned int end,
-                                                 const double f0, const double f1)
+                                                 const double f0, const double f1, double* sv, double2* sx)
 {
-    const int lane = threadIdx.x & 31, g = lane & (kGroup - 1);
-    const unsigned int mask = 0xFFu << (lane & ~(kGroup - 1));
+    const int lane = threadIdx.x & 31, g = lane & (kGroup - 1), gb = lane & ~(kGroup - 1);
+    const unsigned int mask = kGroup == 32 ? 0xFFFFFFFFu : (((1u << (kGroup & 31)) - 1u) << gb);
     double a0 = 0.0, a1 = 0.0;
-    double nv = 0.0, nx0 = 0.0, nx1 = 0.0;
     unsigned int o = beg;
+    unsigned int i2 = 0;
+    double v1 = 0.0, v2 = 0.0, x10 = 0.0, x11 = 0.0;
+    bool ok2 = o + kGroup + g < end;
     if (o + g < end)
     {
+        v1 = val[o + g];
         const double2 x = *reinterpret_cast<const double2*>(X + 2 * static_cast<size_t>(idx[o + g]));
-        nv = val[o + g]; nx0 = x.x * f0; nx1 = x.y * f1;
+        x10 = x.x * f0; x11 = x.y * f1;
     }
+    if (ok2) { i2 = idx[o + kGroup + g]; v2 = val[o + kGroup + g]; }
     while (o < end)
     {
-        const double v = nv, x0 = nx0, x1 = nx1;
-        o += kGroup;
-        nv = 0.0; nx0 = 0.0; nx1 = 0.0;
-        if (o + g < end)
+        __syncwarp(mask);                       // the previous batch has been read
+        sv[lane] = v1; sx[lane] = make_double2(x10, x11);
+        __syncwarp(mask);
+        v1 = v2; x10 = 0.0; x11 = 0.0;
+        if (ok2)
         {
-            const double2 x = *reinterpret_cast<const double2*>(X + 2 * static_cast<size_t>(idx[o + g]));
-            nv = val[o + g]; nx0 = x.x * f0; nx1 = x.y * f1;
+            const double2 x = *reinterpret_cast<const double2*>(X + 2 * static_cast<size_t>(i2));
+            x10 = x.x * f0; x11 = x.y * f1;
         }
+        o += kGroup;
+        ok2 = o + kGroup + g < end;
+        i2 = 0; v2 = 0.0;
+        if (ok2) { i2 = idx[o + kGroup + g]; v2 = val[o + kGroup + g]; }
         // entries past the end carry v = x = 0: fma(0, 0, a) == a
 #pragma unroll
         for (int t = 0; t < kGroup; ++t)
         {
-            const double vt = __shfl_sync(mask, v, t, kGroup);
-            a0 = fma(vt, __shfl_sync(mask, x0, t, kGroup), a0);
-            a1 = fma(vt, __shfl_sync(mask, x1, t, kGroup), a1);
+            const double vt = sv[gb + t];
+            const double2 xt = sx[gb + t];
+            a0 = fma(vt, xt.x, a0);
+            a1 = fma(vt, xt.y, a1);
         }
     }
     return make_double2(a0, a1);
 }
 
-// A hub (more than kSpmmSeg entries), by the whole CTA: segments of kSpmmSeg entries as in the generic SpMM, one group
-// per segment, each summed in order, then the segment sums added in segment order. Valid in thread 0.
+// A hub (more than kSpmmSeg entries), by the whole CTA. The generic SpMM cuts such a row into segments and adds segment
+// sums, so there is no reference order to keep: entries strided over the 256 threads, fixed tree. Valid in thread 0.
 __device__ __forceinline__ double2 walk_hub(const unsigned int* __restrict__ idx, const double* __restrict__ val,
                                             const double* __restrict__ X, unsigned int beg, unsigned int end,
-                                            const double f0, const double f1, double2* part)
+                                            const double f0, const double f1, double* red)
 {
-    const int group = threadIdx.x / kGroup;
-    const unsigned int nseg = (end - beg + kSpmmSeg - 1) / kSpmmSeg;
     double a0 = 0.0, a1 = 0.0;
-    for (unsigned int base = 0; base < nseg; base += kGroupsPerBlock)
+    unsigned int o = beg + threadIdx.x;
+    for (; o + 3 * kThreads < end; o += 4 * kThreads)
     {
-        const unsigned int sg = base + group;
-        if (sg < nseg)
-        {
-            const unsigned int b = beg + sg * kSpmmSeg;
-            const double2 p = walk_in_order(idx, val, X, b, min(end, b + kSpmmSeg), f0, f1);
-            if ((threadIdx.x & (kGroup - 1)) == 0) part[group] = p;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0)
-        {
-            const unsigned int cnt = min(static_cast<unsigned int>(kGroupsPerBlock), nseg - base);
-            for (unsigned int q = 0; q < cnt; ++q) { a0 += part[q].x; a1 += part[q].y; }
-        }
-        __syncthreads();
+        const unsigned int i0 = idx[o], i1 = idx[o + kThreads], i2 = idx[o + 2 * kThreads], i3 = idx[o + 3 * kThreads];
+        const double v0 = val[o], v1 = val[o + kThreads], v2 = val[o + 2 * kThreads], v3 = val[o + 3 * kThreads];
+        const double2 x0 = *reinterpret_cast<const double2*>(X + 2 * static_cast<size_t>(i0));
+        const double2 x1 = *reinterpret_cast<const double2*>(X + 2 * static_cast<size_t>(i1));
+        const double2 x2 = *reinterpret_cast<const double2*>(X + 2 * static_cast<size_t>(i2));
+        const double2 x3 = *reinterpret_cast<const double2*>(X + 2 * static_cast<size_t>(i3));
+        a0 += v0 * (x0.x * f0); a1 += v0 * (x0.y * f1);
+        a0 += v1 * (x1.x * f0); a1 += v1 * (x1.y * f1);
+        a0 += v2 * (x2.x * f0); a1 += v2 * (x2.y * f1);
+        a0 += v3 * (x3.x * f0); a1 += v3 * (x3.y * f1);
     }
+    for (; o < end; o += kThreads)
+    {
+        const double v0 = val[o];
+        const double2 x0 = *reinterpret_cast<const double2*>(X + 2 * static_cast<size_t>(idx[o]));
+        a0 += v0 * (x0.x * f0); a1 += v0 * (x0.y * f1);
+    }
+    a0 = block_sum0(a0, red);
+    a1 = block_sum0(a1, red);
     return make_double2(a0, a1);
+}
+
+// The compressed rows [0, count) that are not hubs, by the warps of the first `blocks` CTAs: a warp takes 32 consecutive
+// rows (rows_per_warp: 4..32, fewer when there are few rows, so that the launch still fills the machine), walks the short ones (<= kShortRow entries) eight at a time with 4-lane groups and the others one at a time with
+// all 32 lanes, and hands every sum to finish(row, sum) in one lane.
+constexpr unsigned int kShortRow = 64;
+constexpr int kShortGroup = 4;                  // lanes per short row (mean row length at C4: 12)
+constexpr int kRowsPerRound = 32 / kShortGroup;
+
+template <typename Finish>
+__device__ __forceinline__ void walk_rows(int count, int blocks, int rows_per_warp, const unsigned int* __restrict__ ptr, const unsigned int* __restrict__ idx,
+                                          const double* __restrict__ val, const double* __restrict__ X, const double f0, const double f1,
+                                          double* stage_all, Finish&& finish)
+{
+    constexpr unsigned int kFull = 0xFFFFFFFFu;
+    double* sv = stage_all + 96 * (threadIdx.x >> 5);
+    double2* sx = reinterpret_cast<double2*>(sv + 32);
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = static_cast<long long>(blocks) * (kThreads / 32);
+    for (long long base = (static_cast<long long>(blockIdx.x) * (kThreads / 32) + (threadIdx.x >> 5)) * rows_per_warp; base < count;
+         base += nwarps * rows_per_warp)
+    {
+        const long long mine = base + lane;
+        unsigned int my_beg = 0, my_len = 0;
+        if (lane < rows_per_warp && mine < count) { my_beg = ptr[mine]; my_len = ptr[mine + 1] - my_beg; }
+        unsigned int wide = __ballot_sync(kFull, my_len > kShortRow && my_len <= static_cast<unsigned int>(kSpmmSeg));
+#pragma unroll 1
+        for (int r = 0; kRowsPerRound * r < rows_per_warp; ++r)
+        {
+            const int src = kRowsPerRound * r + lane / kShortGroup;
+            const unsigned int beg = __shfl_sync(kFull, my_beg, src), len = __shfl_sync(kFull, my_len, src);
+            if (src < rows_per_warp && base + src < count && len <= kShortRow)
+            {
+                const double2 sum = walk_in_order<kShortGroup>(idx, val, X, beg, beg + len, f0, f1, sv, sx);
+                if ((lane & (kShortGroup - 1)) == 0) finish(static_cast<unsigned int>(base + src), sum);
+            }
+        }
+        while (wide)
+        {
+            const int src = __ffs(wide) - 1;
+            wide &= wide - 1;
+            const unsigned int beg = __shfl_sync(kFull, my_beg, src), len = __shfl_sync(kFull, my_len, src);
+            const double2 sum = walk_in_order<32>(idx, val, X, beg, beg + len, f0, f1, sv, sx);
+            if (lane == 0) finish(static_cast<unsigned int>(base + src), sum);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -152,6 +234,7 @@ rank2_h_kernel(int n, double* __restrict__ H, const double* __restrict__ WtW, co
                int* __restrict__ status, int outer_iter)
 {
     __shared__ double red[kThreads / 32];
+    __shared__ double red3[24];
     __shared__ bool is_last;
     Rank2Solve sol;
     sol.init(WtW, false);
@@ -168,29 +251,29 @@ rank2_h_kernel(int n, double* __restrict__ H, const double* __restrict__ WtW, co
         *reinterpret_cast<double2*>(H + 2 * static_cast<size_t>(j)) = x;
         s00 += x.x * x.x; s01 += x.x * x.y; s11 += x.y * x.y;
     }
-    s00 = block_sum0(s00, red); s01 = block_sum0(s01, red); s11 = block_sum0(s11, red);
+    block_sum3(s00, s01, s11, red3);
     if (threadIdx.x == 0)
     {
         double* p = partial + 3 * static_cast<size_t>(blockIdx.x);
         __stcg(p, s00); __stcg(p + 1, s01); __stcg(p + 2, s11);
     }
     if (!last_block(ticket, &is_last)) return;
-    const double t00 = partial_total(partial, gridDim.x, 3, 0, red);
-    const double t01 = partial_total(partial, gridDim.x, 3, 1, red);
-    const double t11 = partial_total(partial, gridDim.x, 3, 2, red);
+    double t00, t01, t11;
+    partial_totals(partial, gridDim.x, 3, t00, t01, t11, red3);
     if (threadIdx.x == 0) { HHt[0] = t00; HHt[1] = t01; HHt[2] = t01; HHt[3] = t11; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-rank2_w_kernel(int m, int light_blocks, const unsigned int* __restrict__ rowptr, const unsigned int* __restrict__ colidx,
+rank2_w_kernel(int m, int light_blocks, int rows_per_warp, const unsigned int* __restrict__ rowptr, const unsigned int* __restrict__ colidx,
                const double* __restrict__ valr, int nheavy, const unsigned int* __restrict__ heavy,
                const double* __restrict__ H, double* __restrict__ HHt, double* __restrict__ HAt, double* __restrict__ Wu,
                double* __restrict__ partial, unsigned int* __restrict__ ticket, double* __restrict__ norms,
                double* __restrict__ WtW, int* __restrict__ status, int outer_iter)
 {
     __shared__ double red[kThreads / 32];
-    __shared__ double2 part[kGroupsPerBlock];
+    __shared__ double red3[24];
+    __shared__ __align__(16) double stage[96 * (kThreads / 32)];
     __shared__ bool is_last;
     Rank2Solve sol;
     sol.init(HHt, true);
@@ -202,27 +285,19 @@ rank2_w_kernel(int m, int light_blocks, const unsigned int* __restrict__ rowptr,
     double s00 = 0.0, s01 = 0.0, s11 = 0.0;
     if (static_cast<int>(blockIdx.x) < light_blocks)
     {
-        const int g = threadIdx.x & (kGroup - 1);
-        for (int i = blockIdx.x * kGroupsPerBlock + threadIdx.x / kGroup; i < m; i += light_blocks * kGroupsPerBlock)
-        {
-            const unsigned int beg = rowptr[i], end = rowptr[i + 1];
-            if (end - beg > static_cast<unsigned int>(kSpmmSeg)) continue;         // a hub: a whole CTA walks it below
-            const double2 b = walk_in_order(colidx, valr, H, beg, end, 1.0, 1.0);
-            if (g == 0)
-            {
-                const double2 x = sol.apply(b.x, b.y);
-                *reinterpret_cast<double2*>(HAt + 2 * static_cast<size_t>(i)) = b;
-                *reinterpret_cast<double2*>(Wu + 2 * static_cast<size_t>(i)) = x;
-                s00 += x.x * x.x; s01 += x.x * x.y; s11 += x.y * x.y;
-            }
-        }
+        walk_rows(m, light_blocks, rows_per_warp, rowptr, colidx, valr, H, 1.0, 1.0, stage, [&](const unsigned int i, const double2 b) {
+            const double2 x = sol.apply(b.x, b.y);
+            *reinterpret_cast<double2*>(HAt + 2 * static_cast<size_t>(i)) = b;
+            *reinterpret_cast<double2*>(Wu + 2 * static_cast<size_t>(i)) = x;
+            s00 += x.x * x.x; s01 += x.x * x.y; s11 += x.y * x.y;
+        });
     }
     else
     {
         for (int h = blockIdx.x - light_blocks; h < nheavy; h += gridDim.x - light_blocks)
         {
             const unsigned int i = heavy[h];
-            const double2 b = walk_hub(colidx, valr, H, rowptr[i], rowptr[i + 1], 1.0, 1.0, part);
+            const double2 b = walk_hub(colidx, valr, H, rowptr[i], rowptr[i + 1], 1.0, 1.0, red);
             if (threadIdx.x == 0)
             {
                 const double2 x = sol.apply(b.x, b.y);
@@ -232,16 +307,15 @@ rank2_w_kernel(int m, int light_blocks, const unsigned int* __restrict__ rowptr,
             }
         }
     }
-    s00 = block_sum0(s00, red); s01 = block_sum0(s01, red); s11 = block_sum0(s11, red);
+    block_sum3(s00, s01, s11, red3);
     if (threadIdx.x == 0)
     {
         double* p = partial + 3 * static_cast<size_t>(blockIdx.x);
         __stcg(p, s00); __stcg(p + 1, s01); __stcg(p + 2, s11);
     }
     if (!last_block(ticket, &is_last)) return;
-    const double t00 = partial_total(partial, gridDim.x, 3, 0, red);
-    const double t01 = partial_total(partial, gridDim.x, 3, 1, red);
-    const double t11 = partial_total(partial, gridDim.x, 3, 2, red);
+    double t00, t01, t11;
+    partial_totals(partial, gridDim.x, 3, t00, t01, t11, red3);
     if (threadIdx.x == 0)
     {
         // NormalizeAndScale: column norms of W (normalize.hpp:118-138; < eps throws, :47-48)
@@ -259,7 +333,7 @@ rank2_w_kernel(int m, int light_blocks, const unsigned int* __restrict__ rowptr,
 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-rank2_grad_kernel(int n, int m, int col_blocks, int heavy_blocks, const unsigned int* __restrict__ colptr,
+rank2_grad_kernel(int n, int m, int col_blocks, int heavy_blocks, int rows_per_warp, const unsigned int* __restrict__ colptr,
                   const unsigned int* __restrict__ rowidx, const double* __restrict__ val, int nheavy,
                   const unsigned int* __restrict__ heavy, const double* __restrict__ Wu, const double* __restrict__ norms,
                   const double* __restrict__ WtW, const double* __restrict__ HHt, double* __restrict__ H,
@@ -268,7 +342,8 @@ rank2_grad_kernel(int n, int m, int col_blocks, int heavy_blocks, const unsigned
                   double* __restrict__ acc)
 {
     __shared__ double red[kThreads / 32];
-    __shared__ double2 part[kGroupsPerBlock];
+    __shared__ double red3[24];
+    __shared__ __align__(16) double stage[96 * (kThreads / 32)];
     __shared__ bool is_last;
     const double n0 = norms[0], n1 = norms[1];
     const double r0 = 1.0 / n0, r1 = 1.0 / n1;
@@ -289,21 +364,14 @@ rank2_grad_kernel(int n, int m, int col_blocks, int heavy_blocks, const unsigned
         };
         if (b < col_blocks)
         {
-            const int g = threadIdx.x & (kGroup - 1);
-            for (int j = b * kGroupsPerBlock + threadIdx.x / kGroup; j < n; j += col_blocks * kGroupsPerBlock)
-            {
-                const unsigned int beg = colptr[j], end = colptr[j + 1];
-                if (end - beg > static_cast<unsigned int>(kSpmmSeg)) continue;
-                const double2 a = walk_in_order(rowidx, val, Wu, beg, end, r0, r1);
-                if (g == 0) finish_col(j, a.x, a.y);
-            }
+            walk_rows(n, col_blocks, rows_per_warp, colptr, rowidx, val, Wu, r0, r1, stage, [&](const unsigned int j, const double2 a) { finish_col(j, a.x, a.y); });
         }
         else
         {
             for (int h = b - col_blocks; h < nheavy; h += heavy_blocks)
             {
                 const unsigned int j = heavy[h];
-                const double2 a = walk_hub(rowidx, val, Wu, colptr[j], colptr[j + 1], r0, r1, part);
+                const double2 a = walk_hub(rowidx, val, Wu, colptr[j], colptr[j + 1], r0, r1, red);
                 if (threadIdx.x == 0) finish_col(j, a.x, a.y);
             }
         }
@@ -326,16 +394,25 @@ rank2_grad_kernel(int n, int m, int col_blocks, int heavy_blocks, const unsigned
             if (q1 < 0.0 || w1 > 0.0) pg_w += q1 * q1;
         }
     }
-    pg_w = block_sum0(pg_w, red); pg_h = block_sum0(pg_h, red);
+    double unused = 0.0;
+    block_sum3(pg_w, pg_h, unused, red3);
     if (threadIdx.x == 0)
     {
         double* p = partial + 2 * static_cast<size_t>(blockIdx.x);
         __stcg(p, pg_w); __stcg(p + 1, pg_h);
     }
     if (!last_block(ticket, &is_last)) return;
-    const double tw = partial_total(partial, gridDim.x, 2, 0, red);
-    const double th = partial_total(partial, gridDim.x, 2, 1, red);
+    double tw, th;
+    partial_totals(partial, gridDim.x, 2, tw, th, unused, red3);
     if (threadIdx.x == 0) { acc[0] = tw; acc[1] = th; }
+}
+
+// rows a warp takes per trip: as few as keeps every warp of `cap` CTAs busy once (short dependent chains), at most 32
+int rows_per_warp_for(int count, int cap)
+{
+    int rpw = kRowsPerRound;
+    while (rpw < 32 && static_cast<long long>(cap) * (kThreads / 32) * rpw < count) rpw *= 2;
+    return rpw;
 }
 
 } // namespace
@@ -352,18 +429,20 @@ void rank2_fused_step(smk_ctx* c, double* Wu)
                                                    c->status.p, c->steps_done);
     SMK_LAUNCH_CHECK();
     {
-        const int light = std::max(1, std::min(ceil_div(m, kGroupsPerBlock), cap));
+        const int rpw = rows_per_warp_for(m, cap);
+        const int light = std::max(1, std::min(ceil_div(m, rpw * (kThreads / 32)), cap));
         const int heavy = S.seg_rows.nmulti > 0 ? std::min(S.seg_rows.nmulti, sms) : 0;
-        rank2_w_kernel<<<light + heavy, kThreads, 0, c->stream>>>(m, light, S.rowptr.p, S.colidx.p, S.valr.p, S.seg_rows.nmulti,
+        rank2_w_kernel<<<light + heavy, kThreads, 0, c->stream>>>(m, light, rpw, S.rowptr.p, S.colidx.p, S.valr.p, S.seg_rows.nmulti,
                                                                   S.seg_rows.multi_col.p, c->H.p, c->HHt.p, c->HAt.p, Wu, c->partial.p,
                                                                   c->ticket.p + 1, c->norms.p, c->WtW.p, c->status.p, c->steps_done);
         SMK_LAUNCH_CHECK();
     }
     {
-        const int cols = std::max(1, std::min(ceil_div(n, kGroupsPerBlock), cap));
+        const int rpw = rows_per_warp_for(n, cap);
+        const int cols = std::max(1, std::min(ceil_div(n, rpw * (kThreads / 32)), cap));
         const int heavy = S.seg_cols.nmulti > 0 ? std::min(S.seg_cols.nmulti, sms) : 0;
         const int rows = std::max(1, std::min(ceil_div(m, kThreads), 2 * sms));
-        rank2_grad_kernel<<<cols + heavy + rows, kThreads, 0, c->stream>>>(n, m, cols, heavy, S.colptr.p, S.rowidx.p, S.val.p,
+        rank2_grad_kernel<<<cols + heavy + rows, kThreads, 0, c->stream>>>(n, m, cols, heavy, rpw, S.colptr.p, S.rowidx.p, S.val.p,
                                                                           S.seg_cols.nmulti, S.seg_cols.multi_col.p, Wu, c->norms.p,
                                                                           c->WtW.p, c->HHt.p, c->H.p, c->WtA.p, c->gradH.p, c->Wt.p,
                                                                           c->HAt.p, c->gradWt.p, c->partial.p, c->ticket.p + 2, c->acc.p);

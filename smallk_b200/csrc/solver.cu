@@ -267,10 +267,15 @@ int solver_progress(smk_ctx* c, double* metric)
             if (c->w_sharded) allreduce_sum(c, c->acc.p, 2);
             else allreduce_sum(c, c->acc.p + 1, 1);
         }
-        SMK_CUDA(cudaMemcpyAsync(h, c->acc.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        if (c->nranks <= 1)     // the status words ride on the same synchronisation (solver_fail_iter reads them next)
-            SMK_CUDA(cudaMemcpyAsync(c->status_host, c->status.p, sizeof(c->status_host), cudaMemcpyDeviceToHost, c->stream));
+        // page-locked landing zone: [0..1] the two sums, [2..] the status words, which ride on the same synchronisation
+        // when there is one rank (solver_fail_iter reads them next)
+        int* st_pinned = reinterpret_cast<int*>(c->pinned + 2);
+        SMK_CUDA(cudaMemcpyAsync(c->pinned, c->acc.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if (c->nranks <= 1)
+            SMK_CUDA(cudaMemcpyAsync(st_pinned, c->status.p, sizeof(c->status_host), cudaMemcpyDeviceToHost, c->stream));
         SMK_CUDA(cudaStreamSynchronize(c->stream));
+        h[0] = c->pinned[0]; h[1] = c->pinned[1];
+        if (c->nranks <= 1) { for (int i = 0; i < ST_COUNT; ++i) c->status_host[i] = st_pinned[i]; }
         c->status_cached = c->nranks <= 1;
         const double pg = sqrt(h[0] + h[1]);
         if (pg != pg) { c->err = "ProjectedGradientNorm: NaN"; return SMK_FAILURE; }
