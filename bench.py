@@ -278,11 +278,14 @@ def main():
     peak, peak_src = measured_fp64_peak() if rank == 0 else (None, None)
     flops_launch = 2.0 * k * m * n_loc
     achieved = flops_launch / (0.5 * (t_wta + t_hat)) * 1e-9
+    # dram__bytes_read + dram__bytes_write of one launch of the dominant kernel, from the committed ncu --set full capture
+    # (profiles/ncu_r01_c2_gemm_skinny.txt); it describes the full-size single-GPU product only
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
+    tpath = os.path.join(ROOT, "profiles", "ncu_r01_c2_gemm_traffic.json")
+    if os.path.exists(tpath) and world == 1 and m == 20000 and n == 20000 and k == 64:
         try:
-            traffic = json.load(open(tpath)).get("gemm_skinny_kernel_dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = float(tj["dram_bytes_read"]) + float(tj["dram_bytes_write"])
         except Exception:
             traffic = None
 
@@ -355,6 +358,7 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "algorithmic_bytes_per_launch": 8.0 * (m * n_loc + k * (m + n_loc)),
                          "kernel": "gemm_skinny_kernel (W'A and H A', 2*k*m*n flop per launch)",
                          "launch_ms": {"WtA": t_wta, "HAt": t_hat}, "peak_source": peak_src,
                          "step_frac_of_peak": flops_per_iter(m, n, k) / world / (ms_per_step * 1e-3) * 1e-12 / peak if peak else None},
