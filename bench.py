@@ -5,7 +5,7 @@ Workload (BASELINE.json configs[1]): dense uniform-random A 2
 k = 64, BPP, W0/H0 injected. One "step" = one outer iteration = one solver(A, W, H, gradW, gradH) call
 plus its progress-metric update (common/include/nmf_solve_generic.hpp:70-98).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--size M]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--size M] [--workload c2|c3|c4]
 
 * value     : outer iterations / s with A, W, H resident in HBM (CUDA events on the launching stream,
               barrier + synchronize on both sides, max over ranks).
@@ -185,10 +185,25 @@ def main():
     ap.add_argument("--impl", default="smallk_b200")
     ap.add_argument("--size", type=int, default=20000, help="m = n of the dense workload (20000 = BASELINE C2)")
     ap.add_argument("--ref-cols", type=int, default=1000, help="columns in the CPU sample of the reference arm")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
+                    help="c2 (default): the headline dense BPP workload; c3 / c4: the sparse HALS and hierclust configurations, one GPU "
+                         "(tools/bench_sparse.py)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    if args.workload != "c2":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return                                   # one GPU: the other ranks of a torchrun launch have nothing to do
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the reference arm is wired for the headline workload (c2); "
+                              f"--workload {args.workload} reports the reference in its cpu_baseline"}), flush=True)
+            return
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_sparse
+        (bench_sparse.run_c3 if args.workload == "c3" else bench_sparse.run_c4)(args)
+        return
 
     if args.impl == "reference":
         run_reference_arm(args)

@@ -1,0 +1,217 @@
+"""bench.py --workload c3 | c4: the sparse configurations of BASELINE.json measured with the same JSON contract as the
+headline line (bench.py's default, C2). One GPU; not part of the driver's default run.
+
+  c3  sparse HALS NMF on the synthetic tf-idf-like CSC 1,000,000 x 200,000, k = 128
+      step      = one outer iteration: Solver_Generic_HALS_Da::operator() + the progress update
+      roofline  = the two sparse products (W'A over the CSC, H A' over the CSR): algorithmic bytes per launch
+                  (12 nnz + 4 (cols + 1) index/value bytes + the dense operand read once + the output written once)
+                  / measured launch time, against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  c4  hierclust (HierNMF2) on the synthetic ~320k-node graph, 64 leaves
+      step      = one rank-2 outer iteration; value = iterations / time inside the factorizations,
+                  e2e = iterations / wall time of the whole Clust call on host CSC arrays (upload, extraction,
+                  random inits, factorizations, priority scores, tree)
+      roofline  = one rank-2 iteration on the root matrix: 2 (12 nnz + 4 (n + 1)) + 128 (m + n) bytes / device time
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+METRIC = "nmf_outer_iterations_per_second"
+UNIT = "iter/s"
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy, burst)"
+        except Exception:
+            pass
+    return 6550.0, "fallback: B200_PROFILING.md measured copy bandwidth (MEASURED_PEAKS.json absent)"
+
+
+def _clock_sampler(index):
+    import bench
+    s = bench.ClockSampler(index)
+    s.start()
+    return s
+
+
+def run_c3(args):
+    import torch
+    import smallk_b200 as sk
+    import workloads
+    m, n, per_col, k = 1000000, 200000, 500, 128
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    colp, rowi, val = workloads.c3_tfidf_csc(m, n, per_col)
+    nnz = int(colp[-1])
+    ctx = sk.Context(0)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    ctx.load_csc((m, n), colp, rowi, val)
+    W0 = np.asfortranarray(np.random.default_rng(22).random((m, k)))
+    # H0 scaled so that mean(W0*H0) = mean(A): from W0*H0 >> A, HALS clamps whole factors to zero in its first sweep
+    H0 = np.asfortranarray(np.random.default_rng(23).random((k, n))) * (float(val.sum()) / m / n / (0.25 * k))
+    opts = sk.make_options(m, n, k, algorithm="HALS", tol=1e-15, min_iter=1, max_iter=args.warmup + args.steps + 8, normalize=False)
+    ctx.solver_begin(W0, H0, opts)
+    metric = None
+    for _ in range(args.warmup):
+        ctx.solver_step(1)
+        metric = ctx.solver_progress()
+    sampler = _clock_sampler(0)
+    launches = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        ctx.solver_step(1)
+        launches += ctx.last_step()[1] + 4
+        metric = ctx.solver_progress()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_per_step = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop()
+    t_wta = ctx.time_product(0, reps=5)
+    t_hat = ctx.time_product(1, reps=5)
+    tiers = {"WtA": ctx.spmm_tier_info(0), "HAt": ctx.spmm_tier_info(1)}
+    peak, peak_src = hbm_peak()
+    bytes_wta = 12.0 * nnz + 4.0 * (n + 1) + 8.0 * k * (m + n)       # A once, Wt read once, W'A written once
+    bytes_hat = 12.0 * nnz + 4.0 * (m + 1) + 8.0 * k * (n + m)
+    achieved = (bytes_wta + bytes_hat) / ((t_wta + t_hat) * 1e-3) * 1e-9
+    B_iter = 2 * (12.0 * nnz + 4 * (n + 1)) + 64.0 * k * (m + n)      # SURVEY §8d compulsory bytes per iteration
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_r01_c3_spmm_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = float(json.load(open(tp))["dram_bytes_both_products"])
+        except Exception:
+            traffic = None
+    ctx.close()
+    del ctx
+
+    e2e = None
+    if not args.no_e2e:
+        ctx2 = sk.Context(0)
+        W = W0.copy(order="F"); H = H0.copy(order="F")
+        o2 = sk.make_options(m, n, k, algorithm="HALS", tol=1e-15, min_iter=args.steps, max_iter=args.steps, normalize=False)
+        t0 = time.perf_counter()
+        ctx2.load_csc((m, n), colp, rowi, val)
+        ctx2.nmf(W, H, o2)
+        t_e2e = time.perf_counter() - t0
+        e2e = {"value": args.steps / t_e2e, "unit": UNIT,
+               "h2d_bytes_per_step": (12.0 * nnz + 4.0 * (n + 1) + 8.0 * k * (m + n)) / args.steps,
+               "d2h_bytes_per_step": 8.0 * k * (m + n) / args.steps,
+               "note": f"smk_load_csc (CSR and segment tables built on the device) + smk_nmf ({args.steps} iterations) on host arrays; wall clock"}
+        ctx2.close()
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            from oracle import Ref
+            ms, ns = 100000, 20000
+            cp, ri, va = workloads.c3_tfidf_csc(ms, ns, per_col, seed=21)
+            Ws = np.asfortranarray(np.random.default_rng(22).random((ms, k)))
+            Hs = np.asfortranarray(np.random.default_rng(23).random((k, ns))) * (float(va.sum()) / ms / ns / (0.25 * k))
+            cores = os.cpu_count() or 1
+            o = Ref().nmf_sparse((ms, ns), cp, ri, va, Ws, Hs, alg="HALS", tol=1e-15, min_iter=3, max_iter=3, max_threads=cores, timed=True)
+            sec = o["elapsed_us"] * 1e-6 / 3
+            f_full = 4.0 * k * nnz + 6.0 * k * k * (m + n)
+            f_s = 4.0 * k * int(cp[-1]) + 6.0 * k * k * (ms + ns)
+            cpu = {"value": 1.0 / (sec * f_full / f_s), "unit": UNIT, "cores": cores, "kind": "reference",
+                   "sample": f"reference sparse HALS (oracle/_ref) on {ms}x{ns} (nnz {int(cp[-1])}) of the same generator, 3 iterations, "
+                             f"{cores} threads, seconds scaled to the full size by the flop ratio {f_full / f_s:.1f}"}
+        except Exception as ex:
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"unavailable: {ex}"}
+
+    line = {"metric": METRIC, "value": 1000.0 / ms_per_step, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"sparse HALS NMF {m}x{n} nnz={nnz} k={k} (BASELINE configs[2], SURVEY C3)", "algorithm": "HALS", "k": k,
+                       "l2": "inputs larger than L2 (CSC + CSR 2.2 GB, W 1 GB)", "step": "solver() + PG_RATIO progress update"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "spmm_seg_tier_kernel (W'A) + spmm_seg_slab_kernel x4 (H A'): algorithmic bytes of both products / both launch times",
+                         "algorithmic_bytes": bytes_wta + bytes_hat, "launch_ms": {"WtA": t_wta, "HAt": t_hat},
+                         "gathered_TBs": {"WtA": nnz * k * 8 / t_wta * 1e-9, "HAt": nnz * k * 8 / t_hat * 1e-9},
+                         "residency_classes(on,smem_rows,share)": tiers, "peak_source": peak_src,
+                         "step_compulsory_GB": B_iter * 1e-9, "step_frac_of_peak": B_iter / (ms_per_step * 1e-3) * 1e-9 / peak},
+            "cpu_baseline": cpu, "progress_metric_last": metric}
+    print(json.dumps(line), flush=True)
+
+
+def run_c4(args):
+    import torch
+    import smallk_b200 as sk
+    import workloads
+    n, edges, clusters = 320000, 2000000, 64
+    torch.cuda.set_device(0)
+    colp, rowi, val = workloads.c4_graph(n, edges)
+    nnz = int(colp[-1])
+    kw = dict(csc=(colp, rowi, val), shape=(n, n), tol=1e-4, min_iter=5, max_iter=5000, seed=32)
+    for _ in range(max(1, args.warmup // 3)):
+        sk.hierclust(num_clusters=4, **kw)                       # warm-up: allocations, lazy module load
+    sampler = _clock_sampler(0)
+    out = sk.hierclust(num_clusters=clusters, **kw)
+    clocks = sampler.stop()
+    iters = int(out["iterations"])
+    prof = out["profile"]
+
+    # one rank-2 iteration on the root matrix, operands hot in L2, no host synchronisation in between
+    ctx = sk.Context(0)
+    ctx.load_csc((n, n), colp, rowi, val)
+    rng = np.random.default_rng(1)
+    opts = sk.make_options(n, n, 2, algorithm="RANK2", tol=1e-15, min_iter=1, max_iter=100000, normalize=False)
+    ctx.solver_begin(rng.random((n, 2)), rng.random((2, n)), opts)
+    ctx.solver_step(20)
+    ctx.solver_step(200)
+    ms200, l200 = ctx.last_step()
+    ctx.close()
+    root_us = ms200 / 200 * 1e3
+    B_root = 2 * (12.0 * nnz + 4 * (n + 1)) + 128.0 * (n + n)
+    peak, peak_src = hbm_peak()
+    achieved = B_root / (root_us * 1e-6) * 1e-9
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            from oracle import Ref
+            ns, es, cs = 40000, 250000, 16
+            cp, ri, va = workloads.c4_graph(ns, es)
+            kws = dict(csc=(cp, ri, va), shape=(ns, ns), num_clusters=cs, tol=1e-4, min_iter=5, max_iter=5000, seed=32)
+            g = sk.hierclust(**kws)
+            t0 = time.perf_counter()
+            r = Ref().hierclust(max_threads=1, **kws)
+            ref_s = time.perf_counter() - t0
+            same = bool(np.array_equal(g["assignments"], r["assignments"]))
+            cpu = {"value": int(g["iterations"]) / ref_s, "unit": UNIT, "cores": 1, "kind": "reference",
+                   "sample": f"reference ClustSparse (oracle/_ref) on the {ns}-node graph of the same generator, {cs} leaves, one thread (its "
+                             f"fastest setting and the one with the sequential initialiser): {ref_s:.2f} s for the {int(g['iterations'])} rank-2 "
+                             f"iterations this library ran in {g['elapsed_s']:.2f} s; identical assignments: {same}"}
+        except Exception as ex:
+            cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"unavailable: {ex}"}
+
+    line = {"metric": METRIC, "value": iters / prof["factor_s"], "unit": UNIT, "n_gpus": 1, "steps": iters, "warmup": args.warmup,
+            "ms_per_step": prof["factor_s"] / iters * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"hierclust rank-2 NMF, {n} nodes / {nnz} stored entries, {clusters} leaves (BASELINE configs[3], SURVEY C4)",
+                       "algorithm": "RANK2", "k": 2, "nmf_count": int(out["nmf_count"]),
+                       "l2": "node matrices fit L2 below the root; the run is latency-bound, not cache-bound",
+                       "step": "one rank-2 outer iteration inside smk_nmf (solver + progress update + stop test), summed over all node factorizations"},
+            "clocks": clocks,
+            "e2e": {"value": iters / out["elapsed_s"], "unit": UNIT, "h2d_bytes_per_step": (12.0 * nnz + 4 * (n + 1)) / iters,
+                    "d2h_bytes_per_step": 0.0, "seconds": out["elapsed_s"], "profile_s": prof,
+                    "note": "ClustSparse on host CSC arrays: upload, per-node extraction, random inits, factorizations (factors up / down per node), "
+                            "priority scores, tree; wall clock of the whole call"},
+            "gpu_launches": 3 * iters,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "rank2_h_kernel + rank2_w_kernel + rank2_grad_kernel: one iteration on the root matrix",
+                         "algorithmic_bytes": B_root, "launch_us": root_us, "launches_per_iteration": l200 / 200, "peak_source": peak_src},
+            "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
