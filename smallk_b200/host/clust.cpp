@@ -190,6 +190,8 @@ struct PriorityScratch
 {
     std::vector<int> pos_p, pos_1, pos_2, pz_1, pz_2, other, rank_p, rank_1, rank_2, perm, tmp_i;
     std::vector<R> keys, wfull, wpart, wsort;
+    std::vector<std::pair<R, int>> pairs;
+    std::vector<unsigned long long> zero_1, zero_2, zero_all;   // one bit per row: zero in child 1 / child 2 / everywhere
 };
 PriorityScratch g_ps;
 
@@ -205,7 +207,17 @@ void sort_rows_desc(const R* v, std::vector<int>& rows, smk_ctx* ctx)
         for (int i = 0; i < cnt; ++i) g_ps.tmp_i[i] = rows[g_ps.perm[i]];
         rows.swap(g_ps.tmp_i);
     }
-    else std::sort(rows.begin(), rows.end(), [v](int a, int b) { return v[a] > v[b] || (v[a] == v[b] && a < b); });
+    else
+    {
+        // (value, row) pairs sort on contiguous keys; the order is the same total order
+        std::vector<std::pair<R, int>>& pr = g_ps.pairs;
+        pr.resize(cnt);
+        for (int i = 0; i < cnt; ++i) pr[i] = std::make_pair(v[rows[i]], rows[i]);
+        std::sort(pr.begin(), pr.end(), [](const std::pair<R, int>& a, const std::pair<R, int>& b) {
+            return a.first > b.first || (a.first == b.first && a.second < b.second);
+        });
+        for (int i = 0; i < cnt; ++i) rows[i] = pr[i].second;
+    }
 }
 
 } // namespace
@@ -213,35 +225,42 @@ void sort_rows_desc(const R* v, std::vector<int>& rows, smk_ctx* ctx)
 R compute_priority_on(smk_ctx* ctx, const R* W_parent, const R* W_child, const int n)
 {
     const R* P = W_parent; const R* C1 = W_child; const R* C2 = W_child + n;
-    // pass 0: counts; anything but non-negative finite entries goes the plain way
-    int np = 0, n1 = 0, n2 = 0;
+    PriorityScratch& S = g_ps;
+    S.pos_p.clear(); S.pos_1.clear(); S.pos_2.clear(); S.pz_1.clear(); S.pz_2.clear(); S.other.clear();
+    if (static_cast<int>(S.rank_p.size()) < n) { S.rank_p.resize(n); S.rank_1.resize(n); S.rank_2.resize(n); }
+    const int nwords = (n + 63) / 64;
+    S.zero_1.assign(nwords, 0ull); S.zero_2.assign(nwords, 0ull); S.zero_all.assign(nwords, 0ull);
+    // one pass over the rows: positive rows of each vector, the zero-row counts that will be looked up (the number of
+    // positives is added once it is known), and three bit masks for the reverse pass of the ideal sum. Anything but
+    // non-negative finite entries goes the plain way.
+    int z1 = 0, z2 = 0;
     bool regular = true;
     for (int i = 0; i < n; ++i)
     {
-        const R p = P[i], a = C1[i], b = C2[i];
-        if (!(p >= 0) || !(a >= 0) || !(b >= 0)) { regular = false; break; }
-        np += p > 0; n1 += a > 0; n2 += b > 0;
+        const R pv = P[i], av = C1[i], bv = C2[i];
+        if (!(pv >= 0) || !(av >= 0) || !(bv >= 0)) { regular = false; break; }
+        const bool p = pv > 0, a = av > 0, b = bv > 0;
+        const unsigned long long bit = 1ull << (i & 63);
+        if (p) S.pos_p.push_back(i);
+        if (a) S.pos_1.push_back(i); else { if (p || b) S.rank_1[i] = z1; if (p) S.pz_1.push_back(i); ++z1; S.zero_1[i >> 6] |= bit; }
+        if (b) S.pos_2.push_back(i); else { if (p || a) S.rank_2[i] = z2; if (p) S.pz_2.push_back(i); ++z2; S.zero_2[i >> 6] |= bit; }
+        if (!p) { if (a || b) S.other.push_back(i); else S.zero_all[i >> 6] |= bit; }
     }
     if (!regular) return compute_priority_plain(ctx, W_parent, W_child, n);
+    const int np = static_cast<int>(S.pos_p.size()), n1 = static_cast<int>(S.pos_1.size()), n2 = static_cast<int>(S.pos_2.size());
     const int n_part = np;
     if (n_part <= 1) return R(-3);
     g_logs.ensure(n);
     const std::vector<double>& ln = g_logs.ln;
     const std::vector<double>& lg2 = g_logs.lg2;
     auto discount_of = [&](const int worst) { const R d = ln[n - worst]; return d == 0 ? ln[2] : d; };
-
-    PriorityScratch& S = g_ps;
-    S.pos_p.clear(); S.pos_1.clear(); S.pos_2.clear(); S.pz_1.clear(); S.pz_2.clear(); S.other.clear();
-    if (static_cast<int>(S.rank_p.size()) < n) { S.rank_p.resize(n); S.rank_1.resize(n); S.rank_2.resize(n); }
-    // pass A: positive rows of each vector; ranks of the zero rows that will be looked up
-    int z1 = 0, z2 = 0;
-    for (int i = 0; i < n; ++i)
+    // zero rows rank after the positives
+    for (const int row : S.pz_1) S.rank_1[row] += n1;
+    for (const int row : S.pz_2) S.rank_2[row] += n2;
+    for (const int row : S.other)
     {
-        const bool p = P[i] > 0, a = C1[i] > 0, b = C2[i] > 0;
-        if (p) S.pos_p.push_back(i);
-        if (a) S.pos_1.push_back(i); else { if (p || b) S.rank_1[i] = n1 + z1; if (p) S.pz_1.push_back(i); ++z1; }
-        if (b) S.pos_2.push_back(i); else { if (p || a) S.rank_2[i] = n2 + z2; if (p) S.pz_2.push_back(i); ++z2; }
-        if (!p && (a || b)) S.other.push_back(i);
+        if (!(C1[row] > 0)) S.rank_1[row] += n1;
+        if (!(C2[row] > 0)) S.rank_2[row] += n2;
     }
     sort_rows_desc(P, S.pos_p, ctx);
     sort_rows_desc(C1, S.pos_1, ctx);
@@ -299,15 +318,21 @@ R compute_priority_on(smk_ctx* ctx, const R* W_parent, const R* W_child, const i
     int pos = 0, head = 0;
     auto take = [&](const R w) { ideal = pos == 0 ? w : ideal + w / lg2[pos + 1]; ++pos; };
     int zb1 = n - n1, zb2 = n - n2;                              // zero rows of each child not yet passed, counting from the end
-    for (int row = n - 1; row >= 0; --row)
+    for (int wd = nwords - 1; wd >= 0; --wd)
     {
-        const bool a0 = !(C1[row] > 0), b0 = !(C2[row] > 0);
-        if (a0) --zb1;
-        if (b0) --zb2;
-        if (!(a0 && b0) || P[row] > 0) continue;
-        const R w = R(1) / discount_of(std::max(n1 + zb1, n2 + zb2));
-        while (head < nw && S.wfull[head] >= w) take(S.wfull[head++]);
-        take(w);
+        const unsigned long long m1 = S.zero_1[wd], m2 = S.zero_2[wd], ma = S.zero_all[wd];
+        if (ma == 0) { zb1 -= __builtin_popcountll(m1); zb2 -= __builtin_popcountll(m2); continue; }
+        const int top = (wd == nwords - 1) ? ((n - 1) & 63) : 63;
+        for (int bpos = top; bpos >= 0; --bpos)
+        {
+            const unsigned long long bit = 1ull << bpos;
+            if (m1 & bit) --zb1;
+            if (m2 & bit) --zb2;
+            if (!(ma & bit)) continue;
+            const R w = R(1) / discount_of(std::max(n1 + zb1, n2 + zb2));
+            while (head < nw && S.wfull[head] >= w) take(S.wfull[head++]);
+            take(w);
+        }
     }
     while (head < nw) take(S.wfull[head++]);
     return (dcg1 / ideal) * (dcg2 / ideal);
