@@ -662,11 +662,13 @@ void spmm_gather_seg(cudaStream_t stream, int ncols, const SegTable& T, const un
     const bool aligned16 = (addr_bits & 15) == 0;
     const bool wide256 = k >= 64 && k <= 256 && (ldb & 3) == 0 && (ldo & 3) == 0 && (addr_bits & 31) == 0 && ngather > 0 && ngather < (1 << 30);
     const bool tiers = T.tiers_on && T.tier_k == k;
-    static const bool slab_enabled = [] { const char* e = getenv("SMK_SPMM_SLAB"); return !(e && atoi(e) == 0); }();
+    // SMK_SPMM_SLAB: 0 = never, 2 = whenever the shape allows (tests), otherwise by operand size
+    const char* slab_env = getenv("SMK_SPMM_SLAB");
+    const int slab_mode = slab_env ? atoi(slab_env) : 1;
     // operand larger than L2 can keep, 32-row slab small enough to stay: one launch per slab
     const size_t operand_bytes = static_cast<size_t>(ngather > 0 ? ngather : 0) * k * sizeof(double);
-    if (wide256 && !tiers && slab_enabled && (k % kSlab) == 0 && operand_bytes > kTierMinOperandBytes &&
-        static_cast<size_t>(ngather) * kSlab * sizeof(double) <= kSlabMaxBytes)
+    const bool slab_fits = operand_bytes > kTierMinOperandBytes && static_cast<size_t>(ngather) * kSlab * sizeof(double) <= kSlabMaxBytes;
+    if (wide256 && !tiers && (k % kSlab) == 0 && slab_mode != 0 && (slab_fits || slab_mode == 2))
     {
         const int groups_per_block = 256 / 8;
         const int blocks = std::max(1, std::min(ceil_div(T.nseg, groups_per_block), 2 * num_sms));

@@ -241,6 +241,50 @@ def test_sparse_gemm_with_residency_classes_matches_oracle(gpu, oracle, k, monke
     assert not gpu.spmm_tier_info(1)[0]                                      # the column gathers are not: plain loads
 
 
+@pytest.mark.parametrize("k", [64, 96, 128, 256])
+def test_sparse_gemm_in_k_slabs_matches_oracle(gpu, oracle, k, monkeypatch):
+    """The k-slab SpMM (one launch per 32 rows of the dense operand; picked by operand size in production) forced on a small
+    matrix: all four product variants, with and without beta, ragged columns and empty rows included."""
+    monkeypatch.setenv("SMK_SPMM_SLAB", "2")
+    m, n = 900, 700
+    S = _zipf_csc(m, n, 40, 29)
+    rng = np.random.default_rng(100 + k)
+    gpu.load_csc((m, n), S.indptr, S.indices, S.data)
+    for variant in (0, 1, 2, 3):
+        shapeB = {0: (n, k), 1: (k, n), 2: (k, m), 3: (m, k)}[variant]
+        shapeC = (m, k) if variant < 2 else (k, n)
+        B = rng.random(shapeB); C = rng.random(shapeC)
+        for alpha, beta in [(1.0, 0.0), (0.7, -1.3)]:
+            got = gpu.sparse_gemm(variant, alpha, B, beta, C)
+            want = oracle.sparse_gemm(variant, alpha, (m, n), S.indptr, S.indices, S.data, B, beta, C)
+            assert rel(got, want) < REL_PRIM
+
+
+def test_sparse_rank2_with_hub_rows_matches_oracle(gpu, oracle):
+    """Rank-2 on a sparse matrix with short rows, rows of 65..512 entries and hubs of more than 512 (the three walks of the
+    fused rank-2 iteration, csrc/rank2_fused.cu), against the oracle's trace."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(41)
+    m, n, iters = 1500, 1400, 15
+    A = sp.random(m, n, density=0.004, random_state=3, format="lil", data_rvs=rng.random)
+    for r in (3, 700, 1499):                                  # hub rows
+        cols = rng.choice(n, 900, replace=False); A[r, cols] = rng.random(900) + 0.1
+    for c in (0, 650):                                        # hub columns
+        rows = rng.choice(m, 800, replace=False); A[rows, c] = rng.random((800, 1)) + 0.1
+    for r in range(20, 60):                                   # rows of 65..512 entries
+        cols = rng.choice(n, 70 + 10 * (r - 20), replace=False); A[r, cols] = rng.random(len(cols)) + 0.1
+    S = A.tocsc(); S.sort_indices()
+    W0 = rng.random((m, 2)); H0 = rng.random((2, n))
+    o = oracle.nmf_sparse((m, n), S.indptr, S.indices, S.data, W0, H0, alg="RANK2", tol=1e-12, min_iter=1, max_iter=iters, trace=True)
+    assert o["rc"] == 0
+    gpu.load_csc((m, n), S.indptr, S.indices, S.data)
+    opts = sk.make_options(m, n, 2, algorithm="RANK2", tol=1e-12, min_iter=1, max_iter=iters, normalize=False)
+    metrics, Ws, Hs = _trace_gpu(gpu, W0, H0, opts, iters)
+    for i in range(iters):
+        assert rel(Ws[i], o["W_trace"][i]) < REL_FACTOR, (i, rel(Ws[i], o["W_trace"][i]))
+        assert rel(Hs[i], o["H_trace"][i]) < REL_FACTOR, (i, rel(Hs[i], o["H_trace"][i]))
+
+
 def test_sparse_hals_with_residency_classes_matches_oracle(gpu, oracle, monkeypatch):
     monkeypatch.setenv("SMK_SPMM_TIER_MIN_KB", "0")
     monkeypatch.setenv("SMK_SPMM_TIER_KEEP_KB", "200")
