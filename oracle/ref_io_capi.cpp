@@ -1,0 +1,54 @@
+// TEST INFRASTRUCTURE — not part of the product.
+//
+// ref_io_capi.cpp: extern "C" entry points around the REFERENCE's own file readers / writers, compiled by
+// oracle/Makefile with the reference's unmodified sources into oracle/_ref/libsmallk_ref.so. Nothing here restates
+// an algorithm; every call lands in reference code:
+//   LoadMatrixMarketFile   common/include/sparse_matrix_io.hpp:117-260 (+ common/src/matrix_market_file.cpp)
+//   LoadDelimitedFile      common/include/delimited_file.hpp:79-135
+//   WriteDelimitedFile     common/include/delimited_file.hpp:49-76
+#include <string>
+#include <vector>
+#include "sparse_matrix.hpp"
+#include "sparse_matrix_io.hpp"
+#include "delimited_file.hpp"
+
+extern "C" {
+
+// Returns 0 and the CSC arrays (up to the capacities given) of the matrix the reference builds from the file; -1 if the
+// reference rejects the file; -2 if a capacity is too small (dimensions are still reported).
+int ref_load_matrix_market(const char* path, unsigned int* height, unsigned int* width, unsigned int* nnz,
+                           unsigned int* col_offsets, unsigned int cap_cols, unsigned int* row_indices, double* data,
+                           unsigned int cap_nz)
+{
+    SparseMatrix<double> A;
+    unsigned int h = 0, w = 0, nz = 0;
+    if (!LoadMatrixMarketFile(std::string(path), A, h, w, nz)) return -1;
+    *height = A.Height(); *width = A.Width(); *nnz = A.Size();
+    if (A.Width() + 1 > cap_cols || A.Size() > cap_nz) return -2;
+    const unsigned int* cp = A.LockedColBuffer();
+    const unsigned int* ri = A.LockedRowBuffer();
+    const double* dv = A.LockedDataBuffer();
+    for (unsigned int c = 0; c <= A.Width(); ++c) col_offsets[c] = cp[c];
+    for (unsigned int e = 0; e < A.Size(); ++e) { row_indices[e] = ri[e]; data[e] = dv[e]; }
+    return 0;
+}
+
+// Column-major buffer (ld = height) the reference reads from a delimited file.
+int ref_load_delimited(const char* path, unsigned int* height, unsigned int* width, double* buffer, unsigned int cap)
+{
+    std::vector<double> buf;
+    unsigned int h = 0, w = 0;
+    if (!LoadDelimitedFile(buf, h, w, std::string(path))) return -1;
+    *height = h; *width = w;
+    if (static_cast<size_t>(h) * w > cap) return -2;
+    for (size_t i = 0; i < static_cast<size_t>(h) * w; ++i) buffer[i] = buf[i];
+    return 0;
+}
+
+int ref_write_delimited(const double* buffer, unsigned int ldim, unsigned int height, unsigned int width, const char* path,
+                        unsigned int precision)
+{
+    return WriteDelimitedFile(buffer, ldim, height, width, std::string(path), precision) ? 0 : -1;
+}
+
+} // extern "C"

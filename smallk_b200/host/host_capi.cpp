@@ -9,6 +9,7 @@
 #include "clust.hpp"
 #include "flat_clust.hpp"
 #include "host_internal.hpp"
+#include "matrix_io.hpp"
 
 R compute_priority_on(smk_ctx* ctx, const R* W_parent, const R* W_child, int n);
 R compute_priority_plain(smk_ctx* ctx, const R* W_parent, const R* W_child, int n);
@@ -169,6 +170,37 @@ double smkh_compute_priority_gpu(const double* W_parent, const double* W_child, 
 {
     EnsureInit();
     return compute_priority_on(NmfContext(), W_parent, W_child, m);
+}
+
+// ---- file formats (host/matrix_io.hpp), unit-testable without a GPU: same contract as oracle/ref_io_capi.cpp ----
+int smkh_load_matrix_market(const char* path, unsigned int* height, unsigned int* width, unsigned int* nnz,
+                            unsigned int* col_offsets, unsigned int cap_cols, unsigned int* row_indices, double* data,
+                            unsigned int cap_nz)
+{
+    smallk_io::CscMatrix A;
+    if (!smallk_io::LoadMatrixMarketFile(path, A)) return -1;
+    *height = A.height; *width = A.width; *nnz = A.nnz();
+    if (A.width + 1 > cap_cols || A.nnz() > cap_nz) return -2;
+    for (unsigned int c = 0; c <= A.width; ++c) col_offsets[c] = A.col_offsets[c];
+    for (unsigned int e = 0; e < A.nnz(); ++e) { row_indices[e] = A.row_indices[e]; data[e] = A.data[e]; }
+    return 0;
+}
+
+int smkh_load_delimited(const char* path, unsigned int* height, unsigned int* width, double* buffer, unsigned int cap)
+{
+    std::vector<double> buf;
+    unsigned int h = 0, w = 0;
+    if (!smallk_io::LoadDelimitedFile(buf, h, w, path)) return -1;
+    *height = h; *width = w;
+    if (static_cast<size_t>(h) * w > cap) return -2;
+    for (size_t i = 0; i < static_cast<size_t>(h) * w; ++i) buffer[i] = buf[i];
+    return 0;
+}
+
+int smkh_write_delimited(const double* buffer, unsigned int ldim, unsigned int height, unsigned int width, const char* path,
+                         unsigned int precision)
+{
+    return smallk_io::WriteDelimitedFile(buffer, ldim, height, width, path, precision) ? 0 : -1;
 }
 
 } // extern "C"

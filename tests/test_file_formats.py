@@ -1,0 +1,128 @@
+"""File formats either side of the NMF path, no GPU needed: the host readers / writers
+(smallk_b200/host/matrix_io.hpp) against the reference's own (common/include/sparse_matrix_io.hpp:117-260,
+delimited_file.hpp:49-135) compiled into oracle/_ref. The CSC arrays a MatrixMarket file turns into (expansion of symmetric
+and skew-symmetric files, pattern values, stable order inside a column, duplicates kept), the buffer a CSV file turns into,
+and the bytes a CSV writer produces must be identical."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import smallk_b200 as sk
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libsmallk_ref.so")
+up = ctypes.POINTER(ctypes.c_uint)
+dp = ctypes.POINTER(ctypes.c_double)
+
+
+def _libs():
+    if not os.path.exists(sk.HOST_LIB_PATH) or not os.path.exists(REF_SO):
+        pytest.skip("host library or oracle/_ref not built on this machine")
+    ref = ctypes.CDLL(REF_SO)
+    if not hasattr(ref, "ref_load_matrix_market"):
+        pytest.skip("oracle/_ref predates the file-format entry points")
+    return ctypes.CDLL(sk.HOST_LIB_PATH), ref
+
+
+def _load_mtx(fn, path, cap_cols=4096, cap_nz=1 << 16):
+    h, w, nz = ctypes.c_uint(0), ctypes.c_uint(0), ctypes.c_uint(0)
+    colp = np.zeros(cap_cols, dtype=np.uint32); rowi = np.zeros(cap_nz, dtype=np.uint32); val = np.zeros(cap_nz)
+    rc = fn(path.encode(), ctypes.byref(h), ctypes.byref(w), ctypes.byref(nz), colp.ctypes.data_as(up), cap_cols,
+            rowi.ctypes.data_as(up), val.ctypes.data_as(dp), cap_nz)
+    if rc != 0:
+        return rc, None
+    return 0, (h.value, w.value, nz.value, colp[: w.value + 1].copy(), rowi[: nz.value].copy(), val[: nz.value].copy())
+
+
+def _write_mtx(path, header, m, n, entries, comments=("% a comment",), blank_tail=False):
+    with open(path, "w") as f:
+        f.write(header + "\n")
+        for c in comments:
+            f.write(c + "\n")
+        f.write(f"{m} {n} {len(entries)}\n")
+        for e in entries:
+            f.write(" ".join(str(x) for x in e) + "\n")
+        if blank_tail:
+            f.write("\n")
+
+
+def _cases(tmp):
+    rng = np.random.default_rng(9)
+    out = []
+    # general real, unsorted, with duplicates
+    m, n = 40, 30
+    ent = [(int(rng.integers(1, m + 1)), int(rng.integers(1, n + 1)), repr(float(rng.random()))) for _ in range(300)]
+    ent += [ent[3], ent[10]]
+    p = os.path.join(tmp, "general.mtx"); _write_mtx(p, "%%MatrixMarket matrix coordinate real general", m, n, ent); out.append(p)
+    # symmetric pattern (what a graph file looks like), lower triangle + diagonal entries
+    m = 50
+    ent = sorted({(int(max(a, b)), int(min(a, b))) for a, b in rng.integers(1, m + 1, size=(200, 2))})
+    p = os.path.join(tmp, "sym_pattern.mtx"); _write_mtx(p, "%%MatrixMarket matrix coordinate pattern symmetric", m, m, ent); out.append(p)
+    # skew-symmetric real
+    ent = [(int(a), int(b), repr(float(v))) for (a, b), v in zip(sorted({(int(max(a, b)), int(min(a, b))) for a, b in rng.integers(1, m + 1, size=(120, 2)) if a != b}), rng.random(200))]
+    p = os.path.join(tmp, "skew.mtx"); _write_mtx(p, "%%MatrixMarket matrix coordinate real skew-symmetric", m, m, ent); out.append(p)
+    # integer general, mixed-case banner, several comment lines
+    ent = [(int(rng.integers(1, 21)), int(rng.integers(1, 26)), int(rng.integers(1, 9))) for _ in range(90)]
+    p = os.path.join(tmp, "integer.mtx")
+    _write_mtx(p, "%%MatrixMarket MATRIX Coordinate Integer General", 20, 25, ent, comments=("%", "% two", "%three")); out.append(p)
+    # symmetric real with exponents and extra spaces
+    ent = [(7, 2, "1.5e-3"), (9, 9, " 2.25E+1"), (10, 1, "-4.0"), (3, 3, "0.125")]
+    p = os.path.join(tmp, "sym_real.mtx"); _write_mtx(p, "%%MatrixMarket matrix coordinate real symmetric", 10, 10, ent); out.append(p)
+    return out
+
+
+def test_matrix_market_reader_builds_the_reference_csc(tmp_path):
+    host, ref = _libs()
+    for path in _cases(str(tmp_path)):
+        rc_r, want = _load_mtx(ref.ref_load_matrix_market, path)
+        rc_h, got = _load_mtx(host.smkh_load_matrix_market, path)
+        assert rc_r == 0 and rc_h == 0, (path, rc_r, rc_h)
+        assert got[:3] == want[:3], (path, got[:3], want[:3])
+        for a, b in zip(got[3:], want[3:]):
+            assert np.array_equal(a, b), path
+
+
+def test_matrix_market_reader_rejects_what_the_reference_rejects(tmp_path):
+    host, ref = _libs()
+    bad = {
+        "array.mtx": "%%MatrixMarket matrix array real general\n2 2\n1\n2\n3\n4\n",
+        "complex.mtx": "%%MatrixMarket matrix coordinate complex general\n2 2 1\n1 1 1.0 0.0\n",
+        "hermitian.mtx": "%%MatrixMarket matrix coordinate real hermitian\n2 2 1\n1 1 1.0\n",
+        "nobanner.mtx": "2 2 1\n1 1 1.0\n",
+        "zeroindex.mtx": "%%MatrixMarket matrix coordinate real general\n2 2 1\n0 1 1.0\n",
+    }
+    for name, text in bad.items():
+        p = os.path.join(str(tmp_path), name)
+        open(p, "w").write(text)
+        rc_r, _ = _load_mtx(ref.ref_load_matrix_market, p)
+        rc_h, _ = _load_mtx(host.smkh_load_matrix_market, p)
+        assert rc_r != 0, name
+        assert rc_h != 0, name
+    assert _load_mtx(host.smkh_load_matrix_market, os.path.join(str(tmp_path), "missing.mtx"))[0] != 0
+
+
+def test_csv_writer_and_reader_match_the_reference(tmp_path):
+    host, ref = _libs()
+    rng = np.random.default_rng(4)
+    for (h, w), prec in (((7, 5), 6), ((1, 9), 4), ((12, 1), 12), ((33, 17), 6)):
+        A = np.asfortranarray(rng.standard_normal((h, w)) * 10.0 ** rng.integers(-8, 8, size=(h, w)))
+        A[0, 0] = 0.0
+        pr, ph = os.path.join(str(tmp_path), f"ref_{h}_{w}.csv"), os.path.join(str(tmp_path), f"host_{h}_{w}.csv")
+        assert ref.ref_write_delimited(A.ctypes.data_as(dp), h, h, w, pr.encode(), prec) == 0
+        assert host.smkh_write_delimited(A.ctypes.data_as(dp), h, h, w, ph.encode(), prec) == 0
+        assert open(pr, "rb").read() == open(ph, "rb").read(), (h, w, prec)
+        for fn in (ref.ref_load_delimited, host.smkh_load_delimited):
+            hh, ww = ctypes.c_uint(0), ctypes.c_uint(0)
+            buf = np.zeros(h * w)
+            assert fn(pr.encode(), ctypes.byref(hh), ctypes.byref(ww), buf.ctypes.data_as(dp), h * w) == 0
+            assert (hh.value, ww.value) == (h, w)
+            back = buf.reshape((w, h)).T
+            assert np.allclose(back, A, rtol=10.0 ** (-prec), atol=0), (h, w)
+        # both readers produce the same bits from the same file
+        b1, b2 = np.zeros(h * w), np.zeros(h * w)
+        hh, ww = ctypes.c_uint(0), ctypes.c_uint(0)
+        ref.ref_load_delimited(pr.encode(), ctypes.byref(hh), ctypes.byref(ww), b1.ctypes.data_as(dp), h * w)
+        host.smkh_load_delimited(pr.encode(), ctypes.byref(hh), ctypes.byref(ww), b2.ctypes.data_as(dp), h * w)
+        assert np.array_equal(b1, b2)
