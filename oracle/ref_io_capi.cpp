@@ -52,3 +52,34 @@ int ref_write_delimited(const double* buffer, unsigned int ldim, unsigned int he
 }
 
 } // extern "C"
+
+// ---- clustering post-processing -------------------------------------------------------------
+//   ComputeAssignments / ComputeFuzzyAssignments   common/include/assignments.hpp:32-113
+//   TopTerms                                       common/include/terms.hpp:62-108
+#include "assignments.hpp"
+#include "terms.hpp"
+
+extern "C" {
+
+void ref_compute_assignments(const double* H, unsigned int ldH, unsigned int k, unsigned int n, unsigned int* out)
+{
+    std::vector<unsigned int> a;
+    ComputeAssignments(a, H, ldH, k, n);
+    for (unsigned int j = 0; j < n; ++j) out[j] = a[j];
+}
+
+void ref_compute_fuzzy_assignments(const double* H, unsigned int ldH, unsigned int k, unsigned int n, float* out)
+{
+    std::vector<float> p;
+    ComputeFuzzyAssignments(p, H, ldH, k, n);
+    for (size_t i = 0; i < static_cast<size_t>(k) * n; ++i) out[i] = p[i];
+}
+
+void ref_top_terms_matrix(int maxterms, const double* W, unsigned int ldW, unsigned int m, unsigned int k, int* out)
+{
+    std::vector<int> ti(static_cast<size_t>(maxterms) * k);
+    TopTerms(maxterms, W, ldW, m, k, ti);
+    for (size_t i = 0; i < ti.size(); ++i) out[i] = ti[i];
+}
+
+} // extern "C"

@@ -203,4 +203,26 @@ int smkh_write_delimited(const double* buffer, unsigned int ldim, unsigned int h
     return smallk_io::WriteDelimitedFile(buffer, ldim, height, width, path, precision) ? 0 : -1;
 }
 
+// ---- clustering post-processing (host/flat_clust.cpp), same contract as oracle/ref_io_capi.cpp ----
+void smkh_compute_assignments(const double* H, unsigned int ldH, unsigned int k, unsigned int n, unsigned int* out)
+{
+    std::vector<unsigned int> a;
+    ComputeAssignments(a, H, ldH, k, n);
+    for (unsigned int j = 0; j < n; ++j) out[j] = a[j];
+}
+
+void smkh_compute_fuzzy_assignments(const double* H, unsigned int ldH, unsigned int k, unsigned int n, float* out)
+{
+    std::vector<float> p;
+    ComputeFuzzyAssignments(p, H, ldH, k, n);
+    for (size_t i = 0; i < static_cast<size_t>(k) * n; ++i) out[i] = p[i];
+}
+
+void smkh_top_terms_matrix(int maxterms, const double* W, unsigned int ldW, unsigned int m, unsigned int k, int* out)
+{
+    std::vector<int> ti(static_cast<size_t>(maxterms) * k);
+    TopTerms(maxterms, W, ldW, m, k, ti);
+    for (size_t i = 0; i < ti.size(); ++i) out[i] = ti[i];
+}
+
 } // extern "C"

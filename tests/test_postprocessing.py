@@ -1,0 +1,77 @@
+"""Clustering post-processing, no GPU needed: ComputeAssignments, ComputeFuzzyAssignments
+(common/include/assignments.hpp:32-113) and TopTerms (common/include/terms.hpp:62-108) of the host layer against the
+reference's own functions compiled into oracle/_ref — identical integers, identical float bits, ties included (TopTerms
+uses an unstable sort: the same libstdc++ call on the same data must be made for ties to fall the same way)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import smallk_b200 as sk
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libsmallk_ref.so")
+dp = ctypes.POINTER(ctypes.c_double)
+
+
+def _libs():
+    if not os.path.exists(sk.HOST_LIB_PATH) or not os.path.exists(REF_SO):
+        pytest.skip("host library or oracle/_ref not built on this machine")
+    ref = ctypes.CDLL(REF_SO)
+    if not hasattr(ref, "ref_compute_assignments"):
+        pytest.skip("oracle/_ref predates the post-processing entry points")
+    return ctypes.CDLL(sk.HOST_LIB_PATH), ref
+
+
+def _factors():
+    rng = np.random.default_rng(12)
+    for m, n, k, ld_extra in ((40, 60, 4, 0), (300, 200, 16, 3), (1000, 50, 2, 0), (64, 64, 64, 1)):
+        W = np.zeros((m + ld_extra, k), order="F"); W[:m] = rng.random((m, k))
+        H = np.zeros((k + ld_extra, n), order="F"); H[:k] = rng.random((k, n))
+        W[:m][rng.random((m, k)) < 0.3] = 0.0                 # exact zeros, as NNLS leaves them
+        H[:k][rng.random((k, n)) < 0.3] = 0.0
+        W[: m // 2, 0] = np.round(W[: m // 2, 0], 1)          # ties among the term weights
+        H[:k, ::5] = 0.25                                     # ties among the cluster weights of a document
+        H[:k, 7] = 0.0                                        # a document with no weight at all
+        yield m, n, k, W, H
+
+
+def test_assignments_match_reference():
+    host, ref = _libs()
+    for m, n, k, W, H in _factors():
+        a, b = np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.uint32)
+        up = ctypes.POINTER(ctypes.c_uint)
+        ref.ref_compute_assignments(H.ctypes.data_as(dp), H.shape[0], k, n, a.ctypes.data_as(up))
+        host.smkh_compute_assignments(H.ctypes.data_as(dp), H.shape[0], k, n, b.ctypes.data_as(up))
+        assert np.array_equal(a, b), (m, n, k)
+
+
+def test_fuzzy_assignments_match_reference_bit_for_bit():
+    host, ref = _libs()
+    fp = ctypes.POINTER(ctypes.c_float)
+    for m, n, k, W, H in _factors():
+        Hc = np.asfortranarray(H[:k])                         # the reference indexes its output with the same ldim: tight H
+        a, b = np.zeros(k * n, dtype=np.float32), np.zeros(k * n, dtype=np.float32)
+        ref.ref_compute_fuzzy_assignments(Hc.ctypes.data_as(dp), k, k, n, a.ctypes.data_as(fp))
+        host.smkh_compute_fuzzy_assignments(Hc.ctypes.data_as(dp), k, k, n, b.ctypes.data_as(fp))
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (m, n, k)
+
+
+def test_top_terms_match_reference_including_ties():
+    host, ref = _libs()
+    ip = ctypes.POINTER(ctypes.c_int)
+    for m, n, k, W, H in _factors():
+        # tight W (ldim == height), the only way the reference's callers pass it: its TopTerms steps from column to column
+        # by `height`, not `ldim` (terms.hpp:93), so a padded buffer would make it rank shifted data. The host version
+        # honours ldim; with a tight buffer the two must agree, ties included.
+        Wt = np.asfortranarray(W[:m])
+        for maxterms in (1, 5, min(m, 12)):
+            a, b = np.zeros(maxterms * k, dtype=np.int32), np.zeros(maxterms * k, dtype=np.int32)
+            ref.ref_top_terms_matrix(maxterms, Wt.ctypes.data_as(dp), m, m, k, a.ctypes.data_as(ip))
+            host.smkh_top_terms_matrix(maxterms, Wt.ctypes.data_as(dp), m, m, k, b.ctypes.data_as(ip))
+            assert np.array_equal(a, b), (m, k, maxterms)
+            if W.shape[0] != m:                               # padded buffer: the host version reads the same columns
+                c = np.zeros(maxterms * k, dtype=np.int32)
+                host.smkh_top_terms_matrix(maxterms, W.ctypes.data_as(dp), W.shape[0], m, k, c.ctypes.data_as(ip))
+                assert np.array_equal(b, c), (m, k, maxterms)
