@@ -83,3 +83,26 @@ void ref_top_terms_matrix(int maxterms, const double* W, unsigned int ldW, unsig
 }
 
 } // extern "C"
+
+// ---- random initialisers --------------------------------------------------------------------------------------
+//   Random                 common/include/random.hpp:22-200
+//   RandomMatrix           common/include/matrix_generator.hpp:61-82 (sequential generator when max_threads == 1)
+#include "random.hpp"
+#include "matrix_generator.hpp"
+#include "thread_utils.hpp"
+
+extern "C" {
+
+// Two consecutive matrices from one seeded generator (W then H, as the clustering drivers draw them), max_threads threads.
+void ref_random_matrices(int seed, int max_threads, unsigned int h1, unsigned int w1, double* buf1, unsigned int h2,
+                         unsigned int w2, double* buf2, int* next_int)
+{
+    SetMaxThreadCount(max_threads);
+    Random rng;
+    rng.SeedFromInt(seed);
+    RandomMatrix(buf1, h1, h1, w1, rng, 0.5, 0.5);
+    RandomMatrix(buf2, h2, h2, w2, rng, 0.5, 0.5);
+    if (next_int) *next_int = rng.RandomInt();
+}
+
+} // extern "C"

@@ -10,6 +10,7 @@
 #include "flat_clust.hpp"
 #include "host_internal.hpp"
 #include "matrix_io.hpp"
+#include "random.hpp"
 
 R compute_priority_on(smk_ctx* ctx, const R* W_parent, const R* W_child, int n);
 R compute_priority_plain(smk_ctx* ctx, const R* W_parent, const R* W_child, int n);
@@ -223,6 +224,17 @@ void smkh_top_terms_matrix(int maxterms, const double* W, unsigned int ldW, unsi
     std::vector<int> ti(static_cast<size_t>(maxterms) * k);
     TopTerms(maxterms, W, ldW, m, k, ti);
     for (size_t i = 0; i < ti.size(); ++i) out[i] = ti[i];
+}
+
+// ---- random initialisers (host/random.hpp), same contract as oracle/ref_io_capi.cpp ----
+void smkh_random_matrices(int seed, unsigned int h1, unsigned int w1, double* buf1, unsigned int h2, unsigned int w2, double* buf2,
+                          int* next_int)
+{
+    Random rng;
+    rng.SeedFromInt(seed);
+    RandomMatrix(buf1, h1, h1, w1, rng, 0.5, 0.5);
+    RandomMatrix(buf2, h2, h2, w2, rng, 0.5, 0.5);
+    if (next_int) *next_int = rng.RandomInt();
 }
 
 } // extern "C"

@@ -75,3 +75,25 @@ def test_top_terms_match_reference_including_ties():
                 c = np.zeros(maxterms * k, dtype=np.int32)
                 host.smkh_top_terms_matrix(maxterms, W.ctypes.data_as(dp), W.shape[0], m, k, c.ctypes.data_as(ip))
                 assert np.array_equal(b, c), (m, k, maxterms)
+
+
+def test_random_initialisers_are_the_reference_sequential_stream():
+    """Random + RandomMatrix (common/include/random.hpp, matrix_generator.hpp:61-82,229-248): the W then H draws of the
+    clustering drivers from one seeded generator. With one thread the reference uses the sequential generator, whose stream
+    the host layer reproduces at every size; with several threads and >= 16k elements the reference switches to per-thread
+    seeds (a different stream: not reproduced)."""
+    host, ref = _libs()
+    if not hasattr(ref, "ref_random_matrices"):
+        pytest.skip("oracle/_ref predates the random-initialiser entry point")
+    for seed, (h1, w1), (h2, w2) in ((1, (50, 2), (2, 70)), (32, (9000, 2), (2, 9000)), (7, (300, 16), (16, 200)), (5, (20000, 2), (2, 3))):
+        a1, a2 = np.zeros(h1 * w1), np.zeros(h2 * w2)
+        b1, b2 = np.zeros(h1 * w1), np.zeros(h2 * w2)
+        ia, ib = ctypes.c_int(0), ctypes.c_int(0)
+        ref.ref_random_matrices(seed, 1, h1, w1, a1.ctypes.data_as(dp), h2, w2, a2.ctypes.data_as(dp), ctypes.byref(ia))
+        host.smkh_random_matrices(seed, h1, w1, b1.ctypes.data_as(dp), h2, w2, b2.ctypes.data_as(dp), ctypes.byref(ib))
+        assert np.array_equal(a1, b1) and np.array_equal(a2, b2) and ia.value == ib.value, (seed, h1, w1)
+    # the parallel generator is a different stream (this is why C4-scale trees are compared with the one-thread reference)
+    a1, a2 = np.zeros(20000 * 2), np.zeros(2 * 3)
+    ref.ref_random_matrices(5, 4, 20000, 2, a1.ctypes.data_as(dp), 2, 3, a2.ctypes.data_as(dp), None)
+    assert not np.array_equal(a1, b1)
+    ref.ref_random_matrices(5, 1, 4, 2, a1.ctypes.data_as(dp), 2, 3, a2.ctypes.data_as(dp), None)     # leave the thread count at 1
