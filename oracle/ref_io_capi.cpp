@@ -106,3 +106,34 @@ void ref_random_matrices(int seed, int max_threads, unsigned int h1, unsigned in
 }
 
 } // extern "C"
+
+// ---- option validation: common/src/nmf_options.cpp:23-110, hierclust/src/clust_options.cpp:24-110, flatclust/src/flat_clust_options.cpp
+#include "nmf.hpp"
+#include "clust.hpp"
+#include "flat_clust.hpp"
+extern "C" {
+
+// which: 0 = IsValid(NmfOptions), 1 = IsValid(ClustOptions), 2 = IsValid(FlatClustOptions). v = {tol, algorithm, prog, height, width, k,
+// min_iter, max_iter, tolcount, max_threads, maxterms, unbalanced, trial_allowance, num_clusters}.
+int ref_is_valid(int which, const double* v, int validate_matrix)
+{
+    NmfOptions o;
+    o.tol = v[0]; o.algorithm = static_cast<NmfAlgorithm>(static_cast<int>(v[1]));
+    o.prog_est_algorithm = static_cast<NmfProgressAlgorithm>(static_cast<int>(v[2]));
+    o.height = static_cast<int>(v[3]); o.width = static_cast<int>(v[4]); o.k = static_cast<int>(v[5]);
+    o.min_iter = static_cast<int>(v[6]); o.max_iter = static_cast<int>(v[7]); o.tolcount = static_cast<int>(v[8]);
+    o.max_threads = static_cast<int>(v[9]); o.verbose = false; o.normalize = true;
+    if (which == 0) return IsValid(o, validate_matrix != 0) ? 1 : 0;
+    if (which == 1)
+    {
+        ClustOptions c;
+        c.nmf_opts = o; c.maxterms = static_cast<int>(v[10]); c.unbalanced = v[11]; c.trial_allowance = static_cast<int>(v[12]);
+        c.num_clusters = static_cast<int>(v[13]); c.verbose = false; c.flat = false;
+        return IsValid(c, validate_matrix != 0) ? 1 : 0;
+    }
+    FlatClustOptions f;
+    f.nmf_opts = o; f.maxterms = static_cast<int>(v[10]); f.num_clusters = static_cast<int>(v[13]); f.verbose = false;
+    return IsValid(f, validate_matrix != 0) ? 1 : 0;
+}
+
+} // extern "C"

@@ -8,10 +8,24 @@
 
 bool IsValid(const FlatClustOptions& opts, bool validate_matrix)
 {
-    // flatclust/src/flat_clust_options.cpp: the NMF options plus maxterms > 0 and a cluster count that matches k
-    if (!IsValid(opts.nmf_opts, validate_matrix)) return false;
-    if (opts.maxterms <= 0) { std::cerr << "error: maxterms must be a positive integer" << std::endl; return false; }
-    if (opts.num_clusters <= 0) { std::cerr << "error: number of clusters must be a positive integer" << std::endl; return false; }
+    // flatclust/src/flat_clust_options.cpp:24-98: the same checks in the same order. Note what it does NOT look at: the
+    // algorithm, tolcount and the RANK2 <-> k == 2 rule (FlatClust rejects an unknown algorithm later, flat_clust.cpp:60-75).
+    using std::cerr; using std::endl;
+    const NmfOptions& o = opts.nmf_opts;
+    if (validate_matrix)
+    {
+        if (o.height <= 0) { cerr << "clustlib error: matrix height must be a positive integer" << endl; return false; }
+        if (o.width <= 0) { cerr << "clustlib error: matrix width must be a positive integer" << endl; return false; }
+        if (o.k <= 0) { cerr << "clustlib error: cluster count must be a positive integer" << endl; return false; }
+        if (o.k > o.width) { cerr << "clustlib error: k value cannot exceed the matrix width" << endl; return false; }
+    }
+    if (opts.num_clusters <= 0) { cerr << "clustlib error: value for --clusters must be a positive integer" << endl; return false; }
+    if (o.tol <= 0.0 || o.tol >= 1.0) { cerr << "clustlib error: tolerance must be in the interval (0.0, 1.0)" << endl; return false; }
+    if (o.min_iter <= 0) { cerr << "clustlib error: miniter must be a positive integer" << endl; return false; }
+    if (o.max_iter <= 0) { cerr << "clustlib error: iteration count must be a positive integer" << endl; return false; }
+    if (opts.maxterms <= 0) { cerr << "clustlib error: maxterms must be a positive integer" << endl; return false; }
+    if (NmfProgressAlgorithm::PG_RATIO != o.prog_est_algorithm && NmfProgressAlgorithm::DELTA_FNORM != o.prog_est_algorithm)
+    { cerr << "clustlib error: unknown stopping criterion " << endl; return false; }
     return true;
 }
 

@@ -97,3 +97,33 @@ def test_random_initialisers_are_the_reference_sequential_stream():
     ref.ref_random_matrices(5, 4, 20000, 2, a1.ctypes.data_as(dp), 2, 3, a2.ctypes.data_as(dp), None)
     assert not np.array_equal(a1, b1)
     ref.ref_random_matrices(5, 1, 4, 2, a1.ctypes.data_as(dp), 2, 3, a2.ctypes.data_as(dp), None)     # leave the thread count at 1
+
+
+def test_option_validation_agrees_with_reference(capfd):
+    """IsValid(NmfOptions / ClustOptions / FlatClustOptions): common/src/nmf_options.cpp:23-110, hierclust/src/clust_options.cpp:24-110,
+    flatclust/src/flat_clust_options.cpp — one field at a time pushed out of range, with and without matrix validation."""
+    host, ref = _libs()
+    if not hasattr(ref, "ref_is_valid"):
+        pytest.skip("oracle/_ref predates the option-validation entry point")
+    #        tol   alg prog  h    w   k  min max tolc thr maxterms unbal trial clusters
+    good = [1e-4, 1,  0,  100, 80,  4,  5, 500,  1,  1,   5,     0.1,   3,    4]
+    edits = [(0, 0.0), (0, 1.0), (0, -1.0), (0, 0.5), (1, 7), (1, 3), (1, 0), (1, 2), (2, 5), (2, 1), (3, 0), (3, -4), (4, 0), (4, 3), (5, 0),
+             (5, 81), (5, 80), (5, 2), (6, 0), (7, 0), (7, -1), (8, 0), (9, 0), (9, -1), (10, 0), (10, -3), (11, -0.1), (11, 1.0), (11, 0.0),
+             (12, -1), (12, 0), (13, 1), (13, 0), (13, 2), (13, 500)]
+    checked = 0
+    for which in (0, 1, 2):
+        for vm in (1, 0):
+            for idx, val in [(None, None)] + edits:
+                for alg in (None, 3):                         # 3 = RANK2: k must be 2
+                    v = list(good)
+                    if alg is not None:
+                        v[1] = alg
+                    if idx is not None:
+                        v[idx] = val
+                    arr = np.array(v, dtype=np.float64)
+                    a = ref.ref_is_valid(which, arr.ctypes.data_as(dp), vm)
+                    b = host.smkh_is_valid(which, arr.ctypes.data_as(dp), vm)
+                    assert a == b, (which, vm, idx, val, alg, a, b)
+                    checked += 1
+    capfd.readouterr()                                        # both sides explain every rejection on stderr
+    assert checked > 400
