@@ -137,3 +137,25 @@ int ref_is_valid(int which, const double* v, int validate_matrix)
 }
 
 } // extern "C"
+
+// ---- flat clustering result files: common/src/flat_clust_output.cpp:52-170 (+ flatclust_{xml,json}_writer.cpp, assignments.cpp)
+#include "flat_clust_output.hpp"
+extern "C" {
+
+// format: 1 = XML, 2 = JSON (FileFormat, file_format.hpp:17-23). dictionary: `m` NUL-terminated strings back to back.
+int ref_flatclust_write_results(const char* outdir, const unsigned int* assignments, const float* probabilities, const char* dictionary,
+                                int dict_count, const int* term_indices, int format, unsigned int maxterms, unsigned int num_docs,
+                                unsigned int num_clusters)
+{
+    std::vector<unsigned int> a(assignments, assignments + num_docs);
+    std::vector<float> p(probabilities, probabilities + static_cast<size_t>(num_clusters) * num_docs);
+    std::vector<std::string> d;
+    const char* s = dictionary;
+    for (int i = 0; i < dict_count; ++i) { d.push_back(std::string(s)); s += d.back().size() + 1; }
+    std::vector<int> t(term_indices, term_indices + static_cast<size_t>(maxterms) * num_clusters);
+    try { FlatClustWriteResults(std::string(outdir), a, p, d, t, static_cast<FileFormat>(format), maxterms, num_docs, num_clusters); }
+    catch (std::exception&) { return -1; }
+    return 0;
+}
+
+} // extern "C"

@@ -10,6 +10,7 @@
 #include "flat_clust.hpp"
 #include "host_internal.hpp"
 #include "matrix_io.hpp"
+#include "flat_clust_output.hpp"
 #include "random.hpp"
 
 R compute_priority_on(smk_ctx* ctx, const R* W_parent, const R* W_child, int n);
@@ -259,6 +260,22 @@ int smkh_is_valid(int which, const double* v, int validate_matrix)
     FlatClustOptions f;
     f.nmf_opts = o; f.maxterms = static_cast<int>(v[10]); f.num_clusters = static_cast<int>(v[13]); f.verbose = false;
     return IsValid(f, validate_matrix != 0) ? 1 : 0;
+}
+
+// ---- flat clustering result files (host/flat_clust_output.hpp), same contract as oracle/ref_io_capi.cpp ----
+int smkh_flatclust_write_results(const char* outdir, const unsigned int* assignments, const float* probabilities, const char* dictionary,
+                                 int dict_count, const int* term_indices, int format, unsigned int maxterms, unsigned int num_docs,
+                                 unsigned int num_clusters)
+{
+    std::vector<unsigned int> a(assignments, assignments + num_docs);
+    std::vector<float> p(probabilities, probabilities + static_cast<size_t>(num_clusters) * num_docs);
+    std::vector<std::string> d;
+    const char* s = dictionary;
+    for (int i = 0; i < dict_count; ++i) { d.push_back(std::string(s)); s += d.back().size() + 1; }
+    std::vector<int> t(term_indices, term_indices + static_cast<size_t>(maxterms) * num_clusters);
+    try { FlatClustWriteResults(std::string(outdir), a, p, d, t, static_cast<FileFormat>(format), maxterms, num_docs, num_clusters); }
+    catch (std::exception&) { return -1; }
+    return 0;
 }
 
 } // extern "C"

@@ -127,3 +127,32 @@ def test_option_validation_agrees_with_reference(capfd):
                     checked += 1
     capfd.readouterr()                                        # both sides explain every rejection on stderr
     assert checked > 400
+
+
+@pytest.mark.parametrize("fmt", [1, 2])           # FileFormat::XML, FileFormat::JSON
+def test_flatclust_result_files_are_byte_identical(tmp_path, fmt):
+    """FlatClustWriteResults (common/src/flat_clust_output.cpp:52-170): assignments_flat_<k>.csv, assignments_fuzzy_<k>.csv and
+    clusters_<k>.{xml,json} written by the host layer and by the reference from the same inputs — an empty cluster included."""
+    host, ref = _libs()
+    if not hasattr(ref, "ref_flatclust_write_results"):
+        pytest.skip("oracle/_ref predates the result-writer entry point")
+    rng = np.random.default_rng(3)
+    up, fp, ip = ctypes.POINTER(ctypes.c_uint), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)
+    for k, n, m, maxterms in ((4, 30, 50, 5), (6, 12, 20, 3), (2, 9, 10, 1)):
+        assign = rng.integers(0, k, size=n).astype(np.uint32)
+        assign[assign == k - 1] = 0                            # the last cluster receives no document
+        prob = rng.random(k * n).astype(np.float32)
+        terms = rng.integers(0, m, size=k * maxterms).astype(np.int32)
+        words = [f"term{i}_{'x' * (i % 4)}" for i in range(m)]
+        blob = b"".join(w.encode() + b"\0" for w in words)
+        dirs = []
+        for name, fn in (("ref", ref.ref_flatclust_write_results), ("host", host.smkh_flatclust_write_results)):
+            d = tmp_path / f"{name}_{k}_{fmt}"
+            d.mkdir()
+            rc = fn(str(d).encode(), assign.ctypes.data_as(up), prob.ctypes.data_as(fp), blob, m, terms.ctypes.data_as(ip), fmt, maxterms, n, k)
+            assert rc == 0, name
+            dirs.append(d)
+        names = sorted(p.name for p in dirs[0].iterdir())
+        assert names == sorted(p.name for p in dirs[1].iterdir()) and len(names) == 3, names
+        for nm in names:
+            assert (dirs[0] / nm).read_bytes() == (dirs[1] / nm).read_bytes(), (k, fmt, nm)
