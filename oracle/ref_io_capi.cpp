@@ -159,3 +159,56 @@ int ref_flatclust_write_results(const char* outdir, const unsigned int* assignme
 }
 
 } // extern "C"
+
+// ---- the tree and its writers, driven by a script (no factorization): Tree<T> hierclust/include/tree.hpp + src/tree.cpp,
+//      HierclustXmlWriter / HierclustJsonWriter hierclust/src/hierclust_{xml,json}_writer.cpp, CreateHierclustWriter
+#include "tree.hpp"
+#include "hierclust_writer_factory.hpp"
+extern "C" {
+
+// Grows a tree of num_clusters leaves from scripted factors (m x 2 topic matrices, 2 x docs membership matrices) and scripted
+// priorities, always splitting the leaf MinMaxLeafPriorities names; writes assignments and the tree. format: 1 XML, 2 JSON.
+int ref_tree_script(int seed, int m, int n, int num_clusters, int maxterms, int format, const char* assign_path, const char* tree_path)
+{
+    // deterministic pseudo-random stream shared by both drivers (values in (0, 1), a quarter of them exactly 0)
+    unsigned long long state = 0x9E3779B97F4A7C15ull * static_cast<unsigned long long>(seed + 1);
+    auto next = [&state]() {
+        state = state * 6364136223846793005ull + 1442695040888963407ull;
+        const unsigned int bits = static_cast<unsigned int>(state >> 33);
+        if ((bits & 3u) == 0u) return 0.0;
+        return (static_cast<double>(bits >> 2) + 0.5) / 536870912.0;
+    };
+
+    Tree<double> tree;
+    tree.Init(num_clusters, 2 * (num_clusters - 1), m, n);
+    std::vector<unsigned int> doc_count(2 * (num_clusters - 1), 0u);
+    DenseMatrix<double> W(m, 2), H(2, n);
+    auto fill = [&](DenseMatrix<double>& M) { for (int c = 0; c < M.Width(); ++c) for (int r = 0; r < M.Height(); ++r) M.Set(r, c, next()); };
+    fill(W); fill(H);
+    tree.SplitRoot(&W, &H);
+    for (int split = 0; ; ++split)
+    {
+        const unsigned int i0 = tree.LeftChildIndex(), i1 = tree.RightChildIndex();
+        doc_count[i0] = tree.LeftChildDocs().size(); doc_count[i1] = tree.RightChildDocs().size();
+        tree.SetNodePriority(i0, doc_count[i0] > 3 ? next() + 0.01 : -1.0);
+        tree.SetNodePriority(i1, doc_count[i1] > 3 ? next() + 0.01 : -1.0);
+        if (split == num_clusters - 2) break;
+        double mn, mx; unsigned int idx;
+        tree.MinMaxLeafPriorities(mn, mx, idx);
+        if (mx < 0.0) break;
+        DenseMatrix<double> Hs(2, doc_count[idx]);
+        fill(W); fill(Hs);
+        tree.Split(idx, &W, &Hs);
+    }
+    tree.ComputeTopTerms(maxterms);
+    tree.ComputeAssignments();
+    if (!tree.WriteAssignments(std::string(assign_path))) return -1;
+    std::vector<std::string> dict;
+    for (int i = 0; i < m; ++i) { std::ostringstream s; s << "w" << i; dict.push_back(s.str()); }
+    IHierclustWriter* writer = CreateHierclustWriter(static_cast<FileFormat>(format));
+    const bool ok = tree.WriteTree(writer, std::string(tree_path), dict);
+    delete writer;
+    return ok ? 0 : -2;
+}
+
+} // extern "C"

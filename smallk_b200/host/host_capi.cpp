@@ -9,6 +9,9 @@
 #include "clust.hpp"
 #include "flat_clust.hpp"
 #include "host_internal.hpp"
+#include "tree.hpp"
+#include "hierclust_writer.hpp"
+#include <sstream>
 #include "matrix_io.hpp"
 #include "flat_clust_output.hpp"
 #include "random.hpp"
@@ -276,6 +279,50 @@ int smkh_flatclust_write_results(const char* outdir, const unsigned int* assignm
     try { FlatClustWriteResults(std::string(outdir), a, p, d, t, static_cast<FileFormat>(format), maxterms, num_docs, num_clusters); }
     catch (std::exception&) { return -1; }
     return 0;
+}
+
+// ---- the tree and its writers driven by a script (host/tree.hpp, hierclust_writer.hpp), same contract as oracle/ref_io_capi.cpp ----
+int smkh_tree_script(int seed, int m, int n, int num_clusters, int maxterms, int format, const char* assign_path, const char* tree_path)
+{
+    // deterministic pseudo-random stream shared by both drivers (values in (0, 1), a quarter of them exactly 0)
+    unsigned long long state = 0x9E3779B97F4A7C15ull * static_cast<unsigned long long>(seed + 1);
+    auto next = [&state]() {
+        state = state * 6364136223846793005ull + 1442695040888963407ull;
+        const unsigned int bits = static_cast<unsigned int>(state >> 33);
+        if ((bits & 3u) == 0u) return 0.0;
+        return (static_cast<double>(bits >> 2) + 0.5) / 536870912.0;
+    };
+
+    Tree<double> tree;
+    tree.Init(num_clusters, 2 * (num_clusters - 1), m, n);
+    std::vector<unsigned int> doc_count(2 * (num_clusters - 1), 0u);
+    std::vector<double> W(static_cast<size_t>(m) * 2), H(static_cast<size_t>(n) * 2);
+    auto fill = [&](std::vector<double>& M, size_t count) { M.resize(count); for (size_t i = 0; i < count; ++i) M[i] = next(); };   // column-major order
+    fill(W, static_cast<size_t>(m) * 2); fill(H, static_cast<size_t>(n) * 2);
+    tree.SplitRoot(W.data(), H.data(), n);
+    for (int split = 0; ; ++split)
+    {
+        const unsigned int i0 = tree.LeftChildIndex(), i1 = tree.RightChildIndex();
+        doc_count[i0] = tree.LeftChildDocs().size(); doc_count[i1] = tree.RightChildDocs().size();
+        tree.SetNodePriority(i0, doc_count[i0] > 3 ? next() + 0.01 : -1.0);
+        tree.SetNodePriority(i1, doc_count[i1] > 3 ? next() + 0.01 : -1.0);
+        if (split == num_clusters - 2) break;
+        double mn = 0, mx = 0; unsigned int idx = 0;
+        tree.MinMaxLeafPriorities(mn, mx, idx);
+        if (mx < 0.0) break;
+        std::vector<double> Hs;
+        fill(W, static_cast<size_t>(m) * 2); fill(Hs, static_cast<size_t>(doc_count[idx]) * 2);
+        tree.Split(idx, W.data(), Hs.data(), doc_count[idx]);
+    }
+    tree.ComputeTopTerms(maxterms);
+    tree.ComputeAssignments();
+    if (!tree.WriteAssignments(std::string(assign_path))) return -1;
+    std::vector<std::string> dict;
+    for (int i = 0; i < m; ++i) { std::ostringstream s; s << "w" << i; dict.push_back(s.str()); }
+    IHierclustWriter* writer = CreateHierclustWriter(static_cast<FileFormat>(format));
+    const bool ok = tree.WriteTree(writer, std::string(tree_path), dict);
+    delete writer;
+    return ok ? 0 : -2;
 }
 
 } // extern "C"
