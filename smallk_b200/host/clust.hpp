@@ -28,14 +28,12 @@ struct ClustStats
 
 struct ClustOptions
 {
-    NmfOptions nmf_opts;
-    int maxterms;
-    R unbalanced;
-    int trial_allowance;
-    int num_clusters;
-    bool verbose;
-    bool flat;
-    std::string initdir;
+    NmfOptions nmf_opts;            // per-node rank-2 factorization: tol, min_iter, max_iter, ... (k and algorithm are overridden)
+    int maxterms;                   // top terms kept per node
+    R unbalanced;                   // a split with a child below this share of the parent is retried on the smaller child
+    int trial_allowance, num_clusters;
+    bool verbose, flat;             // flat: finish with the NnlsHals flat clustering from the leaf topic vectors
+    std::string initdir;            // Winit_<i>.csv / Hinit_<i>.csv initialisers instead of the random ones
 };
 
 bool IsValid(const ClustOptions& opts, bool validate_matrix = true);
