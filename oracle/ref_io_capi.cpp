@@ -16,13 +16,17 @@ extern "C" {
 
 // Returns 0 and the CSC arrays (up to the capacities given) of the matrix the reference builds from the file; -1 if the
 // reference rejects the file; -2 if a capacity is too small (dimensions are still reported).
+static std::string g_io_error;
+const char* ref_io_last_exception() { return g_io_error.c_str(); }
+
 int ref_load_matrix_market(const char* path, unsigned int* height, unsigned int* width, unsigned int* nnz,
                            unsigned int* col_offsets, unsigned int cap_cols, unsigned int* row_indices, double* data,
                            unsigned int cap_nz)
 {
     SparseMatrix<double> A;
     unsigned int h = 0, w = 0, nz = 0;
-    if (!LoadMatrixMarketFile(std::string(path), A, h, w, nz)) return -1;
+    try { if (!LoadMatrixMarketFile(std::string(path), A, h, w, nz)) return -1; }
+    catch (std::exception& e) { g_io_error = e.what(); return -3; }      // SparseMatrix::Load / Compress throw through the reader
     *height = A.Height(); *width = A.Width(); *nnz = A.Size();
     if (A.Width() + 1 > cap_cols || A.Size() > cap_nz) return -2;
     const unsigned int* cp = A.LockedColBuffer();

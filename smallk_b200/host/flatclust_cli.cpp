@@ -154,7 +154,9 @@ int main(int argc, char* argv[])
     smallk_io::CscMatrix A;
     std::vector<double> buf_a;
     unsigned int m = 0, n = 0;
-    bool ok = sparse ? smallk_io::LoadMatrixMarketFile(opts.infile_A, A) : smallk_io::LoadDelimitedFile(buf_a, m, n, opts.infile_A);
+    bool ok = false;
+    try { ok = sparse ? smallk_io::LoadMatrixMarketFile(opts.infile_A, A) : smallk_io::LoadDelimitedFile(buf_a, m, n, opts.infile_A); }
+    catch (std::exception& e) { std::cerr << e.what() << std::endl; NmfFinalize(); return -1; }      // index out of bounds, no entries
     if (!ok) { std::cerr << "\nload failed for file " << opts.infile_A << std::endl; NmfFinalize(); return -1; }
     if (sparse) { m = A.height; n = A.width; }
     if (dictionary.size() < m) { std::cerr << "\ndictionary has fewer terms than the matrix has rows" << std::endl; NmfFinalize(); return -1; }

@@ -157,7 +157,9 @@ int main(int argc, char* argv[])
     smallk_io::CscMatrix csc;
     std::vector<R> buf_a;
     unsigned int m = 0, n = 0;
-    const bool ok = sparse ? smallk_io::LoadMatrixMarketFile(opts.infile_A, csc) : smallk_io::LoadDelimitedFile(buf_a, m, n, opts.infile_A);
+    bool ok = false;
+    try { ok = sparse ? smallk_io::LoadMatrixMarketFile(opts.infile_A, csc) : smallk_io::LoadDelimitedFile(buf_a, m, n, opts.infile_A); }
+    catch (std::exception& e) { std::cerr << e.what() << std::endl; NmfFinalize(); return -1; }      // index out of bounds, no entries
     if (!ok) { std::cerr << "\nload failed for file " << opts.infile_A << std::endl; NmfFinalize(); return -1; }
     if (sparse) { m = csc.height; n = csc.width; }
     if (dictionary.size() < m) { std::cerr << "\ndictionary has fewer terms than the matrix has rows" << std::endl; NmfFinalize(); return -1; }

@@ -178,12 +178,16 @@ double smkh_compute_priority_gpu(const double* W_parent, const double* W_child, 
 }
 
 // ---- file formats (host/matrix_io.hpp), unit-testable without a GPU: same contract as oracle/ref_io_capi.cpp ----
+static std::string g_io_error;
+const char* smkh_io_last_exception() { return g_io_error.c_str(); }
+
 int smkh_load_matrix_market(const char* path, unsigned int* height, unsigned int* width, unsigned int* nnz,
                             unsigned int* col_offsets, unsigned int cap_cols, unsigned int* row_indices, double* data,
                             unsigned int cap_nz)
 {
     smallk_io::CscMatrix A;
-    if (!smallk_io::LoadMatrixMarketFile(path, A)) return -1;
+    try { if (!smallk_io::LoadMatrixMarketFile(path, A)) return -1; }
+    catch (std::exception& e) { g_io_error = e.what(); return -3; }      // the reader throws where the reference's throws
     *height = A.height; *width = A.width; *nnz = A.nnz();
     if (A.width + 1 > cap_cols || A.nnz() > cap_nz) return -2;
     for (unsigned int c = 0; c <= A.width; ++c) col_offsets[c] = A.col_offsets[c];

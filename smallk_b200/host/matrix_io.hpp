@@ -10,42 +10,52 @@
 #include <cstring>
 #include <fstream>
 #include <sstream>
+#include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace smallk_io {
 
 // Column-major buffer (ld = height) from a delimited text file; rows of the file are matrix rows.
+// The reference's reader (delimited_file.hpp:79-135, delimited_file.cpp:36-103) defines the format by what it does, and
+// files in the wild depend on it, so its rules are kept one by one (tests/test_file_formats.py holds both readers to the
+// same buffers on well-formed and malformed input):
+//   * blank lines and lines starting with '#' or '%' are skipped at the top of the file only;
+//   * width = 1 + number of delimiters in the first data line; every later line is a row, blank or not;
+//   * a last line without a terminating newline is not a row (and if it is the first data line the buffer stays zero);
+//   * a row is read with formatted stream extraction, value then one non-blank separator character, `width` times:
+//     short rows leave zeros, text that is not a number reads as 0 and ends the row, and so do "nan" / "inf".
 inline bool LoadDelimitedFile(std::vector<double>& buffer, unsigned int& height, unsigned int& width,
                               const std::string& filename, const char delim = ',')
 {
     std::ifstream in(filename);
     if (!in) return false;
-    std::vector<std::vector<double>> rows;
-    std::string line;
-    while (std::getline(in, line))
+    // every line with a flag: was it terminated by a newline (the stream had not hit end-of-file when it was read)?
+    std::vector<std::pair<std::string, bool>> lines;
     {
-        if (line.empty() || line == "\r") continue;
-        std::vector<double> vals;
-        const char* p = line.c_str();
-        while (*p)
-        {
-            char* end = nullptr;
-            double v = std::strtod(p, &end);
-            if (end == p) break;
-            vals.push_back(v);
-            p = end;
-            while (*p == delim || *p == ' ' || *p == '\t' || *p == '\r') ++p;
-        }
-        if (!vals.empty()) rows.push_back(std::move(vals));
+        std::string text;
+        while (std::getline(in, text)) lines.emplace_back(text, !in.eof());
     }
-    if (rows.empty()) return false;
-    height = static_cast<unsigned int>(rows.size());
-    width = static_cast<unsigned int>(rows[0].size());
-    for (const auto& r : rows) if (r.size() != width) return false;
-    buffer.assign(static_cast<size_t>(height) * width, 0.0);
-    for (unsigned int r = 0; r < height; ++r)
-        for (unsigned int c = 0; c < width; ++c) buffer[static_cast<size_t>(c) * height + r] = rows[r][c];
+    size_t first = 0;
+    while (first < lines.size() && (lines[first].first.empty() || lines[first].first[0] == '#' || lines[first].first[0] == '%')) ++first;
+    if (first == lines.size()) return false;
+    width = 1;
+    for (const char ch : lines[first].first) if (ch == delim) ++width;
+    height = 1;
+    for (size_t i = first + 1; i < lines.size(); ++i) if (lines[i].second) ++height;
+    buffer.resize(static_cast<size_t>(height) * width);
+    unsigned int r = 0;
+    for (size_t i = first; i < lines.size() && lines[i].second; ++i, ++r)
+    {
+        std::istringstream row(lines[i].first);
+        char separator;
+        for (unsigned int c = 0; c != width; ++c)
+        {
+            row >> buffer[static_cast<size_t>(c) * height + r];
+            row >> separator;
+        }
+    }
     return true;
 }
 
@@ -77,7 +87,13 @@ inline bool IsMatrixMarketFile(const std::string& filename)
     return filename.size() >= 4 && filename.compare(filename.size() - 4, 4, ".mtx") == 0;
 }
 
-// Sparse (coordinate) MatrixMarket -> CSC.
+// Sparse (coordinate) MatrixMarket -> CSC. Behaviour on malformed files follows the reference's reader
+// (sparse_matrix_io.hpp:117-260 over SparseMatrix::Load / Compress, sparse_matrix_impl.hpp:158-258), which the tests hold it to:
+//   * every line after the size line counts as an entry line, blank ones included (they carry no entry), and the count
+//     must equal the declared number of entries, otherwise the file is rejected (returns false);
+//   * an index of 0 is rejected; an index beyond the declared shape throws std::runtime_error("SparseMatrix::Load: row | col
+//     index out of bounds"), a file without entries throws std::runtime_error("SparseMatrix::Compress: matrix has no data");
+//   * entries are read with formatted stream extraction (a missing value reads as 0).
 inline bool LoadMatrixMarketFile(const std::string& filename, CscMatrix& A)
 {
     std::ifstream in(filename);
@@ -100,22 +116,29 @@ inline bool LoadMatrixMarketFile(const std::string& filename, CscMatrix& A)
     std::vector<unsigned int> tr, tc;
     std::vector<double> tv;
     tr.reserve((symmetric || skew) ? 2 * nz : nz); tc.reserve(tr.capacity()); tv.reserve(tr.capacity());
-    for (unsigned long long e = 0; e < nz; ++e)
+    unsigned long long line_count = 0;
+    double v = 0.0;
+    while (std::getline(in, line))
     {
-        if (!std::getline(in, line)) return false;
-        const char* p = line.c_str();
-        char* end = nullptr;
-        unsigned long r = std::strtoul(p, &end, 10); p = end;
-        unsigned long c = std::strtoul(p, &end, 10); p = end;
-        double v = pattern ? 1.0 : std::strtod(p, &end);
-        if (r == 0 || c == 0 || r > h || c > w) return false;
-        tr.push_back(static_cast<unsigned int>(r - 1)); tc.push_back(static_cast<unsigned int>(c - 1)); tv.push_back(v);
+        ++line_count;
+        if (line.empty()) continue;
+        std::istringstream entry(line);
+        unsigned int r = 0, c = 0;
+        entry >> r; entry >> c;
+        if (pattern) v = 1.0; else entry >> v;
+        if (r == 0 || c == 0) return false;
+        if (c > w) throw std::runtime_error("SparseMatrix::Load: col index out of bounds");
+        if (r > h) throw std::runtime_error("SparseMatrix::Load: row index out of bounds");
+        tr.push_back(r - 1); tc.push_back(c - 1); tv.push_back(v);
         if ((symmetric || skew) && r != c)
         {
-            tr.push_back(static_cast<unsigned int>(c - 1)); tc.push_back(static_cast<unsigned int>(r - 1));
-            tv.push_back(skew ? -v : v);
+            if (r > w) throw std::runtime_error("SparseMatrix::Load: col index out of bounds");
+            if (c > h) throw std::runtime_error("SparseMatrix::Load: row index out of bounds");
+            tr.push_back(c - 1); tc.push_back(r - 1); tv.push_back(skew ? -v : v);
         }
     }
+    if (tv.empty()) throw std::runtime_error("SparseMatrix::Compress: matrix has no data");
+    if (line_count != nz) return false;
     A.height = static_cast<unsigned int>(h); A.width = static_cast<unsigned int>(w);
     const size_t n = tv.size();
     A.col_offsets.assign(static_cast<size_t>(w) + 1, 0u);

@@ -126,3 +126,74 @@ def test_csv_writer_and_reader_match_the_reference(tmp_path):
         ref.ref_load_delimited(pr.encode(), ctypes.byref(hh), ctypes.byref(ww), b1.ctypes.data_as(dp), h * w)
         host.smkh_load_delimited(pr.encode(), ctypes.byref(hh), ctypes.byref(ww), b2.ctypes.data_as(dp), h * w)
         assert np.array_equal(b1, b2)
+
+
+MM = "%%MatrixMarket matrix coordinate real general\n"
+MALFORMED_MTX = {
+    "trailing_blank": MM + "3 3 2\n1 1 1.5\n3 2 2.5\n\n",          # a blank line counts as an entry line: count mismatch
+    "middle_blank": MM + "3 3 2\n1 1 1.5\n\n3 2 2.5\n",
+    "too_few": MM + "3 3 3\n1 1 1.5\n3 2 2.5\n",
+    "too_many": MM + "3 3 1\n1 1 1.5\n3 2 2.5\n",
+    "no_newline_end": MM + "3 3 2\n1 1 1.5\n3 2 2.5",               # accepted
+    "comment_after_size": MM + "3 3 2\n% c\n1 1 1.5\n3 2 2.5\n",
+    "blank_before_size": MM + "\n3 3 2\n1 1 1.5\n3 2 2.5\n",        # accepted
+    "row_out_of_range": MM + "3 3 1\n4 1 1.0\n",                    # throws
+    "col_out_of_range": MM + "3 3 1\n1 5 1.0\n",                    # throws
+    "negative_index": MM + "3 3 1\n-1 1 1.0\n",                     # wraps to a huge index: throws
+    "no_entries": MM + "3 3 0\n",                                   # throws
+    "crlf": MM.replace("\n", "\r\n") + "3 3 2\r\n1 1 1.5\r\n3 2 2.5\r\n",
+    "pattern_with_values": "%%MatrixMarket matrix coordinate pattern general\n3 3 2\n1 1 9\n2 2\n",
+    "symmetric_upper": "%%MatrixMarket matrix coordinate real symmetric\n3 3 2\n1 2 1.0\n3 3 2.0\n",
+    "symmetric_out_of_range": "%%MatrixMarket matrix coordinate real symmetric\n2 3 1\n1 3 1.0\n",
+    "lowercase_banner": "%%matrixmarket matrix coordinate real general\n3 3 1\n1 1 1.0\n",
+    "tabs": MM + "3\t3\t1\n1\t1\t1.0\n",
+}
+
+
+def test_matrix_market_reader_on_malformed_files_behaves_like_the_reference(tmp_path):
+    """Accept / reject / throw, and what is built when accepted, file by file. (A data line without a value is left out: the
+    reference reads an uninitialised variable there.)"""
+    host, ref = _libs()
+    if not hasattr(ref, "ref_io_last_exception"):
+        pytest.skip("oracle/_ref predates the exception-reporting entry point")
+    ref.ref_io_last_exception.restype = ctypes.c_char_p
+    host.smkh_io_last_exception.restype = ctypes.c_char_p
+    for name, text in MALFORMED_MTX.items():
+        p = os.path.join(str(tmp_path), name + ".mtx")
+        with open(p, "w", newline="") as f:
+            f.write(text)
+        rc_r, want = _load_mtx(ref.ref_load_matrix_market, p)
+        rc_h, got = _load_mtx(host.smkh_load_matrix_market, p)
+        assert rc_r == rc_h, (name, rc_r, rc_h)
+        if rc_r == 0:
+            assert got[:3] == want[:3], name
+            for a, b in zip(got[3:], want[3:]):
+                assert np.array_equal(a, b), name
+        elif rc_r == -3:                                       # both threw: the same exception text
+            assert ref.ref_io_last_exception() == host.smkh_io_last_exception(), name
+
+
+MALFORMED_CSV = {
+    "crlf": "1,2,3\r\n4,5,6\r\n", "blank_lead": "\n\n1,2\n3,4\n", "comment_hash": "# hello\n1,2\n3,4\n", "comment_pct": "% hello\n1,2\n3,4\n",
+    "trailing_blank": "1,2\n3,4\n\n", "middle_blank": "1,2\n\n3,4\n", "spaces": "1, 2 ,3\n 4,5, 6\n", "sci": "1e-3,-2.5E+2,+3\n.5,5.,-0.0\n",
+    "ragged": "1,2,3\n4,5\n", "trailing_comma": "1,2,\n3,4,\n", "single": "7\n", "one_row": "1,2,3,4\n", "one_col": "1\n2\n3\n",
+    "empty": "", "only_comments": "# a\n% b\n", "text": "a,b\n1,2\n", "no_newline_end": "1,2\n3,4", "only_line_no_newline": "1,2",
+    "tabs": "1\t2\n3\t4\n", "nan_inf": "nan,inf\n1,2\n", "comment_in_middle": "1,2\n# x\n3,4\n",
+}
+
+
+def test_csv_reader_on_malformed_files_behaves_like_the_reference(tmp_path):
+    """The reference's reader defines the format by what it does (blank rows are rows, a last line without a newline is not,
+    short rows are padded with zeros, ...): same accept / reject decision, same shape, same buffer."""
+    host, ref = _libs()
+    for name, text in MALFORMED_CSV.items():
+        p = os.path.join(str(tmp_path), name + ".csv")
+        with open(p, "w", newline="") as f:
+            f.write(text)
+        res = []
+        for fn in (ref.ref_load_delimited, host.smkh_load_delimited):
+            h, w = ctypes.c_uint(0), ctypes.c_uint(0)
+            buf = np.full(64, -99.0)
+            rc = fn(p.encode(), ctypes.byref(h), ctypes.byref(w), buf.ctypes.data_as(dp), 64)
+            res.append((rc, h.value, w.value, buf[: h.value * w.value].tolist() if rc == 0 else None))
+        assert res[0] == res[1], (name, res)
