@@ -216,3 +216,22 @@ int ref_tree_script(int seed, int m, int n, int num_clusters, int maxterms, int 
 }
 
 } // extern "C"
+
+// ---- dictionary files: LoadStringsFromFile common/src/utils.cpp:220-239
+#include <cstring>
+#include "utils.hpp"
+extern "C" {
+
+int ref_load_strings(const char* path, char* out, unsigned int cap, int* count)
+{
+    std::vector<std::string> v(1, "preexisting");              // the reader appends
+    if (!LoadStringsFromFile(std::string(path), v)) return -1;
+    std::string joined;
+    for (const auto& t : v) { joined += t; joined += '\n'; }
+    if (joined.size() + 1 > cap) return -2;
+    std::memcpy(out, joined.c_str(), joined.size() + 1);
+    *count = static_cast<int>(v.size());
+    return 0;
+}
+
+} // extern "C"

@@ -23,15 +23,13 @@ inline std::string EnsureTrailingPathSep(const std::string& dir)
 
 inline bool LoadStringsFromFile(const std::string& path, std::vector<std::string>& out)
 {
+    // common/src/utils.cpp:220-239, rule for rule: lines are APPENDED to `out`, a carriage return stays part of the string,
+    // blank lines are strings, and a last line that is not terminated by a newline is not read
+    // (tests/test_file_formats.py::test_dictionary_reader_matches_reference).
     std::ifstream in(path);
     if (!in) return false;
-    out.clear();
     std::string line;
-    while (std::getline(in, line))
-    {
-        if (!line.empty() && line.back() == '\r') line.pop_back();
-        out.push_back(line);
-    }
+    while (std::getline(in, line) && !in.eof()) out.push_back(line);
     return true;
 }
 

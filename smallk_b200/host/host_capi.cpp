@@ -329,4 +329,17 @@ int smkh_tree_script(int seed, int m, int n, int num_clusters, int maxterms, int
     return ok ? 0 : -2;
 }
 
+// dictionary files (host/flat_clust_output.hpp LoadStringsFromFile): the strings joined by '\n' into out (capacity cap)
+int smkh_load_strings(const char* path, char* out, unsigned int cap, int* count)
+{
+    std::vector<std::string> v(1, "preexisting");              // the reader appends
+    if (!LoadStringsFromFile(path, v)) return -1;
+    std::string joined;
+    for (const auto& t : v) { joined += t; joined += '\n'; }
+    if (joined.size() + 1 > cap) return -2;
+    std::memcpy(out, joined.c_str(), joined.size() + 1);
+    *count = static_cast<int>(v.size());
+    return 0;
+}
+
 } // extern "C"

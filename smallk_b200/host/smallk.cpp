@@ -7,6 +7,8 @@
 #include <limits>
 #include <random>
 #include <sstream>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <stdexcept>
 #include <thread>
 
@@ -76,18 +78,18 @@ void SetOutputPrecision(const unsigned int num_digits)
 double GetNmfTolerance() { return nmf_tolerance; }
 void SetNmfTolerance(const double tol)
 {
-    if (tol <= 0.0 || tol >= 1.0) throw std::logic_error("smallk::SetNmfTolerance: tolerance must be in the interval (0.0, 1.0)");
+    if (tol <= 0.0 || tol >= 1.0) throw std::logic_error("smallk error (SetNmfTolerance): require 0.0 < tol < 1.0");
     nmf_tolerance = tol;
 }
 unsigned int GetMaxIter() { return max_iter; }
-void SetMaxIter(const unsigned int v) { max_iter = v; }
+void SetMaxIter(const unsigned int v) { max_iter = v ? v : 1u; }
 unsigned int GetMinIter() { return min_iter; }
-void SetMinIter(const unsigned int v) { min_iter = v; }
+void SetMinIter(const unsigned int v) { min_iter = v ? v : 1u; }
 unsigned int GetMaxThreads() { return max_threads; }
 void SetMaxThreads(const unsigned int v)
 {
-    unsigned int hw = std::max(2u, std::thread::hardware_concurrency());
-    max_threads = std::max(1u, std::min(v, hw));
+    // smallk.cpp:427-433: capped at the hardware thread count, at least 1 (the GPU path does not use it)
+    max_threads = std::max(1u, std::min(v, std::thread::hardware_concurrency()));
 }
 void Reset()
 {
@@ -107,9 +109,10 @@ void SeedRNG(const int seed) { rng.SeedFromInt(seed); }
 // smallk.cpp:652-735
 void LoadDictionary(const std::string& filepath)
 {
+    dictionary.clear();
     dict_loaded = false;
     if (!LoadStringsFromFile(filepath, dictionary))
-        throw std::runtime_error("smallk error (LoadDictionary): load failed for file \"" + filepath + "\"");
+        throw std::runtime_error("smallk error (LoadDictionary): load failed for file " + filepath);
     dict_loaded = true;
 }
 void LoadDictionary(const std::vector<std::string>& terms)
@@ -124,12 +127,15 @@ void SetOutputFormat(const OutputFormat format) { clustfile_format = format; }
 double GetHierNmf2Tolerance() { return hier_nmf2_tolerance; }
 void SetHierNmf2Tolerance(const double tol)
 {
-    if (tol <= 0.0 || tol >= 1.0) throw std::logic_error("smallk error (SetHierNmf2Tolerance): tolerance must be in the interval (0.0, 1.0)");
+    if (tol <= 0.0 || tol >= 1.0) throw std::logic_error("smallk error (SetHierNmf2Tolerance): require 0.0 < tol < 1.0");
     hier_nmf2_tolerance = tol;
 }
 
 void LoadMatrix(const std::string& filepath)
 {
+    // smallk.cpp:168-206: same checks, exception types and texts
+    if (filepath.empty()) throw std::runtime_error("smallk error (LoadMatrix): matrix filename is invalid.");
+    matrix_loaded = false;
     bool ok;
     if (smallk_io::IsMatrixMarketFile(filepath))
     {
@@ -141,19 +147,18 @@ void LoadMatrix(const std::string& filepath)
         ok = smallk_io::LoadDelimitedFile(buf_a, m, n, filepath);
         if (ok) { ldim_a = m; is_sparse = false; }
     }
-    if (!ok)
-    {
-        std::ostringstream msg;
-        msg << "smallk error (LoadMatrix): load failed for file \"" << filepath << "\"";
-        throw std::runtime_error(msg.str());
-    }
+    if (!ok) throw std::runtime_error("smallk error (LoadMatrix): load failed for file " + filepath);
     matrix_loaded = true;
 }
 
 void LoadMatrix(const double* buffer, const unsigned int ldim, const unsigned int height, const unsigned int width)
 {
-    if (nullptr == buffer) throw std::logic_error("smallk error (LoadMatrix): null buffer");
-    if (ldim < height) throw std::logic_error("smallk error (LoadMatrix): leading dimension too small");
+    // smallk.cpp:209-263 (its messages say "LoadSparseMatrixFromBuffer" for the dense overload too)
+    matrix_loaded = false;
+    if (0 == height) throw std::runtime_error("smallk error (LoadSparseMatrixFromBuffer): invalid height input.");
+    if (0 == width) throw std::runtime_error("smallk error (LoadSparseMatrixFromBuffer): invalid width input.");
+    if (nullptr == buffer) throw std::runtime_error("smallk error (LoadSparseMatrixFromBuffer): empty data pointer.");
+    if (ldim < height) throw std::logic_error("smallk error (LoadMatrix): leading dimension too small");      // not checked by the reference
     // The reference swaps its loop bounds here (smallk.cpp:249-255) and is only right for square inputs;
     // this copies every column of the height x width matrix.
     m = height; n = width; ldim_a = height;
@@ -168,7 +173,18 @@ void LoadMatrix(const unsigned int height, const unsigned int width, const unsig
                 const std::vector<double>& data, const std::vector<unsigned int>& row_indices,
                 const std::vector<unsigned int>& col_offsets)
 {
-    if (data.size() < nz || row_indices.size() < nz || col_offsets.size() < static_cast<size_t>(width) + 1)
+    // smallk.cpp:266-333: the reference's checks in the reference's order
+    matrix_loaded = false;
+    const char* who = "smallk error (LoadSparseMatrixFromBuffer): ";
+    if (row_indices.size() != data.size()) throw std::runtime_error(std::string(who) + "invalid input vectors.");
+    if (0 == height) throw std::runtime_error(std::string(who) + "invalid height input.");
+    if (0 == width) throw std::runtime_error(std::string(who) + "invalid width input.");
+    if (data.size() > static_cast<size_t>(height) * width) throw std::runtime_error(std::string(who) + "invalid inputs.");
+    if (data.empty()) throw std::runtime_error(std::string(who) + "empty data vector.");
+    if (row_indices.empty()) throw std::runtime_error(std::string(who) + "empty row_indices vector.");
+    if (col_offsets.empty()) throw std::runtime_error(std::string(who) + "empty col_offsets vector.");
+    // not checked by the reference (it would read past the vectors): the arrays must hold what nz and width promise
+    if (data.size() < nz || col_offsets.size() < static_cast<size_t>(width) + 1)
         throw std::logic_error("smallk error (LoadMatrix): inconsistent sparse arrays");
     A.height = height; A.width = width;
     A.data.assign(data.begin(), data.begin() + nz);
@@ -181,7 +197,22 @@ void LoadMatrix(const unsigned int height, const unsigned int width, const unsig
 
 bool IsMatrixLoaded() { return matrix_loaded; }
 std::string GetOutputDir() { return outdir; }
-void SetOutputDir(const std::string& d) { outdir = EnsureTrailingSep(d); }
+void SetOutputDir(const std::string& output_dir)
+{
+    // smallk.cpp:346-380: a relative path is taken from the current directory; the directory must exist
+    std::string full_path;
+    if (!output_dir.empty() && '/' != output_dir[0])
+    {
+        char cwd[4096];
+        if (nullptr == getcwd(cwd, sizeof(cwd))) throw std::runtime_error("smallk error (SetOutputDir): could not determine current directory.");
+        full_path = EnsureTrailingSep(cwd);
+    }
+    full_path += output_dir;
+    struct stat st;
+    if (0 != stat(full_path.c_str(), &st) || !S_ISDIR(st.st_mode))
+        throw std::logic_error("smallk error (SetOutputDir): the directory \"" + full_path + "\" does not exist.");
+    outdir = EnsureTrailingSep(full_path);
+}
 
 void Nmf(const unsigned int kval, const Algorithm algorithm, const std::string& csv_file_w, const std::string& csv_file_h)
 {

@@ -197,3 +197,26 @@ def test_csv_reader_on_malformed_files_behaves_like_the_reference(tmp_path):
             rc = fn(p.encode(), ctypes.byref(h), ctypes.byref(w), buf.ctypes.data_as(dp), 64)
             res.append((rc, h.value, w.value, buf[: h.value * w.value].tolist() if rc == 0 else None))
         assert res[0] == res[1], (name, res)
+
+
+def test_dictionary_reader_matches_reference(tmp_path):
+    """LoadStringsFromFile (common/src/utils.cpp:220-239): one string per line, appended to what the vector holds."""
+    host, ref = _libs()
+    if not hasattr(ref, "ref_load_strings"):
+        pytest.skip("oracle/_ref predates the dictionary entry point")
+    cases = {"plain": "alpha\nbeta\ngamma\n", "no_newline_end": "alpha\nbeta\ngamma", "crlf": "alpha\r\nbeta\r\n", "blank_lines": "alpha\n\nbeta\n\n",
+             "spaces": "two words\n  padded  \n", "empty": "", "single_no_newline": "alpha"}
+    for name, text in cases.items():
+        p = os.path.join(str(tmp_path), name + ".txt")
+        with open(p, "w", newline="") as f:
+            f.write(text)
+        res = []
+        for fn in (ref.ref_load_strings, host.smkh_load_strings):
+            buf = ctypes.create_string_buffer(4096)
+            cnt = ctypes.c_int(0)
+            rc = fn(p.encode(), buf, 4096, ctypes.byref(cnt))
+            res.append((rc, cnt.value, buf.value))
+        assert res[0] == res[1], (name, res)
+    missing = os.path.join(str(tmp_path), "missing.txt").encode()
+    buf = ctypes.create_string_buffer(64); cnt = ctypes.c_int(0)
+    assert ref.ref_load_strings(missing, buf, 64, ctypes.byref(cnt)) == host.smkh_load_strings(missing, buf, 64, ctypes.byref(cnt)) == -1
