@@ -11,6 +11,8 @@
 #include <vector>
 
 #include "smallk.hpp"
+#include "nmf.hpp"
+#include "flat_clust.hpp"
 
 static void probe(const char* name, const std::function<std::string()>& f)
 {
@@ -96,5 +98,23 @@ int main(int argc, char** argv)
                                         str(GetMinIter()) + " " + str(GetMaxTerms()) + " " + str(static_cast<int>(GetOutputFormat())) + " " + str(GetHierNmf2Tolerance()) +
                                         " [" + GetOutputDir() + "]"; });
     probe("hier_after_reset", [] { HierNmf2(4); return std::string(); });
+    // the L3 functions before NmfInitialize (common/src/nmf.cpp:173-186, flatclust/src/flat_clust.cpp:144-160)
+    {
+        NmfOptions o;
+        o.tol = 0.005; o.algorithm = NmfAlgorithm::BPP; o.prog_est_algorithm = NmfProgressAlgorithm::PG_RATIO;
+        o.height = 3; o.width = 3; o.k = 2; o.min_iter = 1; o.max_iter = 2; o.tolcount = 1; o.max_threads = 1; o.verbose = false; o.normalize = true;
+        std::vector<double> A(9, 1.0), W(6, 0.5), H(6, 0.5), d = {1.0, 2.0, 3.0};
+        std::vector<unsigned int> r = {0, 1, 2}, c = {0, 1, 2, 3};
+        NmfStats st;
+        probe("l3_isinit", [] { return str(static_cast<int>(NmfIsInitialized())); });
+        probe("l3_nmf_uninit", [&] { return str(static_cast<int>(Nmf(o, A.data(), 3, W.data(), 3, H.data(), 2, st))); });
+        probe("l3_nmfsparse_uninit", [&] { return str(static_cast<int>(NmfSparse(o, 3, 3, 3, c.data(), r.data(), d.data(), W.data(), 3, H.data(), 2, st))); });
+        probe("l3_flatclust_uninit", [&] { return str(static_cast<int>(FlatClust(o, A.data(), 3, W.data(), 3, H.data(), 2, st))); });
+        probe("l3_flatclustsparse_uninit", [&] { return str(static_cast<int>(FlatClustSparse(o, 3, 3, 3, c.data(), r.data(), d.data(), W.data(), 3, H.data(), 2, st))); });
+        o.k = 0;
+        probe("l3_isvalid_k0", [&] { return str(IsValid(o)); });
+        o.k = 2; o.algorithm = NmfAlgorithm::RANK2; o.k = 3;
+        probe("l3_isvalid_rank2_k3", [&] { return str(IsValid(o)); });
+    }
     return 0;
 }

@@ -37,8 +37,8 @@ def _run(exe, d):
     return [ln.replace(d, "<DIR>") for ln in lines]
 
 
-def _build(exe, include, libdir, libs):
-    cmd = ["g++", "-std=c++14", "-O1", "-o", exe, PROBE, "-I" + include, "-L" + libdir] + ["-l" + x for x in libs] + ["-Wl,-rpath," + libdir]
+def _build(exe, includes, libdir, libs):
+    cmd = ["g++", "-std=c++14", "-O1", "-o", exe, PROBE] + ["-I" + i for i in includes] + ["-L" + libdir] + ["-l" + x for x in libs] + ["-Wl,-rpath," + libdir]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-3000:]
 
@@ -50,7 +50,7 @@ def host_transcript(tmp_path_factory):
     d = str(tmp_path_factory.mktemp("probe"))
     _inputs(d)
     exe = os.path.join(d, "probe_host")
-    _build(exe, os.path.join(ROOT, "smallk_b200", "host"), HOST_LIB, ["smallk_host", "smallk_b200"])
+    _build(exe, [os.path.join(ROOT, "smallk_b200", "host")], HOST_LIB, ["smallk_host", "smallk_b200"])
     return _run(exe, d), d
 
 
@@ -67,7 +67,7 @@ def test_host_api_matches_live_reference_probe(host_transcript):
     if not (os.path.isdir(REF_INC) and os.path.exists(os.path.join(REF_LIB, "libsmallk_ref.so"))):
         pytest.skip("/root/reference or oracle/_ref not present on this machine")
     exe = os.path.join(d, "probe_ref")
-    _build(exe, REF_INC, REF_LIB, ["smallk_ref"])
+    _build(exe, [REF_INC, "/root/reference/common/include", "/root/reference/flatclust/include"], REF_LIB, ["smallk_ref"])
     want = _run(exe, d)
     if os.environ.get("SMK_REGENERATE_GOLDEN"):
         with open(GOLDEN, "w") as f:
