@@ -91,7 +91,7 @@ bool Parse(int argc, char* argv[], CommandLineOptions& o)
             if (up == "HALS") n.algorithm = NmfAlgorithm::HALS;
             else if (up == "RANK2") n.algorithm = NmfAlgorithm::RANK2;
             else if (up == "BPP") n.algorithm = NmfAlgorithm::BPP;
-            else { std::cerr << "invalid command line value: " << arg << std::endl; return false; }
+            else { std::cerr << "Invalid value specified for command-line argument " << up << std::endl; return false; }
             break;
         case 'k': o.clust_opts.verbose = (0 != std::atoi(optarg)); n.verbose = o.clust_opts.verbose; break;
         case 'l': n.max_threads = std::max(1, std::atoi(optarg)); break;
@@ -103,7 +103,7 @@ bool Parse(int argc, char* argv[], CommandLineOptions& o)
         case 's':
             if (up == "XML") o.format = FileFormat::XML;
             else if (up == "JSON") o.format = FileFormat::JSON;
-            else { std::cerr << "invalid command line value: " << arg << std::endl; return false; }
+            else { std::cerr << "Invalid value specified for command-line argument " << up << std::endl; return false; }
             break;
         case 't': o.fuzzyfile = arg; break;
         case 'u': o.seed = std::atoi(optarg); break;
@@ -138,7 +138,19 @@ int main(int argc, char* argv[])
     }
     if (!opts.outdir.empty() && !DirectoryExists(opts.outdir))
     { std::cerr << "the specified output directory \"" << opts.outdir << "\" does not exist" << std::endl; return -1; }
-    if (!IsValid(opts.clust_opts, false)) return -1;
+    {
+        // flatclust/src/command_line.cpp:386-441: the tool's own checks (its own texts, not FlatClustOptions' IsValid)
+        const NmfOptions& no = opts.clust_opts.nmf_opts;
+        const char* complaint = nullptr;
+        if (opts.clust_opts.num_clusters <= 0) complaint = "value for --clusters must be a positive integer";
+        else if (no.tol <= 0.0 || no.tol >= 1.0) complaint = "tolerance must be in the interval (0.0, 1.0)";
+        else if (no.min_iter <= 0) complaint = "miniter must be a positive integer";
+        else if (no.max_iter <= 0) complaint = "maxiter must be a positive integer";
+        else if (opts.clust_opts.maxterms <= 0) complaint = "maxterms must be a positive integer";
+        else if (NmfProgressAlgorithm::PG_RATIO != no.prog_est_algorithm && NmfProgressAlgorithm::DELTA_FNORM != no.prog_est_algorithm)
+            complaint = "clustlib error: unknown stopping criterion ";
+        if (complaint) { std::cerr << complaint << std::endl; return -1; }
+    }
     Random rng;
     if (opts.seed >= 0) rng.SeedFromInt(opts.seed); else rng.SeedFromTime();
     try { NmfInitialize(argc, argv); }

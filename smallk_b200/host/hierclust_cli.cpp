@@ -103,7 +103,7 @@ bool Parse(int argc, char* argv[], CommandLineOptions& o)
             std::transform(up.begin(), up.end(), up.begin(), ::toupper);
             if (up == "XML") o.format = FileFormat::XML;
             else if (up == "JSON") o.format = FileFormat::JSON;
-            else { std::cerr << "invalid command line value: " << arg << std::endl; return false; }
+            else { std::cerr << "Invalid value specified for command-line argument " << up << std::endl; return false; }
             break;
         }
         case 'u': o.seed = std::atoi(optarg); break;

@@ -80,12 +80,12 @@ bool Parse(int argc, char* argv[], CommandLineOptions& o)
             else if (up == "HALS") o.nmf_opts.algorithm = NmfAlgorithm::HALS;
             else if (up == "RANK2") o.nmf_opts.algorithm = NmfAlgorithm::RANK2;
             else if (up == "BPP") o.nmf_opts.algorithm = NmfAlgorithm::BPP;
-            else { std::cerr << "invalid command line value: " << tmp << std::endl; return false; }
+            else { std::cerr << "Invalid value specified for command-line argument " << up << std::endl; return false; }
             break;
         case 'd':
             if (up == "PG_RATIO") o.nmf_opts.prog_est_algorithm = NmfProgressAlgorithm::PG_RATIO;
             else if (up == "DELTA") o.nmf_opts.prog_est_algorithm = NmfProgressAlgorithm::DELTA_FNORM;
-            else { std::cerr << "invalid command line value: " << tmp << std::endl; return false; }
+            else { std::cerr << "Invalid value specified for command-line argument " << up << std::endl; return false; }
             break;
         case 'e': o.nmf_opts.tol = std::atof(optarg); break;
         case 'f': o.nmf_opts.tolcount = std::atoi(optarg); break;
@@ -114,7 +114,12 @@ bool Parse(int argc, char* argv[], CommandLineOptions& o)
     if (1 == argc) o.show_help = true;
     if (o.show_help) return false;
     if (o.infile_A.empty()) { std::cerr << "required command line argument --matrixfile not found" << std::endl; return false; }
-    if (o.nmf_opts.k <= 0) { std::cerr << "required command line argument --k not found" << std::endl; return false; }
+    // nmf/src/command_line.cpp:331-350: k is "missing" only when it is 0 and the algorithm is not RANK2 (a negative k goes on to
+    // IsValid); RANK2 forces k = 2 with a warning
+    if (0 == o.nmf_opts.k && NmfAlgorithm::RANK2 != o.nmf_opts.algorithm)
+    { std::cerr << "required command line argument --k not found" << std::endl; return false; }
+    if (NmfAlgorithm::RANK2 == o.nmf_opts.algorithm && 2 != o.nmf_opts.k)
+    { std::cerr << "warning: forcing k=2 for RANK2 algorithm" << std::endl; o.nmf_opts.k = 2; }
     return true;
 }
 } // namespace
@@ -127,10 +132,17 @@ int main(int argc, char* argv[])
         if (opts.show_help) { ShowHelp(argv[0]); return 0; }
         return -1;
     }
+    if (!IsValid(opts.nmf_opts, false)) return -1;            // nmf/src/main.cpp:60-61: before the library is initialised
     try { NmfInitialize(argc, argv); }
     catch (std::exception& e) { std::cerr << e.what() << std::endl; return -1; }
 
     const bool sparse = smallk_io::IsMatrixMarketFile(opts.infile_A);
+    {
+        // nmf/src/main.cpp:70-103: .mtx is sparse, .csv is dense, anything else is refused
+        const std::string& f = opts.infile_A;
+        const bool csv = f.size() >= 4 && f.compare(f.size() - 4, 4, ".csv") == 0;
+        if (!sparse && !csv) { std::cerr << "\nunsupported file type: " << f << std::endl; NmfFinalize(); return -1; }
+    }
     std::vector<double> buf_a;
     smallk_io::CscMatrix A;
     unsigned int m = 0, n = 0;
@@ -141,8 +153,6 @@ int main(int argc, char* argv[])
     if (!ok) { std::cerr << "\nload failed for file " << opts.infile_A << std::endl; NmfFinalize(); return -1; }
     if (sparse) { m = A.height; n = A.width; }
     opts.nmf_opts.height = m; opts.nmf_opts.width = n;
-    if (NmfAlgorithm::RANK2 == opts.nmf_opts.algorithm && 2 != opts.nmf_opts.k)
-    { std::cerr << "RANK2 algorithm requires k == 2" << std::endl; NmfFinalize(); return -1; }
     if (!IsValid(opts.nmf_opts)) { NmfFinalize(); return -1; }
     const unsigned int k = opts.nmf_opts.k;
 

@@ -49,9 +49,14 @@ def test_nmf_cli_rejects_bad_options(c1):
     d = c1[0]
     exe = os.path.join(BIN, "nmf")
     r = subprocess.run([exe, "--matrixfile", str(d / "A.csv"), "--k", "16", "--algorithm", "NOPE"], capture_output=True, text=True)
-    assert r.returncode != 0 and "invalid command line value" in r.stderr
-    r = subprocess.run([exe, "--matrixfile", str(d / "A.csv"), "--k", "3", "--algorithm", "RANK2"], capture_output=True, text=True)
-    assert r.returncode != 0
+    assert r.returncode != 0 and "Invalid value specified for command-line argument NOPE" in r.stderr
+    # RANK2 with another k: the reference warns and factors with k = 2 (nmf/src/command_line.cpp:341-349)
+    r = subprocess.run([exe, "--matrixfile", str(d / "A.csv"), "--k", "3", "--algorithm", "RANK2", "--verbose", "0", "--maxiter", "20"],
+                       capture_output=True, text=True, cwd=str(d))
+    assert r.returncode == 0 and "warning: forcing k=2 for RANK2 algorithm" in r.stderr, r.stderr
+    assert np.loadtxt(d / "w.csv", delimiter=",").shape[1] == 2
+    r = subprocess.run([exe, "--matrixfile", str(d / "A.csv"), "--k", "-3"], capture_output=True, text=True)
+    assert r.returncode != 0 and "k-value must be a positive integer" in r.stderr
     r = subprocess.run([exe, "--matrixfile", str(d / "A.csv"), "--k", "300"], capture_output=True, text=True)
     assert r.returncode != 0 and "k value cannot exceed" in r.stderr
 
@@ -173,4 +178,4 @@ def test_flatclust_cli_matches_oracle(oracle, tmp_path):
     # MU is not a flatclust algorithm (flatclust/src/command_line.cpp:233-244)
     r = subprocess.run([os.path.join(BIN, "flatclust"), "--matrixfile", str(tmp_path / "A.csv"), "--dictfile", str(tmp_path / "dict.txt"),
                         "--clusters", str(k), "--algorithm", "MU"], capture_output=True, text=True)
-    assert r.returncode != 0 and "invalid command line value" in r.stderr
+    assert r.returncode != 0 and "Invalid value specified for command-line argument MU" in r.stderr
