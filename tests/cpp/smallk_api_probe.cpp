@@ -52,7 +52,7 @@ int main(int argc, char** argv)
     probe("maxterms0", [] { SetMaxTerms(0); return str(GetMaxTerms()); });
     probe("maxterms7", [] { SetMaxTerms(7); return str(GetMaxTerms()); });
     probe("format", [] { SetOutputFormat(XML); const int a = GetOutputFormat(); SetOutputFormat(); return str(a) + " " + str(static_cast<int>(GetOutputFormat())); });
-    probe("threads", [] { SetMaxThreads(3); return str(GetMaxThreads()); });
+    probe("threads", [] { SetMaxThreads(1); const unsigned int a = GetMaxThreads(); SetMaxThreads(0); return str(a) + " " + str(GetMaxThreads()); });
     probe("outdir_missing_abs", [] { SetOutputDir("/nonexistent_dir_for_probe/x"); return GetOutputDir(); });
     probe("outdir_missing_rel", [] { SetOutputDir("nonexistent_dir_for_probe"); return std::string("set"); });
     probe("outdir_ok", [&] { SetOutputDir(dir); return GetOutputDir(); });
