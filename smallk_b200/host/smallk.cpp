@@ -53,7 +53,8 @@ std::string EnsureTrailingSep(const std::string& s)
 
 namespace smallk
 {
-void Initialize(int& argc, char**& argv) { NmfInitialize(argc, argv); }
+// smallk.cpp:114-119: defaults, a clock-seeded generator (SeedRNG overrides it), then the library
+void Initialize(int& argc, char**& argv) { Reset(); rng.SeedFromTime(); NmfInitialize(argc, argv); }
 bool IsInitialized() { return Result::INITIALIZED == NmfIsInitialized(); }
 void Finalize() { NmfFinalize(); }
 
@@ -98,11 +99,11 @@ void Reset()
     buf_a.clear(); buf_w.clear(); buf_h.clear();
     A = smallk_io::CscMatrix();
     outprecision = 6; max_iter = 5000; min_iter = 5; nmf_tolerance = 0.005;
-    max_threads = std::max(2u, std::thread::hardware_concurrency());
+    max_threads = std::thread::hardware_concurrency() ? std::thread::hardware_concurrency() : 2u;     // smallk.cpp:88-92
     outdir.clear();
     dict_loaded = false; dictionary.clear();
     maxterms = 5; hier_nmf2_tolerance = 0.0001; clustfile_format = JSON;
-    rng.SetDefaultState();
+    // the random generator is left alone, as in the reference (smallk.cpp:81-111): Reset() does not undo SeedRNG()
 }
 void SeedRNG(const int seed) { rng.SeedFromInt(seed); }
 
