@@ -235,3 +235,35 @@ int ref_load_strings(const char* path, char* out, unsigned int cap, int* count)
 }
 
 } // extern "C"
+
+// ---- tf-idf preprocessing: preprocess_tf preprocessor/src/preprocess.cpp:81-250 on a TermFrequencyMatrix
+//      (common/src/term_frequency_matrix.cpp) built from CSC arrays of term counts
+#include "term_frequency_matrix.hpp"
+#include "preprocess.hpp"
+extern "C" {
+
+// In: m x n CSC of term counts. Out (capacities = the input sizes): the pruned matrix as CSC with row indices and counts,
+// its tf-idf scores aligned with them, and for every surviving row / column its original index.
+// Returns 0, or -1 if every column was pruned.
+int ref_preprocess_tf(unsigned int m, unsigned int n, unsigned int nz, const unsigned int* col_offsets, const unsigned int* row_indices,
+                      const double* counts, unsigned int max_iter, unsigned int docs_per_term, unsigned int terms_per_doc,
+                      unsigned int* out_m, unsigned int* out_n, unsigned int* out_nz, unsigned int* out_cols, unsigned int* out_rows,
+                      unsigned int* out_counts, double* out_scores, unsigned int* term_indices, unsigned int* doc_indices)
+{
+    SparseMatrix<double> S(m, n, nz, col_offsets, row_indices, counts);
+    TermFrequencyMatrix M(S, false);
+    std::vector<unsigned int> ti(m), di(n);
+    std::vector<double> scores;
+    const bool ok = preprocess_tf(M, ti, di, scores, max_iter, docs_per_term, terms_per_doc);
+    if (!ok) return -1;
+    *out_m = M.Height(); *out_n = M.Width(); *out_nz = M.Size();
+    const unsigned int* cp = M.LockedColBuffer();
+    const TFData* tf = M.LockedTFDataBuffer();
+    for (unsigned int c = 0; c <= M.Width(); ++c) out_cols[c] = cp[c];
+    for (unsigned int e = 0; e < M.Size(); ++e) { out_rows[e] = tf[e].row; out_counts[e] = tf[e].count; out_scores[e] = scores[e]; }
+    for (unsigned int r = 0; r < M.Height(); ++r) term_indices[r] = ti[r];
+    for (unsigned int c = 0; c < M.Width(); ++c) doc_indices[c] = di[c];
+    return 0;
+}
+
+} // extern "C"
