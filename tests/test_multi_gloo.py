@@ -80,6 +80,74 @@ def _worker(rank, port, alg, m, n, k, iters, q):
         dist.destroy_process_group()
 
 
+def _rank2_nnls(G, B):
+    """min ||.|| over x >= 0 of the 2 x 2 normal equations G x = b, for every column b of B (2 x q): the unconstrained solution
+    where it is positive, else the better single-variable solution (nmf_solver_rank2.hpp:218-318)."""
+    X = np.linalg.solve(G, B)
+    bad = (X[0] <= 0) | (X[1] <= 0)
+    v0, v1 = B[0] / G[0, 0], B[1] / G[1, 1]
+    first = v0 * np.sqrt(G[0, 0]) >= v1 * np.sqrt(G[1, 1])
+    X[0, bad] = np.where(first, v0, 0.0)[bad]
+    X[1, bad] = np.where(first, 0.0, v1)[bad]
+    return X
+
+
+def _worker_rank2(rank, port, m, n, iters, q):
+    """RANK2: the in-loop normalisation couples all rows of W, so the library all-reduces H*A' and every rank updates the whole
+    W (csrc/solver.cu, generic sequence); the H part of the projected-gradient sum is the only other exchange."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    try:
+        rng = np.random.default_rng(78)
+        A = rng.random((m, n)); W = rng.random((m, 2)); Hfull = rng.random((2, n))
+        c0, c1 = column_block(n, rank, WORLD)
+        Al, H = A[:, c0:c1], Hfull[:, c0:c1].copy()
+        WtW = W.T @ W; WtA = W.T @ Al
+        metrics = []
+        for it in range(iters):
+            H = _rank2_nnls(WtW, WtA)                                   # local columns
+            HHt = _allreduce(H @ H.T)
+            AHt = _allreduce(Al @ H.T)                                  # m x 2, summed over the column shards
+            W = _rank2_nnls(HHt, AHt.T.copy()).T                        # replicated
+            s = np.linalg.norm(W, axis=0)
+            W = W / s; H = H * s[:, None]
+            HHt = HHt * np.outer(s, s); AHt = AHt * s
+            gradW = W @ HHt - AHt
+            WtW = W.T @ W; WtA = W.T @ Al
+            gradH = WtW @ H - WtA
+            pg_h = _allreduce(np.array([_pg_sq(gradH, H)]))[0]          # only the H part is a partial sum
+            metrics.append(float(np.sqrt(_pg_sq(gradW, W) + pg_h)))
+        Hall = [torch.empty((2, column_block(n, r, WORLD)[1] - column_block(n, r, WORLD)[0]), dtype=torch.float64) for r in range(WORLD)]
+        dist.all_gather(Hall, torch.from_numpy(np.ascontiguousarray(H)))
+        if rank == 0:
+            q.put((W, np.concatenate([h.numpy() for h in Hall], axis=1), metrics))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_rank2_all_reduce_exchange_matches_single_process_oracle():
+    from oracle import Oracle
+    m, n, iters = 70, 48, 8
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_rank2, args=(r, port, m, n, iters, q)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    W, H, metrics = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(78)
+    A = rng.random((m, n)); W0 = rng.random((m, 2)); H0 = rng.random((2, n))
+    o = Oracle().nmf_dense(A, W0, H0, alg="RANK2", tol=1e-12, min_iter=1, max_iter=iters, normalize=False, trace=True)
+    assert np.linalg.norm(W - o["W"]) <= 1e-9 * np.linalg.norm(o["W"])
+    assert np.linalg.norm(H - o["H"]) <= 1e-9 * np.linalg.norm(o["H"])
+    ratios = np.array(metrics[1:]) / metrics[0]
+    assert np.allclose(ratios, o["metrics"][1:iters], rtol=1e-8)
+
+
 @pytest.mark.parametrize("alg,m,n,k", [("MU", 61, 40, 5), ("BPP", 50, 36, 6)])
 def test_column_sharded_exchange_matches_single_process_oracle(alg, m, n, k):
     from oracle import Oracle
