@@ -20,3 +20,31 @@ def row_slice(m, rank, world):
     r0 = rank * m_loc
     rows = max(0, min(m_loc, m - r0))
     return r0, rows, m_loc
+
+
+def column_block_by_nnz(col_offsets, rank, world):
+    """[c0, c1): this rank's columns of a SPARSE A, cut where the running count of stored entries crosses rank / world of the
+    total, so that every rank walks about the same number of entries per SpMM ("balance by nnz, not by
+    columns"). Contiguous, covers every column exactly once, independent of the rank asking; a rank may get no columns when
+    a single column holds more than its share."""
+    n = len(col_offsets) - 1
+    total = int(col_offsets[n])
+    if total == 0:
+        return column_block(n, rank, world)
+
+    def cut(r):
+        if r <= 0:
+            return 0
+        if r >= world:
+            return n
+        target = (total * r) // world
+        lo, hi = 0, n                    # first column boundary whose offset reaches the target
+        while lo < hi:
+            mid = (lo + hi) // 2
+            if int(col_offsets[mid]) < target:
+                lo = mid + 1
+            else:
+                hi = mid
+        return lo
+
+    return cut(rank), cut(rank + 1)

@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from smallk_b200.sharding import column_block, row_slice      # noqa: E402
+from smallk_b200.sharding import column_block, column_block_by_nnz, row_slice      # noqa: E402
 
 WORLD = 2
 
@@ -180,3 +180,22 @@ def test_partition_helpers_cover_everything_once():
         assert sum(s[1] for s in slices) == n
         assert len({s[2] for s in slices}) == 1 and slices[0][2] * world >= n
         assert all(s[0] == r * s[2] for r, s in enumerate(slices))
+
+
+def test_nnz_balanced_column_blocks():
+    rng = np.random.default_rng(5)
+    for n, world in ((1000, 8), (37, 4), (5, 8), (200000, 8)):
+        lens = np.minimum((1000 ** rng.random(n)).astype(np.int64), 900)            # skewed column lengths
+        colp = np.concatenate([[0], np.cumsum(lens)])
+        blocks = [column_block_by_nnz(colp, r, world) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+        assert all(b[0] <= b[1] for b in blocks)
+        share = np.array([colp[b[1]] - colp[b[0]] for b in blocks], dtype=np.float64)
+        assert share.sum() == colp[-1]
+        if n >= 1000:                                                                 # no rank is off its share by more than one column
+            assert np.all(np.abs(share - colp[-1] / world) <= lens.max())
+            even = np.array([colp[column_block(n, r, world)[1]] - colp[column_block(n, r, world)[0]] for r in range(world)])
+            assert share.max() <= even.max() + lens.max()
+    empty = np.zeros(11, dtype=np.int64)
+    assert [column_block_by_nnz(empty, r, 2) for r in range(2)] == [column_block(10, r, 2) for r in range(2)]
