@@ -1,4 +1,4 @@
-"""Where does the GPU hierclust tree leave the reference's at C4 scale? Runs both for a few cluster counts on the same graph
+"""Manual check (lives under tests/ because it runs the reference checker). Where does the GPU hierclust tree leave the reference's at C4 scale? Runs both for a few cluster counts on the same graph
 and prints the first tree node at which document counts / priorities differ. Needs /root/repo/oracle/_ref (prebuilt)."""
 import json
 import os
@@ -7,7 +7,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 import smallk_b200 as sk          # noqa: E402

@@ -8,4 +8,4 @@ SMK_SPMM_SLAB=0 timeout 300 python tools/measure_c3_c4.py c3 > gpurun_out/c3_nos
 SMK_HALS_OUTER_OCC=3 timeout 300 python tools/measure_c3_c4.py c3 > gpurun_out/c3_occ3.log 2>&1; tail -1 gpurun_out/c3_occ3.log | cut -c1-400
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'hals_block_outer|spmm_seg_slab' -s 10 -c 5 -o gpurun_out/prof_c3_outer_slab -f \
    python tools/measure_c3_c4.py c3 > gpurun_out/prof_c3_outer_slab.log 2>&1
-timeout 900 python tools/measure_c3_c4.py c4 ref > gpurun_out/c4.log 2>&1; grep workload gpurun_out/c4.log | cut -c1-600
+timeout 900 python tools/measure_c3_c4.py c4 > gpurun_out/c4.log 2>&1; grep workload gpurun_out/c4.log | cut -c1-600

@@ -14,7 +14,7 @@ import smallk_b200 as sk          # noqa: E402
 import workloads                  # noqa: E402
 
 
-def c4(n=320000, edges=2000000, clusters=64, with_ref=False):
+def c4(n=320000, edges=2000000, clusters=64):
     t = time.time()
     colp, rowi, val = workloads.c4_graph(n, edges)
     gen_s = time.time() - t
@@ -24,17 +24,6 @@ def c4(n=320000, edges=2000000, clusters=64, with_ref=False):
             "iters_per_s": out["iterations"] / out["elapsed_s"], "profile": out["profile"], "outliers": out["n_outliers"],
             "leaf_sizes": out["doc_count"][out["is_leaf"] == 1].tolist()}
     print(json.dumps(line), flush=True)
-    if with_ref:
-        from oracle import Ref
-        ref = Ref()
-        # one thread: the reference then draws its initial factors from the sequential generator (matrix_generator.hpp:61-82),
-        # as this library always does, so the trees are comparable; it is also the reference's fastest setting at this size
-        for thr in (1,):
-            t = time.time()
-            o = ref.hierclust(csc=(colp, rowi, val), shape=(n, n), num_clusters=clusters, tol=1e-4, min_iter=5, max_iter=5000,
-                              seed=32, max_threads=thr)
-            print(json.dumps({"workload": "C4 reference", "threads": thr, "elapsed_s": time.time() - t, "nmf_count": o["nmf_count"],
-                              "same_assignments_as_gpu": bool(np.array_equal(o["assignments"], out["assignments"]))}), flush=True)
 
 
 def c3(m=1000000, n=200000, per_col=500, k=128, iters=5):
@@ -76,9 +65,9 @@ def c3(m=1000000, n=200000, per_col=500, k=128, iters=5):
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which in ("c4", "all"):
-        c4(with_ref="ref" in sys.argv)
+        c4()
     if which in ("c4small",):
-        c4(40000, 250000, 16, with_ref="ref" in sys.argv)
+        c4(40000, 250000, 16)
     if which in ("c3", "all"):
         c3()
     if which in ("c3small",):
