@@ -1,4 +1,4 @@
-// smallk_b200 — the reference's public C++ API (smallk/include/smallk.hpp:34-332), NMF part, implemented on
+// smallk_b200 — the reference's public C++ API (smallk/include/smallk.hpp:34-332), implemented on
 // the GPU library. Same namespace, names, default arguments and exception types, so a program using
 // smallk::Initialize / LoadMatrix / Nmf / LockedBufferW/H re-links unchanged.
 // HierNmf2 / HierNmf2WithFlat drive the rank-2 solver from the host-side tree code of host/clust.cpp.
