@@ -126,6 +126,66 @@ def _worker_rank2(rank, port, m, n, iters, q):
         dist.destroy_process_group()
 
 
+def _worker_hals(rank, port, m, n, k, iters, q):
+    """HALS: the in-sweep normalisation of W's columns couples all rows, so H*H' and A*H' are all-reduced (at Init and at the end
+    of every iteration, nmf_solver_hals.hpp:141-199) and every rank sweeps the whole W; the H sweep is local to the column block."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    try:
+        rng = np.random.default_rng(79)
+        A = rng.random((m, n)); W = rng.random((m, k)); Hfull = rng.random((k, n)) * (2.0 / k)
+        c0, c1 = column_block(n, rank, WORLD)
+        Al, H = A[:, c0:c1], Hfull[:, c0:c1].copy()
+        HHt = _allreduce(H @ H.T); AHt = _allreduce(Al @ H.T)
+        metrics = []
+        for it in range(iters):
+            for c in range(k):                                           # UpdateW_Hals, replicated
+                w = W[:, c] + (AHt[:, c] - W @ HHt[:, c]) / HHt[c, c]
+                w[np.isnan(w) | (w < 0)] = 0.0
+                if not w.any():
+                    w[:] = np.finfo(np.float64).eps
+                W[:, c] = w / np.linalg.norm(w)
+            WtW = W.T @ W; WtA = W.T @ Al
+            for r in range(k):                                           # UpdateH_Hals, local columns
+                h = H[r] + (WtA[r] - WtW[r] @ H) / WtW[r, r]
+                h[np.isnan(h) | (h < 0)] = 0.0
+                H[r] = h
+            gradH = WtW @ H - WtA
+            HHt = _allreduce(H @ H.T); AHt = _allreduce(Al @ H.T)
+            gradW = W @ HHt - AHt
+            pg_h = _allreduce(np.array([_pg_sq(gradH, H)]))[0]
+            metrics.append(float(np.sqrt(_pg_sq(gradW, W) + pg_h)))
+        Hall = [torch.empty((k, column_block(n, r, WORLD)[1] - column_block(n, r, WORLD)[0]), dtype=torch.float64) for r in range(WORLD)]
+        dist.all_gather(Hall, torch.from_numpy(np.ascontiguousarray(H)))
+        if rank == 0:
+            q.put((W, np.concatenate([h.numpy() for h in Hall], axis=1), metrics))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_hals_all_reduce_exchange_matches_single_process_oracle():
+    from oracle import Oracle
+    m, n, k, iters = 64, 50, 6, 8
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_hals, args=(r, port, m, n, k, iters, q)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    W, H, metrics = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(79)
+    A = rng.random((m, n)); W0 = rng.random((m, k)); H0 = rng.random((k, n)) * (2.0 / k)
+    o = Oracle().nmf_dense(A, W0, H0, alg="HALS", tol=1e-12, min_iter=1, max_iter=iters, normalize=False, trace=True)
+    assert np.linalg.norm(W - o["W"]) <= 1e-9 * np.linalg.norm(o["W"])
+    assert np.linalg.norm(H - o["H"]) <= 1e-9 * np.linalg.norm(o["H"])
+    ratios = np.array(metrics[1:]) / metrics[0]
+    assert np.allclose(ratios, o["metrics"][1:iters], rtol=1e-5)       # the HALS metric is discontinuous in the last ulp (DESIGN.md §3)
+
+
 def test_rank2_all_reduce_exchange_matches_single_process_oracle():
     from oracle import Oracle
     m, n, iters = 70, 48, 8
