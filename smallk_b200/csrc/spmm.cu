@@ -393,7 +393,7 @@ __device__ __forceinline__ d4 tier_load(unsigned int code, const double* __restr
     return ldg256(p);
 }
 
-template <int NV, int U>
+template <int NV, int U, bool PIPE>
 __global__ void __launch_bounds__(512, 1)
 spmm_seg_tier_kernel(int nseg, const unsigned int* __restrict__ scol, const unsigned int* __restrict__ sbeg,
                      const unsigned int* __restrict__ send, const unsigned int* __restrict__ sslot,
@@ -453,6 +453,51 @@ spmm_seg_tier_kernel(int nseg, const unsigned int* __restrict__ scol, const unsi
             const unsigned int my_i = nxt_i; const double my_a = nxt_a;
             o += 32;
             if (o + lane < end) { nxt_i = __ldcs(idx + o + lane); nxt_a = alpha * __ldcs(val + o + lane); }
+            if constexpr (PIPE)
+            {
+                // EXPERIMENTAL (SMK_SPMM_PIPE=1; compiled, not yet run on a GPU — see spmm_seg_slab_pipe_kernel): the batch is
+                // consumed in half-groups of 4 (k <= 128) or 2 entries issued and consumed alternately, so gathers are in flight under every
+                // block of FMAs; storage order is kept, entries past the end carry value 0 and operand 0
+                constexpr int HB = NV == 1 ? 4 : 2;          // entries per half-group: 2 x HB x NV 256-bit operands stay in registers
+                const int nh = (cnt + HB - 1) / HB;
+                d4 bA[HB][NV], bB[HB][NV];
+                double aA[HB], aB[HB];
+                auto issue = [&](const int h, d4 (&b)[HB][NV], double (&a)[HB]) {
+#pragma unroll
+                    for (int u = 0; u < HB; ++u)
+                    {
+                        const int e = HB * h + u;
+                        const unsigned int code = __shfl_sync(0xffffffffu, my_i, e & 31);
+                        a[u] = __shfl_sync(0xffffffffu, my_a, e & 31);
+                        if (e >= cnt) a[u] = 0.0;
+#pragma unroll
+                        for (int v = 0; v < NV; ++v)
+                        {
+                            if (live[v] && e < cnt) b[u][v] = tier_load(code, B, ldb, tier_sh, k, 4 * lane + 128 * v, 32 * v + lane);
+                            else { b[u][v].x = b[u][v].y = b[u][v].z = b[u][v].w = 0.0; }
+                        }
+                    }
+                };
+                auto consume = [&](const d4 (&b)[HB][NV], const double (&a)[HB]) {
+#pragma unroll
+                    for (int u = 0; u < HB; ++u)
+#pragma unroll
+                        for (int v = 0; v < NV; ++v)
+                        {
+                            acc[v].x += a[u] * b[u][v].x; acc[v].y += a[u] * b[u][v].y;
+                            acc[v].z += a[u] * b[u][v].z; acc[v].w += a[u] * b[u][v].w;
+                        }
+                };
+                issue(0, bA, aA);
+                for (int h = 0; h < nh; h += 2)
+                {
+                    if (h + 1 < nh) issue(h + 1, bB, aB);
+                    consume(bA, aA);
+                    if (h + 2 < nh) issue(h + 2, bA, aA);
+                    if (h + 1 < nh) consume(bB, aB);
+                }
+                continue;
+            }
             int t = 0;
             for (; t + U <= cnt; t += U)
             {
@@ -766,11 +811,14 @@ void spmm_gather_seg(cudaStream_t stream, int ncols, const SegTable& T, const un
         const size_t smem_bytes = static_cast<size_t>(smem_rows) * k * sizeof(double);
         const unsigned int* use_idx = tiers ? T.tier_idx.p : idx;
         const int blocks = std::max(1, std::min(ceil_div(T.nseg, 16), num_sms));
+        const char* tier_pipe_env = getenv("SMK_SPMM_PIPE");
+        const bool tier_pipe = tier_pipe_env && atoi(tier_pipe_env) == 1;      // experimental, off by default
 #define SMK_T(NV, U)                                                                                                                  \
         do {                                                                                                                          \
             static bool attr_set = false;                                                                                             \
-            if (!attr_set) { SMK_CUDA(cudaFuncSetAttribute(spmm_seg_tier_kernel<NV, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTierSmemBytes)); attr_set = true; } \
-            spmm_seg_tier_kernel<NV, U><<<blocks, 512, smem_bytes, stream>>>(T.nseg, T.col.p, T.beg.p, T.end.p, T.slot.p, use_idx, val, k, B, ldb, \
+            if (!attr_set) { SMK_CUDA(cudaFuncSetAttribute(spmm_seg_tier_kernel<NV, U, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTierSmemBytes));  \
+                             SMK_CUDA(cudaFuncSetAttribute(spmm_seg_tier_kernel<NV, U, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTierSmemBytes)); attr_set = true; } \
+            (tier_pipe ? spmm_seg_tier_kernel<NV, U, true> : spmm_seg_tier_kernel<NV, U, false>)<<<blocks, 512, smem_bytes, stream>>>(T.nseg, T.col.p, T.beg.p, T.end.p, T.slot.p, use_idx, val, k, B, ldb, \
                                                                              alpha, beta, out, ldo, partial, smem_rows, T.tier_smem_ids.p);      \
         } while (0)
         if (k <= 128) SMK_T(1, 8);
