@@ -74,8 +74,10 @@ int smk_synchronize(smk_ctx* ctx);
 
 /* ---- multi-GPU: one process per GPU; A and H are sharded by column block.
  * The 128-byte id comes from smk_comm_unique_id() on rank 0 and is broadcast by the host
- * program (torch.distributed / MPI). After smk_comm_init the solver all-reduces H*H' (k x k)
- * and H*A' (k x m) over NCCL each outer iteration; everything else stays local. ---- */
+ * program (torch.distributed / MPI). After smk_comm_init the solver sums H*H' (k x k) and H*A' (k x m) over the
+ * ranks each outer iteration and redistributes the row blocks of W; everything else stays local. The exchanges are
+ * the library's own kernels over NVLink peer memory (csrc/peer.cu; all ranks on one NVSwitch node, <= 8); NCCL
+ * bootstraps them and is the selectable alternative (environment SMK_PEER=0). ---- */
 int smk_comm_unique_id(void* id128);
 int smk_comm_init(smk_ctx* ctx, int rank, int nranks, const void* id128);
 
@@ -118,12 +120,21 @@ int smk_solver_begin(smk_ctx* ctx, const smk_nmf_options* opts,
                      const double* W0_host, int ldW, const double* H0_host, int ldH);
 int smk_solver_step(smk_ctx* ctx, int count);
 int smk_solver_progress(smk_ctx* ctx, double* metric);
+/* run   : `count` times { operator(); ProgressEst::Update } — the body of NmfSolve's loop (nmf_solve_generic.hpp:67-123) with
+ *         the metric evaluated every iteration — enqueued back to back with NO host synchronisation in between: the metric
+ *         of every iteration is computed on the device and all of them come back in one copy at the end (metrics may be
+ *         NULL). The first progress evaluation after begin stores pg0, exactly as ProgEstGenericPgRatio::Update does. */
+int smk_solver_run(smk_ctx* ctx, int count, double* metrics);
 int smk_solver_get(smk_ctx* ctx, double* W_host, int ldW, double* H_host, int ldH,
                    double* gradW_host, int ldgW, double* gradH_host, int ldgH);
 int smk_solver_normalize(smk_ctx* ctx);     /* NormalizeAndScale(W, H): common/include/normalize.hpp:118-138 */
 /* Device time of the last smk_solver_step call (CUDA events on the context's stream), and the
  * number of kernels it launched. */
 int smk_solver_last_step_ms(smk_ctx* ctx, float* ms, long long* kernel_launches);
+
+/* Measurement hook (environment SMK_PHASES=1): device time per phase of the solver steps since the last call, as
+ * "name=ms;name=ms;..." (CUDA events between the phases; includes the exchange kernels of the multi-GPU path). */
+int smk_phase_report(smk_ctx* ctx, char* buf, int len);
 
 /* Measurement hook for the roofline line of bench.py: re-runs one of the two big contractions of the
  * current solver state `reps` times (which: 0 = W'A, 1 = H A') and reports the mean device time per
@@ -158,6 +169,9 @@ int smk_gemm(smk_ctx* ctx, int transA, int transB, int M, int N, int K,
              const double* A, int ldA, const double* B, int ldB, double* C, int ldC);
 /* bool NnlsBlockpivot(LHS, RHS, X, Y): common/include/nnls.hpp:144. LHS k x k, RHS/X/Y k x q. */
 int smk_nnls_bpp(smk_ctx* ctx, int k, int q, const double* LHS, const double* RHS, double* X, double* Y);
+/* Diagnostic for the parity tests: how often UpdatePassiveSet's backup rule (common/src/nnls.cpp:64-72: toggle the row
+ * BitMatrix::MaxRowIndex reports, defect for k > 32 included) has fired since the last smk_nnls_bpp / smk_solver_begin. */
+int smk_nnls_backup_count(smk_ctx* ctx, int* count);
 /* Gemm on SparseMatrix (common/include/sparse_gemm.hpp:26-74) against the loaded CSC matrix:
  * variant 0: C = alpha*A*B + beta*C, 1: alpha*A*B' + beta*C, 2: alpha*B*A + beta*C, 3: alpha*B'*A + beta*C.
  * B is Bh x Bw, C is Ch x Cw, tight leading dimensions. */

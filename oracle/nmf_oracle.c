@@ -321,9 +321,10 @@ static unsigned max_row_index(const unsigned char* bits, int k)
 }
 
 /* Work counters (diagnostics for sizing the GPU kernel; not part of the algorithm). */
-static double g_stat_solves = 0.0, g_stat_p3 = 0.0, g_stat_rounds = 0.0, g_stat_calls = 0.0;
+static double g_stat_solves = 0.0, g_stat_p3 = 0.0, g_stat_rounds = 0.0, g_stat_calls = 0.0, g_stat_backup = 0.0;
+double orc_backup_count(void) { return g_stat_backup; }     /* firings of the backup rule since orc_stats_reset */
 void orc_stats_get(double* out4) { out4[0] = g_stat_solves; out4[1] = g_stat_p3; out4[2] = g_stat_rounds; out4[3] = g_stat_calls; }
-void orc_stats_reset(void) { g_stat_solves = g_stat_p3 = g_stat_rounds = g_stat_calls = 0.0; }
+void orc_stats_reset(void) { g_stat_solves = g_stat_p3 = g_stat_rounds = g_stat_calls = g_stat_backup = 0.0; }
 
 /* BppSolveNormalEqNoGroup (nmf_solver_bpp.hpp:146-219) for the listed columns.
  * X columns are fully overwritten (zeros off the passive set). */
@@ -419,6 +420,7 @@ int orc_nnls_bpp(int k, int q, const double* LHS, const double* RHS, double* X, 
                 unsigned r1 = max_row_index(no, k), r2 = max_row_index(in, k);
                 unsigned row = r1 > r2 ? r1 : r2;
                 pc[row] = !pc[row];
+                g_stat_backup += 1.0;
             }
         }
 

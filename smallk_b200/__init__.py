@@ -29,6 +29,7 @@ EXPORTS = [
     "smk_solver_begin", "smk_solver_step", "smk_solver_progress", "smk_solver_get", "smk_solver_normalize",
     "smk_solver_last_step_ms", "smk_solver_time_product", "smk_gemm", "smk_nnls_bpp", "smk_sparse_gemm",
     "smk_select_columns", "smk_select_all", "smk_nnls_hals", "smk_argsort_desc", "smk_sort_desc", "smk_spmm_tier_info",
+    "smk_solver_run", "smk_phase_report", "smk_nnls_backup_count",
 ]
 HOST_LIB_PATH = os.path.join(_HERE, "lib", "libsmallk_host.so")
 HOST_EXPORTS = ["smkh_last_error", "smkh_hierclust_sparse", "smkh_hierclust_dense", "smkh_flatclust", "smkh_compute_priority",
@@ -210,6 +211,23 @@ class Context:
         self._check(self._lib.smk_solver_progress(self._h, ctypes.byref(v)))
         return v.value
 
+    def solver_run(self, count):
+        """`count` x { solver(); progress update } without host synchronisation in between; returns the metrics."""
+        metrics = np.zeros(max(int(count), 1))
+        self._check(self._lib.smk_solver_run(self._h, int(count), _d(metrics)))
+        return metrics[:int(count)]
+
+    def phase_report(self):
+        """{phase: ms} since the last call (SMK_PHASES=1)."""
+        buf = ctypes.create_string_buffer(4096)
+        self._check(self._lib.smk_phase_report(self._h, buf, 4096))
+        out = {}
+        for item in buf.value.decode().split(";"):
+            if "=" in item:
+                name, v = item.split("=")
+                out[name] = float(v)
+        return out
+
     def solver_normalize(self):
         self._check(self._lib.smk_solver_normalize(self._h))
 
@@ -256,6 +274,12 @@ class Context:
         k, q = RHS.shape
         self._check(self._lib.smk_nnls_bpp(self._h, k, q, _d(LHS), _d(RHS), _d(X), _d(Y)))
         return X, Y
+
+    def nnls_backup_count(self):
+        """Firings of UpdatePassiveSet's backup rule since the last nnls_bpp / solver_begin (diagnostic)."""
+        n = ctypes.c_int(0)
+        self._check(self._lib.smk_nnls_backup_count(self._h, ctypes.byref(n)))
+        return n.value
 
     def spmm_tier_info(self, which):
         """(on, smem_rows, share) of the residency classes of product `which` (0 = W'A, 1 = H A')."""

@@ -50,7 +50,7 @@ void ensure_scratch(smk_ctx* c)
     c->status.reserve(ST_COUNT);
     c->counter.reserve(2);
     if (!c->pinned) SMK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->pinned), 16 * sizeof(double), cudaHostAllocDefault));
-    if (!c->ticket.p) { c->ticket.reserve(4); SMK_CUDA(cudaMemsetAsync(c->ticket.p, 0, 4 * sizeof(unsigned int), c->stream)); }
+    if (!c->ticket.p) { c->ticket.reserve(8); SMK_CUDA(cudaMemsetAsync(c->ticket.p, 0, 8 * sizeof(unsigned int), c->stream)); }
     c->partial.reserve(4096 + 512 * 256);
     c->acc.reserve(8);
 }
@@ -142,6 +142,9 @@ void smk_destroy(smk_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    peer_release(c);
+    c->Wt.release(); c->HAt.release();      // possibly views of the exchange region just freed
+    for (cudaEvent_t e : c->phase_pool) cudaEventDestroy(e);
     if (c->comm) ncclCommDestroy(c->comm);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -183,6 +186,8 @@ int smk_comm_init(smk_ctx* c, int rank, int nranks, const void* id128)
     if (!c || nranks < 1 || rank < 0 || rank >= nranks) return SMK_BAD_PARAM;
     return guarded(c, [&]() {
         SMK_CUDA(cudaSetDevice(c->device));
+        peer_release(c);
+        c->Wt.release(); c->HAt.release();
         if (c->comm) { ncclCommDestroy(c->comm); c->comm = nullptr; }
         c->rank = rank; c->nranks = nranks;
         if (nranks == 1) return (int)SMK_OK;
@@ -327,6 +332,34 @@ int smk_solver_step(smk_ctx* c, int count)
     });
 }
 
+int smk_solver_run(smk_ctx* c, int count, double* metrics)
+{
+    if (!c || !c->active || count < 0) return SMK_BAD_PARAM;
+    return guarded(c, [&]() {
+        SMK_CUDA(cudaSetDevice(c->device));
+        const long long l0 = launch_counter();
+        SMK_CUDA(cudaEventRecord(c->ev0, c->stream));
+        const int rc = solver_run(c, count, metrics);
+        SMK_CUDA(cudaEventRecord(c->ev1, c->stream));
+        c->last_launches = launch_counter() - l0;
+        SMK_CUDA(cudaEventSynchronize(c->ev1));
+        SMK_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+        return rc;
+    });
+}
+
+int smk_phase_report(smk_ctx* c, char* buf, int len)
+{
+    if (!c || !buf || len <= 0) return SMK_BAD_PARAM;
+    return guarded(c, [&]() {
+        SMK_CUDA(cudaSetDevice(c->device));
+        const std::string r = solver_phase_report(c);
+        std::strncpy(buf, r.c_str(), static_cast<size_t>(len) - 1);
+        buf[len - 1] = 0;
+        return (int)SMK_OK;
+    });
+}
+
 int smk_solver_last_step_ms(smk_ctx* c, float* ms, long long* launches)
 {
     if (!c) return SMK_BAD_PARAM;
@@ -433,6 +466,9 @@ int smk_nmf(smk_ctx* c, const smk_nmf_options* opts, double* W, int ldW, double*
             {
                 int fi = solver_fail_iter(c);
                 if (fi != INT_MAX) { finish(fi); return fail(c, SMK_FAILURE, "NMF solver failure on iteration " + std::to_string(fi + 1)); }
+                // Solver_Generic_Rank2 normalises inside the iteration (nmf_solver_rank2.hpp:420): the reference throws from there
+                if (opts->algorithm == SMK_RANK2 && c->status_cached && c->status_host[ST_NORM_EPS])
+                { finish(iter); return fail(c, SMK_FAILURE, "Normalize: column norm < machine epsilon"); }
             }
             if (opts->verbose && ((iter + 1) <= 9 || (iter + 1) % 10 == 0)) printf("%d:\tprogress metric: \t%g\n", iter + 1, metric);
             if (metric <= opts->tol)
@@ -509,7 +545,7 @@ int smk_nnls_bpp(smk_ctx* c, int k, int q, const double* LHS, const double* RHS,
         upload_tight(c, LHS, k, k, k, dL.p);
         upload_tight(c, RHS, k, k, q, dR.p);
         upload_tight(c, X, k, k, q, dX.p);
-        int init[ST_COUNT] = {0, INT_MAX, 0, 0, 0};
+        static const int init[ST_COUNT] = {0, INT_MAX, 0, 0, 0, 0, 0, 0};
         SMK_CUDA(cudaMemcpyAsync(c->status.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
         c->deferred.reserve(nnls_deferred_bytes(q, k, c->num_sms));
         nnls_bpp(c->stream, k, q, dL.p, k, dR.p, k, dX.p, k, dY.p, k, c->status.p, c->counter.p, c->deferred.p, 0, c->num_sms);
@@ -520,6 +556,19 @@ int smk_nnls_bpp(smk_ctx* c, int k, int q, const double* LHS, const double* RHS,
         SMK_CUDA(cudaMemcpyAsync(st, c->status.p, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
         SMK_CUDA(cudaStreamSynchronize(c->stream));
         if (st[ST_FAIL_ITER] != INT_MAX) return fail(c, SMK_FAILURE, "NnlsBlockpivot failed (non-HPD sub-problem or iteration limit)");
+        return (int)SMK_OK;
+    });
+}
+
+int smk_nnls_backup_count(smk_ctx* c, int* count)
+{
+    if (!c || !count || !c->status.p) return SMK_BAD_PARAM;
+    return guarded(c, [&]() {
+        SMK_CUDA(cudaSetDevice(c->device));
+        int st[ST_COUNT];
+        SMK_CUDA(cudaMemcpyAsync(st, c->status.p, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+        SMK_CUDA(cudaStreamSynchronize(c->stream));
+        *count = st[ST_BACKUP_COUNT];
         return (int)SMK_OK;
     });
 }

@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "peer.h"
 #include "../../include/smallk_b200.h"
 
 namespace smk {
@@ -18,11 +19,14 @@ struct DevBuf
 {
     T* p = nullptr;
     size_t n = 0;
+    bool owned = true;
     DevBuf() {}
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p && owned) cudaFree(p); p = nullptr; n = 0; owned = true; }
+    // view of memory owned by somebody else (the NVLink exchange region, peer.cu)
+    void alias(T* ptr, size_t count) { release(); p = ptr; n = count; owned = false; }
     // grow-only allocation; contents are not preserved across a growth
     void reserve(size_t count)
     {
@@ -117,6 +121,8 @@ struct smk_ctx
     int steps_done = 0;
     double pg0 = 0.0;
     smk::DevBuf<double> H, Wt, gradH, gradWt, WtW, HHt, WtA, HAt, T1, T2, Wprev, norms;
+    smk::DevBuf<double> prog;       // ProgressEst state on the device: [0] = pg0, [1] = "pg0 captured", [2] = metric of the last update
+    smk::DevBuf<double> trace;      // metric per iteration of smk_solver_run
     bool pg_ready = false;          // the last solver_step left both projected-gradient sums in acc[0..1] (fused rank-2)
     bool status_cached = false;     // status_host holds the status words as of the last solver_progress
     int status_host[smk::ST_COUNT] = {0, INT_MAX, 0, 0, 0};
@@ -131,6 +137,17 @@ struct smk_ctx
     // k x (m_loc * nranks) so that reduce-scatter / all-gather move equal pieces. m_loc == m when nranks == 1.
     int m_loc = 0;
     bool w_sharded = false;
+    // NVLink peer-memory exchange (peer.cu): on by default when nranks > 1, SMK_PEER=0 selects the NCCL collectives.
+    // x_loc = rows per exchanged block of a k x m buffer (= m_loc when the W update is row-sharded).
+    bool use_peer = false;
+    int x_loc = 0;
+    smk::PeerComm peer;
+    smk::DevBuf<unsigned int> peer_ticket;
+    // per-phase device times of solver_step (SMK_PHASES=1): cudaEvent pairs, summed on demand
+    bool phases_on = false;
+    std::vector<std::pair<const char*, cudaEvent_t>> phase_marks;
+    std::vector<cudaEvent_t> phase_pool;
+    size_t phase_pool_used = 0;
     int w_row0() const { return rank * m_loc; }
     int w_rows() const { const int r = m - rank * m_loc; return r < 0 ? 0 : (r < m_loc ? r : m_loc); }
 };

@@ -83,6 +83,62 @@ __global__ void final_sum_kernel(int n, const double* __restrict__ partial, doub
     if (threadIdx.x == 0) *out = s;
 }
 
+// Both projected-gradient sums of one outer iteration (projected_gradient.hpp:125-171: the W part and the H part) in ONE
+// launch: block partials in a fixed grid-stride order, the block that arrives last adds them in block order (deterministic)
+// and, when `prog` is given, finishes ProgressEst::Update on the device (progress_metric below).
+__device__ __forceinline__ void progress_metric(int mode, const double* acc, double* prog, double* metric_out, int* status)
+{
+    if (mode == 0)
+    {
+        // ProgEstGenericPgRatio, progress_estimator_generic.hpp:87-104: the first evaluation stores pg0 and reports 1
+        const double pg = sqrt(acc[0] + acc[1]);
+        if (pg != pg) atomicExch(&status[ST_PG_NAN], 1);
+        if (prog[1] == 0.0) { prog[0] = pg; prog[1] = 1.0; *metric_out = 1.0; }
+        else *metric_out = pg / prog[0];
+    }
+    else *metric_out = sqrt(acc[0]) / sqrt(acc[1]);     // ProgEstGenericDeltaW, :58-69
+}
+
+__global__ void pg_pair_kernel(long long c1, const double* __restrict__ G1, const double* __restrict__ X1,
+                               long long c2, const double* __restrict__ G2, const double* __restrict__ X2,
+                               double* __restrict__ partial, unsigned int* __restrict__ ticket, double* __restrict__ acc,
+                               double* prog, double* metric_out, int* status)
+{
+    __shared__ bool s_last;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    double s1 = 0.0, s2 = 0.0;
+    for (long long i = i0; i < c1; i += stride) { const double g = G1[i]; if (g < 0.0 || X1[i] > 0.0) s1 += g * g; }
+    for (long long i = i0; i < c2; i += stride) { const double g = G2[i]; if (g < 0.0 || X2[i] > 0.0) s2 += g * g; }
+    s1 = block_sum(s1);
+    s2 = block_sum(s2);
+    if (threadIdx.x == 0)
+    {
+        partial[blockIdx.x] = s1;
+        partial[1024 + blockIdx.x] = s2;
+        __threadfence();
+        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    s1 = 0.0; s2 = 0.0;
+    for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += blockDim.x) { s1 += __ldcg(partial + i); s2 += __ldcg(partial + 1024 + i); }
+    s1 = block_sum(s1);
+    s2 = block_sum(s2);
+    if (threadIdx.x == 0)
+    {
+        acc[0] = s1; acc[1] = s2;
+        *ticket = 0u;
+        if (prog) progress_metric(0, acc, prog, metric_out, status);
+    }
+}
+
+__global__ void progress_metric_kernel(int mode, const double* acc, double* prog, double* metric_out, int* status)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) progress_metric(mode, acc, prog, metric_out, status);
+}
+
 int reduce_blocks(long long count, int num_sms)
 {
     long long b = (count + 255) / 256;
@@ -114,6 +170,20 @@ void pg_sumsq(cudaStream_t stream, long long count, const double* G, const doubl
     pg_partial_kernel<<<blocks, 256, 0, stream>>>(count, G, X, partial);
     SMK_LAUNCH_CHECK();
     final_sum_kernel<<<1, 256, 0, stream>>>(blocks, partial, acc_slot);
+    SMK_LAUNCH_CHECK();
+}
+
+void pg_pair(cudaStream_t stream, long long c1, const double* G1, const double* X1, long long c2, const double* G2, const double* X2,
+             double* partial, unsigned int* ticket, double* acc, double* prog, double* metric_out, int* status, int num_sms)
+{
+    const int blocks = reduce_blocks(std::max(c1, c2), num_sms);
+    pg_pair_kernel<<<blocks, 256, 0, stream>>>(c1, G1, X1, c2, G2, X2, partial, ticket, acc, prog, metric_out, status);
+    SMK_LAUNCH_CHECK();
+}
+
+void progress_metric_launch(cudaStream_t stream, int mode, const double* acc, double* prog, double* metric_out, int* status)
+{
+    progress_metric_kernel<<<1, 32, 0, stream>>>(mode, acc, prog, metric_out, status);
     SMK_LAUNCH_CHECK();
 }
 

@@ -53,6 +53,7 @@ struct GemmParams
     const double* D; long long ldd;    // optional: C = acc - D (splits == 1 only)
     int M, N, R;
     int splits, rchunk;                // reduction range per split, multiple of BK
+    int to_partial;                    // write the tile to `partial` even when splits == 1 (the caller reduces / forwards it)
 };
 
 // Copy `nvec` vectors of `len` contiguous doubles (a tile) into shared memory.
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_skinny_kernel(GemmParams p)
     // epilogue
     double* out;
     long long ldo;
-    if (p.splits > 1) { out = p.partial + static_cast<long long>(split) * p.M * p.N; ldo = p.M; }
+    if (p.splits > 1 || p.to_partial) { out = p.partial + static_cast<long long>(split) * p.M * p.N; ldo = p.M; }
     else              { out = p.C; ldo = p.ldc; }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_skinny_kernel(GemmParams p)
                 const int col = n0 + wn * 32 + j * 8 + 2 * t4 + e;
                 if (col >= p.N) continue;
                 double v = acc[i][j][e];
-                if (p.splits == 1 && p.D) v -= p.D[static_cast<long long>(col) * p.ldd + row];
+                if (p.splits == 1 && !p.to_partial && p.D) v -= p.D[static_cast<long long>(col) * p.ldd + row];
                 out[static_cast<long long>(col) * ldo + row] = v;
             }
         }
@@ -234,9 +235,9 @@ int gemm_pick_splits(int M, int N, int R, int num_sms, size_t workspace_bytes)
 void gemm_f64(cudaStream_t stream, bool nt, int M, int N, int R,
               const double* A, long long lda, const double* B, long long ldb,
               double* C, long long ldc, const double* D, long long ldd,
-              double* workspace, size_t workspace_bytes, int num_sms)
+              double* workspace, size_t workspace_bytes, int num_sms, int* partials_only)
 {
-    if (M <= 0 || N <= 0) return;
+    if (M <= 0 || N <= 0) { if (partials_only) *partials_only = 0; return; }
     GemmParams p;
     p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.D = D; p.ldd = ldd;
     p.partial = workspace;
@@ -245,6 +246,7 @@ void gemm_f64(cudaStream_t stream, bool nt, int M, int N, int R,
     int rchunk = ceil_div(ceil_div(R > 0 ? R : 1, splits), BK) * BK;
     splits = R > 0 ? ceil_div(R, rchunk) : 1;
     p.splits = splits; p.rchunk = rchunk;
+    p.to_partial = partials_only ? 1 : 0;
 
     const bool vec2 = aligned16(A) && aligned16(B) && (lda % 2 == 0) && (ldb % 2 == 0);
     dim3 grid(ceil_div(N, BN), ceil_div(M, BM), splits);
@@ -258,6 +260,7 @@ void gemm_f64(cudaStream_t stream, bool nt, int M, int N, int R,
     if (nt) { if (vec2) launch(gemm_skinny_kernel<true, 2>); else launch(gemm_skinny_kernel<true, 1>); }
     else    { if (vec2) launch(gemm_skinny_kernel<false, 2>); else launch(gemm_skinny_kernel<false, 1>); }
 
+    if (partials_only) { *partials_only = splits; return; }     // workspace = [splits][M x N] tiles, ld = M; the caller sums them
     if (splits > 1)
     {
         const long long total = static_cast<long long>(M) * N;

@@ -9,14 +9,16 @@
 namespace smk {
 
 // device status words shared by the kernels of one solver
-enum { ST_ANY_NONOPT = 0, ST_FAIL_ITER = 1, ST_NORM_EPS = 2, ST_DEFER_COUNT = 3, ST_BAD_INDEX = 4, ST_COUNT = 5 };
+enum { ST_ANY_NONOPT = 0, ST_FAIL_ITER = 1, ST_NORM_EPS = 2, ST_DEFER_COUNT = 3, ST_BAD_INDEX = 4, ST_PG_NAN = 5, ST_COMM_TIMEOUT = 6, ST_BACKUP_COUNT = 7, ST_COUNT = 8 };
 
 // ---- gemm_f64.cu ----------------------------------------------------------
 // C (M x N) = A (M x R, col-major) * Bop - D, Bop = B (R x N col-major) if !nt, else B' with B (N x R col-major).
 void gemm_f64(cudaStream_t stream, bool nt, int M, int N, int R,
               const double* A, long long lda, const double* B, long long ldb,
               double* C, long long ldc, const double* D, long long ldd,
-              double* workspace, size_t workspace_bytes, int num_sms);
+              double* workspace, size_t workspace_bytes, int num_sms, int* partials_only = nullptr);
+// partials_only != null: the split-R partial tiles are left in the workspace ([*partials_only][M x N], ld = M, at least one)
+// and NOT summed — the multi-GPU reduce-scatter adds them in split order while it forwards them (peer.cu).
 int gemm_pick_splits(int M, int N, int R, int num_sms, size_t workspace_bytes);
 
 // ---- nnls_bpp.cu ----------------------------------------------------------
@@ -34,6 +36,14 @@ void mu_update(cudaStream_t stream, long long count, double* X, const double* Nu
 // acc[slot] = sum over entries of G^2 where (G < 0 || X > 0)   (projected_gradient.hpp:125-171)
 // partial: device scratch of at least 1024 doubles. Deterministic two-level reduction.
 void pg_sumsq(cudaStream_t stream, long long count, const double* G, const double* X, double* partial, double* acc_slot, int num_sms);
+// Both sums of ProjectedGradientNorm in one launch: acc[0] from (G1, X1), acc[1] from (G2, X2) (either count may be 0).
+// partial: >= 2048 doubles; ticket: one self-resetting arrival counter. With prog != null the last block also runs
+// ProgressEst::Update on the device: prog[0] = pg0, prog[1] = "pg0 captured"; the metric goes to *metric_out.
+void pg_pair(cudaStream_t stream, long long c1, const double* G1, const double* X1, long long c2, const double* G2, const double* X2,
+             double* partial, unsigned int* ticket, double* acc, double* prog, double* metric_out, int* status, int num_sms);
+// ProgressEst::Update from sums already in acc[0..1]: mode 0 = PG ratio (progress_estimator_generic.hpp:87-104),
+// mode 1 = relative delta-W (:58-69: acc[0] = ||W_prev - W||^2, acc[1] = ||W||^2).
+void progress_metric_launch(cudaStream_t stream, int mode, const double* acc, double* prog, double* metric_out, int* status);
 // acc[slot] = sum (A - B)^2 (B may be null -> sum A^2)
 void diff_sumsq(cudaStream_t stream, long long count, const double* A, const double* B, double* partial, double* acc_slot, int num_sms);
 

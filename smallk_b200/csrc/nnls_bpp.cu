@@ -410,7 +410,7 @@ nnls_bpp_fast_kernel(int k, int q, const double* __restrict__ LHS, long long ldl
             if (not_good == 0) break;
             if (round == 0 && lane == 0) atomicOr(&status[ST_ANY_NONOPT], 1);
             if (round >= max_rounds) { failed = true; break; }     // nnls.hpp:195-196
-            update_passive_set(pm, P, Ninf, not_good, nonopt, infeas, k);
+            update_passive_set(pm, P, Ninf, not_good, nonopt, infeas, k, status, lane == 0);
             ++round;
         }
         if (defer)
@@ -589,7 +589,7 @@ __global__ void nnls_bpp_slow_kernel(int k, const double* __restrict__ LHS, long
             if (not_good == 0) break;
             if (round == 0 && lane == 0) atomicOr(&status[ST_ANY_NONOPT], 1);
             if (round >= max_rounds) { failed = true; break; }
-            update_passive_set(pm, P, Ninf, not_good, nonopt, infeas, k);
+            update_passive_set(pm, P, Ninf, not_good, nonopt, infeas, k, status, lane == 0);
             ++round;
         }
         if (failed && lane == 0) atomicMin(&status[ST_FAIL_ITER], outer_iter);

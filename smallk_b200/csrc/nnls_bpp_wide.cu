@@ -345,6 +345,7 @@ nnls_bpp_wide_kernel(int k, int q, const double* __restrict__ G, long long ldg, 
                 const int ra = max_row_index_ref_words(words + 8, k), rb = max_row_index_ref_words(words + 16, k);
                 const int r = ra > rb ? ra : rb;
                 words[r >> 5] ^= (1u << (r & 31));
+                atomicAdd(&status[ST_BACKUP_COUNT], 1);
             }
             __syncthreads();
             ++round;

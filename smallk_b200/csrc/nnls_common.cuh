@@ -30,9 +30,11 @@ __device__ __forceinline__ int max_row_index_ref(unsigned long long mask, int k)
 }
 
 // UpdatePassiveSet for one column (common/src/nnls.cpp:18-74): full exchange, P-counted full exchange,
-// or the backup rule (toggle the largest "wrong" row).
+// or the backup rule (toggle the largest "wrong" row). Every lane of the owning warp runs it on identical state; the
+// `leader` lane counts the backup-rule firings in status[ST_BACKUP_COUNT] (a diagnostic the parity tests read).
 __device__ __forceinline__ void update_passive_set(unsigned long long& pm, int& P, int& Ninf, int not_good,
-                                                   unsigned long long nonopt, unsigned long long infeas, int k)
+                                                   unsigned long long nonopt, unsigned long long infeas, int k,
+                                                   int* status, bool leader)
 {
     if (not_good < Ninf)
     {
@@ -48,6 +50,7 @@ __device__ __forceinline__ void update_passive_set(unsigned long long& pm, int& 
     {
         const int ra = max_row_index_ref(nonopt, k), rb = max_row_index_ref(infeas, k);
         pm ^= (1ull << (ra > rb ? ra : rb));
+        if (leader) atomicAdd(&status[ST_BACKUP_COUNT], 1);
     }
 }
 

@@ -29,17 +29,38 @@ bool rank2_fused_enabled()
     return !(e && atoi(e) == 0);
 }
 
-void allreduce_sum(smk_ctx* c, double* buf, size_t count)
-{
-    if (c->nranks <= 1) return;
-    ncclResult_t r = ncclAllReduce(buf, buf, count, ncclDouble, ncclSum, c->comm, c->stream);
-    if (r != ncclSuccess) throw std::string("ncclAllReduce: ") + ncclGetErrorString(r);
-}
-
 void nccl_check(ncclResult_t r, const char* what)
 {
     if (r != ncclSuccess) throw std::string(what) + ": " + ncclGetErrorString(r);
 }
+
+// sum over the ranks, in place: our own one-shot kernel over peer memory, or NCCL (SMK_PEER=0)
+void allreduce_sum(smk_ctx* c, double* buf, size_t count)
+{
+    if (c->nranks <= 1) return;
+    if (c->use_peer) peer_allreduce(c, buf, static_cast<int>(count), nullptr, nullptr, 0, nullptr, nullptr);
+    else nccl_check(ncclAllReduce(buf, buf, count, ncclDouble, ncclSum, c->comm, c->stream), "ncclAllReduce");
+}
+
+// SMK_PHASES=1: a cudaEvent between the phases of solver_step; solver_phase_report() sums the gaps per name
+struct Phase
+{
+    smk_ctx* c;
+    explicit Phase(smk_ctx* ctx) : c(ctx) { mark("begin"); }
+    void mark(const char* name)
+    {
+        if (!c->phases_on) return;
+        if (c->phase_pool_used == c->phase_pool.size())
+        {
+            cudaEvent_t e;
+            SMK_CUDA(cudaEventCreate(&e));
+            c->phase_pool.push_back(e);
+        }
+        cudaEvent_t e = c->phase_pool[c->phase_pool_used++];
+        SMK_CUDA(cudaEventRecord(e, c->stream));
+        c->phase_marks.emplace_back(name, e);
+    }
+};
 
 // ---- the products of one outer iteration ---------------------------------
 // WtA (k x n) = Wt * A
@@ -58,6 +79,18 @@ void prod_WtA(smk_ctx* c)
 void prod_HAt(smk_ctx* c)
 {
     const int k = c->opts.k;
+    const long long piece = static_cast<long long>(k) * c->x_loc;
+    if (c->use_peer && c->has_dense)
+    {
+        // the GEMM leaves its split-R partial tiles in the workspace; the reduce-scatter kernel adds them in split order
+        // WHILE it stores each row block into its owner's receive slot (peer.cu): reduction pass = NVLink transfer
+        int splits = 0;
+        gemm_f64(c->stream, true, k, c->m, c->n, c->H.p, k, c->dA, c->ldA, c->HAt.p, k, nullptr, 0,
+                 c->ws.p, c->ws.n * sizeof(double), c->num_sms, &splits);
+        peer_reduce_scatter(c, c->ws.p, splits, static_cast<long long>(k) * c->m, piece, c->HAt.p + c->rank * piece);
+        if (!c->w_sharded) peer_allgather(c, 1, piece);
+        return;
+    }
     if (c->has_dense)
         gemm_f64(c->stream, true, k, c->m, c->n, c->H.p, k, c->dA, c->ldA, c->HAt.p, k, nullptr, 0,
                  c->ws.p, c->ws.n * sizeof(double), c->num_sms);
@@ -65,21 +98,26 @@ void prod_HAt(smk_ctx* c)
         spmm_gather_seg(c->stream, c->m, c->Sa->seg_rows, c->Sa->colidx.p, c->Sa->valr.p, k, c->H.p, k, 1.0, 0.0, c->HAt.p, k,
                         c->spmm_partial.p, c->num_sms, c->n);
     if (c->nranks <= 1) return;
-    if (c->w_sharded)
+    if (c->use_peer)
+    {
+        peer_reduce_scatter(c, c->HAt.p, 1, static_cast<long long>(k) * c->m, piece, c->HAt.p + c->rank * piece);
+        if (!c->w_sharded) peer_allgather(c, 1, piece);
+    }
+    else if (c->w_sharded)
     {
         // row-sharded W update: every rank receives the sum of its own k x m_loc slice only
-        const size_t piece = static_cast<size_t>(k) * c->m_loc;
         nccl_check(ncclReduceScatter(c->HAt.p, c->HAt.p + c->rank * piece, piece, ncclDouble, ncclSum, c->comm, c->stream), "ncclReduceScatter");
     }
-    else allreduce_sum(c, c->HAt.p, static_cast<size_t>(k) * c->m);
+    else nccl_check(ncclAllReduce(c->HAt.p, c->HAt.p, static_cast<size_t>(k) * c->m, ncclDouble, ncclSum, c->comm, c->stream), "ncclAllReduce");
 }
 
 // after a row-sharded W update: every rank's slice of Wt to every rank
 void gather_Wt(smk_ctx* c)
 {
     if (c->nranks <= 1 || !c->w_sharded) return;
-    const size_t piece = static_cast<size_t>(c->opts.k) * c->m_loc;
-    nccl_check(ncclAllGather(c->Wt.p + c->rank * piece, c->Wt.p, piece, ncclDouble, c->comm, c->stream), "ncclAllGather");
+    const long long piece = static_cast<long long>(c->opts.k) * c->m_loc;
+    if (c->use_peer) peer_allgather(c, 0, piece);
+    else nccl_check(ncclAllGather(c->Wt.p + c->rank * piece, c->Wt.p, piece, ncclDouble, c->comm, c->stream), "ncclAllGather");
 }
 
 // G (k x k) = X * X' for X k x q
@@ -101,7 +139,16 @@ void compute_HHt(smk_ctx* c)
     gram(c, c->H.p, c->n, c->HHt.p);
     allreduce_sum(c, c->HHt.p, static_cast<size_t>(c->opts.k) * c->opts.k);
 }
-void compute_WtW(smk_ctx* c) { gram(c, c->Wt.p, c->m, c->WtW.p); }
+void compute_WtW(smk_ctx* c)
+{
+    if (c->w_sharded && c->use_peer)
+    {
+        // every rank Grams the rows of W it has just updated; the k x k partials are summed in rank order (peer.cu)
+        gram(c, c->Wt.p + static_cast<size_t>(c->opts.k) * c->w_row0(), c->w_rows(), c->WtW.p);
+        allreduce_sum(c, c->WtW.p, static_cast<size_t>(c->opts.k) * c->opts.k);
+    }
+    else gram(c, c->Wt.p, c->m, c->WtW.p);
+}
 
 void run_nnls(smk_ctx* c, const double* LHS, const double* RHS, double* X, double* Y, int q)
 {
@@ -109,7 +156,10 @@ void run_nnls(smk_ctx* c, const double* LHS, const double* RHS, double* X, doubl
     nnls_bpp(c->stream, k, q, LHS, k, RHS, k, X, k, Y, k, c->status.p, c->counter.p, c->deferred.p, c->steps_done, c->num_sms);
     // "zeroize everything iff any column was non-optimal" couples the column shards: one int, OR-reduced
     if (c->nranks > 1)
-        nccl_check(ncclAllReduce(c->status.p + ST_ANY_NONOPT, c->status.p + ST_ANY_NONOPT, 1, ncclInt, ncclMax, c->comm, c->stream), "ncclAllReduce");
+    {
+        if (c->use_peer) peer_allreduce(c, c->acc.p + 6, 0, c->status.p + ST_ANY_NONOPT, nullptr, 0, nullptr, nullptr);
+        else nccl_check(ncclAllReduce(c->status.p + ST_ANY_NONOPT, c->status.p + ST_ANY_NONOPT, 1, ncclInt, ncclMax, c->comm, c->stream), "ncclAllReduce");
+    }
     nnls_bpp_finish(c->stream, k, q, X, k, Y, k, c->status.p, c->num_sms);
 }
 
@@ -119,13 +169,29 @@ void solver_alloc(smk_ctx* c)
 {
     const size_t k = c->opts.k, n = c->n;
     c->w_sharded = c->nranks > 1 && (c->opts.algorithm == SMK_BPP || c->opts.algorithm == SMK_MU);
-    c->m_loc = c->w_sharded ? (c->m + c->nranks - 1) / c->nranks : c->m;
-    const size_t m = c->w_sharded ? static_cast<size_t>(c->m_loc) * c->nranks : c->m;     // padded
-    c->H.reserve(k * n); c->Wt.reserve(k * m);
+    c->use_peer = c->nranks > 1 && peer_enabled_by_env();
+    c->x_loc = c->nranks > 1 ? (c->m + c->nranks - 1) / c->nranks : c->m;       // rows per exchanged block
+    c->m_loc = c->w_sharded ? c->x_loc : c->m;
+    const bool padded = c->w_sharded || c->use_peer;
+    const size_t m = padded ? static_cast<size_t>(c->x_loc) * c->nranks : c->m;     // padded row count of the k x m buffers
+    c->H.reserve(k * n);
     c->gradH.reserve(k * n); c->gradWt.reserve(k * m);
     c->WtW.reserve(k * k); c->HHt.reserve(k * k);
-    c->WtA.reserve(k * n); c->HAt.reserve(k * m);
-    if (c->w_sharded)
+    c->WtA.reserve(k * n);
+    if (c->use_peer)
+    {
+        // Wt, HAt and the reduce-scatter receive slots live in the exchange region every peer maps (peer.cu)
+        peer_setup(c, k * m);
+        c->Wt.alias(peer_big_buffer(c, 0), k * m);
+        c->HAt.alias(peer_big_buffer(c, 1), k * m);
+    }
+    else
+    {
+        if (!c->Wt.owned) c->Wt.release();
+        if (!c->HAt.owned) c->HAt.release();
+        c->Wt.reserve(k * m); c->HAt.reserve(k * m);
+    }
+    if (padded)
     {
         SMK_CUDA(cudaMemsetAsync(c->Wt.p, 0, k * m * sizeof(double), c->stream));
         SMK_CUDA(cudaMemsetAsync(c->HAt.p, 0, k * m * sizeof(double), c->stream));
@@ -151,8 +217,12 @@ void solver_alloc(smk_ctx* c)
     size_t want = std::max<size_t>(static_cast<size_t>(4 * c->num_sms) * k * k,
                                    std::min<size_t>(static_cast<size_t>(32) * k * std::max(m, n), (size_t(768) << 20) / sizeof(double)));
     c->ws.reserve(want);
-    int init[ST_COUNT] = {0, INT_MAX, 0, 0, 0};
+    static const int init[ST_COUNT] = {0, INT_MAX, 0, 0, 0, 0, 0, 0};
     SMK_CUDA(cudaMemcpyAsync(c->status.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    c->prog.reserve(4);
+    SMK_CUDA(cudaMemsetAsync(c->prog.p, 0, 4 * sizeof(double), c->stream));       // "pg0 not captured yet"
+    const char* ph = getenv("SMK_PHASES");
+    c->phases_on = ph && atoi(ph) != 0;
 }
 
 void solver_init(smk_ctx* c)
@@ -179,20 +249,29 @@ void solver_step(smk_ctx* c)
     const int k = c->opts.k, m = c->m, n = c->n;
     c->pg_ready = false;
     c->status_cached = false;
+    Phase ph(c);
     switch (c->opts.algorithm)
     {
     case SMK_BPP:      // nmf_solver_bpp.hpp:342-377
         run_nnls(c, c->WtW.p, c->WtA.p, c->H.p, c->gradH.p, n);
+        ph.mark("nnls_H");
         compute_HHt(c);
+        ph.mark("HHt");
         prod_HAt(c);
+        ph.mark("HAt");
         {
             const size_t off = static_cast<size_t>(k) * c->w_row0();      // 0 unless the W update is row-sharded
             run_nnls(c, c->HHt.p, c->HAt.p + off, c->Wt.p + off, c->gradWt.p + off, c->w_rows());
+            ph.mark("nnls_W");
             gather_Wt(c);
+            ph.mark("gather_Wt");
         }
         compute_WtW(c);
+        ph.mark("WtW");
         prod_WtA(c);
+        ph.mark("WtA");
         gram_times(c, c->WtW.p, c->H.p, n, c->WtA.p, c->gradH.p);
+        ph.mark("gradH");
         break;
     case SMK_MU:       // nmf_solver_mu.hpp:118-163
         gram_times(c, c->WtW.p, c->H.p, n, nullptr, c->T1.p);
@@ -216,18 +295,27 @@ void solver_step(smk_ctx* c)
         break;
     case SMK_HALS:     // nmf_solver_hals.hpp:166-199
         hals_sweep(c->stream, k, m, c->Wt.p, c->HHt.p, c->HAt.p, /*normalize=*/true, c->norms.p, c->partial.p, c->num_sms, c->T2.p);
+        ph.mark("hals_W");
         compute_WtW(c);
+        ph.mark("WtW");
         prod_WtA(c);
+        ph.mark("WtA");
         hals_sweep(c->stream, k, n, c->H.p, c->WtW.p, c->WtA.p, /*normalize=*/false, c->norms.p, c->partial.p, c->num_sms);
+        ph.mark("hals_H");
         gram_times(c, c->WtW.p, c->H.p, n, c->WtA.p, c->gradH.p);
+        ph.mark("gradH");
         compute_HHt(c);
+        ph.mark("HHt");
         prod_HAt(c);
+        ph.mark("HAt");
         gram_times(c, c->HHt.p, c->Wt.p, m, c->HAt.p, c->gradWt.p);
+        ph.mark("gradW");
         break;
     case SMK_RANK2:    // nmf_solver_rank2.hpp:353-455
         if (c->has_sparse && c->nranks <= 1 && rank2_fused_enabled())
         {
             rank2_fused_step(c, c->T2.p);     // the same iteration in three kernels, projected-gradient sums included
+            ph.mark("rank2_fused");
             c->steps_done += 1;
             c->pg_ready = true;
             return;
@@ -245,54 +333,127 @@ void solver_step(smk_ctx* c)
         gram_times(c, c->WtW.p, c->H.p, n, c->WtA.p, c->gradH.p);
         break;
     }
+    ph.mark("rest");
     c->steps_done += 1;
 }
 
-// ProgressEst::Update for the state after `steps_done` iterations. Synchronises the stream.
-int solver_progress(smk_ctx* c, double* metric)
+// ProgressEst::Update for the state after `steps_done` iterations, entirely on the device: the metric is written to
+// *metric_dev (device memory); no host synchronisation. pg0 lives in c->prog (captured by the first PG evaluation after
+// solver_begin, whenever that is).
+void solver_progress_enqueue(smk_ctx* c, double* metric_dev)
 {
     const long long k = c->opts.k;
-    double h[2] = {0.0, 0.0};
+    Phase ph(c);
     if (c->opts.prog_est_algorithm == SMK_PG_RATIO)
     {
-        // projected_gradient.hpp:125-171; the H part is a sum over this rank's columns
-        // the W part is a sum over this rank's rows when the W update is row-sharded, else every rank has all of it
+        // projected_gradient.hpp:125-171. The H part is a sum over this rank's columns; the W part is a sum over this rank's
+        // rows when the W update is row-sharded, else every rank holds all of gradW and rank 0 alone contributes it.
         const long long woff = c->w_sharded ? k * c->w_row0() : 0;
-        const long long wrows = c->w_sharded ? c->w_rows() : c->m;
+        long long wcount = c->w_sharded ? k * c->w_rows() : k * c->m;
+        if (c->nranks > 1 && !c->w_sharded && c->rank != 0) wcount = 0;
+        double* prog = c->nranks <= 1 ? c->prog.p : nullptr;        // one rank: the reduction kernel finishes the metric itself
         if (!c->pg_ready)
+            pg_pair(c->stream, wcount, c->gradWt.p + woff, c->Wt.p + woff, k * c->n, c->gradH.p, c->H.p, c->partial.p,
+                    c->ticket.p + 4, c->acc.p, prog, metric_dev, c->status.p, c->num_sms);
+        else if (c->nranks <= 1)
+            progress_metric_launch(c->stream, 0, c->acc.p, c->prog.p, metric_dev, c->status.p);
+        if (c->nranks > 1)
         {
-            if (wrows > 0) pg_sumsq(c->stream, k * wrows, c->gradWt.p + woff, c->Wt.p + woff, c->partial.p, c->acc.p + 0, c->num_sms);
-            else SMK_CUDA(cudaMemsetAsync(c->acc.p, 0, sizeof(double), c->stream));
-            pg_sumsq(c->stream, k * c->n, c->gradH.p, c->H.p, c->partial.p, c->acc.p + 1, c->num_sms);
-            if (c->w_sharded) allreduce_sum(c, c->acc.p, 2);
-            else allreduce_sum(c, c->acc.p + 1, 1);
+            if (c->use_peer)    // sums, the failure flag and the metric in one exchange kernel
+                peer_allreduce(c, c->acc.p, 2, nullptr, c->status.p + ST_FAIL_ITER, 0, c->prog.p, metric_dev);
+            else
+            {
+                nccl_check(ncclAllReduce(c->acc.p, c->acc.p, 2, ncclDouble, ncclSum, c->comm, c->stream), "ncclAllReduce");
+                nccl_check(ncclAllReduce(c->status.p + ST_FAIL_ITER, c->status.p + ST_FAIL_ITER, 1, ncclInt, ncclMin, c->comm, c->stream), "ncclAllReduce");
+                progress_metric_launch(c->stream, 0, c->acc.p, c->prog.p, metric_dev, c->status.p);
+            }
         }
-        // page-locked landing zone: [0..1] the two sums, [2..] the status words, which ride on the same synchronisation
-        // when there is one rank (solver_fail_iter reads them next)
-        int* st_pinned = reinterpret_cast<int*>(c->pinned + 2);
-        SMK_CUDA(cudaMemcpyAsync(c->pinned, c->acc.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        if (c->nranks <= 1)
-            SMK_CUDA(cudaMemcpyAsync(st_pinned, c->status.p, sizeof(c->status_host), cudaMemcpyDeviceToHost, c->stream));
-        SMK_CUDA(cudaStreamSynchronize(c->stream));
-        h[0] = c->pinned[0]; h[1] = c->pinned[1];
-        if (c->nranks <= 1) { for (int i = 0; i < ST_COUNT; ++i) c->status_host[i] = st_pinned[i]; }
-        c->status_cached = c->nranks <= 1;
-        const double pg = sqrt(h[0] + h[1]);
-        if (pg != pg) { c->err = "ProjectedGradientNorm: NaN"; return SMK_FAILURE; }
-        if (c->steps_done <= 1) { c->pg0 = pg; *metric = 1.0; }
-        else *metric = pg / c->pg0;
     }
     else
     {
-        // progress_estimator_generic.hpp:58-69
+        // progress_estimator_generic.hpp:58-69 (W is replicated or all-gathered: every rank computes the same numbers)
         diff_sumsq(c->stream, k * c->m, c->Wprev.p, c->Wt.p, c->partial.p, c->acc.p + 0, c->num_sms);
         diff_sumsq(c->stream, k * c->m, c->Wt.p, nullptr, c->partial.p, c->acc.p + 1, c->num_sms);
         SMK_CUDA(cudaMemcpyAsync(c->Wprev.p, c->Wt.p, sizeof(double) * k * c->m, cudaMemcpyDeviceToDevice, c->stream));
-        SMK_CUDA(cudaMemcpyAsync(h, c->acc.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        SMK_CUDA(cudaStreamSynchronize(c->stream));
-        *metric = sqrt(h[0]) / sqrt(h[1]);
+        progress_metric_launch(c->stream, 1, c->acc.p, c->prog.p, metric_dev, c->status.p);
     }
+    ph.mark("progress");
+}
+
+namespace {
+// the status words as of now, through page-locked memory; `extra` doubles from extra_dev ride on the same synchronisation
+void read_status(smk_ctx* c, const double* extra_dev, int extra)
+{
+    int* st_pinned = reinterpret_cast<int*>(c->pinned + 8);
+    if (extra > 0) SMK_CUDA(cudaMemcpyAsync(c->pinned, extra_dev, extra * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SMK_CUDA(cudaMemcpyAsync(st_pinned, c->status.p, sizeof(c->status_host), cudaMemcpyDeviceToHost, c->stream));
+    SMK_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < ST_COUNT; ++i) c->status_host[i] = st_pinned[i];
+    c->status_cached = true;
+}
+
+int status_verdict(smk_ctx* c)
+{
+    if (c->status_host[ST_COMM_TIMEOUT]) { c->err = "peer exchange timed out (a rank died or fell more than 60 s behind)"; return SMK_FAILURE; }
+    if (c->status_host[ST_PG_NAN]) { c->err = "ProjectedGradientNorm: NaN"; return SMK_FAILURE; }
     return SMK_OK;
+}
+} // namespace
+
+// ProgressEst::Update + the metric on the host. Synchronises the stream.
+int solver_progress(smk_ctx* c, double* metric)
+{
+    solver_progress_enqueue(c, c->prog.p + 2);
+    read_status(c, c->prog.p + 2, 1);
+    *metric = c->pinned[0];
+    return status_verdict(c);
+}
+
+// `count` outer iterations, each followed by its progress update, with no host synchronisation in between; the metrics
+// come back in one copy at the end (metrics_host may be null). Returns SMK_FAILURE if a solver step failed.
+int solver_run(smk_ctx* c, int count, double* metrics_host)
+{
+    c->trace.reserve(static_cast<size_t>(std::max(count, 1)));
+    for (int i = 0; i < count; ++i)
+    {
+        solver_step(c);
+        solver_progress_enqueue(c, c->trace.p + i);
+    }
+    if (c->nranks > 1 && c->opts.prog_est_algorithm != SMK_PG_RATIO)
+    {
+        // the failure flag did not ride on a progress exchange: all ranks must take the same exit
+        if (c->use_peer) peer_allreduce(c, c->acc.p + 6, 0, nullptr, c->status.p + ST_FAIL_ITER, 0, nullptr, nullptr);
+        else nccl_check(ncclAllReduce(c->status.p + ST_FAIL_ITER, c->status.p + ST_FAIL_ITER, 1, ncclInt, ncclMin, c->comm, c->stream), "ncclAllReduce");
+    }
+    if (metrics_host && count > 0)
+        SMK_CUDA(cudaMemcpyAsync(metrics_host, c->trace.p, sizeof(double) * count, cudaMemcpyDeviceToHost, c->stream));
+    read_status(c, nullptr, 0);
+    if (c->status_host[ST_FAIL_ITER] != INT_MAX) { c->err = "NMF solver failure on iteration " + std::to_string(c->status_host[ST_FAIL_ITER] + 1); return SMK_FAILURE; }
+    if (c->opts.algorithm == SMK_RANK2 && c->status_host[ST_NORM_EPS]) { c->err = "Normalize: column norm < machine epsilon"; return SMK_FAILURE; }
+    return status_verdict(c);
+}
+
+// "name=ms;name=ms;..." summed over the solver steps since the last report (SMK_PHASES=1), then reset. Synchronises.
+std::string solver_phase_report(smk_ctx* c)
+{
+    std::string out;
+    if (!c->phases_on || c->phase_marks.empty()) return out;
+    SMK_CUDA(cudaStreamSynchronize(c->stream));
+    std::vector<std::pair<std::string, double>> acc;
+    for (size_t i = 1; i < c->phase_marks.size(); ++i)
+    {
+        const char* name = c->phase_marks[i].first;
+        if (std::string(name) == "begin") continue;
+        float ms = 0.f;
+        SMK_CUDA(cudaEventElapsedTime(&ms, c->phase_marks[i - 1].second, c->phase_marks[i].second));
+        bool found = false;
+        for (auto& a : acc) if (a.first == name) { a.second += ms; found = true; break; }
+        if (!found) acc.emplace_back(name, ms);
+    }
+    for (auto& a : acc) out += a.first + "=" + std::to_string(a.second) + ";";
+    c->phase_marks.clear();
+    c->phase_pool_used = 0;
+    return out;
 }
 
 // NormalizeAndScale(W, H): normalize.hpp:118-138. Returns SMK_FAILURE if a column norm < eps.
@@ -341,16 +502,19 @@ int solver_nnls_hals(smk_ctx* c, double tol, int max_iter, int* iterations)
 
 void solver_product(smk_ctx* c, int which) { if (which == 0) prod_WtA(c); else prod_HAt(c); }
 
-// First outer iteration (0-based) in which a kernel reported solver failure, or INT_MAX.
+// First outer iteration (0-based) in which a kernel reported solver failure, or INT_MAX. Synchronises unless the last
+// solver_progress already brought the (rank-reduced) status words to the host.
 int solver_fail_iter(smk_ctx* c)
 {
-    if (c->status_cached) return c->status_host[ST_FAIL_ITER];
-    int st[ST_COUNT];
+    const bool reduced_by_progress = c->nranks <= 1 || c->opts.prog_est_algorithm == SMK_PG_RATIO;
+    if (c->status_cached && reduced_by_progress) return c->status_host[ST_FAIL_ITER];
     if (c->nranks > 1)      // all ranks must take the same exit
-        nccl_check(ncclAllReduce(c->status.p + ST_FAIL_ITER, c->status.p + ST_FAIL_ITER, 1, ncclInt, ncclMin, c->comm, c->stream), "ncclAllReduce");
-    SMK_CUDA(cudaMemcpyAsync(st, c->status.p, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
-    SMK_CUDA(cudaStreamSynchronize(c->stream));
-    return st[ST_FAIL_ITER];
+    {
+        if (c->use_peer) peer_allreduce(c, c->acc.p + 6, 0, nullptr, c->status.p + ST_FAIL_ITER, 0, nullptr, nullptr);
+        else nccl_check(ncclAllReduce(c->status.p + ST_FAIL_ITER, c->status.p + ST_FAIL_ITER, 1, ncclInt, ncclMin, c->comm, c->stream), "ncclAllReduce");
+    }
+    read_status(c, nullptr, 0);
+    return c->status_host[ST_FAIL_ITER];
 }
 
 } // namespace smk

@@ -9,6 +9,9 @@ void solver_alloc(smk_ctx* c);
 void solver_init(smk_ctx* c);
 void solver_step(smk_ctx* c);
 int solver_progress(smk_ctx* c, double* metric);
+void solver_progress_enqueue(smk_ctx* c, double* metric_dev);
+int solver_run(smk_ctx* c, int count, double* metrics_host);
+std::string solver_phase_report(smk_ctx* c);
 int solver_normalize(smk_ctx* c);
 int solver_fail_iter(smk_ctx* c);
 void solver_product(smk_ctx* c, int which);

@@ -59,7 +59,7 @@ def golden_inputs(name):
                 normalize=normalize, A=A, sp=sp, W0=W0, H0=H0)
 
 
-def nnls_inputs(seed, k, q, shift=0.35):
+def nnls_inputs(seed, k, q, shift=0.35, cold=False):
     """shift sets how much of the unconstrained solution is negative: 0.35 leaves ~10 % of the entries passive,
     0.01 leaves most of them passive (|P| > k/2: the complement path of the GPU kernels)."""
     rng = np.random.default_rng(seed)
@@ -74,13 +74,48 @@ def nnls_inputs(seed, k, q, shift=0.35):
         return LHS, RHS, X0
     RHS = W.T @ A - shift * rng.random((k, q)) * np.abs(W.T @ A).mean()
     X0 = rng.random((k, q)) * (rng.random((k, q)) > 0.3)
+    if cold:
+        # all-nonpositive initial guess: the passive set starts with NO bit set. IsEmpty(passive_set) in
+        # BppSolveNormalEqNoGroup (nmf_solver_bpp.hpp:173) tests for a zero-SIZED BitMatrix (bit_matrix_ops.cpp:24-27), not
+        # for an all-zero one, so the reference takes the per-column path and leaves X = 0 for the first dual evaluation
+        X0 = -X0
     return LHS, RHS, X0
 
 
 NNLS_CASES = {"nnls_k16_q64": (21, 16, 64), "nnls_k40_q90": (22, 40, 90), "nnls_k64_q120": (23, 64, 120),
               "nnls_k100_q150": (24, 100, 150), "nnls_k200_q90": (25, 200, 90), "nnls_k256_q64": (26, 256, 64),
               "nnls_k60_q100_dense": (27, 60, 100, -0.15), "nnls_k200_q80_dense": (28, 200, 80, -0.2),
-              "nnls_k256_q60_dense": (29, 256, 60, -0.1), "nnls_k250_q40_half": (30, 250, 40, -0.5)}
+              "nnls_k256_q60_dense": (29, 256, 60, -0.1), "nnls_k250_q40_half": (30, 250, 40, -0.5),
+              "nnls_k48_q80_cold": (31, 48, 80, 0.35, True), "nnls_k130_q50_cold": (32, 130, 50, 0.35, True)}
+
+
+# ---- NNLS cases in which UpdatePassiveSet's BACKUP rule fires (common/src/nnls.cpp:64-72) --------------------------
+# Block pivoting falls back to single-variable toggles only when full exchanges cycle, which random well-conditioned
+# problems never do. A small system with strongly correlated columns does (found by search: s = 5, seed 6 -> 18 firings in
+# 2000 columns); it is embedded at rows [at, at + s) of an otherwise diagonal k x k problem, so that the row the rule
+# toggles is reported by BitMatrix::MaxRowIndex from word 0 / the partial last word (correct) or from a full word > 0
+# (common/src/bit_matrix.cpp:459-467: 32 rows too low -> the wrong row is toggled, the column cycles until MAX_ITER = 5k
+# and the REFERENCE returns failure). name -> (k, at, s, seed); the fixture records the reference's rc, X, Y.
+BACKUP_CASES = {"nnls_backup_k64_word0": (64, 27, 5, 6), "nnls_backup_k48_partial": (48, 43, 5, 6),
+                "nnls_backup_k100_word0": (100, 10, 5, 6), "nnls_backup_k200_word0": (200, 20, 6, 9),
+                "nnls_backup_k64_defect": (64, 59, 5, 6), "nnls_backup_k100_defect": (100, 60, 5, 6)}
+
+
+def backup_inputs(k, at, s, seed, q=2000):
+    rng = np.random.default_rng(seed * 100 + s)
+    rows = s + int(rng.integers(0, 3))
+    Ws = rng.standard_normal((rows, s)) + 2.0 * rng.standard_normal((rows, 1))
+    S = Ws.T @ Ws + 1e-6 * np.eye(s)
+    Rs = rng.standard_normal((s, q)) * 3
+    Xs = (rng.random((s, q)) > 0.5) * rng.random((s, q))
+    rng = np.random.default_rng(seed + 7)
+    LHS = np.diag(1.0 + rng.random(k))
+    LHS[at:at + s, at:at + s] = S
+    RHS = 0.5 + rng.random((k, q))
+    RHS[at:at + s] = Rs
+    X0 = rng.random((k, q))
+    X0[at:at + s] = Xs
+    return LHS, RHS, X0
 
 
 def main():
@@ -116,6 +151,13 @@ def main():
         assert rc == 0
         np.savez_compressed(os.path.join(HERE, name + ".npz"), X=X, Y=Y)
         print(f"{name}: passive density {np.mean(X > 0):.3f}")
+    for name, args in BACKUP_CASES.items():
+        if only and name not in only:
+            continue
+        LHS, RHS, X0 = backup_inputs(*args)
+        rc, X, Y = ref.nnls_bpp(LHS, RHS, X0)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), rc=rc, X=X, Y=Y)
+        print(f"{name}: reference rc {rc}")
 
 
 if __name__ == "__main__":

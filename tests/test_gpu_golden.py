@@ -58,3 +58,29 @@ def test_gpu_nnls_reproduces_reference_fixture(gpu, name):
     X, Y = gpu.nnls_bpp(LHS, RHS, X0)
     assert np.array_equal(X > 0, z["X"] > 0)
     assert rel(X, z["X"]) < 1e-10
+
+
+@pytest.mark.parametrize("name", sorted(mg.BACKUP_CASES))
+def test_gpu_backup_rule_fires_as_in_the_reference(gpu, oracle, name):
+    """Crafted NNLS problems in which UpdatePassiveSet's backup rule fires (common/src/nnls.cpp:64-72). The GPU kernels must
+    fire it exactly as often as the CPU restatement (itself pinned to the reference's rc / X / Y by the fixture), give the
+    reference's solution where the reference succeeds, and FAIL where BitMatrix::MaxRowIndex's off-by-one-word defect
+    (common/src/bit_matrix.cpp:459-467) makes the reference cycle to MAX_ITER (k > 32, row in a full word > 0)."""
+    import ctypes
+    LHS, RHS, X0 = mg.backup_inputs(*mg.BACKUP_CASES[name])
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    oracle.lib.orc_backup_count.restype = ctypes.c_double
+    oracle.lib.orc_stats_reset()
+    rc_o, Xo, Yo = oracle.nnls_bpp(LHS, RHS, X0)
+    fired = int(oracle.lib.orc_backup_count())
+    assert fired > 0 and rc_o == int(z["rc"])
+    if int(z["rc"]) == 0:
+        X, Y = gpu.nnls_bpp(LHS, RHS, X0)
+        assert np.array_equal(X > 0, z["X"] > 0)
+        assert rel(X, z["X"]) < 1e-10
+        assert np.abs(Y - z["Y"]).max() < 1e-9 * max(1.0, np.abs(z["Y"]).max())
+    else:
+        with pytest.raises(sk.SmallkError) as e:
+            gpu.nnls_bpp(LHS, RHS, X0)
+        assert e.value.code == sk.FAILURE
+    assert gpu.nnls_backup_count() == fired

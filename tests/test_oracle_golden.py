@@ -54,6 +54,24 @@ def test_oracle_nnls_reproduces_reference_fixture(oracle, name):
     assert rel(X, z["X"]) < 1e-10 and np.abs(Y - z["Y"]).max() < 1e-9 * max(1.0, np.abs(z["Y"]).max())
 
 
+@pytest.mark.parametrize("name", sorted(mg.BACKUP_CASES))
+def test_oracle_backup_rule_cases_reproduce_reference_fixture(oracle, name):
+    """UpdatePassiveSet's backup rule (nnls.cpp:64-72) fires in these cases; where MaxRowIndex's defect (bit_matrix.cpp:459-467)
+    picks the wrong row the reference itself fails (rc -4), and so must the restatement."""
+    import ctypes
+    LHS, RHS, X0 = mg.backup_inputs(*mg.BACKUP_CASES[name])
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    oracle.lib.orc_backup_count.restype = ctypes.c_double
+    oracle.lib.orc_stats_reset()
+    rc, X, Y = oracle.nnls_bpp(LHS, RHS, X0)
+    assert oracle.lib.orc_backup_count() > 0
+    assert rc == int(z["rc"])
+    assert (rc == 0) == ("defect" not in name)
+    if rc == 0:
+        assert np.array_equal(X > 0, z["X"] > 0)
+        assert rel(X, z["X"]) < 1e-10 and np.abs(Y - z["Y"]).max() < 1e-9 * max(1.0, np.abs(z["Y"]).max())
+
+
 needs_ref = pytest.mark.skipif(not Ref.available(), reason="oracle/_ref not built (no /root/reference on this box)")
 
 

@@ -44,106 +44,140 @@ def _clock_sampler(index):
     return s
 
 
-def run_c3(args):
+def run_c3(args, env=None, steps=None, warmup=None):
+    """Returns the JSON line (a dict). With env (bench.Env) and more than one rank: A and H are split into contiguous column
+    blocks holding equal shares of the stored entries (smallk_b200.sharding.column_block_by_nnz), W is replicated (the in-sweep
+    column norms of HALS couple its rows), H A' is summed over the ranks by the library's exchange kernels."""
     import torch
     import smallk_b200 as sk
     import workloads
+    from smallk_b200.sharding import column_block_by_nnz
+    steps = steps or args.steps
+    warmup = warmup or args.warmup
     m, n, per_col, k = 1000000, 200000, 500, 128
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(0)
-    colp, rowi, val = workloads.c3_tfidf_csc(m, n, per_col)
+    world = env.world if env is not None else 1
+    rank = env.rank if env is not None else 0
+    local = env.local if env is not None else 0
+    torch.cuda.set_device(local)
+    colp, rowi, val = workloads.c3_tfidf_csc(m, n, per_col, device=f"cuda:{local}")
     nnz = int(colp[-1])
-    ctx = sk.Context(0)
-    stream = torch.cuda.current_stream()
-    ctx.set_stream(stream.cuda_stream)
-    ctx.load_csc((m, n), colp, rowi, val)
+    val_sum = float(val.sum())
+    c0, c1 = column_block_by_nnz(colp, rank, world)
+    if world > 1:
+        e0, e1 = int(colp[c0]), int(colp[c1])
+        colp_l = (colp[c0:c1 + 1].astype(np.int64) - e0).astype(np.uint32)
+        rowi_l, val_l = rowi[e0:e1], val[e0:e1]
+    else:
+        colp_l, rowi_l, val_l = colp, rowi, val
+    n_loc, nnz_loc = c1 - c0, int(colp_l[-1])
+    if env is not None:
+        ctx, stream = env.ctx, env.stream
+    else:
+        ctx = sk.Context(0)
+        stream = torch.cuda.current_stream()
+        ctx.set_stream(stream.cuda_stream)
+    ctx.load_csc((m, n_loc), colp_l, rowi_l, val_l)
     W0 = np.asfortranarray(np.random.default_rng(22).random((m, k)))
-    # H0 scaled so that mean(W0*H0) = mean(A): from W0*H0 >> A, HALS clamps whole factors to zero in its first sweep
-    H0 = np.asfortranarray(np.random.default_rng(23).random((k, n))) * (float(val.sum()) / m / n / (0.25 * k))
-    opts = sk.make_options(m, n, k, algorithm="HALS", tol=1e-15, min_iter=1, max_iter=args.warmup + args.steps + 8, normalize=False)
+    # H0 scaled so that mean(W0*H0) = mean(A): from W0*H0 >> A, HALS clamps whole factors to zero in its first sweep (DESIGN.md section 3)
+    H0 = np.asfortranarray(np.random.default_rng(23).random((k, n))[:, c0:c1]) * workloads.hals_h0_scale(val_sum, m, n, k)
+    opts = sk.make_options(m, n, k, algorithm="HALS", tol=1e-15, min_iter=1, max_iter=warmup + steps + 8, normalize=False)
     ctx.solver_begin(W0, H0, opts)
-    metric = None
-    for _ in range(args.warmup):
-        ctx.solver_step(1)
-        metric = ctx.solver_progress()
-    sampler = _clock_sampler(0)
-    launches = 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record(stream)
-    for _ in range(args.steps):
-        ctx.solver_step(1)
-        launches += ctx.last_step()[1] + 4
-        metric = ctx.solver_progress()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    ms_per_step = e0.elapsed_time(e1) / args.steps
-    clocks = sampler.stop()
+    if env is not None:
+        ms_per_step, trace, launches, clocks, phases = env.timed_run(ctx, warmup, steps, sample_clocks=(world == 1))
+    else:
+        import bench
+        trace = list(ctx.solver_run(warmup))
+        sampler = _clock_sampler(0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        trace += list(ctx.solver_run(steps))
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms_per_step = e0.elapsed_time(e1) / steps
+        launches = ctx.last_step()[1]
+        clocks = sampler.stop()
+        phases = {name: v / (steps + warmup) for name, v in ctx.phase_report().items()} if os.environ.get("SMK_PHASES") else None
+    metric = trace[-1]
     t_wta = ctx.time_product(0, reps=5)
     t_hat = ctx.time_product(1, reps=5)
     tiers = {"WtA": ctx.spmm_tier_info(0), "HAt": ctx.spmm_tier_info(1)}
     peak, peak_src = hbm_peak()
-    bytes_wta = 12.0 * nnz + 4.0 * (n + 1) + 8.0 * k * (m + n)       # A once, Wt read once, W'A written once
-    bytes_hat = 12.0 * nnz + 4.0 * (m + 1) + 8.0 * k * (n + m)
+    bytes_wta = 12.0 * nnz_loc + 4.0 * (n_loc + 1) + 8.0 * k * (m + n_loc)       # A once, Wt read once, W'A written once
+    bytes_hat = 12.0 * nnz_loc + 4.0 * (m + 1) + 8.0 * k * (n_loc + m)
     achieved = (bytes_wta + bytes_hat) / ((t_wta + t_hat) * 1e-3) * 1e-9
-    B_iter = 2 * (12.0 * nnz + 4 * (n + 1)) + 64.0 * k * (m + n)      # SURVEY §8d compulsory bytes per iteration
+    B_iter = 2 * (12.0 * nnz + 4 * (n + 1)) + 64.0 * k * (m + n)      # SURVEY section 8(d) compulsory bytes per iteration (whole job)
+    # every stored entry gathers one k-vector of the dense operand through L2: 8 k nnz bytes per product. The L2 slices deliver
+    # ~6300 B/clk chip-wide (B300_MICROARCH.md, "LTS throughput cap"), ~12.4 TB/s at 1965 MHz: the bound of a gather SpMM at this k
+    l2_cap = 6300.0 * 1965e6 * 1e-12
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "ncu_r01_c3_spmm_traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = float(json.load(open(tp))["dram_bytes_both_products"])
-        except Exception:
-            traffic = None
-    ctx.close()
-    del ctx
+    for tname in ("ncu_r02_c3_spmm_traffic.json", "ncu_r01_c3_spmm_traffic.json"):
+        tp = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tp) and world == 1:
+            try:
+                traffic = float(json.load(open(tp))["dram_bytes_both_products"])
+            except Exception:
+                traffic = None
+            break
+    if env is None:
+        ctx.close()
+        del ctx
 
     e2e = None
-    if not args.no_e2e:
-        ctx2 = sk.Context(0)
+    if not args.no_e2e and world == 1:
+        ctx2 = sk.Context(local)
         W = W0.copy(order="F"); H = H0.copy(order="F")
-        o2 = sk.make_options(m, n, k, algorithm="HALS", tol=1e-15, min_iter=args.steps, max_iter=args.steps, normalize=False)
+        o2 = sk.make_options(m, n, k, algorithm="HALS", tol=1e-15, min_iter=steps, max_iter=steps, normalize=False)
         t0 = time.perf_counter()
         ctx2.load_csc((m, n), colp, rowi, val)
         ctx2.nmf(W, H, o2)
         t_e2e = time.perf_counter() - t0
-        e2e = {"value": args.steps / t_e2e, "unit": UNIT,
-               "h2d_bytes_per_step": (12.0 * nnz + 4.0 * (n + 1) + 8.0 * k * (m + n)) / args.steps,
-               "d2h_bytes_per_step": 8.0 * k * (m + n) / args.steps,
-               "note": f"smk_load_csc (CSR and segment tables built on the device) + smk_nmf ({args.steps} iterations) on host arrays; wall clock"}
+        e2e = {"value": steps / t_e2e, "unit": UNIT,
+               "h2d_bytes_per_step": (12.0 * nnz + 4.0 * (n + 1) + 8.0 * k * (m + n)) / steps,
+               "d2h_bytes_per_step": 8.0 * k * (m + n) / steps, "seconds": t_e2e,
+               "note": f"smk_load_csc (CSR and segment tables built on the device) + smk_nmf ({steps} iterations) on host arrays; wall clock"}
         ctx2.close()
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         try:
             from oracle import Ref
-            ms, ns = 100000, 20000
-            cp, ri, va = workloads.c3_tfidf_csc(ms, ns, per_col, seed=21)
-            Ws = np.asfortranarray(np.random.default_rng(22).random((ms, k)))
-            Hs = np.asfortranarray(np.random.default_rng(23).random((k, ns))) * (float(va.sum()) / ms / ns / (0.25 * k))
+            ms_, ns_ = 100000, 20000
+            cp, ri, va = workloads.tfidf_csc_numpy(ms_, ns_, 50, 21)
+            Ws = np.asfortranarray(np.random.default_rng(22).random((ms_, k)))
+            Hs = np.asfortranarray(np.random.default_rng(23).random((k, ns_))) * workloads.hals_h0_scale(va.sum(), ms_, ns_, k)
             cores = os.cpu_count() or 1
-            o = Ref().nmf_sparse((ms, ns), cp, ri, va, Ws, Hs, alg="HALS", tol=1e-15, min_iter=3, max_iter=3, max_threads=cores, timed=True)
+            o = Ref(blas_threads=cores).nmf_sparse((ms_, ns_), cp, ri, va, Ws, Hs, alg="HALS", tol=1e-15, min_iter=3, max_iter=3, max_threads=cores, timed=True)
             sec = o["elapsed_us"] * 1e-6 / 3
             f_full = 4.0 * k * nnz + 6.0 * k * k * (m + n)
-            f_s = 4.0 * k * int(cp[-1]) + 6.0 * k * k * (ms + ns)
+            f_s = 4.0 * k * int(cp[-1]) + 6.0 * k * k * (ms_ + ns_)
             cpu = {"value": 1.0 / (sec * f_full / f_s), "unit": UNIT, "cores": cores, "kind": "reference",
-                   "sample": f"reference sparse HALS (oracle/_ref) on {ms}x{ns} (nnz {int(cp[-1])}) of the same generator, 3 iterations, "
-                             f"{cores} threads, seconds scaled to the full size by the flop ratio {f_full / f_s:.1f}"}
+                   "measured_iter_per_s_on_sample": 1.0 / sec,
+                   "sample": f"reference sparse HALS (oracle/_ref, {cores} threads) on the same generator at {ms_}x{ns_} (nnz {int(cp[-1])}: same density; the "
+                             f"matrix of the scale_c3r_hals parity fixture), 3 iterations incl. Init; `value` scales its seconds to the full size by the "
+                             f"flop ratio {f_full / f_s:.1f} (the full matrix does not fit a few-minute CPU run: 128 Gemv passes over a 1 GB W per iteration)"}
         except Exception as ex:
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"unavailable: {ex}"}
 
-    line = {"metric": METRIC, "value": 1000.0 / ms_per_step, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": METRIC, "value": 1000.0 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"sparse HALS NMF {m}x{n} nnz={nnz} k={k} (BASELINE configs[2], SURVEY C3)", "algorithm": "HALS", "k": k,
-                       "l2": "inputs larger than L2 (CSC + CSR 2.2 GB, W 1 GB)", "step": "solver() + PG_RATIO progress update"},
+                       "sharding": f"columns [{c0}, {c1}) of {n} on rank {rank} of {world}: {nnz_loc} stored entries (balanced by nnz)",
+                       "l2": "inputs larger than L2 (CSC + CSR 2.8 GB, W 1 GB)", "step": "solver() + PG_RATIO progress update, enqueued by one smk_solver_run call"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "spmm_seg_tier_kernel (W'A) + spmm_seg_slab_kernel x4 (H A'): algorithmic bytes of both products / both launch times",
                          "algorithmic_bytes": bytes_wta + bytes_hat, "launch_ms": {"WtA": t_wta, "HAt": t_hat},
-                         "gathered_TBs": {"WtA": nnz * k * 8 / t_wta * 1e-9, "HAt": nnz * k * 8 / t_hat * 1e-9},
+                         "gathered_TBs": {"WtA": nnz_loc * k * 8 / t_wta * 1e-9, "HAt": nnz_loc * k * 8 / t_hat * 1e-9},
+                         "l2_gather_bound": {"cap_TBs": l2_cap, "frac_WtA": nnz_loc * k * 8 / t_wta * 1e-9 / l2_cap, "frac_HAt": nnz_loc * k * 8 / t_hat * 1e-9 / l2_cap,
+                                             "note": "a gather SpMM moves 8*k*nnz bytes of dense operand from L2 to the SMs per product (no on-chip reuse exists at 0.05 % "
+                                                     "density); the L2 slice throughput cap (6300 B/clk chip-wide) bounds it, not HBM"},
                          "residency_classes(on,smem_rows,share)": tiers, "peak_source": peak_src,
-                         "step_compulsory_GB": B_iter * 1e-9, "step_frac_of_peak": B_iter / (ms_per_step * 1e-3) * 1e-9 / peak},
+                         "step_compulsory_GB": B_iter * 1e-9, "step_frac_of_peak": B_iter / world / (ms_per_step * 1e-3) * 1e-9 / peak},
             "cpu_baseline": cpu, "progress_metric_last": metric}
-    print(json.dumps(line), flush=True)
+    if phases:
+        line["phases_ms_per_step"] = phases
+    return line
 
 
 def run_c4(args):
@@ -214,4 +248,4 @@ def run_c4(args):
                          "kernel": "rank2_h_kernel + rank2_w_kernel + rank2_grad_kernel: one iteration on the root matrix",
                          "algorithmic_bytes": B_root, "launch_us": root_us, "launches_per_iteration": l200 / 200, "peak_source": peak_src},
             "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    return line
