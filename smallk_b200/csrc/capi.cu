@@ -145,6 +145,12 @@ void smk_destroy(smk_ctx* c)
     peer_release(c);
     c->Wt.release(); c->HAt.release();      // possibly views of the exchange region just freed
     for (cudaEvent_t e : c->phase_pool) cudaEventDestroy(e);
+    for (smk_ctx::InvBuf* b : {&c->invH, &c->invW})
+    {
+        if (b->fork) cudaEventDestroy(b->fork);
+        if (b->join) cudaEventDestroy(b->join);
+    }
+    if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
     if (c->comm) ncclCommDestroy(c->comm);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -525,7 +531,8 @@ int smk_gemm(smk_ctx* c, int transA, int transB, int M, int N, int K,
             transpose_f64(c->stream, K, M, dA.p, K, dAt.p, M);
             Aop = dAt.p;
         }
-        ws.reserve(std::min<size_t>(static_cast<size_t>(64) * M * N, (size_t(256) << 20) / sizeof(double)));
+        ws.reserve(std::min<size_t>(static_cast<size_t>(64) * std::max(M, 64) * std::max(N, 128), (size_t(256) << 20) / sizeof(double)) + 8192);
+        gemm_workspace_prepare(c->stream, ws.p, ws.n * sizeof(double));
         gemm_f64(c->stream, transB != 0, M, N, K, Aop, M, dB.p, b_rows, dC.p, M, nullptr, 0, ws.p, ws.n * sizeof(double), c->num_sms);
         download_tight(c, dC.p, M, N, C, ldC);
         SMK_CUDA(cudaStreamSynchronize(c->stream));

@@ -143,6 +143,16 @@ struct smk_ctx
     int x_loc = 0;
     smk::PeerComm peer;
     smk::DevBuf<unsigned int> peer_ticket;
+    // G^-1 for the NNLS solves of BPP (nnls_prepare_inverse), computed on the side stream under the big product that precedes
+    // each solve: invH = (W'W)^-1 for the H side, invW = (H H')^-1 for the W side
+    struct InvBuf
+    {
+        smk::DevBuf<double> Ginv;
+        smk::DevBuf<int> ok;
+        cudaEvent_t fork = nullptr, join = nullptr;
+        bool pending = false;
+    } invH, invW;
+    cudaStream_t side = nullptr;        // helper stream (highest priority) for work overlapped with the big products
     // per-phase device times of solver_step (SMK_PHASES=1): cudaEvent pairs, summed on demand
     bool phases_on = false;
     std::vector<std::pair<const char*, cudaEvent_t>> phase_marks;

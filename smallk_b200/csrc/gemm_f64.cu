@@ -22,10 +22,16 @@
 //   * cp.async 3-stage shared-memory pipeline, zero-filled tails; smem leading
 //     dimensions are = 4 (mod 16) doubles so every fragment LDS.64 is conflict free.
 //   * Split over the reduction ("split-R") so the grid fills 148 SMs whatever the
-//     shape; partial tiles go to a workspace and are summed in a FIXED order by
-//     reduce_partials_kernel, so results do not depend on scheduling.
+//     shape. The splits of one output tile are neighbours in launch order (they run
+//     in the same wave), each stores its partial tile in the workspace (fragment
+//     order: fully coalesced, L2-resident) and takes a ticket; the CTA that arrives
+//     LAST adds the partials in ASCENDING SPLIT ORDER — a fixed order, so results do
+//     not depend on scheduling — and writes the tile. No second kernel, no DRAM round
+//     trip of the partials (r01: reduce_partials_kernel, 0.31 GB per big product).
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
+#include "peer_device.cuh"
 
 namespace smk {
 
@@ -54,6 +60,13 @@ struct GemmParams
     int M, N, R;
     int splits, rchunk;                // reduction range per split, multiple of BK
     int to_partial;                    // write the tile to `partial` even when splits == 1 (the caller reduces / forwards it)
+    int fixup;                         // splits > 1: in-kernel reduction by the last-arriving CTA of each tile (1-D grid)
+    int ntn;                           // tiles along N
+    unsigned int* tickets;             // one arrival counter per tile, zero on entry, left zero
+    double* slots;                     // [tile][split][32][256] partial tiles in fragment order
+    // multi-GPU H*A': the finished tile goes straight to the receive slot of the rank that owns its columns (peer.cu layout),
+    // and the CTA that finishes the LAST tile publishes the epoch to every peer: product, reduction and NVLink transfer in one kernel
+    GemmScatter sc;
 };
 
 // Copy `nvec` vectors of `len` contiguous doubles (a tile) into shared memory.
@@ -88,9 +101,12 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_skinny_kernel(GemmParams p)
     const int wm = warp & 1, wn = warp >> 1;       // 2 x 4 warps
     const int g = lane >> 2, t4 = lane & 3;
 
-    const int n0 = blockIdx.x * BN;
-    const int m0 = blockIdx.y * BM;
-    const int split = blockIdx.z;
+    int tile_n, tile_m, split_;
+    if (p.fixup) { split_ = blockIdx.x % p.splits; const int tile = blockIdx.x / p.splits; tile_n = tile % p.ntn; tile_m = tile / p.ntn; }
+    else { tile_n = blockIdx.x; tile_m = blockIdx.y; split_ = blockIdx.z; }
+    const int n0 = tile_n * BN;
+    const int m0 = tile_m * BM;
+    const int split = split_;
     const int r_begin = split * p.rchunk;
     const int r_end = min(p.R, r_begin + p.rchunk);
     const int nchunks = (r_end > r_begin) ? (r_end - r_begin + BK - 1) / BK : 0;
@@ -153,10 +169,47 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_skinny_kernel(GemmParams p)
     }
     cp_async_wait<0>();
 
+    if (p.fixup)
+    {
+        // ---- split-R fix-up: partial tile to the workspace, ticket, the last arriver sums in split order
+        __shared__ bool s_last;
+        const int tile = blockIdx.x / p.splits;
+        double* slot0 = p.slots + static_cast<long long>(tile) * p.splits * (BM * BN);
+        double* mine = slot0 + static_cast<long long>(split) * (BM * BN) + tid;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+            {
+                mine[((i * 4 + j) * 2 + 0) * THREADS] = acc[i][j][0];
+                mine[((i * 4 + j) * 2 + 1) * THREADS] = acc[i][j][1];
+            }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(p.tickets + tile, 1u) == static_cast<unsigned int>(p.splits - 1));
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        if (tid == 0) p.tickets[tile] = 0u;                 // ready for the next launch
+        for (int z = 0; z < p.splits; ++z)
+        {
+            const double* src = slot0 + static_cast<long long>(z) * (BM * BN) + tid;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                {
+                    const double v0 = __ldcg(src + ((i * 4 + j) * 2 + 0) * THREADS), v1 = __ldcg(src + ((i * 4 + j) * 2 + 1) * THREADS);
+                    if (z == 0) { acc[i][j][0] = v0; acc[i][j][1] = v1; }
+                    else { acc[i][j][0] += v0; acc[i][j][1] += v1; }
+                }
+        }
+    }
+
     // epilogue
     double* out;
     long long ldo;
-    if (p.splits > 1 || p.to_partial) { out = p.partial + static_cast<long long>(split) * p.M * p.N; ldo = p.M; }
+    if (!p.fixup && (p.splits > 1 || p.to_partial)) { out = p.partial + static_cast<long long>(split) * p.M * p.N; ldo = p.M; }
     else              { out = p.C; ldo = p.ldc; }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -172,10 +225,34 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_skinny_kernel(GemmParams p)
                 const int col = n0 + wn * 32 + j * 8 + 2 * t4 + e;
                 if (col >= p.N) continue;
                 double v = acc[i][j][e];
-                if (p.splits == 1 && !p.to_partial && p.D) v -= p.D[static_cast<long long>(col) * p.ldd + row];
-                out[static_cast<long long>(col) * ldo + row] = v;
+                if ((p.fixup || (p.splits == 1 && !p.to_partial)) && p.D) v -= p.D[static_cast<long long>(col) * p.ldd + row];
+                if (p.sc.nranks > 0)
+                {
+                    const int g = col / p.sc.cols_per_rank;
+                    double* dst = reinterpret_cast<double*>(p.sc.table.base[g] + p.sc.recv_off) + static_cast<long long>(p.sc.rank) * p.sc.piece +
+                                  static_cast<long long>(col - g * p.sc.cols_per_rank) * p.M + row;
+                    *dst = v;
+                }
+                else out[static_cast<long long>(col) * ldo + row] = v;
             }
         }
+    }
+    if (p.sc.nranks > 0)
+    {
+        // all tiles stored -> publish. Every CTA that wrote a final tile counts; the last one signals the peers.
+        __shared__ bool s_pub;
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0)
+        {
+            const unsigned int t = atomicAdd(p.sc.done, 1u);
+            s_pub = (t == static_cast<unsigned int>(p.sc.ntiles - 1));
+            if (s_pub) *p.sc.done = 0u;
+        }
+        __syncthreads();
+        if (s_pub && tid < p.sc.nranks)
+            st_release_sys(reinterpret_cast<unsigned long long*>(p.sc.table.base[tid] + kPeerFlagOffset) + kFlagScatter * kPeerMaxRanks + p.sc.rank,
+                           p.sc.epoch);
     }
 }
 
@@ -206,28 +283,64 @@ size_t gemm_workspace_bytes(int M, int N, int max_splits)
     return static_cast<size_t>(max_splits) * M * N * sizeof(double);
 }
 
+// The first kGemmTicketBytes of every split-R workspace hold the per-tile arrival counters of the in-kernel fix-up; they
+// must be zero before the first product (gemm_workspace_prepare) and every launch leaves them zero.
+constexpr size_t kGemmTicketBytes = 64 * 1024;
+constexpr long long kGemmMaxTickets = kGemmTicketBytes / sizeof(unsigned int);
+
+void gemm_workspace_prepare(cudaStream_t stream, double* workspace, size_t workspace_bytes)
+{
+    if (workspace && workspace_bytes >= kGemmTicketBytes) SMK_CUDA(cudaMemsetAsync(workspace, 0, kGemmTicketBytes, stream));
+}
+
 // Pick the split count that best fills `slots` CTAs-in-flight.
-int gemm_pick_splits(int M, int N, int R, int num_sms, size_t workspace_bytes)
+int gemm_pick_splits(int M, int N, int R, int num_sms, size_t workspace_bytes, bool whole_tiles)
 {
     const long long tiles = static_cast<long long>(ceil_div(N, BN)) * ceil_div(M, BM);
     const int max_by_r = ceil_div(R, BK);
-    long long max_by_ws = static_cast<long long>(workspace_bytes / (sizeof(double) * static_cast<size_t>(M) * N));
-    int smax = static_cast<int>(std::min<long long>(std::min<long long>(max_by_r, max_by_ws), 4LL * num_sms));
+    // the in-kernel reduction stores partial tiles whole (64 x 128 slots, whatever part of them exists); the reduction kernel's
+    // layout is [split][M x N]
+    const size_t usable = workspace_bytes > kGemmTicketBytes ? workspace_bytes - kGemmTicketBytes : 0;
+    const size_t per_split = whole_tiles ? static_cast<size_t>(BM * BN) * static_cast<size_t>(tiles) : static_cast<size_t>(M) * N;
+    long long max_by_ws = static_cast<long long>(usable / (sizeof(double) * per_split));
+    const int chunks = ceil_div(R, BK);
+    const bool few_tiles = tiles < 8;                      // Gram matrices: one tile, the reduction kernel adds hundreds of partials grid-wide
+    int smax = static_cast<int>(std::min<long long>(std::min<long long>(max_by_r, max_by_ws), few_tiles ? 4LL * num_sms : 32LL));
     if (smax < 1) smax = 1;
     if (tiles >= 4LL * num_sms) smax = std::min(smax, 1);   // plenty of tiles already
-    double best_eff = -1.0;
     int best = 1;
+    if (few_tiles)
+    {
+        // the split that fills the waves best (ties: fewer splits)
+        double best_eff = -1.0;
+        for (int s = 1; s <= smax; ++s)
+        {
+            const int per = ceil_div(chunks, s);               // chunks per CTA (rchunk is a multiple of BK)
+            const int eff_s = ceil_div(chunks, per);
+            const long long ctas = tiles * eff_s;
+            const long long waves = (ctas + num_sms - 1) / num_sms;
+            const double eff = static_cast<double>(ctas) / (static_cast<double>(waves) * num_sms);
+            const double score = eff - 1e-4 * s;
+            if (score > best_eff + 1e-12) { best_eff = score; best = s; }
+        }
+        return best;
+    }
+    // The big products: a cost model in units of one reduction chunk, fitted to a sweep of s = 1..32 on the column shards of C2
+    // at 1, 2, 4 and 8 GPUs (tools/sweep_splits.py, profiles/sweep_r02_splits_c2.json; its pick is within 1.3 % of the best
+    // measured split on average, 5.6 % at worst). A CTA costs (chunks + kOverhead): pipeline prologue, epilogue, partial tile.
+    // `num_sms` CTAs run at a time (two per SM); a last wave that leaves every SM at most ONE CTA costs only kLoneWave of a
+    // full wave, because a CTA that has its SM to itself runs almost twice as fast as two that share the FP64 pipe.
+    constexpr double kOverhead = 2.0, kLoneWave = 0.55;
+    double best_cost = 1e300;
     for (int s = 1; s <= smax; ++s)
     {
-        // real chunking: rchunk is a multiple of BK, so the effective split count may be lower
-        int rchunk = ceil_div(ceil_div(R, s), BK) * BK;
-        int eff_s = ceil_div(R, rchunk);
-        long long ctas = tiles * eff_s;
-        long long waves = (ctas + num_sms - 1) / num_sms;
-        double eff = static_cast<double>(ctas) / (static_cast<double>(waves) * num_sms);
-        // prefer fewer splits on ties (less partial traffic); small penalty per split
-        double score = eff - 1e-4 * s;
-        if (score > best_eff + 1e-12) { best_eff = score; best = s; }
+        const int per = ceil_div(chunks, s);
+        const int eff_s = ceil_div(chunks, per);
+        const long long ctas = tiles * eff_s;
+        const long long full = ctas / num_sms, rem = ctas % num_sms;
+        const double unit = per + kOverhead;
+        const double cost = unit * (static_cast<double>(full) + (rem == 0 ? 0.0 : (rem <= num_sms / 2 ? kLoneWave : 1.0)));
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
     }
     return best;
 }
@@ -235,21 +348,54 @@ int gemm_pick_splits(int M, int N, int R, int num_sms, size_t workspace_bytes)
 void gemm_f64(cudaStream_t stream, bool nt, int M, int N, int R,
               const double* A, long long lda, const double* B, long long ldb,
               double* C, long long ldc, const double* D, long long ldd,
-              double* workspace, size_t workspace_bytes, int num_sms, int* partials_only)
+              double* workspace, size_t workspace_bytes, int num_sms, int* partials_only, const GemmScatter* scatter)
 {
     if (M <= 0 || N <= 0) { if (partials_only) *partials_only = 0; return; }
     GemmParams p;
+    if (scatter) p.sc = *scatter; else p.sc.nranks = 0;
     p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.D = D; p.ldd = ldd;
     p.partial = workspace;
     p.M = M; p.N = N; p.R = R;
-    int splits = (workspace && R > 0) ? gemm_pick_splits(M, N, R, 2 * num_sms, workspace_bytes) : 1;   // 2 CTAs per SM
+    const char* fx = getenv("SMK_GEMM_FIXUP");              // =1: in-kernel reduction on one GPU too (measurements)
+    const bool want_fixup = scatter || (!partials_only && fx && atoi(fx) == 1 && M * static_cast<long long>(N) > 65536);
+    int splits = (workspace && R > 0) ? gemm_pick_splits(M, N, R, 2 * num_sms, workspace_bytes, want_fixup) : 1;   // 2 CTAs per SM
+    if (workspace && R > 0 && M * static_cast<long long>(N) > 65536)
+    {
+        // SMK_GEMM_SPLITS_NN / SMK_GEMM_SPLITS_NT = n force the split count of the big products W'A / H A' (measurements)
+        const char* e = getenv(nt ? "SMK_GEMM_SPLITS_NT" : "SMK_GEMM_SPLITS_NN");
+        const int forced = e ? atoi(e) : 0;
+        if (forced > 0)
+        {
+            const long long tl = static_cast<long long>(ceil_div(N, BN)) * ceil_div(M, BM);
+            const size_t usable = workspace_bytes > kGemmTicketBytes ? workspace_bytes - kGemmTicketBytes : 0;
+            const long long cap = static_cast<long long>(usable / (sizeof(double) * static_cast<size_t>(BM * BN) * static_cast<size_t>(tl)));
+            splits = static_cast<int>(std::max<long long>(1, std::min<long long>(forced, cap)));
+        }
+    }
     int rchunk = ceil_div(ceil_div(R > 0 ? R : 1, splits), BK) * BK;
     splits = R > 0 ? ceil_div(R, rchunk) : 1;
     p.splits = splits; p.rchunk = rchunk;
     p.to_partial = partials_only ? 1 : 0;
+    p.ntn = ceil_div(N, BN);
+    const long long tiles = static_cast<long long>(p.ntn) * ceil_div(M, BM);
+    // In-kernel reduction (the last-arriving CTA of a tile adds its partials): used where the finished tile has to leave through
+    // the kernel's own epilogue, i.e. the multi-GPU scatter. On one GPU the separate grid-wide reduction kernel is FASTER
+    // (measured r02, C2: 1.66 ms product + reduction kernel vs 1.71 ms with the fix-up: the tile-major launch order and the
+    // serial additions of the last arriver cost more than the 75 us kernel they replace), and the Gram matrices (one tile,
+    // hundreds of splits) need the grid-wide reduction anyway.
+    p.fixup = (want_fixup && splits > 1 && splits <= 32 && tiles <= kGemmMaxTickets) ? 1 : 0;
+    if (scatter)
+    {
+        if (splits > 1 && !p.fixup) throw std::string("gemm_f64: the scatter epilogue needs the in-kernel reduction");
+        p.sc.ntiles = static_cast<int>(tiles);
+    }
+    p.tickets = reinterpret_cast<unsigned int*>(workspace);
+    p.slots = workspace ? workspace + kGemmTicketBytes / sizeof(double) : nullptr;
+    if (!p.fixup && workspace) p.partial = workspace + kGemmTicketBytes / sizeof(double);     // [splits][M x N] layout behind the tickets
 
     const bool vec2 = aligned16(A) && aligned16(B) && (lda % 2 == 0) && (ldb % 2 == 0);
     dim3 grid(ceil_div(N, BN), ceil_div(M, BM), splits);
+    if (p.fixup) grid = dim3(static_cast<unsigned int>(tiles * splits), 1, 1);
     const size_t smem = static_cast<size_t>(STAGES) * (nt ? stage_doubles<true>() : stage_doubles<false>()) * sizeof(double);
 
     auto launch = [&](auto kern) {
@@ -260,14 +406,16 @@ void gemm_f64(cudaStream_t stream, bool nt, int M, int N, int R,
     if (nt) { if (vec2) launch(gemm_skinny_kernel<true, 2>); else launch(gemm_skinny_kernel<true, 1>); }
     else    { if (vec2) launch(gemm_skinny_kernel<false, 2>); else launch(gemm_skinny_kernel<false, 1>); }
 
-    if (partials_only) { *partials_only = splits; return; }     // workspace = [splits][M x N] tiles, ld = M; the caller sums them
-    if (splits > 1)
+    if (partials_only) { *partials_only = splits; return; }     // gemm_partials(workspace) = [splits][M x N] tiles, ld = M; the caller sums them
+    if (splits > 1 && !p.fixup)
     {
         const long long total = static_cast<long long>(M) * N;
         int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 8LL * num_sms));
-        reduce_partials_kernel<<<blocks, 256, 0, stream>>>(workspace, splits, M, N, C, ldc, D, ldd);
+        reduce_partials_kernel<<<blocks, 256, 0, stream>>>(p.partial, splits, M, N, C, ldc, D, ldd);
         SMK_LAUNCH_CHECK();
     }
 }
+
+const double* gemm_partials(const double* workspace) { return workspace + kGemmTicketBytes / sizeof(double); }
 
 } // namespace smk

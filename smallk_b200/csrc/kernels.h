@@ -6,25 +6,49 @@
 #include <string>
 #include <algorithm>
 
+#include "peer.h"
+
 namespace smk {
 
 // device status words shared by the kernels of one solver
 enum { ST_ANY_NONOPT = 0, ST_FAIL_ITER = 1, ST_NORM_EPS = 2, ST_DEFER_COUNT = 3, ST_BAD_INDEX = 4, ST_PG_NAN = 5, ST_COMM_TIMEOUT = 6, ST_BACKUP_COUNT = 7, ST_COUNT = 8 };
 
 // ---- gemm_f64.cu ----------------------------------------------------------
+// Optional epilogue of gemm_f64 for the column-sharded H*A' (peer.cu): column c of C belongs to rank c / cols_per_rank and is
+// stored into that rank's receive slot [rank] instead of C; the CTA finishing the last tile publishes `epoch` to all peers.
+struct GemmScatter
+{
+    PeerTable table;
+    size_t recv_off = 0;            // byte offset of the receive slots in every rank's exchange region
+    long long piece = 0;            // doubles per (owner, sender) slot = M * cols_per_rank
+    int cols_per_rank = 1;
+    int rank = 0, nranks = 0;       // nranks == 0: epilogue off
+    int ntiles = 0;                 // filled by gemm_f64
+    unsigned long long epoch = 0;
+    unsigned int* done = nullptr;   // device counter, zero on entry, left zero
+};
 // C (M x N) = A (M x R, col-major) * Bop - D, Bop = B (R x N col-major) if !nt, else B' with B (N x R col-major).
 void gemm_f64(cudaStream_t stream, bool nt, int M, int N, int R,
               const double* A, long long lda, const double* B, long long ldb,
               double* C, long long ldc, const double* D, long long ldd,
-              double* workspace, size_t workspace_bytes, int num_sms, int* partials_only = nullptr);
+              double* workspace, size_t workspace_bytes, int num_sms, int* partials_only = nullptr,
+              const GemmScatter* scatter = nullptr);
 // partials_only != null: the split-R partial tiles are left in the workspace ([*partials_only][M x N], ld = M, at least one)
 // and NOT summed — the multi-GPU reduce-scatter adds them in split order while it forwards them (peer.cu).
-int gemm_pick_splits(int M, int N, int R, int num_sms, size_t workspace_bytes);
+int gemm_pick_splits(int M, int N, int R, int num_sms, size_t workspace_bytes, bool whole_tiles = false);
+// Zeroes the arrival counters at the head of a split-R workspace: once after allocating it (launches leave them zero).
+void gemm_workspace_prepare(cudaStream_t stream, double* workspace, size_t workspace_bytes);
+// where gemm_f64(..., partials_only) leaves its partial tiles inside the workspace
+const double* gemm_partials(const double* workspace);
 
 // ---- nnls_bpp.cu ----------------------------------------------------------
 void nnls_bpp(cudaStream_t stream, int k, int q, const double* LHS, long long ldl,
               const double* RHS, long long ldr, double* X, long long ldx, double* Y, long long ldy,
-              int* status, unsigned int* counter, void* deferred, int outer_iter, int num_sms);
+              int* status, unsigned int* counter, void* deferred, int outer_iter, int num_sms,
+              const double* Ginv = nullptr, const int* ginv_flag = nullptr);
+// LHS^-1 (k x k, tight) + success flag for nnls_bpp's complement path (k > 32), one launch; when the caller does not pass them
+// nnls_bpp forms them itself on `stream`. The solvers run it on a side stream under the big product preceding the solve.
+void nnls_prepare_inverse(cudaStream_t stream, int k, const double* LHS, long long ldl, double* Ginv, int* ok);
 size_t nnls_deferred_bytes(int q, int k, int num_sms);
 void nnls_bpp_finish(cudaStream_t stream, int k, int q, double* X, long long ldx, double* Y, long long ldy, int* status, int num_sms);
 

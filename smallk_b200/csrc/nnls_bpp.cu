@@ -145,33 +145,62 @@ __device__ __forceinline__ bool gather_solve_any(const double* __restrict__ sM, 
     return gather_solve<32>(sM, k, list, n, rhs, sT, sRow, lane, xout);
 }
 
-// In-place Gauss-Jordan inversion of the SPD k x k matrix S (shared memory, ld k) by the whole CTA.
-// Returns false (uniformly) if a pivot is not positive; S is then garbage.
-__device__ bool cta_invert_spd(double* __restrict__ S, int k, double* __restrict__ scol, double* __restrict__ srow)
+// Gauss-Jordan inversion of the SPD k x k matrix G by ONE CTA, the matrix held in shared memory (k <= 160). ok[0] = 1 on
+// success, 0 if a pivot is not positive (Ginv is then garbage and the callers fall back to the direct method).
+// Thread t owns the entries e = t, t + 1024, ...: their row / column indices follow by increments (no division in the
+// loop), every elimination step is two barriers and one multiply-add per owned entry.
+constexpr int kInvThreads = 1024;
+constexpr int kInvSmemMaxK = 160;
+
+__global__ void __launch_bounds__(kInvThreads, 1)
+spd_inverse_smem_kernel(int k, const double* __restrict__ G, long long ldg, double* __restrict__ Ginv, int* __restrict__ ok)
 {
+    extern __shared__ __align__(16) double sinv[];
+    double* S = sinv;                 // k x k, ld k
+    double* scol = S + k * k;         // k
+    double* srow = scol + k;          // k
+    const int kk = k * k;
+    // entry e = threadIdx.x + s * kInvThreads is (row i, column c); stepping s moves (i, c) by (di, dc) with one carry
+    const int i0 = threadIdx.x % k, c0 = threadIdx.x / k;
+    const int di = kInvThreads % k, dc = kInvThreads / k;
+    {
+        int i = i0, c = c0;
+        for (int e = threadIdx.x; e < kk; e += kInvThreads)
+        {
+            S[e] = G[static_cast<long long>(c) * ldg + i];
+            i += di; c += dc;
+            if (i >= k) { i -= k; c += 1; }
+        }
+    }
+    __syncthreads();
+    bool good = true;
     for (int j = 0; j < k; ++j)
     {
         const double piv = S[j + j * k];
-        if (!(piv > 0.0)) return false;            // uniform: everyone reads the same word after the barrier
+        if (!(piv > 0.0)) { good = false; break; }           // uniform: everyone reads the same word after the barrier
         const double ip = 1.0 / piv;
-        for (int i = threadIdx.x; i < k; i += blockDim.x)
+        for (int i = threadIdx.x; i < k; i += kInvThreads)
         {
             scol[i] = S[i + j * k];
             srow[i] = S[j + i * k] * ip;
         }
         __syncthreads();
-        for (int e = threadIdx.x; e < k * k; e += blockDim.x)
+        int i = i0, c = c0;
+        for (int e = threadIdx.x; e < kk; e += kInvThreads)
         {
-            const int i = e % k, c = e / k;
             double v;
             if (i == j) v = (c == j) ? ip : srow[c];
             else if (c == j) v = -scol[i] * ip;
             else v = S[e] - scol[i] * srow[c];
             S[e] = v;
+            i += di; c += dc;
+            if (i >= k) { i -= k; c += 1; }
         }
         __syncthreads();
     }
-    return true;
+    if (good)
+        for (int e = threadIdx.x; e < kk; e += kInvThreads) Ginv[e] = S[e];
+    if (threadIdx.x == 0) ok[0] = good ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -193,6 +222,7 @@ struct FastSmem
 
 __global__ void __launch_bounds__(kFastWarps * 32, 1)
 nnls_bpp_fast_kernel(int k, int q, const double* __restrict__ LHS, long long ldl,
+                     const double* __restrict__ Ginv_g, const int* __restrict__ ginv_flag,
                      const double* __restrict__ RHS, long long ldr,
                      double* __restrict__ X, long long ldx, double* __restrict__ Y, long long ldy,
                      int* __restrict__ status, unsigned int* __restrict__ counter, int outer_iter,
@@ -213,19 +243,14 @@ nnls_bpp_fast_kernel(int k, int q, const double* __restrict__ LHS, long long ldl
     double* sz = sx + k;             // 32  solution of the small system
     int* list = reinterpret_cast<int*>(sz + 32);   // k ints
 
+    // G and (k > 32) its inverse, formed ONCE per call by spd_inverse_kernel (normally on a side stream under the big product
+    // that precedes this solve) instead of by every CTA: the in-CTA Gauss-Jordan was a fixed ~0.19 ms of each call
     for (int i = threadIdx.x; i < k * k; i += blockDim.x)
     {
-        const double v = LHS[static_cast<long long>(i / k) * ldl + (i % k)];
-        sG[i] = v;
-        if (k > 32) sGinv[i] = v;
+        sG[i] = LHS[static_cast<long long>(i / k) * ldl + (i % k)];
+        if (k > 32) sGinv[i] = Ginv_g[i];
     }
-    __syncthreads();
-    if (k > 32)
-    {
-        const bool ok = cta_invert_spd(sGinv, k, smem + L.rowcol(), smem + L.rowcol() + k);
-        if (threadIdx.x == 0) s_ginv_ok = ok ? 1 : 0;
-    }
-    else if (threadIdx.x == 0) s_ginv_ok = 0;
+    if (threadIdx.x == 0) s_ginv_ok = (k > 32 && ginv_flag[0] != 0) ? 1 : 0;
     __syncthreads();
     const bool ginv_ok = s_ginv_ok != 0;
 
@@ -623,26 +648,55 @@ __global__ void zeroize_if_flag_kernel(const int* __restrict__ status, int k, lo
 size_t nnls_wide_scratch_bytes(int k, int num_sms);
 void nnls_bpp_wide(cudaStream_t stream, int k, int q, const double* LHS, long long ldl, const double* RHS, long long ldr,
                    double* X, long long ldx, double* Y, long long ldy, int* status, unsigned int* counter, void* scratch,
-                   int outer_iter, int num_sms);
+                   int outer_iter, int num_sms, const double* Ginv, const int* ginv_flag);
+void invert_spd_global(cudaStream_t stream, int k, const double* G, long long ldg, double* Ginv, int* ok);
 
-// bytes of the `deferred` buffer nnls_bpp needs: the fast->slow hand-over list (k <= 64) or the wide kernel's scratch
+// G^-1 (k x k, tight) and its success flag for nnls_bpp: one launch, meant to run on a side stream under the big product that
+// precedes the NNLS solve (solver.cu). Not needed (and not computed) for k <= 32, where every passive-set system is solved directly.
+void nnls_prepare_inverse(cudaStream_t stream, int k, const double* LHS, long long ldl, double* Ginv, int* ok)
+{
+    if (k <= 32) return;
+    if (k <= kInvSmemMaxK)
+    {
+        const size_t smem = (static_cast<size_t>(k) * k + 2 * static_cast<size_t>(k)) * sizeof(double);
+        SMK_CUDA(cudaFuncSetAttribute(spd_inverse_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        spd_inverse_smem_kernel<<<1, kInvThreads, smem, stream>>>(k, LHS, ldl, Ginv, ok);
+        SMK_LAUNCH_CHECK();
+    }
+    else invert_spd_global(stream, k, LHS, ldl, Ginv, ok);
+}
+
+// bytes of the `deferred` buffer nnls_bpp needs: the fast->slow hand-over list (k <= 64) or the wide kernel's scratch,
+// + room for G^-1 and its flag when the caller does not bring them
 size_t nnls_deferred_bytes(int q, int k, int num_sms)
 {
-    return std::max(static_cast<size_t>(q) * sizeof(BppColState), nnls_wide_scratch_bytes(k, num_sms));
+    return std::max(static_cast<size_t>(q) * sizeof(BppColState), nnls_wide_scratch_bytes(k, num_sms)) +
+           static_cast<size_t>(k) * k * sizeof(double) + 64;
 }
 
 // status: device int[ST_COUNT]; counter: device unsigned[2]; deferred: nnls_deferred_bytes(q) bytes.
 void nnls_bpp(cudaStream_t stream, int k, int q, const double* LHS, long long ldl,
               const double* RHS, long long ldr, double* X, long long ldx, double* Y, long long ldy,
-              int* status, unsigned int* counter, void* deferred, int outer_iter, int num_sms)
+              int* status, unsigned int* counter, void* deferred, int outer_iter, int num_sms,
+              const double* Ginv, const int* ginv_flag)
 {
     SMK_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned int), stream));
     SMK_CUDA(cudaMemsetAsync(&status[ST_ANY_NONOPT], 0, sizeof(int), stream));
     SMK_CUDA(cudaMemsetAsync(&status[ST_DEFER_COUNT], 0, sizeof(int), stream));
     if (q <= 0) return;          // a rank may own no rows; the flags above are still reset for the reduction that follows
+    if (!Ginv && k > 32)
+    {
+        // the caller did not prepare G^-1: form it here, at the tail of the scratch buffer
+        unsigned char* tail = static_cast<unsigned char*>(deferred) + nnls_deferred_bytes(q, k, num_sms) - (static_cast<size_t>(k) * k * sizeof(double) + 64);
+        tail = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tail) + 15) & ~static_cast<uintptr_t>(15));
+        double* gi = reinterpret_cast<double*>(tail);
+        int* fl = reinterpret_cast<int*>(gi + static_cast<size_t>(k) * k);
+        nnls_prepare_inverse(stream, k, LHS, ldl, gi, fl);
+        Ginv = gi; ginv_flag = fl;
+    }
     if (k > 64)
     {
-        nnls_bpp_wide(stream, k, q, LHS, ldl, RHS, ldr, X, ldx, Y, ldy, status, counter, deferred, outer_iter, num_sms);
+        nnls_bpp_wide(stream, k, q, LHS, ldl, RHS, ldr, X, ldx, Y, ldy, status, counter, deferred, outer_iter, num_sms, Ginv, ginv_flag);
         return;
     }
     BppColState* def = static_cast<BppColState*>(deferred);
@@ -652,8 +706,8 @@ void nnls_bpp(cudaStream_t stream, int k, int q, const double* LHS, long long ld
         const size_t smem = L.total_bytes(kFastWarps);
         const int grid = std::min(num_sms, ceil_div(q, kFastWarps));
         SMK_CUDA(cudaFuncSetAttribute(nnls_bpp_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        nnls_bpp_fast_kernel<<<grid, kFastWarps * 32, smem, stream>>>(k, q, LHS, ldl, RHS, ldr, X, ldx, Y, ldy, status, counter,
-                                                                     outer_iter, def);
+        nnls_bpp_fast_kernel<<<grid, kFastWarps * 32, smem, stream>>>(k, q, LHS, ldl, Ginv, ginv_flag, RHS, ldr, X, ldx, Y, ldy, status,
+                                                                     counter, outer_iter, def);
         SMK_LAUNCH_CHECK();
     }
     {

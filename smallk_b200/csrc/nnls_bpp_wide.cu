@@ -361,22 +361,25 @@ size_t nnls_wide_scratch_bytes(int k, int num_sms)
 {
     if (k <= 64) return 0;
     const size_t tri_k = static_cast<size_t>(k) * (k + 1) / 2;
-    return (static_cast<size_t>(k) * k + static_cast<size_t>(3 * num_sms) * (tri_k + 512)) * sizeof(double) + 64;
+    return static_cast<size_t>(3 * num_sms) * (tri_k + 512) * sizeof(double) + 64;
 }
 
-// scratch layout: [Ginv k*k doubles][per-CTA packed triangles][flag int]
+// G^-1 by one CTA working in global memory (k > 160: the matrix does not fit shared memory)
+void invert_spd_global(cudaStream_t stream, int k, const double* G, long long ldg, double* Ginv, int* ok)
+{
+    invert_spd_kernel<<<1, 1024, 0, stream>>>(k, G, ldg, Ginv, ok);
+    SMK_LAUNCH_CHECK();
+}
+
+// scratch: per-CTA packed triangles of the direct-method fallback. Ginv / ginv_flag: nnls_prepare_inverse's output.
 void nnls_bpp_wide(cudaStream_t stream, int k, int q, const double* LHS, long long ldl, const double* RHS, long long ldr,
                    double* X, long long ldx, double* Y, long long ldy, int* status, unsigned int* counter, void* scratch,
-                   int outer_iter, int num_sms)
+                   int outer_iter, int num_sms, const double* Ginv, const int* flag)
 {
     if (k > 256) throw std::string("nnls_bpp: k > 256 is not supported");
     const size_t tri_k = static_cast<size_t>(k) * (k + 1) / 2;
-    double* Ginv = static_cast<double*>(scratch);
-    double* gscr = Ginv + static_cast<size_t>(k) * k;
+    double* gscr = static_cast<double*>(scratch);
     const int grid = std::min(3 * num_sms, q);
-    int* flag = reinterpret_cast<int*>(gscr + static_cast<size_t>(3 * num_sms) * (tri_k + 512));
-    invert_spd_kernel<<<1, 1024, 0, stream>>>(k, LHS, ldl, Ginv, flag);
-    SMK_LAUNCH_CHECK();
     const WideSmem L{k};
     const size_t smem = L.total_bytes();
     SMK_CUDA(cudaFuncSetAttribute(nnls_bpp_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

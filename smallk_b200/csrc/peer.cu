@@ -26,63 +26,11 @@
 #include <cstring>
 #include "context.h"
 #include "peer.h"
+#include "peer_device.cuh"
 
 namespace smk {
 
 namespace {
-
-constexpr unsigned long long kSpinTimeoutNs = 60ull * 1000ull * 1000ull * 1000ull;
-
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long global_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t));
-    return t;
-}
-
-// thread `t` < nranks waits until sender t has published `epoch`; false on timeout
-__device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsigned long long epoch)
-{
-    if (ld_acquire_sys(flag) >= epoch) return true;
-    const unsigned long long t0 = global_ns();
-    for (;;)
-    {
-        for (int i = 0; i < 64; ++i)
-            if (ld_acquire_sys(flag) >= epoch) return true;
-        if (global_ns() - t0 > kSpinTimeoutNs) return false;
-        __nanosleep(64);
-    }
-}
-
-// All threads of the CTA have issued their peer stores. Returns true (to every thread) in the CTA that arrives last.
-__device__ __forceinline__ bool stores_done_last_cta(unsigned int* ticket, bool* s_flag)
-{
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0)
-    {
-        const unsigned int t = atomicAdd(ticket, 1u);
-        *s_flag = (t == gridDim.x - 1);
-        if (*s_flag) *ticket = 0u;
-    }
-    __syncthreads();
-    return *s_flag;
-}
-
-__device__ __forceinline__ unsigned long long* flag_ptr(const PeerTable& t, int receiver, int cls, int sender)
-{
-    return reinterpret_cast<unsigned long long*>(t.base[receiver] + kPeerFlagOffset) + cls * kPeerMaxRanks + sender;
-}
 
 // ---------------------------------------------------------------------------
 // one-shot all-reduce (sum) of `count` doubles, in place in `data`, + optional flags:
@@ -281,6 +229,13 @@ bool peer_enabled_by_env()
     return !(e && atoi(e) == 0);
 }
 
+// SMK_PEER_FUSED=0 keeps the GEMM and the reduce-scatter producer as two kernels (A/B measurements)
+bool peer_fused_by_env()
+{
+    const char* e = getenv("SMK_PEER_FUSED");
+    return !(e && atoi(e) == 0);
+}
+
 void peer_release(smk_ctx* c)
 {
     PeerComm& P = c->peer;
@@ -369,6 +324,31 @@ void peer_reduce_scatter(smk_ctx* c, const double* partial, int splits, long lon
     SMK_LAUNCH_CHECK();
     const int grid2 = static_cast<int>(std::max<long long>(1, std::min<long long>((piece + 255) / 256, 2LL * c->num_sms)));
     peer_gather_sum_kernel<<<grid2, 256, 0, c->stream>>>(P.table, P.rank, P.nranks, epoch, piece, recv_off, out, c->status.p);
+    SMK_LAUNCH_CHECK();
+}
+
+// Fused variant: the GEMM's own epilogue is the producer half (GemmScatter); this returns the descriptor for the next
+// launch and peer_reduce_scatter_finish() runs the consumer half.
+GemmScatter peer_scatter_begin(smk_ctx* c, int rows_k, int cols_per_rank)
+{
+    PeerComm& P = c->peer;
+    GemmScatter sc;
+    sc.table = P.table;
+    sc.recv_off = kPeerBigOffset + 2 * P.big_bytes;
+    sc.piece = static_cast<long long>(rows_k) * cols_per_rank;
+    sc.cols_per_rank = cols_per_rank;
+    sc.rank = P.rank; sc.nranks = P.nranks;
+    sc.epoch = ++P.epoch[kFlagScatter];
+    sc.done = c->peer_ticket.p + 3;
+    return sc;
+}
+
+void peer_reduce_scatter_finish(smk_ctx* c, long long piece, double* out)
+{
+    PeerComm& P = c->peer;
+    const size_t recv_off = kPeerBigOffset + 2 * P.big_bytes;
+    const int grid2 = static_cast<int>(std::max<long long>(1, std::min<long long>((piece + 255) / 256, 2LL * c->num_sms)));
+    peer_gather_sum_kernel<<<grid2, 256, 0, c->stream>>>(P.table, P.rank, P.nranks, P.epoch[kFlagScatter], piece, recv_off, out, c->status.p);
     SMK_LAUNCH_CHECK();
 }
 

@@ -40,5 +40,9 @@ double* peer_big_buffer(smk_ctx* c, int which);
 void peer_allreduce(smk_ctx* c, double* data, int count, int* or_flag, int* fail_iter, int metric_mode, double* prog, double* metric_out);
 void peer_reduce_scatter(smk_ctx* c, const double* partial, int splits, long long valid, long long piece, double* out);
 void peer_allgather(smk_ctx* c, int which_buffer, long long piece);
+struct GemmScatter;
+GemmScatter peer_scatter_begin(smk_ctx* c, int rows_k, int cols_per_rank);
+void peer_reduce_scatter_finish(smk_ctx* c, long long piece, double* out);
+bool peer_fused_by_env();
 
 } // namespace smk

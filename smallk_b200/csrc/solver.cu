@@ -84,10 +84,22 @@ void prod_HAt(smk_ctx* c)
     {
         // the GEMM leaves its split-R partial tiles in the workspace; the reduce-scatter kernel adds them in split order
         // WHILE it stores each row block into its owner's receive slot (peer.cu): reduction pass = NVLink transfer
-        int splits = 0;
-        gemm_f64(c->stream, true, k, c->m, c->n, c->H.p, k, c->dA, c->ldA, c->HAt.p, k, nullptr, 0,
-                 c->ws.p, c->ws.n * sizeof(double), c->num_sms, &splits);
-        peer_reduce_scatter(c, c->ws.p, splits, static_cast<long long>(k) * c->m, piece, c->HAt.p + c->rank * piece);
+        if (peer_fused_by_env())
+        {
+            // ONE kernel: product, split-R reduction by the last-arriving CTA of each tile, and that CTA stores the finished tile
+            // straight into the receive slot of the rank owning those rows of W; the last tile publishes the epoch (gemm_f64.cu)
+            const GemmScatter sc = peer_scatter_begin(c, k, c->x_loc);
+            gemm_f64(c->stream, true, k, c->m, c->n, c->H.p, k, c->dA, c->ldA, c->HAt.p, k, nullptr, 0,
+                     c->ws.p, c->ws.n * sizeof(double), c->num_sms, nullptr, &sc);
+            peer_reduce_scatter_finish(c, piece, c->HAt.p + c->rank * piece);
+        }
+        else
+        {
+            int splits = 0;
+            gemm_f64(c->stream, true, k, c->m, c->n, c->H.p, k, c->dA, c->ldA, c->HAt.p, k, nullptr, 0,
+                     c->ws.p, c->ws.n * sizeof(double), c->num_sms, &splits);
+            peer_reduce_scatter(c, gemm_partials(c->ws.p), splits, static_cast<long long>(k) * c->m, piece, c->HAt.p + c->rank * piece);
+        }
         if (!c->w_sharded) peer_allgather(c, 1, piece);
         return;
     }
@@ -134,10 +146,37 @@ void gram_times(smk_ctx* c, const double* G, const double* X, int q, const doubl
     gemm_f64(c->stream, false, k, q, k, G, k, X, k, out, k, R, k, nullptr, 0, c->num_sms);
 }
 
+// BPP, k > 32: G^-1 for the next NNLS solve against G, on the side stream — it runs under the big product that the main stream
+// launches next (the inverse was a fixed ~0.19 ms inside every NNLS launch when each CTA formed it for itself)
+void prepare_inverse(smk_ctx* c, const double* G, smk_ctx::InvBuf& b)
+{
+    const int k = c->opts.k;
+    if (c->opts.algorithm != SMK_BPP || k <= 32) return;
+    if (!c->side)
+    {
+        int lo = 0, hi = 0;
+        SMK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        SMK_CUDA(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi));
+    }
+    if (!b.fork)
+    {
+        SMK_CUDA(cudaEventCreateWithFlags(&b.fork, cudaEventDisableTiming));
+        SMK_CUDA(cudaEventCreateWithFlags(&b.join, cudaEventDisableTiming));
+    }
+    b.Ginv.reserve(static_cast<size_t>(k) * k);
+    b.ok.reserve(1);
+    SMK_CUDA(cudaEventRecord(b.fork, c->stream));
+    SMK_CUDA(cudaStreamWaitEvent(c->side, b.fork, 0));
+    nnls_prepare_inverse(c->side, k, G, k, b.Ginv.p, b.ok.p);
+    SMK_CUDA(cudaEventRecord(b.join, c->side));
+    b.pending = true;
+}
+
 void compute_HHt(smk_ctx* c)
 {
     gram(c, c->H.p, c->n, c->HHt.p);
     allreduce_sum(c, c->HHt.p, static_cast<size_t>(c->opts.k) * c->opts.k);
+    prepare_inverse(c, c->HHt.p, c->invW);
 }
 void compute_WtW(smk_ctx* c)
 {
@@ -148,12 +187,22 @@ void compute_WtW(smk_ctx* c)
         allreduce_sum(c, c->WtW.p, static_cast<size_t>(c->opts.k) * c->opts.k);
     }
     else gram(c, c->Wt.p, c->m, c->WtW.p);
+    prepare_inverse(c, c->WtW.p, c->invH);
 }
 
-void run_nnls(smk_ctx* c, const double* LHS, const double* RHS, double* X, double* Y, int q)
+void run_nnls(smk_ctx* c, const double* LHS, const double* RHS, double* X, double* Y, int q, smk_ctx::InvBuf& inv)
 {
     const int k = c->opts.k;
-    nnls_bpp(c->stream, k, q, LHS, k, RHS, k, X, k, Y, k, c->status.p, c->counter.p, c->deferred.p, c->steps_done, c->num_sms);
+    const double* Ginv = nullptr;
+    const int* ginv_ok = nullptr;
+    if (inv.pending)
+    {
+        SMK_CUDA(cudaStreamWaitEvent(c->stream, inv.join, 0));
+        inv.pending = false;
+        Ginv = inv.Ginv.p; ginv_ok = inv.ok.p;
+    }
+    nnls_bpp(c->stream, k, q, LHS, k, RHS, k, X, k, Y, k, c->status.p, c->counter.p, c->deferred.p, c->steps_done, c->num_sms,
+             Ginv, ginv_ok);
     // "zeroize everything iff any column was non-optimal" couples the column shards: one int, OR-reduced
     if (c->nranks > 1)
     {
@@ -216,7 +265,8 @@ void solver_alloc(smk_ctx* c)
     // split-R workspace: enough for the gram matrices at 4*SMs splits and for the big products at a few splits
     size_t want = std::max<size_t>(static_cast<size_t>(4 * c->num_sms) * k * k,
                                    std::min<size_t>(static_cast<size_t>(32) * k * std::max(m, n), (size_t(768) << 20) / sizeof(double)));
-    c->ws.reserve(want);
+    c->ws.reserve(want + 8192);
+    gemm_workspace_prepare(c->stream, c->ws.p, c->ws.n * sizeof(double));
     static const int init[ST_COUNT] = {0, INT_MAX, 0, 0, 0, 0, 0, 0};
     SMK_CUDA(cudaMemcpyAsync(c->status.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
     c->prog.reserve(4);
@@ -253,7 +303,7 @@ void solver_step(smk_ctx* c)
     switch (c->opts.algorithm)
     {
     case SMK_BPP:      // nmf_solver_bpp.hpp:342-377
-        run_nnls(c, c->WtW.p, c->WtA.p, c->H.p, c->gradH.p, n);
+        run_nnls(c, c->WtW.p, c->WtA.p, c->H.p, c->gradH.p, n, c->invH);
         ph.mark("nnls_H");
         compute_HHt(c);
         ph.mark("HHt");
@@ -261,7 +311,7 @@ void solver_step(smk_ctx* c)
         ph.mark("HAt");
         {
             const size_t off = static_cast<size_t>(k) * c->w_row0();      // 0 unless the W update is row-sharded
-            run_nnls(c, c->HHt.p, c->HAt.p + off, c->Wt.p + off, c->gradWt.p + off, c->w_rows());
+            run_nnls(c, c->HHt.p, c->HAt.p + off, c->Wt.p + off, c->gradWt.p + off, c->w_rows(), c->invW);
             ph.mark("nnls_W");
             gather_Wt(c);
             ph.mark("gather_Wt");

@@ -393,7 +393,7 @@ __device__ __forceinline__ d4 tier_load(unsigned int code, const double* __restr
     return ldg256(p);
 }
 
-template <int NV, int U, bool PIPE>
+template <int NV, int U>
 __global__ void __launch_bounds__(512, 1)
 spmm_seg_tier_kernel(int nseg, const unsigned int* __restrict__ scol, const unsigned int* __restrict__ sbeg,
                      const unsigned int* __restrict__ send, const unsigned int* __restrict__ sslot,
@@ -453,51 +453,6 @@ spmm_seg_tier_kernel(int nseg, const unsigned int* __restrict__ scol, const unsi
             const unsigned int my_i = nxt_i; const double my_a = nxt_a;
             o += 32;
             if (o + lane < end) { nxt_i = __ldcs(idx + o + lane); nxt_a = alpha * __ldcs(val + o + lane); }
-            if constexpr (PIPE)
-            {
-                // EXPERIMENTAL (SMK_SPMM_PIPE=1; compiled, not yet run on a GPU — see spmm_seg_slab_pipe_kernel): the batch is
-                // consumed in half-groups of 4 (k <= 128) or 2 entries issued and consumed alternately, so gathers are in flight under every
-                // block of FMAs; storage order is kept, entries past the end carry value 0 and operand 0
-                constexpr int HB = NV == 1 ? 4 : 2;          // entries per half-group: 2 x HB x NV 256-bit operands stay in registers
-                const int nh = (cnt + HB - 1) / HB;
-                d4 bA[HB][NV], bB[HB][NV];
-                double aA[HB], aB[HB];
-                auto issue = [&](const int h, d4 (&b)[HB][NV], double (&a)[HB]) {
-#pragma unroll
-                    for (int u = 0; u < HB; ++u)
-                    {
-                        const int e = HB * h + u;
-                        const unsigned int code = __shfl_sync(0xffffffffu, my_i, e & 31);
-                        a[u] = __shfl_sync(0xffffffffu, my_a, e & 31);
-                        if (e >= cnt) a[u] = 0.0;
-#pragma unroll
-                        for (int v = 0; v < NV; ++v)
-                        {
-                            if (live[v] && e < cnt) b[u][v] = tier_load(code, B, ldb, tier_sh, k, 4 * lane + 128 * v, 32 * v + lane);
-                            else { b[u][v].x = b[u][v].y = b[u][v].z = b[u][v].w = 0.0; }
-                        }
-                    }
-                };
-                auto consume = [&](const d4 (&b)[HB][NV], const double (&a)[HB]) {
-#pragma unroll
-                    for (int u = 0; u < HB; ++u)
-#pragma unroll
-                        for (int v = 0; v < NV; ++v)
-                        {
-                            acc[v].x += a[u] * b[u][v].x; acc[v].y += a[u] * b[u][v].y;
-                            acc[v].z += a[u] * b[u][v].z; acc[v].w += a[u] * b[u][v].w;
-                        }
-                };
-                issue(0, bA, aA);
-                for (int h = 0; h < nh; h += 2)
-                {
-                    if (h + 1 < nh) issue(h + 1, bB, aB);
-                    consume(bA, aA);
-                    if (h + 2 < nh) issue(h + 2, bA, aA);
-                    if (h + 1 < nh) consume(bB, aB);
-                }
-                continue;
-            }
             int t = 0;
             for (; t + U <= cnt; t += U)
             {
@@ -618,81 +573,6 @@ spmm_seg_slab_kernel(int nseg, const unsigned int* __restrict__ scol, const unsi
     }
 }
 
-// EXPERIMENTAL, off unless SMK_SPMM_PIPE=1 — written at the end of round 1 without a GPU at hand: it compiles, it has not
-// run. The slab kernel above issues 8 gathers, waits for all of them, does 8 x 4 fused multiply-adds, and only then issues
-// the next 8: the memory pipe drains while the FMAs run (ncu r01: L2 47 %, DRAM 14 %, 16 warps/SM — latency-bound). Here the
-// batch of 8 is split in two halves of 4 that are issued and consumed alternately, so 4 to 8 gathers per lane are always in
-// flight, the next batch's indices being prefetched one batch ahead as before. Entries are consumed in storage order;
-// entries past the end carry value 0 and operand 0 (an exact no-op), so the sums are those of spmm_seg_slab_kernel.
-__global__ void __launch_bounds__(256, 2)
-spmm_seg_slab_pipe_kernel(int nseg, const unsigned int* __restrict__ scol, const unsigned int* __restrict__ sbeg,
-                          const unsigned int* __restrict__ send, const unsigned int* __restrict__ sslot,
-                          const unsigned int* __restrict__ idx, const double* __restrict__ val, int k, int koff,
-                          const double* __restrict__ B, long long ldb, double alpha, double beta,
-                          double* __restrict__ out, long long ldo, double* __restrict__ partial)
-{
-    const int lane = threadIdx.x & 31, g = lane & 7;
-    const unsigned int mask = 0xFFu << (lane & ~7);
-    const long long ngroups = static_cast<long long>(gridDim.x) * (blockDim.x >> 3);
-    const int off = koff + 4 * g;
-    for (long long it = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3; it < nseg; it += ngroups)
-    {
-        const unsigned int j = scol[it], slot = sslot[it];
-        const bool direct = slot == 0xFFFFFFFFu;
-        d4 acc; acc.x = acc.y = acc.z = acc.w = 0.0;
-        if (direct && beta != 0.0)
-        {
-            const double* c0 = out + j * ldo + off;
-            const double2 lo = *reinterpret_cast<const double2*>(c0), hi = *reinterpret_cast<const double2*>(c0 + 2);
-            acc.x = lo.x * beta; acc.y = lo.y * beta; acc.z = hi.x * beta; acc.w = hi.y * beta;
-        }
-        const unsigned int end = send[it];
-        unsigned int o = sbeg[it];
-        unsigned int cur_i = 0, nxt_i = 0;
-        double cur_a = 0.0, nxt_a = 0.0;
-        if (o + g < end) { cur_i = __ldcs(idx + o + g); cur_a = alpha * __ldcs(val + o + g); }
-        if (o + 8 + g < end) { nxt_i = __ldcs(idx + o + 8 + g); nxt_a = alpha * __ldcs(val + o + 8 + g); }
-        d4 bA[4], bB[4];
-        double aA[4], aB[4];
-        auto issue = [&](const int half, d4 (&b)[4], double (&a)[4]) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-            {
-                const int t = 4 * half + u;
-                const unsigned int iu = __shfl_sync(mask, cur_i, t, 8);
-                a[u] = __shfl_sync(mask, cur_a, t, 8);
-                if (o + t < end) b[u] = ldg256(B + iu * ldb + off);
-                else { b[u].x = b[u].y = b[u].z = b[u].w = 0.0; a[u] = 0.0; }
-            }
-        };
-        auto consume = [&](const d4 (&b)[4], const double (&a)[4]) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { acc.x += a[u] * b[u].x; acc.y += a[u] * b[u].y; acc.z += a[u] * b[u].z; acc.w += a[u] * b[u].w; }
-        };
-        if (o < end)
-        {
-            issue(0, bA, aA);
-            while (true)
-            {
-                issue(1, bB, aB);
-                consume(bA, aA);
-                o += 8;
-                if (o >= end) { consume(bB, aB); break; }
-                cur_i = nxt_i; cur_a = nxt_a;
-                nxt_i = 0; nxt_a = 0.0;
-                if (o + 8 + g < end) { nxt_i = __ldcs(idx + o + 8 + g); nxt_a = alpha * __ldcs(val + o + 8 + g); }
-                // half A of the new batch goes out before half B of the old one is consumed; the shuffles read cur_*,
-                // which now hold the new batch, so B's values were captured in aB / bB above
-                issue(0, bA, aA);
-                consume(bB, aB);
-            }
-        }
-        double* p = (direct ? out + j * ldo : partial + static_cast<long long>(slot) * k) + off;
-        *reinterpret_cast<double2*>(p) = make_double2(acc.x, acc.y);
-        *reinterpret_cast<double2*>(p + 2) = make_double2(acc.z, acc.w);
-    }
-}
-
 // residency class of every gatherable vector from its rank in decreasing degree order
 __global__ void tier_code_kernel(int count, const unsigned int* __restrict__ ids_by_degree, int smem_rows, int keep_rows,
                                  unsigned int* __restrict__ code, unsigned int* __restrict__ smem_ids)
@@ -790,18 +670,12 @@ void spmm_gather_seg(cudaStream_t stream, int ncols, const SegTable& T, const un
     const bool slab_fits = operand_bytes > kTierMinOperandBytes && static_cast<size_t>(ngather) * kSlab * sizeof(double) <= kSlabMaxBytes;
     if (wide256 && !tiers && (k % kSlab) == 0 && slab_mode != 0 && (slab_fits || slab_mode == 2))
     {
-        const char* pipe_env = getenv("SMK_SPMM_PIPE");
-        const bool slab_pipe = pipe_env && atoi(pipe_env) == 1;      // experimental software-pipelined variant, off by default
         const int groups_per_block = 256 / 8;
         const int blocks = std::max(1, std::min(ceil_div(T.nseg, groups_per_block), 2 * num_sms));
         for (int koff = 0; koff < k; koff += kSlab)
         {
-            if (slab_pipe)
-                spmm_seg_slab_pipe_kernel<<<blocks, 256, 0, stream>>>(T.nseg, T.col.p, T.beg.p, T.end.p, T.slot.p, idx, val, k, koff, B, ldb,
-                                                                      alpha, beta, out, ldo, partial);
-            else
-                spmm_seg_slab_kernel<<<blocks, 256, 0, stream>>>(T.nseg, T.col.p, T.beg.p, T.end.p, T.slot.p, idx, val, k, koff, B, ldb,
-                                                                 alpha, beta, out, ldo, partial);
+            spmm_seg_slab_kernel<<<blocks, 256, 0, stream>>>(T.nseg, T.col.p, T.beg.p, T.end.p, T.slot.p, idx, val, k, koff, B, ldb,
+                                                             alpha, beta, out, ldo, partial);
             SMK_LAUNCH_CHECK();
         }
     }
@@ -811,14 +685,11 @@ void spmm_gather_seg(cudaStream_t stream, int ncols, const SegTable& T, const un
         const size_t smem_bytes = static_cast<size_t>(smem_rows) * k * sizeof(double);
         const unsigned int* use_idx = tiers ? T.tier_idx.p : idx;
         const int blocks = std::max(1, std::min(ceil_div(T.nseg, 16), num_sms));
-        const char* tier_pipe_env = getenv("SMK_SPMM_PIPE");
-        const bool tier_pipe = tier_pipe_env && atoi(tier_pipe_env) == 1;      // experimental, off by default
 #define SMK_T(NV, U)                                                                                                                  \
         do {                                                                                                                          \
             static bool attr_set = false;                                                                                             \
-            if (!attr_set) { SMK_CUDA(cudaFuncSetAttribute(spmm_seg_tier_kernel<NV, U, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTierSmemBytes));  \
-                             SMK_CUDA(cudaFuncSetAttribute(spmm_seg_tier_kernel<NV, U, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTierSmemBytes)); attr_set = true; } \
-            (tier_pipe ? spmm_seg_tier_kernel<NV, U, true> : spmm_seg_tier_kernel<NV, U, false>)<<<blocks, 512, smem_bytes, stream>>>(T.nseg, T.col.p, T.beg.p, T.end.p, T.slot.p, use_idx, val, k, B, ldb, \
+            if (!attr_set) { SMK_CUDA(cudaFuncSetAttribute(spmm_seg_tier_kernel<NV, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTierSmemBytes)); attr_set = true; } \
+            spmm_seg_tier_kernel<NV, U><<<blocks, 512, smem_bytes, stream>>>(T.nseg, T.col.p, T.beg.p, T.end.p, T.slot.p, use_idx, val, k, B, ldb, \
                                                                              alpha, beta, out, ldo, partial, smem_rows, T.tier_smem_ids.p);      \
         } while (0)
         if (k <= 128) SMK_T(1, 8);

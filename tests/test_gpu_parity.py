@@ -260,51 +260,6 @@ def test_sparse_gemm_in_k_slabs_matches_oracle(gpu, oracle, k, monkeypatch):
             assert rel(got, want) < REL_PRIM
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("SMK_TEST_EXPERIMENTAL"), reason="experimental kernel (SMK_SPMM_PIPE=1), not yet run on a GPU: "
-                    "set SMK_TEST_EXPERIMENTAL=1 to include it")
-@pytest.mark.parametrize("k", [64, 128, 256])
-def test_sparse_gemm_in_pipelined_k_slabs_matches_oracle(gpu, oracle, k, monkeypatch):
-    """The software-pipelined slab kernel (spmm_seg_slab_pipe_kernel) must give the sums of the plain one."""
-    monkeypatch.setenv("SMK_SPMM_SLAB", "2")
-    monkeypatch.setenv("SMK_SPMM_PIPE", "1")
-    m, n = 900, 700
-    S = _zipf_csc(m, n, 40, 29)
-    rng = np.random.default_rng(100 + k)
-    gpu.load_csc((m, n), S.indptr, S.indices, S.data)
-    for variant in (0, 1, 2, 3):
-        shapeB = {0: (n, k), 1: (k, n), 2: (k, m), 3: (m, k)}[variant]
-        shapeC = (m, k) if variant < 2 else (k, n)
-        B = rng.random(shapeB); C = rng.random(shapeC)
-        for alpha, beta in [(1.0, 0.0), (0.7, -1.3)]:
-            got = gpu.sparse_gemm(variant, alpha, B, beta, C)
-            want = oracle.sparse_gemm(variant, alpha, (m, n), S.indptr, S.indices, S.data, B, beta, C)
-            assert rel(got, want) < REL_PRIM
-
-
-@pytest.mark.skipif(not __import__("os").environ.get("SMK_TEST_EXPERIMENTAL"), reason="experimental kernel (SMK_SPMM_PIPE=1), not yet run on a GPU: "
-                    "set SMK_TEST_EXPERIMENTAL=1 to include it")
-@pytest.mark.parametrize("k", [96, 128, 200, 256])
-def test_sparse_gemm_pipelined_with_residency_classes_matches_oracle(gpu, oracle, k, monkeypatch):
-    """spmm_seg_tier_kernel<NV, U, PIPE = true>: the pipelined variant of the tiered kernel, all residency classes in use."""
-    monkeypatch.setenv("SMK_SPMM_PIPE", "1")
-    monkeypatch.setenv("SMK_SPMM_SLAB", "0")
-    monkeypatch.setenv("SMK_SPMM_TIER_MIN_KB", "0")
-    monkeypatch.setenv("SMK_SPMM_TIER_KEEP_KB", str(300 * k * 8 // 1024))
-    m, n = 4000, 500
-    S = _zipf_csc(m, n, 60, 17)
-    rng = np.random.default_rng(k)
-    gpu.load_csc((m, n), S.indptr, S.indices, S.data)
-    for variant in (2, 3, 0, 1):
-        shapeB = {0: (n, k), 1: (k, n), 2: (k, m), 3: (m, k)}[variant]
-        shapeC = (m, k) if variant < 2 else (k, n)
-        B = rng.random(shapeB); C = rng.random(shapeC)
-        for alpha, beta in [(1.0, 0.0), (0.7, -1.3)]:
-            got = gpu.sparse_gemm(variant, alpha, B, beta, C)
-            want = oracle.sparse_gemm(variant, alpha, (m, n), S.indptr, S.indices, S.data, B, beta, C)
-            assert rel(got, want) < REL_PRIM
-    assert gpu.spmm_tier_info(0)[0]
-
-
 def test_sparse_rank2_with_hub_rows_matches_oracle(gpu, oracle):
     """Rank-2 on a sparse matrix with short rows, rows of 65..512 entries and hubs of more than 512 (the three walks of the
     fused rank-2 iteration, csrc/rank2_fused.cu), against the oracle's trace."""
