@@ -150,8 +150,10 @@ struct smk_ctx
         smk::DevBuf<double> Ginv;
         smk::DevBuf<int> ok;
         cudaEvent_t fork = nullptr, join = nullptr;
-        bool pending = false;
+        bool pending = false;       // side-stream work recorded in `join` has not been waited for by the main stream yet
+        bool valid = false;         // Ginv / ok belong to the current Gram matrix
     } invH, invW;
+    smk::DevBuf<double> ws_side;    // split-R workspace of the Gram matrices computed on the side stream
     cudaStream_t side = nullptr;        // helper stream (highest priority) for work overlapped with the big products
     // per-phase device times of solver_step (SMK_PHASES=1): cudaEvent pairs, summed on demand
     bool phases_on = false;

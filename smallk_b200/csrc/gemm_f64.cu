@@ -92,7 +92,10 @@ __device__ __forceinline__ void load_tile(double* s, const double* g, long long 
     }
 }
 
-template <bool NT, int VEC>
+// FIX = false: the plain kernel (grid = tiles x splits, tile or split-R partial written as is).
+// FIX = true : 1-D grid, in-kernel split-R reduction by the last-arriving CTA of each tile and, optionally, the multi-GPU scatter
+//              epilogue. A separate instantiation so that the plain kernel's code (registers, schedule) is untouched by it.
+template <bool NT, int VEC, bool FIX>
 __global__ void __launch_bounds__(THREADS, 2) gemm_skinny_kernel(GemmParams p)
 {
     extern __shared__ __align__(16) double smem[];
@@ -102,7 +105,9 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_skinny_kernel(GemmParams p)
     const int g = lane >> 2, t4 = lane & 3;
 
     int tile_n, tile_m, split_;
-    if (p.fixup) { split_ = blockIdx.x % p.splits; const int tile = blockIdx.x / p.splits; tile_n = tile % p.ntn; tile_m = tile / p.ntn; }
+    // split-major launch order in both forms: concurrently running CTAs work on the same reduction range of neighbouring tiles
+    // (measured r02: with the splits of one tile as neighbours the same kernel is 6 % slower)
+    if (FIX) { const int ntiles = p.ntn * ((p.M + BM - 1) / BM); split_ = blockIdx.x / ntiles; const int tile = blockIdx.x % ntiles; tile_n = tile % p.ntn; tile_m = tile / p.ntn; }
     else { tile_n = blockIdx.x; tile_m = blockIdx.y; split_ = blockIdx.z; }
     const int n0 = tile_n * BN;
     const int m0 = tile_m * BM;
@@ -169,11 +174,11 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_skinny_kernel(GemmParams p)
     }
     cp_async_wait<0>();
 
-    if (p.fixup)
+    if (FIX && p.splits > 1)
     {
         // ---- split-R fix-up: partial tile to the workspace, ticket, the last arriver sums in split order
         __shared__ bool s_last;
-        const int tile = blockIdx.x / p.splits;
+        const int tile = tile_m * p.ntn + tile_n;
         double* slot0 = p.slots + static_cast<long long>(tile) * p.splits * (BM * BN);
         double* mine = slot0 + static_cast<long long>(split) * (BM * BN) + tid;
 #pragma unroll
@@ -209,7 +214,7 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_skinny_kernel(GemmParams p)
     // epilogue
     double* out;
     long long ldo;
-    if (!p.fixup && (p.splits > 1 || p.to_partial)) { out = p.partial + static_cast<long long>(split) * p.M * p.N; ldo = p.M; }
+    if (!FIX && (p.splits > 1 || p.to_partial)) { out = p.partial + static_cast<long long>(split) * p.M * p.N; ldo = p.M; }
     else              { out = p.C; ldo = p.ldc; }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -225,8 +230,8 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_skinny_kernel(GemmParams p)
                 const int col = n0 + wn * 32 + j * 8 + 2 * t4 + e;
                 if (col >= p.N) continue;
                 double v = acc[i][j][e];
-                if ((p.fixup || (p.splits == 1 && !p.to_partial)) && p.D) v -= p.D[static_cast<long long>(col) * p.ldd + row];
-                if (p.sc.nranks > 0)
+                if ((FIX || (p.splits == 1 && !p.to_partial)) && p.D) v -= p.D[static_cast<long long>(col) * p.ldd + row];
+                if (FIX && p.sc.nranks > 0)
                 {
                     const int g = col / p.sc.cols_per_rank;
                     double* dst = reinterpret_cast<double*>(p.sc.table.base[g] + p.sc.recv_off) + static_cast<long long>(p.sc.rank) * p.sc.piece +
@@ -237,7 +242,7 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_skinny_kernel(GemmParams p)
             }
         }
     }
-    if (p.sc.nranks > 0)
+    if (FIX && p.sc.nranks > 0)
     {
         // all tiles stored -> publish. Every CTA that wrote a final tile counts; the last one signals the peers.
         __shared__ bool s_pub;
@@ -395,7 +400,6 @@ void gemm_f64(cudaStream_t stream, bool nt, int M, int N, int R,
 
     const bool vec2 = aligned16(A) && aligned16(B) && (lda % 2 == 0) && (ldb % 2 == 0);
     dim3 grid(ceil_div(N, BN), ceil_div(M, BM), splits);
-    if (p.fixup) grid = dim3(static_cast<unsigned int>(tiles * splits), 1, 1);
     const size_t smem = static_cast<size_t>(STAGES) * (nt ? stage_doubles<true>() : stage_doubles<false>()) * sizeof(double);
 
     auto launch = [&](auto kern) {
@@ -403,8 +407,18 @@ void gemm_f64(cudaStream_t stream, bool nt, int M, int N, int R,
         kern<<<grid, THREADS, smem, stream>>>(p);
         SMK_LAUNCH_CHECK();
     };
-    if (nt) { if (vec2) launch(gemm_skinny_kernel<true, 2>); else launch(gemm_skinny_kernel<true, 1>); }
-    else    { if (vec2) launch(gemm_skinny_kernel<false, 2>); else launch(gemm_skinny_kernel<false, 1>); }
+    const bool fix = p.fixup || scatter;          // the scatter epilogue lives in the FIX instantiation also when splits == 1
+    if (fix) grid = dim3(static_cast<unsigned int>(tiles * splits), 1, 1);
+    if (fix)
+    {
+        if (nt) { if (vec2) launch(gemm_skinny_kernel<true, 2, true>); else launch(gemm_skinny_kernel<true, 1, true>); }
+        else    { if (vec2) launch(gemm_skinny_kernel<false, 2, true>); else launch(gemm_skinny_kernel<false, 1, true>); }
+    }
+    else
+    {
+        if (nt) { if (vec2) launch(gemm_skinny_kernel<true, 2, false>); else launch(gemm_skinny_kernel<true, 1, false>); }
+        else    { if (vec2) launch(gemm_skinny_kernel<false, 2, false>); else launch(gemm_skinny_kernel<false, 1, false>); }
+    }
 
     if (partials_only) { *partials_only = splits; return; }     // gemm_partials(workspace) = [splits][M x N] tiles, ld = M; the caller sums them
     if (splits > 1 && !p.fixup)

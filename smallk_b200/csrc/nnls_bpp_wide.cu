@@ -110,6 +110,181 @@ __device__ bool cta_spd_solve_packed(double* M, double* __restrict__ vb, int n, 
     return true;
 }
 
+// The same solve, blocked by panels of kPB columns with look-ahead, for a triangle in SHARED memory (n <= 128).
+//   factor(p)   ONE warp factors the kPB x kPB diagonal block of panel p in registers (a column per lane, rows handed round
+//               by shuffles) and publishes it (U above the diagonal, 1 / U(j,j) ON the diagonal) in sD[p & 1];
+//   panel(p)    every trailing column — and the right-hand side, which rides along as one more column, so the forward solve
+//               costs nothing extra — gets its kPB panel entries by one thread (a kPB-step substitution against sD);
+//   update(p)   the kPB rank-1 updates of the trailing columns in one pass; warp 0 takes the kPB columns of panel p + 1 first
+//               and then runs factor(p + 1) while the other warps update the rest: the serial factorization of the next
+//               diagonal block hides under the bulk of the update (r02 ncu of the first blocked version: 45 % of the stall
+//               samples were the other seven warps waiting for factor() and for the diagonal back-solve).
+// The backward solve goes panel by panel as well. 2 barriers per kPB columns instead of 3 per column + two triangular solves
+// on one warp. Pivots use rsqrt + multiply (as nnls_bpp.cu: 1-2 ulp from the sqrt / divide form; parity is held to 1e-9, not
+// bitwise) and the packed triangle keeps 1 / U(j,j) on its diagonal. sD: scratch of 2 * 72 doubles.
+constexpr int kPB = 8;
+constexpr int kPBS = kPB * kPB + 8;      // one published diagonal block: kPB x kPB + flag
+
+// warp-collective: factor the diagonal block at j0 (nb columns) of M, write it back and to D; D[kPB * kPB] = 1 ok / 0 not SPD
+__device__ __forceinline__ void warp_factor_diag(double* M, int j0, int nb, double* __restrict__ D, int lane)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    double a[kPB];
+    const int cl = j0 + min(lane, nb - 1);
+#pragma unroll
+    for (int i = 0; i < kPB; ++i) a[i] = (lane < nb && i <= lane) ? M[tri(cl) + j0 + i] : ((i == lane) ? 1.0 : 0.0);
+    bool ok = true;
+#pragma unroll
+    for (int jj = 0; jj < kPB; ++jj)
+    {
+        if (jj < nb && ok)
+        {
+            const double ajj = __shfl_sync(FULL, a[jj], jj);
+            if (!(ajj > 0.0)) ok = false;                       // uniform: every lane sees the same pivot
+            else
+            {
+                const double r = rsqrt(ajj);
+                const double ujc = (lane == jj) ? r : a[jj] * r;    // U(jj, lane) for lane > jj; the reciprocal pivot on the diagonal
+                a[jj] = ujc;
+#pragma unroll
+                for (int i = jj + 1; i < kPB; ++i)
+                {
+                    const double uji = __shfl_sync(FULL, ujc, i);   // U(jj, i) lives on lane i
+                    a[i] = fma(-uji, ujc, a[i]);                    // meaningful for jj < i <= lane
+                }
+            }
+        }
+    }
+    if (lane < nb)
+    {
+#pragma unroll
+        for (int i = 0; i < kPB; ++i)
+            if (i <= lane) { M[tri(j0 + lane) + j0 + i] = a[i]; D[i * kPB + lane] = a[i]; }
+    }
+    if (lane == 0) D[kPB * kPB] = ok ? 1.0 : 0.0;
+}
+
+// rows (rows i in [ibeg, iend]) of column `col` -= sum_t U(j0 + t, i) * uc[t]   (nb pivots), lanes over rows
+__device__ __forceinline__ void warp_update_column(const double* M, double* col, int j0, int nb, const double (&uc)[kPB], int ibeg, int iend, int lane)
+{
+    if (nb == kPB)
+    {
+        for (int i = ibeg + lane; i <= iend; i += 32)
+        {
+            const double* ui = M + tri(i) + j0;                 // U(j0 + t, i): contiguous in t; conflict-free across lanes
+            double v = col[i];
+#pragma unroll
+            for (int t = 0; t < kPB; ++t) v = fma(-ui[t], uc[t], v);
+            col[i] = v;
+        }
+    }
+    else
+    {
+        for (int i = ibeg + lane; i <= iend; i += 32)
+        {
+            const double* ui = M + tri(i) + j0;
+            double v = col[i];
+            for (int t = 0; t < nb; ++t) v = fma(-ui[t], uc[t], v);
+            col[i] = v;
+        }
+    }
+}
+
+__device__ bool cta_spd_solve_blocked(double* M, double* __restrict__ vb, int n, double* __restrict__ sD)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    if (warp == 0) warp_factor_diag(M, 0, min(kPB, n), sD, lane);
+    __syncthreads();
+    int pidx = 0;
+    for (int j0 = 0; j0 < n; j0 += kPB, pidx ^= 1)
+    {
+        const int nb = min(kPB, n - j0);
+        const double* D = sD + pidx * kPBS;
+        if (D[kPB * kPB] == 0.0) return false;                          // uniform
+        // ---- panel entries of the trailing columns and of the right-hand side: U_D' u = a, one thread per column
+        const int ntrail = n - j0 - nb;
+        if (tid <= ntrail)
+        {
+            double* colp = (tid == ntrail) ? (vb + j0) : (M + tri(j0 + nb + tid) + j0);
+            double u[kPB];
+#pragma unroll
+            for (int t = 0; t < kPB; ++t)
+            {
+                if (t < nb)
+                {
+                    double v = colp[t];
+#pragma unroll
+                    for (int r = 0; r < kPB; ++r)
+                        if (r < t) v = fma(-D[r * kPB + t], u[r], v);
+                    u[t] = v * D[t * kPB + t];                          // the diagonal holds 1 / U(t,t)
+                    colp[t] = u[t];
+                }
+                else u[t] = 0.0;
+            }
+        }
+        __syncthreads();
+        // ---- trailing update with look-ahead. Columns c in (j0 + nb, n), column n = the right-hand side.
+        const int j1 = j0 + nb;                                         // first column of the next panel
+        const int nb1 = min(kPB, n - j1);                               // its width (<= 0: no next panel)
+        if (warp == 0)
+        {
+            for (int c = j1; c < j1 + nb1; ++c)
+            {
+                double uc[kPB];
+#pragma unroll
+                for (int t = 0; t < kPB; ++t) uc[t] = (t < nb) ? M[tri(c) + j0 + t] : 0.0;
+                warp_update_column(M, M + tri(c), j0, nb, uc, j1, c, lane);
+            }
+            __syncwarp();
+            if (nb1 > 0) warp_factor_diag(M, j1, nb1, sD + (pidx ^ 1) * kPBS, lane);
+        }
+        else
+        {
+            for (int c = j1 + max(nb1, 0) + (warp - 1); c <= n; c += nwarps - 1)
+            {
+                const bool is_rhs = (c == n);
+                const double* pc = is_rhs ? (vb + j0) : (M + tri(c) + j0);
+                double uc[kPB];
+#pragma unroll
+                for (int t = 0; t < kPB; ++t) uc[t] = (t < nb) ? pc[t] : 0.0;
+                warp_update_column(M, is_rhs ? vb : (M + tri(c)), j0, nb, uc, j1, is_rhs ? n - 1 : c, lane);
+            }
+        }
+        __syncthreads();
+    }
+    // ---- U x = y (y sits in vb), panels from the last to the first; the diagonal of M holds 1 / U(j,j)
+    for (int j0 = ((n - 1) / kPB) * kPB; j0 >= 0; j0 -= kPB)
+    {
+        const int nb = min(kPB, n - j0);
+        if (warp == 0)
+        {
+            double yv = (lane < nb) ? vb[j0 + lane] : 0.0;
+#pragma unroll
+            for (int qq = kPB - 1; qq >= 0; --qq)
+            {
+                if (qq < nb)
+                {
+                    const double* colq = M + tri(j0 + qq) + j0;
+                    const double xq = __shfl_sync(FULL, yv * colq[qq], qq);
+                    if (lane == qq) yv = xq;
+                    else if (lane < qq) yv = fma(-colq[lane], xq, yv);
+                }
+            }
+            if (lane < nb) vb[j0 + lane] = yv;
+        }
+        __syncthreads();
+        if (tid < j0)
+        {
+            double v = vb[tid];
+            for (int t = nb - 1; t >= 0; --t) v = fma(-M[tri(j0 + t) + tid], vb[j0 + t], v);
+            vb[tid] = v;
+        }
+        __syncthreads();
+    }
+    return true;
+}
+
 // BitMatrix::MaxRowIndex as the reference computes it (defect included) on a multi-word column mask.
 __device__ __forceinline__ int max_row_index_ref_words(const unsigned int* w, int k)
 {
@@ -130,12 +305,12 @@ struct WideSmem
     __host__ __device__ size_t tri_doubles() const { return static_cast<size_t>(kWideNmax) * (kWideNmax + 1) / 2; }
     __host__ __device__ size_t total_bytes() const
     {
-        // U | rowj[128] | vb[128] | sb[256] | sx[256] | su[256] | list[256] shorts | words[64]   (75,008 bytes: 3 CTAs per SM)
-        return (tri_doubles() + 2 * kWideNmax + 3 * 256) * sizeof(double) + 256 * sizeof(unsigned short) + 64 * sizeof(unsigned int);
+        // U | rowj[144] | vb[128] | sb[256] | sx[256] | su[256] | list[256] shorts | words[64]   (75,136 bytes: 3 CTAs per SM)
+        return (tri_doubles() + 2 * kWideNmax + 16 + 3 * 256) * sizeof(double) + 256 * sizeof(unsigned short) + 64 * sizeof(unsigned int);
     }
 };
 
-__global__ void __launch_bounds__(kWideThreads)
+__global__ void __launch_bounds__(kWideThreads, 3)
 nnls_bpp_wide_kernel(int k, int q, const double* __restrict__ G, long long ldg, const double* __restrict__ Ginv,
                      const int* __restrict__ ginv_flag, const double* __restrict__ RHS, long long ldr,
                      double* __restrict__ X, long long ldx, double* __restrict__ Y, long long ldy,
@@ -146,7 +321,7 @@ nnls_bpp_wide_kernel(int k, int q, const double* __restrict__ G, long long ldg, 
     const WideSmem L{k};
     double* sU = smem;
     double* s_rowj = sU + L.tri_doubles();
-    double* s_vb = s_rowj + kWideNmax;
+    double* s_vb = s_rowj + kWideNmax + 16;     // s_rowj: 144 doubles (two published diagonal blocks of the blocked solve)
     double* sb = s_vb + kWideNmax;
     double* sx = sb + 256;
     double* su = sx + 256;
@@ -231,7 +406,7 @@ nnls_bpp_wide_kernel(int k, int q, const double* __restrict__ G, long long ldg, 
                     }
                     if (t < p) vb[t] = sb[list[t]];
                     __syncthreads();
-                    if (!cta_spd_solve_packed(M, vb, p, small ? s_rowj : g_rowj)) { failed = true; break; }
+                    if (!(small ? cta_spd_solve_blocked(M, vb, p, s_rowj) : cta_spd_solve_packed(M, vb, p, g_rowj))) { failed = true; break; }
                     x = in ? vb[pos_in] : 0.0;
                     solved = true;
                 }
@@ -241,9 +416,14 @@ nnls_bpp_wide_kernel(int k, int q, const double* __restrict__ G, long long ldg, 
                     const int na = k - p;
                     if (!have_u)
                     {
+                        // the L2-resident matrix is read with eight loads in flight per thread (the loop is latency-bound otherwise)
                         double u = 0.0;
                         if (valid)
-                            for (int cc = 0; cc < k; ++cc) u = fma(Ginv[static_cast<long long>(cc) * k + t], sb[cc], u);
+                        {
+                            const double* gp = Ginv + t;
+#pragma unroll 8
+                            for (int cc = 0; cc < k; ++cc) u = fma(__ldg(gp + static_cast<long long>(cc) * k), sb[cc], u);
+                        }
                         su[t] = u;
                         have_u = true;
                     }
@@ -258,10 +438,13 @@ nnls_bpp_wide_kernel(int k, int q, const double* __restrict__ G, long long ldg, 
                     }
                     if (t < na) s_vb[t] = su[list[t]];
                     __syncthreads();
-                    if (na > 0 && !cta_spd_solve_packed(sU, s_vb, na, s_rowj)) { use_complement = false; continue; }
+                    if (na > 0 && !cta_spd_solve_blocked(sU, s_vb, na, s_rowj)) { use_complement = false; continue; }
                     double a = su[t];
                     if (in)
-                        for (int e = 0; e < na; ++e) a = fma(-Ginv[static_cast<long long>(list[e]) * k + t], s_vb[e], a);
+                    {
+#pragma unroll 8
+                        for (int e = 0; e < na; ++e) a = fma(-__ldg(Ginv + static_cast<long long>(list[e]) * k + t), s_vb[e], a);
+                    }
                     x = in ? a : 0.0;
                     solved = true;
                 }
@@ -275,11 +458,14 @@ nnls_bpp_wide_kernel(int k, int q, const double* __restrict__ G, long long ldg, 
             // ---- dual y = G x - b over the passive columns (nnls.hpp:168-169, 219-220)
             double s = 0.0;
             if (valid)
+            {
+#pragma unroll 8
                 for (int e = 0; e < p; ++e)
                 {
                     const int cc = list[e];
-                    s = fma(G[static_cast<long long>(cc) * ldg + t], sx[cc], s);
+                    s = fma(__ldg(G + static_cast<long long>(cc) * ldg + t), sx[cc], s);
                 }
+            }
             y = s - b;
             if (use_complement && p > kWideNmax)
             {
@@ -313,11 +499,14 @@ nnls_bpp_wide_kernel(int k, int q, const double* __restrict__ G, long long ldg, 
                     __syncthreads();
                     s = 0.0;
                     if (valid)
+                    {
+#pragma unroll 8
                         for (int e = 0; e < p; ++e)
                         {
                             const int cc = list[e];
-                            s = fma(G[static_cast<long long>(cc) * ldg + t], sx[cc], s);
+                            s = fma(__ldg(G + static_cast<long long>(cc) * ldg + t), sx[cc], s);
                         }
+                    }
                     y = s - b;
                 }
             }

@@ -299,13 +299,15 @@ double* peer_big_buffer(smk_ctx* c, int which)
     return reinterpret_cast<double*>(c->peer.local + kPeerBigOffset + static_cast<size_t>(which) * c->peer.big_bytes);
 }
 
-void peer_allreduce(smk_ctx* c, double* data, int count, int* or_flag, int* fail_iter, int metric_mode, double* prog, double* metric_out)
+void peer_allreduce(smk_ctx* c, double* data, int count, int* or_flag, int* fail_iter, int metric_mode, double* prog, double* metric_out,
+                    cudaStream_t stream)
 {
+    if (!stream) stream = c->stream;
     PeerComm& P = c->peer;
     if (count + 2 > kPeerSmallCap) throw std::string("peer_allreduce: vector too long");
     const unsigned long long epoch = ++P.epoch[kFlagSmall];
     const int grid = (prog || count <= 2048) ? 1 : std::min(32, ceil_div(count, 2048));
-    peer_allreduce_kernel<<<grid, 512, 0, c->stream>>>(P.table, P.rank, P.nranks, epoch, data, count, or_flag, fail_iter,
+    peer_allreduce_kernel<<<grid, 512, 0, stream>>>(P.table, P.rank, P.nranks, epoch, data, count, or_flag, fail_iter,
                                                      c->peer_ticket.p + 0, c->status.p, metric_mode, prog, metric_out);
     SMK_LAUNCH_CHECK();
 }

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cstddef>
+#include <cuda_runtime.h>
 
 struct smk_ctx;
 
@@ -37,7 +38,9 @@ void peer_release(smk_ctx* c);
 double* peer_big_buffer(smk_ctx* c, int which);
 // in-place sum over the ranks of data[0..count) (+ OR of *or_flag, + "a failure anywhere fails everywhere" for *fail_iter);
 // with prog != null the same launch finishes ProgressEst::Update on data[0..1] (metric_mode as progress_metric_launch)
-void peer_allreduce(smk_ctx* c, double* data, int count, int* or_flag, int* fail_iter, int metric_mode, double* prog, double* metric_out);
+// (stream: 0 = the context's main stream)
+void peer_allreduce(smk_ctx* c, double* data, int count, int* or_flag, int* fail_iter, int metric_mode, double* prog, double* metric_out,
+                    cudaStream_t stream = nullptr);
 void peer_reduce_scatter(smk_ctx* c, const double* partial, int splits, long long valid, long long piece, double* out);
 void peer_allgather(smk_ctx* c, int which_buffer, long long piece);
 struct GemmScatter;

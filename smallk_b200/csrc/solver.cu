@@ -138,6 +138,12 @@ void gram(smk_ctx* c, const double* X, int q, double* G)
     const int k = c->opts.k;
     gemm_f64(c->stream, true, k, k, q, X, k, X, k, G, k, nullptr, 0, c->ws.p, c->ws.n * sizeof(double), c->num_sms);
 }
+// the same on the side stream, with the side stream's own split-R workspace (the main stream's is busy with a big product)
+void gram_side(smk_ctx* c, const double* X, int q, double* G)
+{
+    const int k = c->opts.k;
+    gemm_f64(c->side, true, k, k, q, X, k, X, k, G, k, nullptr, 0, c->ws_side.p, c->ws_side.n * sizeof(double), c->num_sms);
+}
 
 // out (k x q) = G (k x k) * X (k x q) - R   (R may be null)
 void gram_times(smk_ctx* c, const double* G, const double* X, int q, const double* R, double* out)
@@ -146,12 +152,9 @@ void gram_times(smk_ctx* c, const double* G, const double* X, int q, const doubl
     gemm_f64(c->stream, false, k, q, k, G, k, X, k, out, k, R, k, nullptr, 0, c->num_sms);
 }
 
-// BPP, k > 32: G^-1 for the next NNLS solve against G, on the side stream — it runs under the big product that the main stream
-// launches next (the inverse was a fixed ~0.19 ms inside every NNLS launch when each CTA formed it for itself)
-void prepare_inverse(smk_ctx* c, const double* G, smk_ctx::InvBuf& b)
+// ---- work overlapped with the big products: a side stream (highest priority) forked from / joined to the main stream -------
+void side_begin(smk_ctx* c, smk_ctx::InvBuf& b)
 {
-    const int k = c->opts.k;
-    if (c->opts.algorithm != SMK_BPP || k <= 32) return;
     if (!c->side)
     {
         int lo = 0, hi = 0;
@@ -163,13 +166,47 @@ void prepare_inverse(smk_ctx* c, const double* G, smk_ctx::InvBuf& b)
         SMK_CUDA(cudaEventCreateWithFlags(&b.fork, cudaEventDisableTiming));
         SMK_CUDA(cudaEventCreateWithFlags(&b.join, cudaEventDisableTiming));
     }
-    b.Ginv.reserve(static_cast<size_t>(k) * k);
-    b.ok.reserve(1);
     SMK_CUDA(cudaEventRecord(b.fork, c->stream));
     SMK_CUDA(cudaStreamWaitEvent(c->side, b.fork, 0));
-    nnls_prepare_inverse(c->side, k, G, k, b.Ginv.p, b.ok.p);
+}
+void side_end(smk_ctx* c, smk_ctx::InvBuf& b)
+{
     SMK_CUDA(cudaEventRecord(b.join, c->side));
     b.pending = true;
+}
+void side_join(smk_ctx* c, smk_ctx::InvBuf& b)
+{
+    if (!b.pending) return;
+    SMK_CUDA(cudaStreamWaitEvent(c->stream, b.join, 0));
+    b.pending = false;
+}
+// G^-1 for the NNLS solves against G (BPP, k > 32), on the side stream, between side_begin and side_end
+void inverse_side(smk_ctx* c, const double* G, smk_ctx::InvBuf& b)
+{
+    const int k = c->opts.k;
+    b.valid = false;
+    if (c->opts.algorithm != SMK_BPP || k <= 32) return;
+    b.Ginv.reserve(static_cast<size_t>(k) * k);
+    b.ok.reserve(1);
+    nnls_prepare_inverse(c->side, k, G, k, b.Ginv.p, b.ok.p);
+    b.valid = true;
+}
+// BPP, k > 32: G^-1 for the next NNLS solve against G — it runs under the big product that the main stream launches next
+// (the inverse was a fixed ~0.19 ms inside every NNLS launch when each CTA formed it for itself)
+void prepare_inverse(smk_ctx* c, const double* G, smk_ctx::InvBuf& b)
+{
+    if (c->opts.algorithm != SMK_BPP || c->opts.k <= 32) return;
+    side_begin(c, b);
+    inverse_side(c, G, b);
+    side_end(c, b);
+}
+// BPP: may the Gram matrices (+ their rank sums + inverses) run on the side stream under the big products? Not with the NCCL
+// exchange (collectives must be issued in one order on one stream); SMK_SIDE_GRAM=0 turns it off (measurements).
+bool side_gram_enabled(const smk_ctx* c)
+{
+    if (c->opts.algorithm != SMK_BPP || (c->nranks > 1 && !c->use_peer)) return false;
+    const char* e = getenv("SMK_SIDE_GRAM");
+    return !(e && atoi(e) == 0);
 }
 
 void compute_HHt(smk_ctx* c)
@@ -195,12 +232,8 @@ void run_nnls(smk_ctx* c, const double* LHS, const double* RHS, double* X, doubl
     const int k = c->opts.k;
     const double* Ginv = nullptr;
     const int* ginv_ok = nullptr;
-    if (inv.pending)
-    {
-        SMK_CUDA(cudaStreamWaitEvent(c->stream, inv.join, 0));
-        inv.pending = false;
-        Ginv = inv.Ginv.p; ginv_ok = inv.ok.p;
-    }
+    side_join(c, inv);
+    if (inv.valid) { Ginv = inv.Ginv.p; ginv_ok = inv.ok.p; }
     nnls_bpp(c->stream, k, q, LHS, k, RHS, k, X, k, Y, k, c->status.p, c->counter.p, c->deferred.p, c->steps_done, c->num_sms,
              Ginv, ginv_ok);
     // "zeroize everything iff any column was non-optimal" couples the column shards: one int, OR-reduced
@@ -267,6 +300,11 @@ void solver_alloc(smk_ctx* c)
                                    std::min<size_t>(static_cast<size_t>(32) * k * std::max(m, n), (size_t(768) << 20) / sizeof(double)));
     c->ws.reserve(want + 8192);
     gemm_workspace_prepare(c->stream, c->ws.p, c->ws.n * sizeof(double));
+    if (c->opts.algorithm == SMK_BPP)
+    {
+        c->ws_side.reserve(static_cast<size_t>(4 * c->num_sms) * k * k + 8192);
+        gemm_workspace_prepare(c->stream, c->ws_side.p, c->ws_side.n * sizeof(double));
+    }
     static const int init[ST_COUNT] = {0, INT_MAX, 0, 0, 0, 0, 0, 0};
     SMK_CUDA(cudaMemcpyAsync(c->status.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
     c->prog.reserve(4);
@@ -305,7 +343,16 @@ void solver_step(smk_ctx* c)
     case SMK_BPP:      // nmf_solver_bpp.hpp:342-377
         run_nnls(c, c->WtW.p, c->WtA.p, c->H.p, c->gradH.p, n, c->invH);
         ph.mark("nnls_H");
-        compute_HHt(c);
+        if (side_gram_enabled(c))
+        {
+            // H H' (+ its sum over the ranks + its inverse) on the side stream, under the H A' product
+            side_begin(c, c->invW);
+            gram_side(c, c->H.p, n, c->HHt.p);
+            if (c->nranks > 1) peer_allreduce(c, c->HHt.p, k * k, nullptr, nullptr, 0, nullptr, nullptr, c->side);
+            inverse_side(c, c->HHt.p, c->invW);
+            side_end(c, c->invW);
+        }
+        else compute_HHt(c);
         ph.mark("HHt");
         prod_HAt(c);
         ph.mark("HAt");
@@ -313,13 +360,29 @@ void solver_step(smk_ctx* c)
             const size_t off = static_cast<size_t>(k) * c->w_row0();      // 0 unless the W update is row-sharded
             run_nnls(c, c->HHt.p, c->HAt.p + off, c->Wt.p + off, c->gradWt.p + off, c->w_rows(), c->invW);
             ph.mark("nnls_W");
-            gather_Wt(c);
-            ph.mark("gather_Wt");
+            if (side_gram_enabled(c))
+            {
+                // W'W from the rows this rank has just updated (+ rank sum + inverse) on the side stream, under the
+                // all-gather of W and the W'A product
+                side_begin(c, c->invH);
+                gram_side(c, c->Wt.p + off, c->w_rows(), c->WtW.p);
+                if (c->nranks > 1) peer_allreduce(c, c->WtW.p, k * k, nullptr, nullptr, 0, nullptr, nullptr, c->side);
+                inverse_side(c, c->WtW.p, c->invH);
+                side_end(c, c->invH);
+                gather_Wt(c);
+                ph.mark("gather_Wt");
+            }
+            else
+            {
+                gather_Wt(c);
+                ph.mark("gather_Wt");
+                compute_WtW(c);
+            }
         }
-        compute_WtW(c);
         ph.mark("WtW");
         prod_WtA(c);
         ph.mark("WtA");
+        side_join(c, c->invH);          // gradH needs W'W (a no-op when it was computed on the main stream)
         gram_times(c, c->WtW.p, c->H.p, n, c->WtA.p, c->gradH.p);
         ph.mark("gradH");
         break;
