@@ -154,6 +154,21 @@ int smk_spmm_tier_info(smk_ctx* ctx, int which, int* on, int* smem_rows, double*
 int smk_nnls_hals(smk_ctx* ctx, int k, double* W_host, int ldW, double* H_host, int ldH, double tol, int max_iter,
                   int* iterations);
 
+/* ---- bool preprocess_tf(TermFrequencyMatrix& A, term_indices, doc_indices, scores, MAX_ITER, DOCS_PER_TERM, TERMS_PER_DOC):
+ * preprocessor/src/preprocess.cpp:81-250 — the tf-idf pipeline that produces the sparse matrices NmfSparse factors: rows sorted
+ * inside every column, rounds of term pruning (total count < docs_per_term, or present in every document), document pruning
+ * (< terms_per_doc distinct terms) and removal of duplicated documents (the copy with the largest index stays) until a round
+ * removes nothing, then scores (1 + ln count) * ln(width / document frequency) scaled to unit column norm. In: m x n CSC of
+ * term counts (host arrays, counts as doubles as the MatrixMarket loader delivers them). Out (host arrays with capacities of the
+ * INPUT sizes: n + 1, nnz, nnz, nnz, m, n): the pruned matrix, its scores aligned with its entries, and for every surviving
+ * row / column its original index. Index outputs are bit-identical to the reference's; scores agree to rounding level.
+ * SMK_FAILURE = every document was pruned (the reference returns false). ---- */
+int smk_preprocess_tf(smk_ctx* ctx, unsigned int m, unsigned int n, unsigned int nnz, const unsigned int* col_offsets,
+                      const unsigned int* row_indices, const double* counts, unsigned int max_iter, unsigned int docs_per_term,
+                      unsigned int terms_per_doc, unsigned int* out_m, unsigned int* out_n, unsigned int* out_nnz,
+                      unsigned int* out_col_offsets, unsigned int* out_row_indices, unsigned int* out_counts, double* out_scores,
+                      unsigned int* term_indices, unsigned int* doc_indices);
+
 /* ---- ordering primitives for the host-side tree code of hierclust ----
  * desc_ordered(values) of hierclust/include/clust_hier_util.hpp:46-57: the permutation that lists the indices by
  * decreasing value, ties by increasing index (a stable descending radix sort on the device; -0.0 is treated as 0.0,

@@ -29,7 +29,7 @@ EXPORTS = [
     "smk_solver_begin", "smk_solver_step", "smk_solver_progress", "smk_solver_get", "smk_solver_normalize",
     "smk_solver_last_step_ms", "smk_solver_time_product", "smk_gemm", "smk_nnls_bpp", "smk_sparse_gemm",
     "smk_select_columns", "smk_select_all", "smk_nnls_hals", "smk_argsort_desc", "smk_sort_desc", "smk_spmm_tier_info",
-    "smk_solver_run", "smk_phase_report", "smk_nnls_backup_count",
+    "smk_solver_run", "smk_phase_report", "smk_nnls_backup_count", "smk_preprocess_tf",
 ]
 HOST_LIB_PATH = os.path.join(_HERE, "lib", "libsmallk_host.so")
 HOST_EXPORTS = ["smkh_last_error", "smkh_hierclust_sparse", "smkh_hierclust_dense", "smkh_flatclust", "smkh_compute_priority",
@@ -274,6 +274,28 @@ class Context:
         k, q = RHS.shape
         self._check(self._lib.smk_nnls_bpp(self._h, k, q, _d(LHS), _d(RHS), _d(X), _d(Y)))
         return X, Y
+
+    def preprocess_tf(self, m, n, colptr, rows, counts, max_iter=1000, docs_per_term=3, terms_per_doc=5):
+        """preprocess_tf (preprocessor/src/preprocess.cpp:81-250) on the device. Returns None if every document was pruned,
+        else a dict like oracle.preprocess_oracle.preprocess_tf's."""
+        colptr = np.ascontiguousarray(colptr, dtype=np.uint32)
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        counts = np.ascontiguousarray(counts, dtype=np.float64)
+        nz = len(rows)
+        om, on, onz = ctypes.c_uint(0), ctypes.c_uint(0), ctypes.c_uint(0)
+        oc = np.zeros(n + 1, dtype=np.uint32); orow = np.zeros(max(nz, 1), dtype=np.uint32); ocnt = np.zeros(max(nz, 1), dtype=np.uint32)
+        osc = np.zeros(max(nz, 1)); ti = np.zeros(m, dtype=np.uint32); di = np.zeros(n, dtype=np.uint32)
+        rc = self._lib.smk_preprocess_tf(self._h, ctypes.c_uint(m), ctypes.c_uint(n), ctypes.c_uint(nz), colptr.ctypes.data_as(_up),
+                                         rows.ctypes.data_as(_up), _d(counts), ctypes.c_uint(max_iter), ctypes.c_uint(docs_per_term),
+                                         ctypes.c_uint(terms_per_doc), ctypes.byref(om), ctypes.byref(on), ctypes.byref(onz),
+                                         oc.ctypes.data_as(_up), orow.ctypes.data_as(_up), ocnt.ctypes.data_as(_up), _d(osc),
+                                         ti.ctypes.data_as(_up), di.ctypes.data_as(_up))
+        if rc == FAILURE:
+            return None
+        self._check(rc)
+        h, w, z = om.value, on.value, onz.value
+        return {"m": h, "n": w, "colptr": oc[: w + 1].astype(np.int64), "rows": orow[:z].astype(np.int64), "counts": ocnt[:z].astype(np.int64),
+                "scores": osc[:z], "term_indices": ti[:h].astype(np.int64), "doc_indices": di[:w].astype(np.int64)}
 
     def nnls_backup_count(self):
         """Firings of UpdatePassiveSet's backup rule since the last nnls_bpp / solver_begin (diagnostic)."""

@@ -567,6 +567,24 @@ int smk_nnls_bpp(smk_ctx* c, int k, int q, const double* LHS, const double* RHS,
     });
 }
 
+int smk_preprocess_tf(smk_ctx* c, unsigned int m, unsigned int n, unsigned int nnz, const unsigned int* col_offsets,
+                      const unsigned int* row_indices, const double* counts, unsigned int max_iter, unsigned int docs_per_term,
+                      unsigned int terms_per_doc, unsigned int* out_m, unsigned int* out_n, unsigned int* out_nnz,
+                      unsigned int* out_col_offsets, unsigned int* out_row_indices, unsigned int* out_counts, double* out_scores,
+                      unsigned int* term_indices, unsigned int* doc_indices)
+{
+    if (!c || !col_offsets || (nnz && (!row_indices || !counts)) || !out_m || !out_n || !out_nnz || !out_col_offsets || !out_row_indices ||
+        !out_counts || !out_scores || !term_indices || !doc_indices || m == 0 || n == 0)
+        return SMK_BAD_PARAM;
+    return guarded(c, [&]() {
+        SMK_CUDA(cudaSetDevice(c->device));
+        const int rc = preprocess_tf_device(c, m, n, nnz, col_offsets, row_indices, counts, max_iter, docs_per_term, terms_per_doc, out_m, out_n,
+                                            out_nnz, out_col_offsets, out_row_indices, out_counts, out_scores, term_indices, doc_indices);
+        if (rc != SMK_OK) c->err = "preprocess_tf: every document was pruned";
+        return rc;
+    });
+}
+
 int smk_nnls_backup_count(smk_ctx* c, int* count)
 {
     if (!c || !count || !c->status.p) return SMK_BAD_PARAM;

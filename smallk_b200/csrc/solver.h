@@ -28,4 +28,10 @@ void select_all(smk_ctx* c);
 // ---- sort.cu: stable descending sort of a host array on the device; exactly one of order_host / sorted_host is set
 void device_sort_desc(smk_ctx* c, const double* host_in, int n, int* order_host, double* sorted_host);
 
+// ---- preprocess.cu: preprocess_tf (preprocessor/src/preprocess.cpp:81-250) on the device
+int preprocess_tf_device(smk_ctx* c, unsigned int m, unsigned int n, unsigned int nnz, const unsigned int* col_offsets, const unsigned int* row_indices,
+                         const double* counts_in, unsigned int max_iter, unsigned int docs_per_term, unsigned int terms_per_doc,
+                         unsigned int* out_m, unsigned int* out_n, unsigned int* out_nnz, unsigned int* out_colptr, unsigned int* out_rows,
+                         unsigned int* out_counts, double* out_scores, unsigned int* term_indices, unsigned int* doc_indices);
+
 } // namespace smk
