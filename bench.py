@@ -22,7 +22,8 @@ call plus its progress-metric update (common/include/nmf_solve_generic.hpp:70-98
               on the box's host cores, on the FULL workload, iteration count bounded.
 * extra     : the other BASELINE configurations, each with its own value / roofline / e2e / cpu_baseline where they apply:
               c1 (nmf CLI, 256 x 256, k = 16), c5 (dense BPP 100000 x 50000, k = 256; any N), c3 (sparse HALS 1e6 x 2e5,
-              k = 128; any N, column blocks balanced by nnz), c4 (hierclust, 320k nodes, 64 leaves; N = 1).
+              k = 128; any N, column blocks balanced by nnz), c4 (hierclust, 320k nodes, 64 leaves; N = 1), preprocess (the
+              tf-idf pipeline upstream of the sparse path; N = 1).
 N > 1: A and H are sharded by column block, one process per GPU (torchrun); the exchanges (k x k Grams, the k x m product
 H*A', the row blocks of W) are the library's own kernels over NVLink peer memory (csrc/peer.cu). Total work is fixed ("strong").
 """
@@ -545,6 +546,66 @@ def run_c1(env, args):
     return out
 
 
+def run_preprocess(env, args):
+    """the tf-idf preprocessing (preprocess_tf, preprocessor/src/preprocess.cpp:81-250) of a synthetic
+    term-count matrix, device pipeline (smk_preprocess_tf, host arrays in / out) next to the reference's own function on one core
+    (it is single-threaded). Index outputs must be identical."""
+    import ctypes
+    m, n, per_doc = 200000, 100000, 120
+    rng = np.random.default_rng(51)
+    t = np.minimum((float(m) ** rng.random((n, per_doc))).astype(np.int64), m - 1)          # Zipf(1) term draws per document
+    t[n - 2000:] = t[rng.integers(0, n // 2, 2000)]                                         # 2 % exact copies of earlier documents
+    key, cnt = np.unique((np.arange(n, dtype=np.int64)[:, None] * m + t).ravel(), return_counts=True)
+    cols = key // m
+    rows = (key - cols * m).astype(np.uint32)
+    colptr = np.zeros(n + 1, dtype=np.uint32)
+    colptr[1:] = np.cumsum(np.bincount(cols, minlength=n))
+    counts = cnt.astype(np.float64)
+    nnz = len(rows)
+    ctx = env.ctx
+    ctx.preprocess_tf(m, n, colptr, rows, counts)                                          # warm-up (allocations, CUB temp sizes)
+    t0 = time.perf_counter()
+    got = ctx.preprocess_tf(m, n, colptr, rows, counts, 1000, 3, 5)
+    gpu_s = time.perf_counter() - t0
+    out = {"metric": "term_count_entries_per_second", "value": nnz / gpu_s, "unit": "entries/s", "seconds": gpu_s, "n_gpus": 1,
+           "config": {"workload": f"preprocess_tf on a synthetic {m} x {n} term-count matrix, {nnz} entries, docs_per_term 3, terms_per_doc 5",
+                      "result": f"{got['m']} x {got['n']}, {len(got['rows'])} entries"},
+           "e2e": {"value": nnz / gpu_s, "unit": "entries/s", "h2d_bytes_per_step": 16.0 * nnz + 4.0 * (n + 1),
+                   "d2h_bytes_per_step": 16.0 * len(got["rows"]) + 4.0 * (got["m"] + 2 * got["n"]),
+                   "note": "smk_preprocess_tf on host arrays: upload, sort, pruning rounds, scores, download; wall clock (value is this same number: "
+                           "the pipeline has no device-resident entry point)"},
+           "roofline": None, "roofline_note": "a handful of HBM passes over 8-byte (row, count) pairs per round; launch- and readback-bound at this size"}
+    try:
+        from oracle import REF_SO
+        lib = ctypes.CDLL(REF_SO)
+        up, dp = ctypes.POINTER(ctypes.c_uint), ctypes.POINTER(ctypes.c_double)
+        om, on, onz = ctypes.c_uint(0), ctypes.c_uint(0), ctypes.c_uint(0)
+        oc = np.zeros(n + 1, dtype=np.uint32); orow = np.zeros(nnz, dtype=np.uint32); ocnt = np.zeros(nnz, dtype=np.uint32)
+        osc = np.zeros(nnz); ti = np.zeros(m, dtype=np.uint32); di = np.zeros(n, dtype=np.uint32)
+        sys.stdout.flush()
+        saved = os.dup(1)                        # the reference narrates on stdout; this process's stdout carries the JSON line
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(devnull, 1)
+        try:
+            t0 = time.perf_counter()
+            rc = lib.ref_preprocess_tf(m, n, nnz, colptr.ctypes.data_as(up), rows.ctypes.data_as(up), counts.ctypes.data_as(dp), 1000, 3, 5,
+                                       ctypes.byref(om), ctypes.byref(on), ctypes.byref(onz), oc.ctypes.data_as(up), orow.ctypes.data_as(up),
+                                       ocnt.ctypes.data_as(up), osc.ctypes.data_as(dp), ti.ctypes.data_as(up), di.ctypes.data_as(up))
+            ref_s = time.perf_counter() - t0
+        finally:
+            os.dup2(saved, 1); os.close(saved); os.close(devnull)
+        same = bool(rc == 0 and om.value == got["m"] and on.value == got["n"] and np.array_equal(orow[:onz.value], got["rows"]) and
+                    np.array_equal(oc[:on.value + 1], got["colptr"]) and np.array_equal(di[:on.value], got["doc_indices"]) and
+                    np.array_equal(ti[:om.value], got["term_indices"]))
+        out["cpu_baseline"] = {"value": nnz / ref_s, "unit": "entries/s", "seconds": ref_s, "cores": 1, "kind": "reference",
+                               "sample": "the reference's preprocess_tf (oracle/_ref) on the same matrix, full size, one thread (the reference's is serial)"}
+        out["parity"] = {"identical_pruned_matrix_and_index_maps": same,
+                         "max_rel_score_diff": float(np.max(np.abs(osc[:onz.value] - got["scores"]) / np.abs(osc[:onz.value]))) if same else None}
+    except Exception as ex:
+        out["cpu_baseline"] = {"value": None, "unit": "entries/s", "cores": 1, "kind": "reference", "sample": f"unavailable: {ex}"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -561,7 +622,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
-    ap.add_argument("--extras", default="c1,c5,c3,c4", help="which of the other configurations to nest under `extra`")
+    ap.add_argument("--extras", default="c1,c5,c3,c4,preprocess", help="which of the other configurations to nest under `extra`")
     ap.add_argument("--write-trace", action="store_true", help="N = 1: store the metric trace as tests/golden/bench_c2_trace_n1.json")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -597,6 +658,8 @@ def main():
                     res = bench_sparse.run_c3(args, env=env, steps=10, warmup=3)
                 elif name == "c1" and env.world == 1:
                     res = run_c1(env, args)
+                elif name == "preprocess" and env.world == 1:
+                    res = run_preprocess(env, args)
                 elif name == "c4" and env.world == 1:
                     # its own process: hierclust's host driver is timed by wall clock, keep it clear of this process's leftovers
                     r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", "c4", "--steps", str(args.steps), "--warmup",

@@ -452,6 +452,20 @@ int smk_nmf(smk_ctx* c, const smk_nmf_options* opts, double* W, int ldW, double*
         // exists there anyway) and once at the end; a failed iteration index is still reported exactly.
         for (iter = 0; iter < opts->max_iter; ++iter)
         {
+            if (iter == opts->min_iter && iter > 0)
+            {
+                // from here on every iteration is followed by the stop test: hand the rest of the loop to the device
+                // (one CUDA graph with a WHILE node, nmf_loop.cu); falls through to the host loop when that is not possible
+                int giter = iter, grc = SMK_OK;
+                bool gsuccess = false;
+                if (nmf_loop_graph(c, iter, &giter, &gsuccess, &grc))
+                {
+                    iter = giter;
+                    if (grc != SMK_OK) { finish(iter); return grc; }
+                    success = gsuccess;
+                    break;
+                }
+            }
             solver_step(c);
             if (iter < opts->min_iter)
             {

@@ -122,7 +122,8 @@ struct smk_ctx
     double pg0 = 0.0;
     smk::DevBuf<double> H, Wt, gradH, gradWt, WtW, HHt, WtA, HAt, T1, T2, Wprev, norms;
     smk::DevBuf<double> prog;       // ProgressEst state on the device: [0] = pg0, [1] = "pg0 captured", [2] = metric of the last update
-    smk::DevBuf<double> trace;      // metric per iteration of smk_solver_run
+    smk::DevBuf<double> trace;      // metric per iteration of smk_solver_run / of the device-side loop (nmf_loop.cu)
+    smk::DevBuf<int> loop_state;    // device-side loop of smk_nmf: iteration, success count, outcome
     bool pg_ready = false;          // the last solver_step left both projected-gradient sums in acc[0..1] (fused rank-2)
     bool status_cached = false;     // status_host holds the status words as of the last solver_progress
     int status_host[smk::ST_COUNT] = {0, INT_MAX, 0, 0, 0};

@@ -12,6 +12,8 @@ int solver_progress(smk_ctx* c, double* metric);
 void solver_progress_enqueue(smk_ctx* c, double* metric_dev);
 int solver_run(smk_ctx* c, int count, double* metrics_host);
 std::string solver_phase_report(smk_ctx* c);
+// nmf_loop.cu: iterations [first_iter, max_iter) of NmfSolve's loop as one CUDA graph with a device-side WHILE (see the file)
+bool nmf_loop_graph(smk_ctx* c, int first_iter, int* iter, bool* success, int* rc);
 int solver_normalize(smk_ctx* c);
 int solver_fail_iter(smk_ctx* c);
 void solver_product(smk_ctx* c, int which);
