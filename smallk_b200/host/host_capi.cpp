@@ -18,6 +18,7 @@
 
 R compute_priority_on(smk_ctx* ctx, const R* W_parent, const R* W_child, int n);
 R compute_priority_plain(smk_ctx* ctx, const R* W_parent, const R* W_child, int n);
+R compute_priority_rows(smk_ctx* ctx, const R* W_parent, const R* W_child, int n, const unsigned int* child_rows, int n_child_rows);
 
 namespace {
 
@@ -170,6 +171,11 @@ int smkh_flatclust(int alg, int m, int n, int k, double tol, int min_iter, int m
 double smkh_compute_priority(const double* W_parent, const double* W_child, int m) { return compute_priority(W_parent, W_child, m); }
 // the full-length evaluation the streaming one is checked against
 double smkh_compute_priority_plain(const double* W_parent, const double* W_child, int m) { return compute_priority_plain(nullptr, W_parent, W_child, m); }
+// the evaluation the tree driver uses: the caller names the rows where the child factors can be non-zero
+double smkh_compute_priority_rows(const double* W_parent, const double* W_child, int m, const unsigned int* child_rows, int n_child_rows)
+{
+    return compute_priority_rows(nullptr, W_parent, W_child, m, child_rows, n_child_rows);
+}
 // the same with the large sorts on the GPU (what the tree driver uses): must give the identical value
 double smkh_compute_priority_gpu(const double* W_parent, const double* W_child, int m)
 {

@@ -18,6 +18,7 @@ def _host():
     lib = ctypes.CDLL(sk.HOST_LIB_PATH)
     lib.smkh_compute_priority.restype = ctypes.c_double
     lib.smkh_compute_priority_plain.restype = ctypes.c_double
+    lib.smkh_compute_priority_rows.restype = ctypes.c_double
     return lib
 
 
@@ -47,6 +48,31 @@ def test_streaming_priority_equals_plain_evaluation_bit_for_bit():
     lib = _host()
     for n, mode, P, C in _cases():
         a = lib.smkh_compute_priority(P.ctypes.data_as(dp), C.ctypes.data_as(dp), n)
+        b = lib.smkh_compute_priority_plain(P.ctypes.data_as(dp), C.ctypes.data_as(dp), n)
+        assert a == b, (n, mode, a, b)
+
+
+def test_row_list_priority_equals_plain_evaluation_bit_for_bit():
+    """The evaluation the tree driver uses (compute_priority_rows: the caller names the rows where the child factors can be
+    non-zero; everything else in O(rows) + one lean pass for the ideal sum) against the plain one, also with a row list that
+    holds more rows than the factors touch and with an m far larger than the node."""
+    lib = _host()
+    up = ctypes.POINTER(ctypes.c_uint)
+    rng = np.random.default_rng(11)
+    cases = list(_cases())
+    # big, mostly empty vectors: the shape of a deep hierclust node
+    for n, npart, nchild in [(120000, 900, 400), (120000, 30000, 9000), (50000, 3, 2)]:
+        P = np.zeros(n); C = np.zeros((n, 2), order="F")
+        rows = np.sort(rng.choice(n, npart, replace=False))
+        P[rows] = rng.random(npart) * (rng.random(npart) > 0.2)
+        sub = rng.choice(rows, nchild, replace=False)
+        C[sub, 0] = rng.random(nchild) * (rng.random(nchild) > 0.3); C[sub, 1] = rng.random(nchild) * (rng.random(nchild) > 0.3)
+        cases.append((n, "deep", P, C))
+    for n, mode, P, C in cases:
+        touched = np.flatnonzero((C[:, 0] != 0) | (C[:, 1] != 0))
+        extra = rng.choice(n, min(n, 17), replace=False)                       # rows of the node that ended up zero in both factors
+        child_rows = np.unique(np.concatenate([touched, extra])).astype(np.uint32)
+        a = lib.smkh_compute_priority_rows(P.ctypes.data_as(dp), C.ctypes.data_as(dp), n, child_rows.ctypes.data_as(up), len(child_rows))
         b = lib.smkh_compute_priority_plain(P.ctypes.data_as(dp), C.ctypes.data_as(dp), n)
         assert a == b, (n, mode, a, b)
 
