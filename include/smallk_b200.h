@@ -141,12 +141,6 @@ int smk_phase_report(smk_ctx* ctx, char* buf, int len);
  * launch from CUDA events on the context's stream. State is left as a solver step would leave it. */
 int smk_solver_time_product(smk_ctx* ctx, int which, int reps, float* mean_ms);
 
-/* Measurement hook: the residency classes the sparse products of the loaded matrix use (csrc/spmm.cu). which: 0 = W'A
- * (CSC walk, gathers rows of W), 1 = H A' (CSR walk, gathers columns of H). on = 0 when the operand is small or the
- * degrees are unskewed (plain 256-bit gathers); smem_rows = vectors served from shared memory; share = fraction of
- * the stored entries whose operand is resident (shared memory or L2-kept). No reference counterpart. */
-int smk_spmm_tier_info(smk_ctx* ctx, int which, int* on, int* smem_rows, double* share);
-
 /* bool NnlsHals(A, W, H, tol, verbose, max_iter): common/include/nnls.hpp:249-316 — the flat-clustering step of
  * HierNmf2WithFlat (hierclust/include/clust_flat_generic.hpp:33-74). W (m x k) is fixed, H (k x n) carries the
  * initial guess in and the solution out; on success (pg < tol * pg0) W's columns are normalised and H's rows

@@ -28,7 +28,7 @@ EXPORTS = [
     "smk_comm_unique_id", "smk_comm_init", "smk_load_dense", "smk_load_dense_device", "smk_load_csc", "smk_nmf",
     "smk_solver_begin", "smk_solver_step", "smk_solver_progress", "smk_solver_get", "smk_solver_normalize",
     "smk_solver_last_step_ms", "smk_solver_time_product", "smk_gemm", "smk_nnls_bpp", "smk_sparse_gemm",
-    "smk_select_columns", "smk_select_all", "smk_nnls_hals", "smk_argsort_desc", "smk_sort_desc", "smk_spmm_tier_info",
+    "smk_select_columns", "smk_select_all", "smk_nnls_hals", "smk_argsort_desc", "smk_sort_desc",
     "smk_solver_run", "smk_phase_report", "smk_nnls_backup_count", "smk_preprocess_tf",
 ]
 HOST_LIB_PATH = os.path.join(_HERE, "lib", "libsmallk_host.so")
@@ -302,12 +302,6 @@ class Context:
         n = ctypes.c_int(0)
         self._check(self._lib.smk_nnls_backup_count(self._h, ctypes.byref(n)))
         return n.value
-
-    def spmm_tier_info(self, which):
-        """(on, smem_rows, share) of the residency classes of product `which` (0 = W'A, 1 = H A')."""
-        on, rows, share = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_double(0.0)
-        self._check(self._lib.smk_spmm_tier_info(self._h, which, ctypes.byref(on), ctypes.byref(rows), ctypes.byref(share)))
-        return bool(on.value), rows.value, share.value
 
     def sparse_gemm(self, variant, alpha, B, beta, C):
         B = _f(B)

@@ -391,16 +391,6 @@ int smk_solver_time_product(smk_ctx* c, int which, int reps, float* mean_ms)
     });
 }
 
-int smk_spmm_tier_info(smk_ctx* c, int which, int* on, int* smem_rows, double* share)
-{
-    if (!c || !c->has_sparse || which < 0 || which > 1) return SMK_BAD_PARAM;
-    const SegTable& T = which == 0 ? c->S.seg_cols : c->S.seg_rows;
-    if (on) *on = T.tiers_on ? 1 : 0;
-    if (smem_rows) *smem_rows = T.tiers_on ? T.tier_smem_rows : 0;
-    if (share) *share = T.tiers_on ? T.tier_share : 0.0;
-    return SMK_OK;
-}
-
 int smk_solver_progress(smk_ctx* c, double* metric)
 {
     if (!c || !c->active || !metric) return SMK_BAD_PARAM;
@@ -653,15 +643,6 @@ int smk_sparse_gemm(smk_ctx* c, int variant, double alpha, const double* B, int 
             Ck = dCt.p;
         }
         c->spmm_partial.reserve(static_cast<size_t>(std::max(S.seg_cols.nslots, S.seg_rows.nslots)) * k + 1);
-        if (c->Sa == &c->S)      // residency classes of the gathers, as the solvers build them (a no-op for small operands)
-        {
-            SegTable& T = variant <= 1 ? c->S.seg_rows : c->S.seg_cols;
-            if (!(T.tiers_on && T.tier_k == k))
-            {
-                if (variant <= 1) build_gather_tiers(c->stream, T, n, c->S.colptr.p, c->S.colidx.p, c->S.nnz, k, c->num_sms);
-                else build_gather_tiers(c->stream, T, m, c->S.rowptr.p, c->S.rowidx.p, c->S.nnz, k, c->num_sms);
-            }
-        }
         if (variant <= 1)   // C = A*op(B): rows of A -> CSR walk, output k x m
             spmm_gather_seg(c->stream, m, S.seg_rows, S.colidx.p, S.valr.p, k, Bk, k, alpha, beta, Ck, k, c->spmm_partial.p, c->num_sms, n);
         else                // C = op(B)*A: columns of A -> CSC walk, output k x n

@@ -48,12 +48,6 @@ struct SegTable
     DevBuf<unsigned int> multi_col;             // the columns that have more than one segment
     DevBuf<unsigned int> t_cnt, t_first, t_mpos; // build temporaries (kept: the column-subset matrix is rebuilt many times)
     DevBuf<unsigned char> t_scan;
-    // residency classes of the gathered vectors (spmm.cu, build_gather_tiers): a copy of the index array whose two top
-    // bits say where the operand of each stored entry is served from (shared memory / L2 kept / L2 dropped)
-    bool tiers_on = false;
-    int tier_k = 0, tier_smem_rows = 0;
-    double tier_share = 0.0;                    // share of the stored entries covered by the two resident tiers
-    DevBuf<unsigned int> tier_idx, tier_smem_ids;
 };
 
 struct SparseDev

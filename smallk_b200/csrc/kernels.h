@@ -108,10 +108,6 @@ void build_segments(cudaStream_t stream, int ncols, const unsigned int* ptr, Seg
 void spmm_gather_seg(cudaStream_t stream, int ncols, const SegTable& T, const unsigned int* idx, const double* val,
                      int k, const double* B, long long ldb, double alpha, double beta, double* out, long long ldo,
                      double* partial, int num_sms, int ngather);
-// Residency classes for the gathers of a table (k-dependent; a no-op unless the dense operand is far larger than L2
-// and the degrees of the gathered vectors are skewed). ngather vectors with degrees degree_ptr[r+1]-degree_ptr[r].
-void build_gather_tiers(cudaStream_t stream, SegTable& T, int ngather, const unsigned int* degree_ptr, const unsigned int* idx,
-                        unsigned int nnz, int k, int num_sms);
 // Builds rowptr/colidx/valr (CSR = stable transpose) from the CSC arrays already on the device.
 void build_csr(cudaStream_t stream, SparseDev& S, bool keep_scratch = false);
 

@@ -280,15 +280,6 @@ void solver_alloc(smk_ctx* c)
         SMK_CUDA(cudaMemsetAsync(c->gradWt.p, 0, k * m * sizeof(double), c->stream));
     }
     c->norms.reserve(k);
-    if (c->has_sparse && c->Sa == &c->S)
-    {
-        // residency classes of the SpMM gathers (k-dependent; only for operands far larger than L2, see spmm.cu)
-        SparseDev& S = c->S;
-        if (!(S.seg_cols.tiers_on && S.seg_cols.tier_k == c->opts.k))
-            build_gather_tiers(c->stream, S.seg_cols, S.m, S.rowptr.p, S.rowidx.p, S.nnz, c->opts.k, c->num_sms);
-        if (!(S.seg_rows.tiers_on && S.seg_rows.tier_k == c->opts.k))
-            build_gather_tiers(c->stream, S.seg_rows, S.n, S.colptr.p, S.colidx.p, S.nnz, c->opts.k, c->num_sms);
-    }
     if (c->has_sparse) c->spmm_partial.reserve(static_cast<size_t>(std::max(c->Sa->seg_cols.nslots, c->Sa->seg_rows.nslots)) * k + 1);
     c->deferred.reserve(nnls_deferred_bytes(static_cast<int>(std::max(m, n)), c->opts.k, c->num_sms));
     if (c->opts.algorithm == SMK_MU) { c->T1.reserve(k * n); c->T2.reserve(k * m); }    // m is the padded row count here

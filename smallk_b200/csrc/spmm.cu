@@ -331,105 +331,76 @@ spmm_seg_wide_kernel(int nseg, const unsigned int* __restrict__ scol, const unsi
 }
 
 // ---------------------------------------------------------------------------
-// Tiered variant (k % 4 == 0, 64 <= k <= 256, fewer than 2^30 gathered vectors): 256-bit gathers + residency classes.
-//
-// A gather SpMM moves k*8 bytes of the dense operand per stored entry (C3: 1 KB x 7.7e7 = 79 GB per product), ~60x the
-// compulsory HBM bytes, so what bounds it is where those bytes come from. Term frequencies are Zipf-like: a few
-// hundred rows of A take a quarter of the entries and a few percent of the rows take three quarters, while the
-// operand as a whole (C3: Wt = 1 GB) is far larger than L2 and the long tail of cold rows keeps flushing the
-// popular ones out of it. The two top bits of a private copy of the index array therefore carry a residency class
-// per entry, chosen once per matrix from the degree of the gathered vector (build_gather_tiers):
-//     10 | slot : the vector is one of the `smem_rows` most popular ones and is served from shared memory, which
-//                 every CTA fills once (conflict-free LDS.128 pairs; no L2 traffic at all for these entries),
-//     01 | id   : popular enough to be kept in L2   -> LDG.E.EL.ELL2.256  (L1 and L2 evict_last),
-//     11 | id   : cold tail, touched and dropped    -> LDG.E.NA.EFL2.256  (L1 no_allocate, L2 evict_first),
-//     00 | id   : no tiers built (small or unskewed operand): plain LDG.E.256.
-// Lane l owns the four consecutive doubles 4l..4l+3 (+128v) of the k-vector, so one gathered operand is NV 256-bit
-// loads per lane (sm_100 LDG.256) instead of 2 NV LDG.128. Entries are still added in storage order, one fused
-// multiply-add per entry and output element: results are those of the kernels above.
+// 256-bit gather kernels (k % 4 == 0, 64 <= k <= 256, 32-byte aligned operands): lane l owns the four consecutive doubles
+// 4l..4l+3 (+128v) of the k-vector, so one gathered operand is NV LDG.E.256 per lane. Two shapes:
+//   spmm_seg_wide256_kernel: a warp per segment, the whole k-vector per gather (operands that fit L2, or whose popular vectors
+//       do: a gather SpMM moves k*8 bytes of dense operand per stored entry — C3: 1 KB x 1e8 = 102 GB per product, 40x the
+//       compulsory HBM bytes — so what bounds it is the rate at which L2 delivers gathered vectors to the SMs,
+//       tools/l2_gather_peak.cu: 19-20 TB/s for an L2-resident table on B200);
+//   spmm_seg_slab_kernel: an operand larger than L2 whose 32-row slab fits (C3: H = 205 MB, slab 51 MB) is gathered one
+//       slab per launch, so every gather after the first touch of a vector is an L2 hit; A's index / value arrays are
+//       streamed once per slab (12 bytes per entry against the 256 bytes the entry gathers). 8 lanes own a segment, four
+//       segments per warp.
+// Entries are added in storage order, one fused multiply-add per entry and output element (the reference's order).
 // ---------------------------------------------------------------------------
 struct d4 { double x, y, z, w; };
 
-__device__ __forceinline__ d4 ldg256(const double* p)
-{
-    d4 r;
-    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ d4 ldg256_keep(const double* p)
-{
-    d4 r;
-    asm("ld.global.nc.L1::evict_last.L2::evict_last.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ d4 ldg256_drop(const double* p)
-{
-    d4 r;
-    asm("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
-    return r;
-}
-
-constexpr int kTierSmemBytes = 200 * 1024;                    // shared-memory tier per CTA (one 512-thread CTA per SM)
-constexpr size_t kTierKeepBytes = size_t(48) << 20;           // L2-resident tier: well under half of the 126 MB L2
-constexpr size_t kTierMinOperandBytes = size_t(96) << 20;     // smaller operands live in L2 without help
+constexpr size_t kSlabMinOperandBytes = size_t(96) << 20;     // smaller operands live in L2 whole
 constexpr size_t kSlabMaxBytes = size_t(64) << 20;            // a 32-row operand slab of at most this size is gathered from L2
-constexpr unsigned int kTierSmem = 0x80000000u, kTierKeep = 0x40000000u, kTierDrop = 0xC0000000u, kTierMask = 0xC0000000u;
+constexpr int kSlab = 32;
 
-// one gathered operand piece, by residency class (the class is warp-uniform: no divergence)
-__device__ __forceinline__ d4 tier_load(unsigned int code, const double* __restrict__ B, long long ldb, const double* sh, int k, int off, int q)
+// ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// How the loops are written, and why (the round-1 forms of these kernels ran at 60 % of this rate; their ncu source view,
+// profiles/ncu_r02_c3_spmm_source.txt, showed 69 % of the stall samples on warps waiting, IN ORDER, for a load whose value a
+// select or multiply consumed right behind it — `nxt_a = alpha * val[...]` exposed the DRAM latency of the index stream in
+// every batch, `b[t] = (t < cnt) ? load : 0` made each gather wait for the previous one — plus a serial tail loop and 270
+// instructions per 8 entries for residency-class branches and 64-bit address arithmetic):
+//   * every load is unconditional, from a clamped (always valid) address, and nothing touches a loaded register before the
+//     multiply-adds: an entry past the end of a segment is a copy of the segment's last entry with weight 0 (the weight is
+//     zeroed when the batch is consumed, two batches after its load), so its FMA adds +-0;
+//   * the (index, value) stream runs two batches ahead, in two register pairs used alternately (no loop-carried move that
+//     would wait for the load just issued);
+//   * one code path for full and partial batches; no residency classes (the shared-memory tier bought 3 % and cost a
+//     branch per gather; L2's own replacement keeps the popular vectors); addresses are one 32 x 32 -> 64 bit multiply-add.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ d4 ldg256_stream(const char* p)
 {
-    const unsigned int cls = code & kTierMask;
-    if (cls == kTierSmem)
-    {
-        const double* row = sh + static_cast<size_t>(code & ~kTierMask) * k;
-        const double2 lo = *reinterpret_cast<const double2*>(row + 2 * q);
-        const double2 hi = *reinterpret_cast<const double2*>(row + (k >> 1) + 2 * q);
-        d4 r; r.x = lo.x; r.y = lo.y; r.z = hi.x; r.w = hi.y;
-        return r;
-    }
-    const double* p = B + static_cast<long long>(code & ~kTierMask) * ldb + off;
-    if (cls == kTierDrop) return ldg256_drop(p);
-    if (cls == kTierKeep) return ldg256_keep(p);
-    return ldg256(p);
+    d4 r;
+    // volatile: keeps the shuffle -> address -> load sequence of one entry together (ptxas otherwise hoists all the address
+    // arithmetic of a group above its first load and runs out of registers)
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
 }
-
 template <int NV, int U>
 __global__ void __launch_bounds__(512, 1)
-spmm_seg_tier_kernel(int nseg, const unsigned int* __restrict__ scol, const unsigned int* __restrict__ sbeg,
-                     const unsigned int* __restrict__ send, const unsigned int* __restrict__ sslot,
-                     const unsigned int* __restrict__ idx, const double* __restrict__ val, int k,
-                     const double* __restrict__ B, long long ldb, double alpha, double beta,
-                     double* __restrict__ out, long long ldo, double* __restrict__ partial,
-                     int smem_rows, const unsigned int* __restrict__ smem_ids)
+spmm_seg_wide256_kernel(int nseg, const unsigned int* __restrict__ scol, const unsigned int* __restrict__ sbeg,
+                      const unsigned int* __restrict__ send, const unsigned int* __restrict__ sslot,
+                      const unsigned int* __restrict__ idx, const double* __restrict__ val, int k,
+                      const double* __restrict__ B, unsigned int ldb_bytes, double alpha, double beta,
+                      double* __restrict__ out, long long ldo, double* __restrict__ partial)
 {
-    extern __shared__ __align__(16) double tier_sh[];
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5;
     bool live[NV];
+    const char* Bl[NV];          // this lane's piece of vector 0 (dead lanes of a ragged k point at a valid piece; their sums are not stored)
 #pragma unroll
-    for (int v = 0; v < NV; ++v) live[v] = 4 * lane + 128 * v < k;
-    // shared-memory tier: row s = operand vector smem_ids[s]; the piece (lane, v) is stored as two double2 halves,
-    // k/2 doubles apart, at double2 index q = 32v + lane, so both LDS.128 of a warp are contiguous
-    for (int s = warp; s < smem_rows; s += wpb)
+    for (int v = 0; v < NV; ++v)
     {
-        const double* src = B + static_cast<long long>(smem_ids[s]) * ldb;
-        double* row = tier_sh + static_cast<size_t>(s) * k;
-#pragma unroll
-        for (int v = 0; v < NV; ++v)
-            if (live[v])
-            {
-                const d4 x = ldg256_keep(src + 4 * lane + 128 * v);
-                const int q = 32 * v + lane;
-                *reinterpret_cast<double2*>(row + 2 * q) = make_double2(x.x, x.y);
-                *reinterpret_cast<double2*>(row + (k >> 1) + 2 * q) = make_double2(x.z, x.w);
-            }
+        live[v] = 4 * lane + 128 * v < k;
+        Bl[v] = reinterpret_cast<const char*>(B + (live[v] ? 4 * lane + 128 * v : 0));
     }
-    __syncthreads();
-
-    for (long long it = blockIdx.x * static_cast<long long>(wpb) + warp; it < nseg; it += static_cast<long long>(gridDim.x) * wpb)
+    const long long stride = static_cast<long long>(gridDim.x) * wpb;
+    long long it = blockIdx.x * static_cast<long long>(wpb) + warp;
+    // record of the next segment, read while the current one is summed
+    unsigned int nj = 0, nslot = 0, nbeg = 0, nend = 0;
+    if (it < nseg) { nj = scol[it]; nslot = sslot[it]; nbeg = sbeg[it]; nend = send[it]; }
+    for (; it < nseg; it += stride)
     {
-        const unsigned int j = scol[it], slot = sslot[it];
+        const unsigned int j = nj, slot = nslot, end = nend;
+        unsigned int o = nbeg;
+        if (it + stride < nseg) { nj = scol[it + stride]; nslot = sslot[it + stride]; nbeg = sbeg[it + stride]; nend = send[it + stride]; }
         const bool direct = slot == 0xFFFFFFFFu;
         d4 acc[NV];
 #pragma unroll
@@ -443,53 +414,46 @@ spmm_seg_tier_kernel(int nseg, const unsigned int* __restrict__ scol, const unsi
                 acc[v].x = lo.x * beta; acc[v].y = lo.y * beta; acc[v].z = hi.x * beta; acc[v].w = hi.y * beta;
             }
         }
-        const unsigned int end = send[it];
-        unsigned int o = sbeg[it];
-        unsigned int nxt_i = 0; double nxt_a = 0.0;
-        if (o + lane < end) { nxt_i = __ldcs(idx + o + lane); nxt_a = alpha * __ldcs(val + o + lane); }
-        while (o < end)
+        if (o < end)
         {
-            const int cnt = min(32u, end - o);
-            const unsigned int my_i = nxt_i; const double my_a = nxt_a;
-            o += 32;
-            if (o + lane < end) { nxt_i = __ldcs(idx + o + lane); nxt_a = alpha * __ldcs(val + o + lane); }
-            int t = 0;
-            for (; t + U <= cnt; t += U)
-            {
-                d4 b[U][NV];
-                double a[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u)
+            const unsigned int last = end - 1;
+            unsigned int i0, i1; double v0, v1;
+            { const unsigned int p = min(o + lane, last); i0 = __ldcs(idx + p); v0 = __ldcs(val + p); }
+            { const unsigned int p = min(o + 32 + lane, last); i1 = __ldcs(idx + p); v1 = __ldcs(val + p); }
+            auto batch = [&](unsigned int& ci, double& cv) {
+                const unsigned int left = end - o;                       // >= 1 entries of this segment from o on
+                const unsigned int my_i = ci;
+                const double my_v = static_cast<unsigned int>(lane) < left ? alpha * cv : 0.0;    // past the end: a copy of the last entry, weight 0
+                { const unsigned int p = min(o + 64 + lane, last); ci = __ldcs(idx + p); cv = __ldcs(val + p); }   // two batches ahead
+                const int ngr = static_cast<int>((min(left, 32u) + U - 1) / U);
+                for (int gq = 0; gq < ngr; ++gq)
                 {
-                    const unsigned int code = __shfl_sync(0xffffffffu, my_i, t + u);
-                    a[u] = __shfl_sync(0xffffffffu, my_a, t + u);
+                    d4 b[U][NV];
 #pragma unroll
-                    for (int v = 0; v < NV; ++v)
+                    for (int u = 0; u < U; ++u)
                     {
-                        if (live[v]) b[u][v] = tier_load(code, B, ldb, tier_sh, k, 4 * lane + 128 * v, 32 * v + lane);
-                        else { b[u][v].x = b[u][v].y = b[u][v].z = b[u][v].w = 0.0; }
+                        const unsigned int id = __shfl_sync(0xffffffffu, my_i, gq * U + u);
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) b[u][v] = ldg256_stream(Bl[v] + static_cast<unsigned long long>(id) * ldb_bytes);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                    {
+                        const double au = __shfl_sync(0xffffffffu, my_v, gq * U + u);
+#pragma unroll
+                        for (int v = 0; v < NV; ++v)
+                        {
+                            acc[v].x += au * b[u][v].x; acc[v].y += au * b[u][v].y;
+                            acc[v].z += au * b[u][v].z; acc[v].w += au * b[u][v].w;
+                        }
                     }
                 }
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-#pragma unroll
-                    for (int v = 0; v < NV; ++v)
-                    {
-                        acc[v].x += a[u] * b[u][v].x; acc[v].y += a[u] * b[u][v].y;
-                        acc[v].z += a[u] * b[u][v].z; acc[v].w += a[u] * b[u][v].w;
-                    }
-            }
-            for (; t < cnt; ++t)
+                o += 32;
+            };
+            for (;;)
             {
-                const unsigned int code = __shfl_sync(0xffffffffu, my_i, t);
-                const double au = __shfl_sync(0xffffffffu, my_a, t);
-#pragma unroll
-                for (int v = 0; v < NV; ++v)
-                    if (live[v])
-                    {
-                        const d4 bv = tier_load(code, B, ldb, tier_sh, k, 4 * lane + 128 * v, 32 * v + lane);
-                        acc[v].x += au * bv.x; acc[v].y += au * bv.y; acc[v].z += au * bv.z; acc[v].w += au * bv.w;
-                    }
+                batch(i0, v0); if (o >= end) break;
+                batch(i1, v1); if (o >= end) break;
             }
         }
         double* dst = direct ? out + j * ldo : partial + static_cast<long long>(slot) * k;
@@ -504,30 +468,27 @@ spmm_seg_tier_kernel(int nseg, const unsigned int* __restrict__ scol, const unsi
     }
 }
 
-// ---------------------------------------------------------------------------
-// k-slab variant: an operand that is larger than L2 but whose 32-row slab fits (C3: H = 205 MB, slab 51 MB) is gathered
-// one slab per launch, so every gather after the first touch of a vector is an L2 hit; A's index/value arrays are
-// streamed once per slab (12 bytes per entry, against the 256 bytes the entry gathers). 8 lanes own a segment (lane g
-// the doubles koff + 4g .. 4g+3 of the k-vector: one LDG.E.256 per lane and entry), four segments per warp; the
-// (index, value) pairs are read 8 at a time and handed round inside the group. Entries are added in storage order
-// with one fused multiply-add per entry and output element: bit for bit the sums of the kernels above.
-// ---------------------------------------------------------------------------
-constexpr int kSlab = 32;
-
-__global__ void __launch_bounds__(256, 2)
+template <int U, int MINB>      // U gathers in flight per lane (8 / U sub-batches per batch of 8 entries), MINB CTAs per SM
+__global__ void __launch_bounds__(256, MINB)
 spmm_seg_slab_kernel(int nseg, const unsigned int* __restrict__ scol, const unsigned int* __restrict__ sbeg,
-                     const unsigned int* __restrict__ send, const unsigned int* __restrict__ sslot,
-                     const unsigned int* __restrict__ idx, const double* __restrict__ val, int k, int koff,
-                     const double* __restrict__ B, long long ldb, double alpha, double beta,
-                     double* __restrict__ out, long long ldo, double* __restrict__ partial)
+                      const unsigned int* __restrict__ send, const unsigned int* __restrict__ sslot,
+                      const unsigned int* __restrict__ idx, const double* __restrict__ val, int k, int koff,
+                      const double* __restrict__ B, unsigned int ldb_bytes, double alpha, double beta,
+                      double* __restrict__ out, long long ldo, double* __restrict__ partial)
 {
     const int lane = threadIdx.x & 31, g = lane & 7;
     const unsigned int mask = 0xFFu << (lane & ~7);
     const long long ngroups = static_cast<long long>(gridDim.x) * (blockDim.x >> 3);
     const int off = koff + 4 * g;
-    for (long long it = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3; it < nseg; it += ngroups)
+    const char* Bl = reinterpret_cast<const char*>(B + off);
+    long long it = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
+    unsigned int nj = 0, nslot = 0, nbeg = 0, nend = 0;
+    if (it < nseg) { nj = scol[it]; nslot = sslot[it]; nbeg = sbeg[it]; nend = send[it]; }
+    for (; it < nseg; it += ngroups)
     {
-        const unsigned int j = scol[it], slot = sslot[it];
+        const unsigned int j = nj, slot = nslot, end = nend;
+        unsigned int o = nbeg;
+        if (it + ngroups < nseg) { nj = scol[it + ngroups]; nslot = sslot[it + ngroups]; nbeg = sbeg[it + ngroups]; nend = send[it + ngroups]; }
         const bool direct = slot == 0xFFFFFFFFu;
         d4 acc; acc.x = acc.y = acc.z = acc.w = 0.0;
         if (direct && beta != 0.0)
@@ -536,66 +497,47 @@ spmm_seg_slab_kernel(int nseg, const unsigned int* __restrict__ scol, const unsi
             const double2 lo = *reinterpret_cast<const double2*>(c0), hi = *reinterpret_cast<const double2*>(c0 + 2);
             acc.x = lo.x * beta; acc.y = lo.y * beta; acc.z = hi.x * beta; acc.w = hi.y * beta;
         }
-        const unsigned int end = send[it];
-        unsigned int o = sbeg[it];
-        unsigned int nxt_i = 0; double nxt_a = 0.0;
-        if (o + g < end) { nxt_i = __ldcs(idx + o + g); nxt_a = alpha * __ldcs(val + o + g); }
-        while (o < end)
+        if (o < end)
         {
-            const int cnt = min(8u, end - o);
-            const unsigned int my_i = nxt_i; const double my_a = nxt_a;
-            o += 8;
-            nxt_i = 0; nxt_a = 0.0;
-            if (o + g < end) { nxt_i = __ldcs(idx + o + g); nxt_a = alpha * __ldcs(val + o + g); }
-            d4 b[8];
-            double a[8];
+            const unsigned int last = end - 1;
+            unsigned int i0, i1; double v0, v1;
+            { const unsigned int p = min(o + g, last); i0 = __ldcs(idx + p); v0 = __ldcs(val + p); }
+            { const unsigned int p = min(o + 8 + g, last); i1 = __ldcs(idx + p); v1 = __ldcs(val + p); }
+            auto batch = [&](unsigned int& ci, double& cv) {
+                const unsigned int left = end - o;
+                const unsigned int my_i = ci;
+                const double my_v = static_cast<unsigned int>(g) < left ? alpha * cv : 0.0;      // past the end: a copy of the last entry, weight 0
+                { const unsigned int p = min(o + 16 + g, last); ci = __ldcs(idx + p); cv = __ldcs(val + p); }      // two batches ahead
 #pragma unroll
-            for (int t = 0; t < 8; ++t)
-            {
-                const unsigned int iu = __shfl_sync(mask, my_i, t, 8);
-                a[t] = __shfl_sync(mask, my_a, t, 8);
-                if (t < cnt) b[t] = ldg256(B + iu * ldb + off);
-                else { b[t].x = b[t].y = b[t].z = b[t].w = 0.0; }
-            }
-            if (cnt == 8)
-            {
+                for (int h = 0; h < 8; h += U)
+                {
+                    if (U < 8 && static_cast<unsigned int>(h) >= left) break;      // group-uniform
+                    d4 b[U];
 #pragma unroll
-                for (int t = 0; t < 8; ++t) { acc.x += a[t] * b[t].x; acc.y += a[t] * b[t].y; acc.z += a[t] * b[t].z; acc.w += a[t] * b[t].w; }
-            }
-            else
+                    for (int t = 0; t < U; ++t)
+                    {
+                        const unsigned int iu = __shfl_sync(mask, my_i, h + t, 8);
+                        b[t] = ldg256_stream(Bl + static_cast<unsigned long long>(iu) * ldb_bytes);
+                    }
+#pragma unroll
+                    for (int t = 0; t < U; ++t)
+                    {
+                        const double at = __shfl_sync(mask, my_v, h + t, 8);
+                        acc.x += at * b[t].x; acc.y += at * b[t].y; acc.z += at * b[t].z; acc.w += at * b[t].w;
+                    }
+                }
+                o += 8;
+            };
+            for (;;)
             {
-                for (int t = 0; t < cnt; ++t) { acc.x += a[t] * b[t].x; acc.y += a[t] * b[t].y; acc.z += a[t] * b[t].z; acc.w += a[t] * b[t].w; }
+                batch(i0, v0); if (o >= end) break;
+                batch(i1, v1); if (o >= end) break;
             }
         }
         double* p = (direct ? out + j * ldo : partial + static_cast<long long>(slot) * k) + off;
         *reinterpret_cast<double2*>(p) = make_double2(acc.x, acc.y);
         *reinterpret_cast<double2*>(p + 2) = make_double2(acc.z, acc.w);
     }
-}
-
-// residency class of every gatherable vector from its rank in decreasing degree order
-__global__ void tier_code_kernel(int count, const unsigned int* __restrict__ ids_by_degree, int smem_rows, int keep_rows,
-                                 unsigned int* __restrict__ code, unsigned int* __restrict__ smem_ids)
-{
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < count; r += gridDim.x * blockDim.x)
-    {
-        const unsigned int id = ids_by_degree[r];
-        unsigned int c;
-        if (r < smem_rows) { c = kTierSmem | static_cast<unsigned int>(r); smem_ids[r] = id; }
-        else if (r < smem_rows + keep_rows) c = kTierKeep | id;
-        else c = kTierDrop | id;
-        code[id] = c;
-    }
-}
-
-__global__ void tier_degree_kernel(int count, const unsigned int* __restrict__ ptr, unsigned int* __restrict__ deg, unsigned int* __restrict__ ids)
-{
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < count; r += gridDim.x * blockDim.x) { deg[r] = ptr[r + 1] - ptr[r]; ids[r] = r; }
-}
-
-__global__ void tier_apply_kernel(unsigned int nnz, const unsigned int* __restrict__ idx, const unsigned int* __restrict__ code, unsigned int* __restrict__ out)
-{
-    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += gridDim.x * blockDim.x) out[i] = code[idx[i]];
 }
 
 // out(:, j) = beta * out(:, j) + sum of the partials of column j, in segment order
@@ -660,41 +602,37 @@ void spmm_gather_seg(cudaStream_t stream, int ncols, const SegTable& T, const un
     if (ncols <= 0 || T.nseg <= 0) return;
     const uintptr_t addr_bits = reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(partial);
     const bool aligned16 = (addr_bits & 15) == 0;
-    const bool wide256 = k >= 64 && k <= 256 && (ldb & 3) == 0 && (ldo & 3) == 0 && (addr_bits & 31) == 0 && ngather > 0 && ngather < (1 << 30);
-    const bool tiers = T.tiers_on && T.tier_k == k;
+    const bool wide256 = k >= 64 && k <= 256 && (ldb & 3) == 0 && (ldo & 3) == 0 && (addr_bits & 31) == 0 && ngather > 0 &&
+                         ldb > 0 && ldb < (1LL << 28);            // byte offsets of a gathered vector: one 32 x 32 -> 64 bit multiply
     // SMK_SPMM_SLAB: 0 = never, 2 = whenever the shape allows (tests), otherwise by operand size
     const char* slab_env = getenv("SMK_SPMM_SLAB");
     const int slab_mode = slab_env ? atoi(slab_env) : 1;
     // operand larger than L2 can keep, 32-row slab small enough to stay: one launch per slab
     const size_t operand_bytes = static_cast<size_t>(ngather > 0 ? ngather : 0) * k * sizeof(double);
-    const bool slab_fits = operand_bytes > kTierMinOperandBytes && static_cast<size_t>(ngather) * kSlab * sizeof(double) <= kSlabMaxBytes;
-    if (wide256 && !tiers && (k % kSlab) == 0 && slab_mode != 0 && (slab_fits || slab_mode == 2))
+    const bool slab_fits = operand_bytes > kSlabMinOperandBytes && static_cast<size_t>(ngather) * kSlab * sizeof(double) <= kSlabMaxBytes;
+    const unsigned int ldb_bytes = static_cast<unsigned int>(ldb * 8);
+    if (wide256 && (k % kSlab) == 0 && slab_mode != 0 && (slab_fits || slab_mode == 2))
     {
+        // 32 warps per SM with 4 gathers in flight per lane (C3 H*A': 6.27 ms against 6.50 ms for 16 warps x 8, r02)
         const int groups_per_block = 256 / 8;
-        const int blocks = std::max(1, std::min(ceil_div(T.nseg, groups_per_block), 2 * num_sms));
+        const int blocks = std::max(1, std::min(ceil_div(T.nseg, groups_per_block), 4 * num_sms));
         for (int koff = 0; koff < k; koff += kSlab)
         {
-            spmm_seg_slab_kernel<<<blocks, 256, 0, stream>>>(T.nseg, T.col.p, T.beg.p, T.end.p, T.slot.p, idx, val, k, koff, B, ldb,
-                                                             alpha, beta, out, ldo, partial);
+            spmm_seg_slab_kernel<4, 4><<<blocks, 256, 0, stream>>>(T.nseg, T.col.p, T.beg.p, T.end.p, T.slot.p, idx, val, k, koff, B,
+                                                                   ldb_bytes, alpha, beta, out, ldo, partial);
             SMK_LAUNCH_CHECK();
         }
     }
     else if (wide256 && k >= 96 && (k & 3) == 0)
     {
-        const int smem_rows = tiers ? T.tier_smem_rows : 0;
-        const size_t smem_bytes = static_cast<size_t>(smem_rows) * k * sizeof(double);
-        const unsigned int* use_idx = tiers ? T.tier_idx.p : idx;
+        // one 512-thread CTA per SM, 8 (k <= 128) or 4 x 2 gathered pieces in flight per lane: 128 KB of gathers in flight per SM
         const int blocks = std::max(1, std::min(ceil_div(T.nseg, 16), num_sms));
-#define SMK_T(NV, U)                                                                                                                  \
-        do {                                                                                                                          \
-            static bool attr_set = false;                                                                                             \
-            if (!attr_set) { SMK_CUDA(cudaFuncSetAttribute(spmm_seg_tier_kernel<NV, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTierSmemBytes)); attr_set = true; } \
-            spmm_seg_tier_kernel<NV, U><<<blocks, 512, smem_bytes, stream>>>(T.nseg, T.col.p, T.beg.p, T.end.p, T.slot.p, use_idx, val, k, B, ldb, \
-                                                                             alpha, beta, out, ldo, partial, smem_rows, T.tier_smem_ids.p);      \
-        } while (0)
-        if (k <= 128) SMK_T(1, 8);
-        else SMK_T(2, 4);
-#undef SMK_T
+        if (k <= 128)
+            spmm_seg_wide256_kernel<1, 8><<<blocks, 512, 0, stream>>>(T.nseg, T.col.p, T.beg.p, T.end.p, T.slot.p, idx, val, k, B, ldb_bytes,
+                                                                      alpha, beta, out, ldo, partial);
+        else
+            spmm_seg_wide256_kernel<2, 4><<<blocks, 512, 0, stream>>>(T.nseg, T.col.p, T.beg.p, T.end.p, T.slot.p, idx, val, k, B, ldb_bytes,
+                                                                      alpha, beta, out, ldo, partial);
         SMK_LAUNCH_CHECK();
     }
     else if (k >= 64 && k <= 256 && (k & 1) == 0 && (ldb & 1) == 0 && (ldo & 1) == 0 && aligned16)
@@ -733,58 +671,8 @@ void spmm_gather_seg(cudaStream_t stream, int ncols, const SegTable& T, const un
     }
 }
 
-// Residency classes for the gathers of one orientation (see spmm_seg_tier_kernel). count = number of gatherable
-// vectors, degree_ptr = offsets of the OTHER orientation (degree of vector r = degree_ptr[r+1] - degree_ptr[r]).
-// Built only when the operand is much larger than L2 and the degrees are skewed enough for a static choice to beat
-// L2's own replacement: the two resident tiers must cover at least twice the share of the stored entries that the same
-// number of average vectors would. Synchronises the stream.
-void build_gather_tiers(cudaStream_t stream, SegTable& T, int count, const unsigned int* degree_ptr, const unsigned int* idx,
-                        unsigned int nnz, int k, int num_sms)
-{
-    T.tiers_on = false;
-    if (k < 96 || k > 256 || (k & 3) || count <= 0 || count >= (1 << 30) || nnz == 0) return;
-    // tuning / test knobs: SMK_SPMM_TIERS=0 turns the classes off; the two *_KB values shrink the thresholds so that
-    // small test matrices exercise all four classes
-    if (const char* e = getenv("SMK_SPMM_TIERS")) if (atoi(e) == 0) return;
-    size_t min_operand = kTierMinOperandBytes, keep_bytes = kTierKeepBytes;
-    if (const char* e = getenv("SMK_SPMM_TIER_MIN_KB")) min_operand = static_cast<size_t>(atoll(e)) << 10;
-    if (const char* e = getenv("SMK_SPMM_TIER_KEEP_KB")) keep_bytes = static_cast<size_t>(atoll(e)) << 10;
-    const size_t vec_bytes = static_cast<size_t>(k) * sizeof(double);
-    if (static_cast<size_t>(count) * vec_bytes <= min_operand) return;
-    const int smem_rows = static_cast<int>(std::min<size_t>(count, kTierSmemBytes / vec_bytes));
-    const int keep_rows = static_cast<int>(std::min<size_t>(count - smem_rows, keep_bytes / vec_bytes));
-    DevBuf<unsigned int> deg, ids, deg_s, ids_s, code;
-    DevBuf<unsigned char> tmp;
-    deg.reserve(count); ids.reserve(count); deg_s.reserve(count); ids_s.reserve(count);
-    const int blocks = std::max(1, std::min(ceil_div(count, 256), 8 * num_sms));
-    tier_degree_kernel<<<blocks, 256, 0, stream>>>(count, degree_ptr, deg.p, ids.p);
-    SMK_LAUNCH_CHECK();
-    size_t bytes = 0;
-    SMK_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, deg.p, deg_s.p, ids.p, ids_s.p, count, 0, 32, stream));
-    tmp.reserve(bytes);
-    SMK_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp.p, bytes, deg.p, deg_s.p, ids.p, ids_s.p, count, 0, 32, stream));
-    launch_counter() += 4;
-    std::vector<unsigned int> top(static_cast<size_t>(smem_rows) + keep_rows);
-    SMK_CUDA(cudaMemcpyAsync(top.data(), deg_s.p, top.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
-    SMK_CUDA(cudaStreamSynchronize(stream));
-    double covered = 0.0;
-    for (unsigned int d : top) covered += d;
-    const double share = covered / nnz, uniform_share = static_cast<double>(top.size()) / count;
-    if (share < 2.0 * uniform_share) return;
-    code.reserve(count);
-    T.tier_idx.reserve(nnz);
-    T.tier_smem_ids.reserve(std::max(1, smem_rows));
-    tier_code_kernel<<<blocks, 256, 0, stream>>>(count, ids_s.p, smem_rows, keep_rows, code.p, T.tier_smem_ids.p);
-    SMK_LAUNCH_CHECK();
-    tier_apply_kernel<<<std::min<unsigned int>((nnz + 255) / 256, 64u * num_sms), 256, 0, stream>>>(nnz, idx, code.p, T.tier_idx.p);
-    SMK_LAUNCH_CHECK();
-    SMK_CUDA(cudaStreamSynchronize(stream));
-    T.tiers_on = true; T.tier_k = k; T.tier_smem_rows = smem_rows; T.tier_share = share;
-}
-
 void build_segments(cudaStream_t stream, int ncols, const unsigned int* ptr, SegTable& T, int num_sms)
 {
-    T.tiers_on = false;                      // residency classes belong to the matrix the table was built for
     const size_t n1 = static_cast<size_t>(ncols) + 1;
     T.t_cnt.reserve(3 * n1);                // cnt | mcnt | flag
     T.t_first.reserve(n1); T.first_slot.reserve(n1); T.t_mpos.reserve(n1);

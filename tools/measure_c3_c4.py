@@ -50,15 +50,13 @@ def c3(m=1000000, n=200000, per_col=500, k=128, iters=5):
         times.append(ctx.last_step()[0])
     metric = ctx.solver_progress()
     prod_ms = {"WtA": ctx.time_product(0, 5), "HAt": ctx.time_product(1, 5)}
-    tiers = {"WtA": ctx.spmm_tier_info(0), "HAt": ctx.spmm_tier_info(1)}
     nnz = int(colp[-1])
     B = 2 * (12 * nnz + 4 * (n + 1)) + 64 * k * (m + n)
     ms = float(np.median(times))
     print(json.dumps({"workload": "C3 sparse HALS", "m": m, "n": n, "nnz": nnz, "k": k, "gen_s": gen_s, "load_s": load_s,
                       "ms_per_iter": ms, "iters_per_s": 1000.0 / ms, "algorithmic_GB": B * 1e-9,
                       "achieved_GBs": B / ms * 1e-6, "launches": ctx.last_step()[1], "metric": metric,
-                      "spmm_ms": prod_ms, "spmm_gather_TBs": {kk: nnz * k * 8 / v * 1e-9 for kk, v in prod_ms.items()},
-                      "spmm_tiers(on,smem_rows,share)": tiers}), flush=True)
+                      "spmm_ms": prod_ms, "spmm_gather_TBs": {kk: nnz * k * 8 / v * 1e-9 for kk, v in prod_ms.items()}}), flush=True)
     ctx.close()
 
 

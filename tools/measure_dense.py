@@ -34,15 +34,18 @@ def main():
     for _ in range(3):
         ctx.solver_step(1)
         ctx.solver_progress()
+    if os.environ.get("SMK_PHASES"):
+        ctx.phase_report()
     times = []
     for _ in range(iters):
         ctx.solver_step(1)
         times.append(ctx.last_step()[0])
+    phases = {nm: v / iters for nm, v in ctx.phase_report().items()} if os.environ.get("SMK_PHASES") else None
     metric = ctx.solver_progress()
     ms = float(np.median(times))
     F = 4.0 * k * m * n + (6.0 * k * k * n + 4.0 * k * k * m if alg == "BPP" else 6.0 * k * k * (m + n))
     print(json.dumps({"workload": f"dense {alg} {m}x{n} k={k}", "ms_per_iter": ms, "iters_per_s": 1000.0 / ms, "flop_per_iter": F,
-                      "achieved_TFLOPs": F / ms * 1e-9, "launches": ctx.last_step()[1], "times_ms": times, "metric": metric}), flush=True)
+                      "achieved_TFLOPs": F / ms * 1e-9, "launches": ctx.last_step()[1], "times_ms": times, "metric": metric, "phases_ms": phases}), flush=True)
     ctx.close()
 
 
