@@ -293,33 +293,14 @@ nnls_bpp_fast_kernel(int k, int q, const double* __restrict__ LHS, long long ldl
             const bool in0 = (pm >> r0) & 1ull, in1 = v1 && ((pm >> r1) & 1ull);
             bool quick = false;
             double zq = 0.0;
-            if (p == 0)
+            // The passive-set system is solved on the smaller of P (direct) and its complement A (block-inverse identity, see the
+            // head of the file). Both forms go through ONE call of the register-resident solver: its four size classes are 2 800
+            // SASS instructions each, and a second call site doubled a kernel that already overflowed the instruction cache.
+            const bool direct = p <= 32;
+            const int na = k - p;
+            const int nsel = direct ? p : na;
+            if (!direct)
             {
-                x0 = 0.0; x1 = 0.0;
-                if (v0) sx[r0] = 0.0;
-                if (v1) sx[r1] = 0.0;
-            }
-            else if (p <= 32)
-            {
-                // ---- direct: G_PP x_P = b_P
-                if (in0) list[__popcll(pm & ((1ull << r0) - 1ull))] = r0;
-                if (in1) list[__popcll(pm & ((1ull << r1) - 1ull))] = r1;
-                __syncwarp();
-                const double rv = (lane < p) ? sb[list[lane]] : 0.0;
-                double z;
-                if (!gather_solve_any(sG, k, list, p, rv, sT, sRow, lane, z)) { failed = true; break; }
-                if (round > 0 && fabs(z) < kZeroThresh) z = 0.0;     // ZeroizeSmallValues(Xsub), nnls.hpp:215
-                if (v0) sx[r0] = 0.0;
-                if (v1) sx[r1] = 0.0;
-                __syncwarp();
-                if (lane < p) sx[list[lane]] = z;
-                __syncwarp();
-                x0 = v0 ? sx[r0] : 0.0;
-                x1 = v1 ? sx[r1] : 0.0;
-            }
-            else
-            {
-                // ---- complement: solve on A = ~P, |A| = k - p < 32
                 if (!ginv_ok) { defer = true; break; }
                 if (!have_u)
                 {
@@ -337,19 +318,42 @@ nnls_bpp_fast_kernel(int k, int q, const double* __restrict__ LHS, long long ldl
                     have_u = true;
                     __syncwarp();
                 }
-                const unsigned long long am = ~pm & kmask;
-                const int na = k - p;
-                if (v0 && !in0) list[__popcll(am & ((1ull << r0) - 1ull))] = r0;
-                if (v1 && !in1) list[__popcll(am & ((1ull << r1) - 1ull))] = r1;
+            }
+            {
+                // the index list of the system: P in ascending order (direct) or A = ~P (complement)
+                const unsigned long long sel = direct ? pm : (~pm & kmask);
+                if (v0 && ((sel >> r0) & 1ull)) list[__popcll(sel & ((1ull << r0) - 1ull))] = r0;
+                if (v1 && ((sel >> r1) & 1ull)) list[__popcll(sel & ((1ull << r1) - 1ull))] = r1;
                 __syncwarp();
-                double z = 0.0;
-                if (na > 0)
+            }
+            double z = 0.0;
+            if (nsel > 0)
+            {
+                const double* rsel = direct ? sb : su;
+                const double rv = (lane < nsel) ? rsel[list[lane]] : 0.0;
+                if (!gather_solve_any(direct ? sG : sGinv, k, list, nsel, rv, sT, sRow, lane, z))
                 {
-                    const double rv = (lane < na) ? su[list[lane]] : 0.0;
-                    if (!gather_solve_any(sGinv, k, list, na, rv, sT, sRow, lane, z)) { defer = true; break; }
-                    if (lane < na) sz[lane] = z;
-                    __syncwarp();
+                    if (direct) failed = true; else defer = true;      // not positive definite: G itself (failure) or the identity's (G^-1)_AA (redo directly)
+                    break;
                 }
+            }
+            if (direct)
+            {
+                // ---- direct: x_P = z (G_PP z = b_P); p == 0 leaves x = 0
+                if (round > 0 && fabs(z) < kZeroThresh) z = 0.0;     // ZeroizeSmallValues(Xsub), nnls.hpp:215
+                if (v0) sx[r0] = 0.0;
+                if (v1) sx[r1] = 0.0;
+                __syncwarp();
+                if (lane < p) sx[list[lane]] = z;
+                __syncwarp();
+                x0 = v0 ? sx[r0] : 0.0;
+                x1 = v1 ? sx[r1] : 0.0;
+            }
+            else
+            {
+                // ---- complement: z = (G^-1)_AA^-1 u_A, x_P = u_P - (G^-1)_PA z, |A| = k - p < 32
+                if (lane < na) sz[lane] = z;
+                __syncwarp();
                 double a0 = v0 ? su[r0] : 0.0, a1 = v1 ? su[r1] : 0.0;
                 for (int t = 0; t < na; ++t)
                 {
@@ -373,17 +377,35 @@ nnls_bpp_fast_kernel(int k, int q, const double* __restrict__ LHS, long long ldl
             }
             // ---- dual y = LHS * x - rhs (nnls.hpp:168-169, 219-220)
             // full_y: the product over the passive columns, as the reference forms it.
+            // sx is zero outside the passive set, so the dense loop adds the same terms in the same (ascending) order as a walk
+            // over the set bits of pm — fma(g, 0, s) == s exactly — without the 17 instructions of 64-bit mask arithmetic per
+            // passive column that the walk costs (it was 31 % of the kernel's instructions, profiles/ncu_r02_nnls_fast_lines.txt)
             auto full_y = [&](double& o0, double& o1) {
                 double s0 = 0.0, s1 = 0.0;
-                unsigned long long mm = pm;
-                while (mm)
+                const double* col0 = sG + (v0 ? r0 : 0);
+                const double* col1 = sG + (v1 ? r1 : 0);
+                if (4 * __popcll(pm) < k)
                 {
-                    const int cc = __ffsll(static_cast<long long>(mm)) - 1;
-                    mm &= mm - 1ull;
-                    const double xv = sx[cc];
-                    const double* col = sG + cc * k;
-                    if (v0) s0 = fma(col[r0], xv, s0);
-                    if (v1) s1 = fma(col[r1], xv, s1);
+                    // a small passive set: the walk over its bits is still the shorter loop
+                    unsigned long long mm = pm;
+                    while (mm)
+                    {
+                        const int cc = __ffsll(static_cast<long long>(mm)) - 1;
+                        mm &= mm - 1ull;
+                        const double xv = sx[cc];
+                        s0 = fma(col0[cc * k], xv, s0);
+                        s1 = fma(col1[cc * k], xv, s1);
+                    }
+                }
+                else
+                {
+#pragma unroll 8
+                    for (int cc = 0; cc < k; ++cc)
+                    {
+                        const double xv = sx[cc];
+                        s0 = fma(col0[cc * k], xv, s0);
+                        s1 = fma(col1[cc * k], xv, s1);
+                    }
                 }
                 o0 = s0 - b0; o1 = s1 - b1;
             };
