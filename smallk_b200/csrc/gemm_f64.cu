@@ -29,6 +29,7 @@
 //     not depend on scheduling — and writes the tile. No second kernel, no DRAM round
 //     trip of the partials (r01: reduce_partials_kernel, 0.31 GB per big product).
 #include <cstdlib>
+#include <cuda.h>
 #include "common.cuh"
 #include "kernels.h"
 #include "peer_device.cuh"
@@ -89,6 +90,108 @@ __device__ __forceinline__ void load_tile(double* s, const double* g, long long 
         const double* src = (rem > 0) ? (g + static_cast<long long>(v) * ldg + off) : g;
         if (VEC == 2) cp_async16(s + v * LDS + off, src, rem * 8);
         else          cp_async8(s + v * LDS + off, src, rem * 8);
+    }
+}
+
+// What every GEMM kernel of this file does with its 64 x 128 accumulator tile: (FIX) the in-kernel split-R reduction by the
+// last-arriving CTA of the tile, then the store — to C (minus D), to the split's partial tile, or (multi-GPU H*A') straight into
+// the receive slot of the rank that owns the columns. All threads of the CTA call it (it synchronises); threads with
+// `active` false (the TMA kernel's producer warp) own no accumulators and only take part in the barriers.
+template <bool FIX>
+__device__ __forceinline__ void gemm_finish(const GemmParams& p, double (&acc)[4][4][2], int tile_m, int tile_n, int split, int tid, bool active)
+{
+    const int lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 1, wn = warp >> 1;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int n0 = tile_n * BN;
+    const int m0 = tile_m * BM;
+    if (FIX && p.splits > 1)
+    {
+        // ---- split-R fix-up: partial tile to the workspace, ticket, the last arriver sums in split order
+        __shared__ bool s_last;
+        const int tile = tile_m * p.ntn + tile_n;
+        double* slot0 = p.slots + static_cast<long long>(tile) * p.splits * (BM * BN);
+        double* mine = slot0 + static_cast<long long>(split) * (BM * BN) + tid;
+        if (active)
+        {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                {
+                    mine[((i * 4 + j) * 2 + 0) * THREADS] = acc[i][j][0];
+                    mine[((i * 4 + j) * 2 + 1) * THREADS] = acc[i][j][1];
+                }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(p.tickets + tile, 1u) == static_cast<unsigned int>(p.splits - 1));
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        if (tid == 0) p.tickets[tile] = 0u;                 // ready for the next launch
+        for (int z = 0; active && z < p.splits; ++z)
+        {
+            const double* src = slot0 + static_cast<long long>(z) * (BM * BN) + tid;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                {
+                    const double v0 = __ldcg(src + ((i * 4 + j) * 2 + 0) * THREADS), v1 = __ldcg(src + ((i * 4 + j) * 2 + 1) * THREADS);
+                    if (z == 0) { acc[i][j][0] = v0; acc[i][j][1] = v1; }
+                    else { acc[i][j][0] += v0; acc[i][j][1] += v1; }
+                }
+        }
+    }
+
+    // epilogue
+    double* out;
+    long long ldo;
+    if (!FIX && (p.splits > 1 || p.to_partial)) { out = p.partial + static_cast<long long>(split) * p.M * p.N; ldo = p.M; }
+    else              { out = p.C; ldo = p.ldc; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+        const int row = m0 + wm * 32 + i * 8 + g;
+        if (row >= p.M || !active) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+            {
+                const int col = n0 + wn * 32 + j * 8 + 2 * t4 + e;
+                if (col >= p.N) continue;
+                double v = acc[i][j][e];
+                if ((FIX || (p.splits == 1 && !p.to_partial)) && p.D) v -= p.D[static_cast<long long>(col) * p.ldd + row];
+                if (FIX && p.sc.nranks > 0)
+                {
+                    const int g = col / p.sc.cols_per_rank;
+                    double* dst = reinterpret_cast<double*>(p.sc.table.base[g] + p.sc.recv_off) + static_cast<long long>(p.sc.rank) * p.sc.piece +
+                                  static_cast<long long>(col - g * p.sc.cols_per_rank) * p.M + row;
+                    *dst = v;
+                }
+                else out[static_cast<long long>(col) * ldo + row] = v;
+            }
+        }
+    }
+    if (FIX && p.sc.nranks > 0)
+    {
+        // all tiles stored -> publish. Every CTA that wrote a final tile counts; the last one signals the peers.
+        __shared__ bool s_pub;
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0)
+        {
+            const unsigned int t = atomicAdd(p.sc.done, 1u);
+            s_pub = (t == static_cast<unsigned int>(p.sc.ntiles - 1));
+            if (s_pub) *p.sc.done = 0u;
+        }
+        __syncthreads();
+        if (s_pub && tid < p.sc.nranks)
+            st_release_sys(reinterpret_cast<unsigned long long*>(p.sc.table.base[tid] + kPeerFlagOffset) + kFlagScatter * kPeerMaxRanks + p.sc.rank,
+                           p.sc.epoch);
     }
 }
 
@@ -174,91 +277,172 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_skinny_kernel(GemmParams p)
     }
     cp_async_wait<0>();
 
-    if (FIX && p.splits > 1)
-    {
-        // ---- split-R fix-up: partial tile to the workspace, ticket, the last arriver sums in split order
-        __shared__ bool s_last;
-        const int tile = tile_m * p.ntn + tile_n;
-        double* slot0 = p.slots + static_cast<long long>(tile) * p.splits * (BM * BN);
-        double* mine = slot0 + static_cast<long long>(split) * (BM * BN) + tid;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-            {
-                mine[((i * 4 + j) * 2 + 0) * THREADS] = acc[i][j][0];
-                mine[((i * 4 + j) * 2 + 1) * THREADS] = acc[i][j][1];
-            }
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) s_last = (atomicAdd(p.tickets + tile, 1u) == static_cast<unsigned int>(p.splits - 1));
-        __syncthreads();
-        if (!s_last) return;
-        __threadfence();
-        if (tid == 0) p.tickets[tile] = 0u;                 // ready for the next launch
-        for (int z = 0; z < p.splits; ++z)
-        {
-            const double* src = slot0 + static_cast<long long>(z) * (BM * BN) + tid;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                {
-                    const double v0 = __ldcg(src + ((i * 4 + j) * 2 + 0) * THREADS), v1 = __ldcg(src + ((i * 4 + j) * 2 + 1) * THREADS);
-                    if (z == 0) { acc[i][j][0] = v0; acc[i][j][1] = v1; }
-                    else { acc[i][j][0] += v0; acc[i][j][1] += v1; }
-                }
-        }
-    }
+    gemm_finish<FIX>(p, acc, tile_m, tile_n, split, tid, true);
+}
 
-    // epilogue
-    double* out;
-    long long ldo;
-    if (!FIX && (p.splits > 1 || p.to_partial)) { out = p.partial + static_cast<long long>(split) * p.M * p.N; ldo = p.M; }
-    else              { out = p.C; ldo = p.ldc; }
+// ---------------------------------------------------------------------------
+// The same product with the tiles moved by TMA (cp.async.bulk.tensor + mbarrier), for the A-sized contractions.
+//
+//   * One producer warp (one elected lane) issues the tensor copies of a reduction chunk — the 64 x 32 tile of Aop and the
+//     128 x 32 tile of Bop, 12 (NN) or 24 (NT) boxes — into a two-stage ring; eight consumer warps wait on the stage's `full` mbarrier, run their
+//     8 x 16 DMMA.8x8x4 and arrive on its `empty` mbarrier. No block-wide barrier in the main loop, no per-thread address
+//     arithmetic or copy instructions in the math warps (the cp.async form spends 12 LDGSTS + their addresses per thread
+//     and chunk and one __syncthreads per chunk).
+//   * Layout. A TMA box is written densely, so the padded leading dimensions that keep the cp.async form free of bank
+//     conflicts are not available; the 64-byte swizzle is used instead. Every box has an innermost extent of 8 doubles
+//     (64 bytes) of the CONTIGUOUS global dimension:
+//         Aop  (M x R, contiguous in M)      : map (M, R), box (8, 32),  8 boxes per tile  -> smem [m/8][r][m%8]
+//         B NT (N x R, contiguous in N)      : map (N, R), box (8, 32), 16 boxes per tile  -> smem [n/8][r][n%8]
+//         B NN (R x N, contiguous in R)      : map (R, N), box (8, 128), 4 boxes per tile  -> smem [r/8][n][r%8]
+//     64-byte rows XOR-swizzled by address bits 7-8 are conflict-free for the m8n8k4 fragments PROVIDED the four reduction
+//     indices a quad of lanes holds are {0, 1, 4, 5} (+2 for the second step) of each group of eight —
+//     rho(t4, s) = (t4 & 1) + 4 (t4 >> 1) + 2 s — instead of four consecutive ones: then the 16 lanes of a half-warp hit 16
+//     different 8-byte banks in all three layouts (bank bits = {r & 1 | n & 1, 16-byte chunk ^ row bits, low bit of the
+//     contiguous index}). The order in which the reduction indices of a group of eight are added is therefore
+//     0,1,4,5 | 2,3,6,7: fixed, but not the cp.async kernel's.
+//   * Out-of-range parts of a box (ragged M or N, the tail of the reduction) are zero-filled by TMA.
+// Needs even leading dimensions and 16-byte aligned bases; gemm_f64 falls back to the cp.async kernel otherwise.
+// ---------------------------------------------------------------------------
+constexpr int TMA_STAGES = 2;
+constexpr int TMA_THREADS = THREADS + 32;                 // 8 math warps + the producer warp
+constexpr int TMA_A_BYTES = BM * BK * 8, TMA_B_BYTES = BN * BK * 8;
+constexpr int TMA_STAGE_BYTES = TMA_A_BYTES + TMA_B_BYTES;
+constexpr int TMA_SMEM_BYTES = TMA_STAGES * TMA_STAGE_BYTES + 1024 /* alignment slack */ + 64 /* mbarriers */;
+
+__device__ __forceinline__ void mbar_init(unsigned int bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned int bar, int bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned int bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned int bar, unsigned int parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(unsigned int dst, const CUtensorMap* map, int c0, int c1, unsigned int bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+template <bool NT, bool FIX>
+__global__ void __launch_bounds__(TMA_THREADS, 2)
+gemm_tma_kernel(GemmParams p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB)
+{
+    extern __shared__ unsigned char tma_smem_raw[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const bool math = warp < THREADS / 32;
+    const int wm = warp & 1, wn = (warp >> 1) & 3;     // 2 x 4 math warps
+    const int g = lane >> 2, t4 = lane & 3;
+
+    int tile_n, tile_m, split;
+    if (FIX) { const int ntiles = p.ntn * ((p.M + BM - 1) / BM); split = blockIdx.x / ntiles; const int tile = blockIdx.x % ntiles; tile_n = tile % p.ntn; tile_m = tile / p.ntn; }
+    else { tile_n = blockIdx.x; tile_m = blockIdx.y; split = blockIdx.z; }
+    const int n0 = tile_n * BN;
+    const int m0 = tile_m * BM;
+    const int r_begin = split * p.rchunk;
+    const int r_end = min(p.R, r_begin + p.rchunk);
+    const int nchunks = (r_end > r_begin) ? (r_end - r_begin + BK - 1) / BK : 0;
+
+    // stage ring, 1024-byte aligned (the swizzle pattern is a function of the shared-memory address bits), then the mbarriers
+    const unsigned int raw = static_cast<unsigned int>(__cvta_generic_to_shared(tma_smem_raw));
+    const unsigned int base = (raw + 1023u) & ~1023u;
+    const unsigned int bars = base + TMA_STAGES * TMA_STAGE_BYTES;       // full[s] at bars + 8 s, empty[s] at bars + 8 (TMA_STAGES + s)
+    const unsigned char* stage0 = tma_smem_raw + (base - raw);
+    if (tid == 0)
+    {
+#pragma unroll
+        for (int s = 0; s < TMA_STAGES; ++s) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 8 * (TMA_STAGES + s), THREADS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    double acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    if (!math)
     {
-        const int row = m0 + wm * 32 + i * 8 + g;
-        if (row >= p.M) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
+        if (lane == 0)
         {
-#pragma unroll
-            for (int e = 0; e < 2; ++e)
+            for (int it = 0; it < nchunks; ++it)
             {
-                const int col = n0 + wn * 32 + j * 8 + 2 * t4 + e;
-                if (col >= p.N) continue;
-                double v = acc[i][j][e];
-                if ((FIX || (p.splits == 1 && !p.to_partial)) && p.D) v -= p.D[static_cast<long long>(col) * p.ldd + row];
-                if (FIX && p.sc.nranks > 0)
+                const int s = it % TMA_STAGES;
+                if (it >= TMA_STAGES) mbar_wait(bars + 8 * (TMA_STAGES + s), ((it / TMA_STAGES) - 1) & 1);
+                const unsigned int full = bars + 8 * s;
+                const unsigned int As = base + s * TMA_STAGE_BYTES, Bs = As + TMA_A_BYTES;
+                const int r0 = r_begin + it * BK;
+                mbar_expect_tx(full, TMA_STAGE_BYTES);
+#pragma unroll
+                for (int b = 0; b < BM / 8; ++b) tma_load_2d(As + b * (8 * BK * 8), &mapA, m0 + 8 * b, r0, full);
+                if (NT)
                 {
-                    const int g = col / p.sc.cols_per_rank;
-                    double* dst = reinterpret_cast<double*>(p.sc.table.base[g] + p.sc.recv_off) + static_cast<long long>(p.sc.rank) * p.sc.piece +
-                                  static_cast<long long>(col - g * p.sc.cols_per_rank) * p.M + row;
-                    *dst = v;
+#pragma unroll
+                    for (int b = 0; b < BN / 8; ++b) tma_load_2d(Bs + b * (8 * BK * 8), &mapB, n0 + 8 * b, r0, full);
                 }
-                else out[static_cast<long long>(col) * ldo + row] = v;
+                else
+                {
+#pragma unroll
+                    for (int b = 0; b < BK / 8; ++b) tma_load_2d(Bs + b * (8 * BN * 8), &mapB, r0 + 8 * b, n0, full);
+                }
             }
         }
     }
-    if (FIX && p.sc.nranks > 0)
+    else
     {
-        // all tiles stored -> publish. Every CTA that wrote a final tile counts; the last one signals the peers.
-        __shared__ bool s_pub;
-        __threadfence_system();
-        __syncthreads();
-        if (tid == 0)
+        // byte offsets of this lane's fragment elements inside a stage, for the two reduction steps s2 of a group of eight
+        unsigned int offA[2], offB[2];
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2)
         {
-            const unsigned int t = atomicAdd(p.sc.done, 1u);
-            s_pub = (t == static_cast<unsigned int>(p.sc.ntiles - 1));
-            if (s_pub) *p.sc.done = 0u;
+            const int rho = (t4 & 1) + 4 * (t4 >> 1) + 2 * s2;
+            const int sw = (rho >> 1) & 3;              // row bits 1-2 of a [..][r][8] tile = the swizzle term
+            offA[s2] = static_cast<unsigned int>(((wm * 4) * 32 + rho) * 64 + (((g >> 1) ^ sw) << 4) + ((g & 1) << 3));
+            if (NT) offB[s2] = static_cast<unsigned int>(((wn * 4) * 32 + rho) * 64 + (((g >> 1) ^ sw) << 4) + ((g & 1) << 3));
+            else    offB[s2] = static_cast<unsigned int>((wn * 32 + g) * 64 + (((rho >> 1) ^ ((g >> 1) & 3)) << 4) + ((rho & 1) << 3));
         }
-        __syncthreads();
-        if (s_pub && tid < p.sc.nranks)
-            st_release_sys(reinterpret_cast<unsigned long long*>(p.sc.table.base[tid] + kPeerFlagOffset) + kFlagScatter * kPeerMaxRanks + p.sc.rank,
-                           p.sc.epoch);
+        for (int it = 0; it < nchunks; ++it)
+        {
+            const int s = it % TMA_STAGES;
+            mbar_wait(bars + 8 * s, (it / TMA_STAGES) & 1);
+            const unsigned char* As = stage0 + s * TMA_STAGE_BYTES;
+            const unsigned char* Bs = As + TMA_A_BYTES;
+#pragma unroll
+            for (int k8 = 0; k8 < BK / 8; ++k8)
+#pragma unroll
+                for (int s2 = 0; s2 < 2; ++s2)
+                {
+                    double a[4], b[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const double*>(As + offA[s2] + i * 2048 + k8 * 512);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const double*>(Bs + offB[s2] + (NT ? j * 2048 + k8 * 512 : j * 512 + k8 * 8192));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + 8 * (TMA_STAGES + s));
+        }
     }
+    gemm_finish<FIX>(p, acc, tile_m, tile_n, split, tid, math);
 }
 
 // C = sum_s partial[s] (- D), partials added in ascending split order.
@@ -277,6 +461,33 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, int s
         if (D) s -= D[col * ldd + row];
         C[col * ldc + row] = s;
     }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+// 2-D map of a column-major d0 x d1 matrix of doubles (leading dimension ld), boxes of b0 x b1, 64-byte swizzle
+bool make_map_2d(CUtensorMap* map, const double* base, long long d0, long long d1, long long ld, int b0, int b1)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(d0), static_cast<cuuint64_t>(d1)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * sizeof(double)};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(b0), static_cast<cuuint32_t>(b1)};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -400,6 +611,29 @@ void gemm_f64(cudaStream_t stream, bool nt, int M, int N, int R,
 
     const bool vec2 = aligned16(A) && aligned16(B) && (lda % 2 == 0) && (ldb % 2 == 0);
     dim3 grid(ceil_div(N, BN), ceil_div(M, BM), splits);
+    const bool fix = p.fixup || scatter;          // the scatter epilogue lives in the FIX instantiation also when splits == 1
+    if (fix) grid = dim3(static_cast<unsigned int>(tiles * splits), 1, 1);
+
+    // the A-sized contractions: tiles by TMA (SMK_GEMM_TMA=0 keeps the cp.async kernel: measurements)
+    static const bool tma_on = [] { const char* e = getenv("SMK_GEMM_TMA"); return !(e && atoi(e) == 0); }();
+    bool launched = false;
+    if (tma_on && vec2 && workspace && R >= 4 * BK && M * static_cast<long long>(N) > 65536 && lda < (1LL << 36) && ldb < (1LL << 36))
+    {
+        CUtensorMap mapA, mapB;
+        const bool ok = make_map_2d(&mapA, A, M, R, lda, 8, BK) &&
+                        (nt ? make_map_2d(&mapB, B, N, R, ldb, 8, BK) : make_map_2d(&mapB, B, R, N, ldb, 8, BN));
+        if (ok)
+        {
+            auto launch_tma = [&](auto kern) {
+                SMK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES));
+                kern<<<grid, TMA_THREADS, TMA_SMEM_BYTES, stream>>>(p, mapA, mapB);
+                SMK_LAUNCH_CHECK();
+            };
+            if (nt) { if (fix) launch_tma(gemm_tma_kernel<true, true>); else launch_tma(gemm_tma_kernel<true, false>); }
+            else    { if (fix) launch_tma(gemm_tma_kernel<false, true>); else launch_tma(gemm_tma_kernel<false, false>); }
+            launched = true;
+        }
+    }
     const size_t smem = static_cast<size_t>(STAGES) * (nt ? stage_doubles<true>() : stage_doubles<false>()) * sizeof(double);
 
     auto launch = [&](auto kern) {
@@ -407,9 +641,8 @@ void gemm_f64(cudaStream_t stream, bool nt, int M, int N, int R,
         kern<<<grid, THREADS, smem, stream>>>(p);
         SMK_LAUNCH_CHECK();
     };
-    const bool fix = p.fixup || scatter;          // the scatter epilogue lives in the FIX instantiation also when splits == 1
-    if (fix) grid = dim3(static_cast<unsigned int>(tiles * splits), 1, 1);
-    if (fix)
+    if (launched) {}
+    else if (fix)
     {
         if (nt) { if (vec2) launch(gemm_skinny_kernel<true, 2, true>); else launch(gemm_skinny_kernel<true, 1, true>); }
         else    { if (vec2) launch(gemm_skinny_kernel<false, 2, true>); else launch(gemm_skinny_kernel<false, 1, true>); }

@@ -29,6 +29,12 @@ def rel(a, b):
     (False, False, 64, 513, 64),      # WtW * H
     (False, True, 64, 64, 5000),      # H H'
     (True, False, 130, 200, 300),     # k > 64: two M tiles
+    (True, False, 64, 1300, 4100),    # the TMA kernel (M * N > 65536): NN, ragged N tile, reduction tail of 4
+    (False, True, 64, 1304, 2052),    # the TMA kernel: NT, ragged N tile and reduction tail
+    (True, False, 128, 700, 1000),    # the TMA kernel: two M tiles
+    (True, False, 72, 1000, 1000),    # the TMA kernel: ragged M (zero-filled boxes)
+    (False, True, 40, 2000, 777),     # the TMA kernel: NT, M < one tile, odd reduction length
+    (True, False, 72, 1000, 999),     # odd leading dimension: back to the cp.async kernel
 ])
 def test_gemm_matches_numpy(gpu, tA, tB, M, N, K):
     rng = np.random.default_rng(M * 1000 + N + K)
@@ -37,6 +43,18 @@ def test_gemm_matches_numpy(gpu, tA, tB, M, N, K):
     C = gpu.gemm(A, B, transA=tA, transB=tB)
     ref = (A.T if tA else A) @ (B.T if tB else B)
     assert rel(C, ref) < REL_PRIM
+
+
+@pytest.mark.parametrize("tB,M,N,K", [(False, 64, 1300, 4100), (True, 64, 1304, 2052), (True, 128, 900, 3000)])
+def test_gemm_in_kernel_split_reduction_matches_numpy(gpu, tB, M, N, K, monkeypatch):
+    """The FIX instantiations (split-R reduction by the last-arriving CTA of a tile; on several GPUs the scatter epilogue lives
+    there) forced on one GPU, TMA and cp.async main loops."""
+    monkeypatch.setenv("SMK_GEMM_FIXUP", "1")
+    rng = np.random.default_rng(M + N + K)
+    A = rng.random((K, M))
+    B = rng.random((N, K) if tB else (K, N))
+    ref = A.T @ (B.T if tB else B)
+    assert rel(gpu.gemm(A, B, transA=True, transB=tB), ref) < REL_PRIM
 
 
 # ---------------------------------------------------------------------------
