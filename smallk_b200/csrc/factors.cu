@@ -255,15 +255,25 @@ hals_block_outer_kernel(int k, int q, int c0, double* __restrict__ X, const doub
             dmma884(c00, c01, a0, b);
             dmma884(c10, c11, a1, b);
         };
-        // rows before the previous block, and rows after this block: read from X
-        auto plain = [&](int st) {
-            const int p = 4 * st + kk;
-            double b = xcol[min(p, k - 1)];
-            if (p >= k || !livecol) b = 0.0;
-            mma_step(st, b);
+        // rows before the previous block, and rows after this block: read from X. Nothing selects on a loaded value here (a
+        // select behind each load made the warp wait for it before issuing the next one: 79 % of the stall samples, r02):
+        // a row index past k is clamped and meets a zero column of the masked Gram block, a column index past q is clamped
+        // and only feeds accumulator columns that are never stored.
+        // eight loads are issued before the first DMMA consumes one (volatile asm keeps that order: left to itself the compiler
+        // re-used two registers and every DMMA waited for the load just before it — 86 % of the stall samples)
+        auto plain8 = [&](int st0, int st_end) {
+            double b[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+            {
+                const int p = 4 * (st0 + u) + kk;
+                asm volatile("ld.global.f64 %0, [%1];" : "=d"(b[u]) : "l"(xcol + min(p, k - 1)));
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (st0 + u < st_end) mma_step(st0 + u, b[u]);
         };
-#pragma unroll 8
-        for (int st = 0; st < max(st_prev, 0); ++st) plain(st);
+        for (int st = 0; st < max(st_prev, 0); st += 8) plain8(st, max(st_prev, 0));
         if (c0 > 0)
         {
             // the previous block: finished values from its compact buffer (row c0-1 still needs its scaling)
@@ -274,7 +284,6 @@ hals_block_outer_kernel(int k, int q, int c0, double* __restrict__ X, const doub
                 double b = Xb_prev[static_cast<long long>(t) * q + jc];
                 if (t == kHalsB - 1) b = (fill_prev ? DBL_EPSILON : b) * inv_prev;
                 wb[u] = b;
-                if (!livecol) b = 0.0;
                 mma_step(st_prev + u, b);
             }
         }
@@ -283,14 +292,10 @@ hals_block_outer_kernel(int k, int q, int c0, double* __restrict__ X, const doub
         for (int u = 0; u < BS; ++u)
         {
             const int p = c0 + 4 * u + kk;
-            double b = xcol[min(p, k - 1)];
-            if (p >= k) b = 0.0;
-            cur[u] = b;
-            if (!livecol) b = 0.0;
-            if (st_cur + u < ksteps) mma_step(st_cur + u, b);
+            cur[u] = xcol[min(p, k - 1)];
+            if (st_cur + u < ksteps) mma_step(st_cur + u, cur[u]);
         }
-#pragma unroll 8
-        for (int st = st_cur + BS; st < ksteps; ++st) plain(st);
+        for (int st = st_cur + BS; st < ksteps; st += 8) plain8(st, ksteps);
 
         const int row = lane >> 2, col = 2 * (lane & 3);
 #pragma unroll
@@ -311,7 +316,7 @@ hals_block_outer_kernel(int k, int q, int c0, double* __restrict__ X, const doub
             {
                 const int t = 4 * u + kk;
                 if (c0 > 0) X[j * k + (c0 - kHalsB) + t] = wb[u];
-                Xb_cur[static_cast<long long>(t) * q + j] = cur[u];
+                Xb_cur[static_cast<long long>(t) * q + j] = (c0 + t < k) ? cur[u] : 0.0;
             }
         }
     }
@@ -361,6 +366,203 @@ hals_block_step_kernel(int k, int q, int c0, double* __restrict__ Xb, const doub
         sumsq += w * w;
     }
     publish_row_norm(sumsq, zeros, c, q, partial, rowinfo, ticket, norms, red);
+}
+
+// ---------------------------------------------------------------------------
+// Phase B of a block as ONE cooperative kernel (replaces the 16 step launches when the columns of X fit): the grid-wide
+// coupling of a step is a single scalar, the norm of the row just updated, so every thread keeps its columns for the whole
+// block and the steps are separated by grid barriers instead of kernel boundaries. The 16 rows are taken in sub-blocks of
+// kSubB = 4 whose running right-hand sides V(r, j) = Q(l, j) + sum_{t < l} G(c0+t, c0+l) y_t(j) stay in SHARED memory
+// (4 x q doubles over the grid: 216 KB per SM at q = 1e6), so a step reads one row of the block (x_l) and writes one (y_l-1)
+// instead of re-reading all finished rows: 72 row passes per block instead of 184.
+//   per column j and step l:  y_{l-1} = scale(w_{l-1});  V(r', j) += G(c0+l-1, c0+r') y_{l-1} for the sub-block's later rows;
+//                             w_l = max(0, x_l - V(l, j) / G(c, c)), NaN -> 0;  partial sums of w_l^2 and of the zero count
+//   barrier; every CTA adds the per-CTA partials in CTA order (same value everywhere, independent of scheduling).
+// The block's last row stays unscaled in Xb with its 1/norm in rowinfo, as the step kernels leave it.
+// ---------------------------------------------------------------------------
+constexpr int kSubB = 4;
+constexpr int kSweepThreads = 1024;
+
+// grid barrier state of the cooperative launch: bar[0] = arrival count, bar[1] = generation (both zero before the first use)
+constexpr int kSweepColsMax = 8;       // columns per thread (two groups of four): 8 x 1024 >= the 6 912 columns whose four rows fill the shared memory of an SM
+
+// sum over the CTA of two values at once; every warp ends up with the totals (one barrier, fixed order)
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* red)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    __syncthreads();                      // the previous use of red is over
+    if (lane == 0) { red[warp] = a; red[32 + warp] = b; }
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    a = warp_sum(lane < nw ? red[lane] : 0.0);
+    b = warp_sum(lane < nw ? red[32 + lane] : 0.0);
+}
+
+__global__ void __launch_bounds__(kSweepThreads, 1)
+hals_block_sweep_kernel(int k, int q, int c0, int nb, int cpc, double* __restrict__ Xb, const double* __restrict__ G,
+                        const double* __restrict__ Q, double* __restrict__ partial, double* __restrict__ rowinfo,
+                        unsigned int* __restrict__ bar, double* __restrict__ norms)
+{
+    extern __shared__ __align__(16) double sV[];           // [kSubB][cpc]
+    __shared__ double sg[kHalsB][kHalsB + 1];              // sg[l][t] = G(c0 + l, c0 + t)
+    __shared__ double red[64];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < kHalsB * kHalsB)
+    {
+        const int l = tid >> 4, t = tid & 15;
+        sg[l][t] = (l < nb && t < nb) ? G[static_cast<long long>(c0 + l) * k + c0 + t] : 0.0;
+    }
+    __syncthreads();
+    const long long j_begin = static_cast<long long>(blockIdx.x) * cpc;
+    const int ncol = static_cast<int>(max(0LL, min(static_cast<long long>(cpc), q - j_begin)));
+    const long long qq = q;
+    double* xb0 = Xb + j_begin;                            // column jl of this CTA in row t: xb0[t * qq + jl]
+    const double* q0 = Q + j_begin;
+    unsigned int parity = 0;
+    double inv_prev = 1.0;
+    bool fill_prev = false;
+    for (int l0 = 0; l0 < nb; l0 += kSubB)
+    {
+        const int ns = min(kSubB, nb - l0);
+        // right-hand sides of the sub-block from everything before it (and the scaling of row l0 - 1, whose norm is known now);
+        // two columns at a time: their 8 + 2 (l0 - 1) loads are in flight together
+        for (int jl = tid; jl < ncol; jl += 2 * kSweepThreads)
+        {
+            const int jl2 = jl + kSweepThreads;
+            const bool two = jl2 < ncol;
+            const int jb = two ? jl2 : jl;
+            double va[kSubB], vb[kSubB];
+#pragma unroll
+            for (int r = 0; r < kSubB; ++r)
+            {
+                const long long row = static_cast<long long>(l0 + min(r, ns - 1)) * qq;
+                va[r] = q0[row + jl];
+                vb[r] = q0[row + jb];
+            }
+            double ya = 0.0, yb = 0.0;
+            if (l0 > 0)
+            {
+                ya = (fill_prev ? DBL_EPSILON : sV[(kSubB - 1) * cpc + jl]) * inv_prev;
+                yb = (fill_prev ? DBL_EPSILON : sV[(kSubB - 1) * cpc + jb]) * inv_prev;
+                xb0[static_cast<long long>(l0 - 1) * qq + jl] = ya;
+                if (two) xb0[static_cast<long long>(l0 - 1) * qq + jb] = yb;
+            }
+            for (int t = 0; t < l0 - 1; ++t)
+            {
+                const double y1 = xb0[static_cast<long long>(t) * qq + jl], y2 = xb0[static_cast<long long>(t) * qq + jb];
+#pragma unroll
+                for (int r = 0; r < kSubB; ++r) { va[r] = fma(sg[l0 + r][t], y1, va[r]); vb[r] = fma(sg[l0 + r][t], y2, vb[r]); }
+            }
+            if (l0 > 0)
+            {
+#pragma unroll
+                for (int r = 0; r < kSubB; ++r) { va[r] = fma(sg[l0 + r][l0 - 1], ya, va[r]); vb[r] = fma(sg[l0 + r][l0 - 1], yb, vb[r]); }
+            }
+#pragma unroll
+            for (int r = 0; r < kSubB; ++r)
+            {
+                sV[r * cpc + jl] = va[r];
+                if (two) sV[r * cpc + jb] = vb[r];
+            }
+        }
+        for (int r = 0; r < ns; ++r)
+        {
+            const int l = l0 + r;
+            const double gcc = sg[l][l];
+            double sumsq = 0.0, zeros = 0.0;
+            double* xrow = xb0 + static_cast<long long>(l) * qq;             // row l of the block (input, old values)
+            double* yrow = xb0 + static_cast<long long>(l - 1) * qq;         // row l - 1 (output, scaled); unused when r == 0
+            const double* vcur = sV + r * cpc;
+            // G(c0 + l - 1, c0 + l0 + r2) for the sub-block's rows from r on (zero past the sub-block's end: nothing is added)
+            double gp[kSubB];
+#pragma unroll
+            for (int r2 = 0; r2 < kSubB; ++r2) gp[r2] = (r > 0 && r2 >= r && r2 < ns) ? sg[l0 + r2][l - 1] : 0.0;
+            const double scale_prev = inv_prev;
+            const bool fill = fill_prev;
+            // this thread's entries of row l in two groups (4 + 3 columns); a group's loads are all requested before its first
+            // value is used (one DRAM latency per group, not per column; the whole row at once does not fit 64 registers)
+#pragma unroll 1
+            for (int c0g = 0; c0g < kSweepColsMax; c0g += 4)
+            {
+                double xv[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                {
+                    const int jl = tid + (c0g + c) * kSweepThreads;
+                    xv[c] = xrow[ncol > 0 ? static_cast<long long>(min(jl, ncol - 1)) : -j_begin];     // always a valid address
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                {
+                    const int jl = tid + (c0g + c) * kSweepThreads;
+                    if (jl < ncol)
+                    {
+                        double v = vcur[jl];
+                        if (r > 0)
+                        {
+                            const double wp = sV[(r - 1) * cpc + jl];
+                            const double y = (fill ? DBL_EPSILON : wp) * scale_prev;
+                            yrow[jl] = y;
+                            v = fma(gp[r], y, v);
+#pragma unroll
+                            for (int r2 = 1; r2 < kSubB; ++r2)
+                                if (r2 > r && r2 < ns) sV[r2 * cpc + jl] = fma(gp[r2], y, sV[r2 * cpc + jl]);
+                        }
+                        double w = xv[c] - v / gcc;
+                        if (isnan(w) || w < 0.0) { w = 0.0; zeros += 1.0; }
+                        sV[r * cpc + jl] = w;
+                        if (l == nb - 1) xrow[jl] = w;      // the block's last row stays unscaled in Xb
+                        sumsq += w * w;
+                    }
+                }
+            }
+            block_sum2(sumsq, zeros, red);
+            double* pp = partial + parity * 2 * kSweepBlocks;
+            if (tid == 0) { pp[blockIdx.x] = sumsq; pp[kSweepBlocks + blockIdx.x] = zeros; }
+            // grid barrier; then ONE warp per CTA adds the per-CTA partials (in CTA order: the same norm on every SM) and hands
+            // the totals to the others through shared memory — all 32 warps of all CTAs reading the same ten cache lines
+            // serialised on their L2 slices (a third of the kernel's stall samples)
+            __syncthreads();
+            if (tid < 32)
+            {
+                if (tid == 0)
+                {
+                    volatile unsigned int* gen = bar + 1;
+                    const unsigned int g0 = *gen;
+                    __threadfence();
+                    if (atomicAdd(bar, 1u) == gridDim.x - 1)
+                    {
+                        bar[0] = 0u;
+                        __threadfence();
+                        atomicExch(bar + 1, g0 + 1u);
+                    }
+                    else
+                        while (*gen == g0) { }
+                    __threadfence();
+                }
+                __syncwarp();
+                double s1 = 0.0, z1 = 0.0;
+                for (int i = lane; i < static_cast<int>(gridDim.x); i += 32) { s1 += __ldcg(pp + i); z1 += __ldcg(pp + kSweepBlocks + i); }
+                s1 = warp_sum(s1);
+                z1 = warp_sum(z1);
+                if (lane == 0) { red[0] = s1; red[1] = z1; }
+            }
+            __syncthreads();
+            const double s = red[0], z = red[1];
+            fill_prev = (z == static_cast<double>(q));
+            const double norm = fill_prev ? DBL_EPSILON * sqrt(static_cast<double>(q)) : sqrt(s);
+            inv_prev = 1.0 / norm;
+            if (blockIdx.x == 0 && tid == 0)
+            {
+                norms[c0 + l] = norm;
+                rowinfo[2 * (c0 + l)] = inv_prev;
+                rowinfo[2 * (c0 + l) + 1] = fill_prev ? 1.0 : 0.0;
+            }
+            parity ^= 1u;
+        }
+    }
 }
 
 // End of the sweep: the last block goes back to X, its last row (row k-1) scaled to unit norm.
@@ -648,7 +850,18 @@ void hals_sweep(cudaStream_t stream, int k, int q, double* X, const double* G, c
         double* Xb[2] = {scratch + static_cast<size_t>(kHalsB) * q, scratch + 2 * static_cast<size_t>(kHalsB) * q};
         double* rowinfo = scratch + 3 * static_cast<size_t>(kHalsB) * q;
         unsigned int* ticket = reinterpret_cast<unsigned int*>(rowinfo + 2 * 256);
-        SMK_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), stream));
+        SMK_CUDA(cudaMemsetAsync(ticket, 0, 2 * sizeof(unsigned int), stream));
+        // phase B as one cooperative kernel per block when a CTA per SM can hold its share of 4 rows in shared memory (SMK_HALS_SWEEP=0: step kernels)
+        static const bool sweep_on = [] { const char* e = getenv("SMK_HALS_SWEEP"); return !(e && atoi(e) == 0); }();
+        const int sweep_grid = std::max(1, std::min(num_sms, ceil_div(q, 256)));
+        const int cpc = ceil_div(q, sweep_grid);
+        const size_t sweep_smem = static_cast<size_t>(kSubB) * cpc * sizeof(double);
+        const bool use_sweep = sweep_on && sweep_smem <= 216 * 1024 + 512 && sweep_grid <= kSweepBlocks && cpc <= kSweepColsMax * kSweepThreads;
+        if (use_sweep)
+        {
+            static bool attr_set = false;
+            if (!attr_set) { SMK_CUDA(cudaFuncSetAttribute(hals_block_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)); attr_set = true; }
+        }
         int cur = 0, c_last = 0;
         for (int c0 = 0; c0 < k; c0 += kHalsB, cur ^= 1)
         {
@@ -656,6 +869,17 @@ void hals_sweep(cudaStream_t stream, int k, int q, double* X, const double* G, c
                                                                             rowinfo);
             SMK_LAUNCH_CHECK();
             const int nb = std::min(kHalsB, k - c0);
+            if (use_sweep)
+            {
+                int k_ = k, q_ = q, c0_ = c0, nb_ = nb, cpc_ = cpc;
+                double* xb = Xb[cur];
+                const double* g_ = G; const double* qs_ = Qs;
+                void* args[] = {&k_, &q_, &c0_, &nb_, &cpc_, &xb, &g_, &qs_, &partial, &rowinfo, &ticket, &norms};
+                SMK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(hals_block_sweep_kernel), dim3(sweep_grid), dim3(kSweepThreads),
+                                                     args, sweep_smem, stream));
+                SMK_LAUNCH_CHECK();
+            }
+            else
             for (int l = 0; l < nb; ++l)
             {
 #define SMK_STEP(L) case L: launch_block_step<L>(stream, step_blocks, k, q, c0, Xb[cur], G, Qs, partial, rowinfo, ticket, norms); break;

@@ -377,9 +377,33 @@ RowsScratch g_rs;
 
 } // namespace
 
+namespace {
+// SMK_PRIORITY_PROF=1: seconds per section of compute_priority_rows, summed over the calls, on stderr at process exit
+struct PriorityProf
+{
+    bool on = false;
+    double t[6] = {0, 0, 0, 0, 0, 0};
+    long long calls = 0, rows = 0;
+    PriorityProf() { const char* e = getenv("SMK_PRIORITY_PROF"); on = e && atoi(e) != 0; }
+    ~PriorityProf()
+    {
+        if (on) fprintf(stderr, "compute_priority_rows: %lld calls, %lld rows of U; scan+merge %.3f s, classify %.3f s, three sorts %.3f s, weights+dcg %.3f s, "
+                                "weight sort %.3f s, ideal sum %.3f s\n", calls, rows, t[0], t[1], t[2], t[3], t[4], t[5]);
+    }
+};
+PriorityProf g_pprof;
+struct Lap
+{
+    std::chrono::steady_clock::time_point t0;
+    Lap() : t0(std::chrono::steady_clock::now()) {}
+    void mark(int i) { if (!g_pprof.on) return; const auto t1 = std::chrono::steady_clock::now(); g_pprof.t[i] += std::chrono::duration<double>(t1 - t0).count(); t0 = t1; }
+};
+} // namespace
+
 R compute_priority_rows(smk_ctx* ctx, const R* W_parent, const R* W_child, const int n, const unsigned int* child_rows, const int n_child_rows)
 {
     if (!child_rows) return compute_priority_on(ctx, W_parent, W_child, n);
+    Lap lap;
     const R* P = W_parent; const R* C1 = W_child; const R* C2 = W_child + n;
     PriorityScratch& S = g_ps;
     RowsScratch& Q = g_rs;
@@ -401,6 +425,8 @@ R compute_priority_rows(smk_ctx* ctx, const R* W_parent, const R* W_child, const
         }
     }
     const int nu = static_cast<int>(Q.u.size());
+    lap.mark(0);
+    if (g_pprof.on) { g_pprof.calls += 1; g_pprof.rows += nu; }
     Q.a1.resize(nu); Q.a2.resize(nu); Q.allzero.resize(nu);
     // one pass over U: the lists compute_priority_on builds from all m rows, with the zero-row counts in closed form
     int c1 = 0, c2 = 0;                     // positive rows of child 1 / child 2 seen so far
@@ -439,9 +465,11 @@ R compute_priority_rows(smk_ctx* ctx, const R* W_parent, const R* W_child, const
         if (!(C1[row] > 0)) S.rank_1[row] += n1;
         if (!(C2[row] > 0)) S.rank_2[row] += n2;
     }
+    lap.mark(1);
     sort_rows_desc(P, S.pos_p, ctx);
     sort_rows_desc(C1, S.pos_1, ctx);
     sort_rows_desc(C2, S.pos_2, ctx);
+    lap.mark(2);
     for (int q = 0; q < np; ++q) S.rank_p[S.pos_p[q]] = q;
     for (int q = 0; q < n1; ++q) S.rank_1[S.pos_1[q]] = q;
     for (int q = 0; q < n2; ++q) S.rank_2[S.pos_2[q]] = q;
@@ -480,6 +508,7 @@ R compute_priority_rows(smk_ctx* ctx, const R* W_parent, const R* W_child, const
     const R dcg1 = dcg(S.pos_1, S.pz_1, S.rank_1, P);
     const R dcg2 = dcg(S.pos_2, S.pz_2, S.rank_2, P);
 
+    lap.mark(3);
     // ideal score: sorted irregular weights merged with the all-zero rows' weights, last row first
     const int nw = static_cast<int>(S.wfull.size());
     if (ctx && nw >= kDeviceSortMin)
@@ -487,6 +516,7 @@ R compute_priority_rows(smk_ctx* ctx, const R* W_parent, const R* W_child, const
         if (smk_sort_desc(ctx, S.wfull.data(), nw) != SMK_OK) throw std::runtime_error(smk_last_error(ctx));
     }
     else std::sort(S.wfull.begin(), S.wfull.end(), std::greater<R>());
+    lap.mark(4);
     const R* wf = S.wfull.data();
     const double* l2 = lg2.data();
     R ideal = 0;
@@ -516,6 +546,7 @@ R compute_priority_rows(smk_ctx* ctx, const R* W_parent, const R* W_child, const
     }
     if (hi >= 0) run(hi, 0, std::max(n1, n2));
     while (head < nw) { ideal = pos == 0 ? wf[head] : ideal + wf[head] / l2[pos + 1]; ++pos; ++head; }
+    lap.mark(5);
     return (dcg1 / ideal) * (dcg2 / ideal);
 }
 
