@@ -16,7 +16,7 @@ call plus its progress-metric update (common/include/nmf_solve_generic.hpp:70-98
               (tests/golden/scale_c2_bpp.npz, 1e-9), at every rank count; later iterations against the committed single-GPU trace.
 * e2e       : the same metric through the host-buffer call a user of the reference makes (Nmf(opts, A, W, H): smk_load_dense +
               smk_nmf on pinned host buffers): upload of A, W0, H0, K iterations, download of W, H, all inside the timed region.
-* roofline  : the dominant kernel (gemm_skinny_kernel, the two A-sized contractions) against the FP64 tensor-pipe peak
+* roofline  : the dominant kernel (gemm_tma_kernel, the two A-sized contractions) against the FP64 tensor-pipe peak
               measured on this GPU by tools/dmma_peak (MEASURED_PEAKS.json has no FP64 entry).
 * cpu_baseline / --impl reference : the reference's own sources (oracle/_ref: reference code + El.hpp shim + the venv's OpenBLAS)
               on the box's host cores, on the FULL workload, iteration count bounded.
@@ -424,7 +424,7 @@ def run_c2(env, args):
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_note,
                      "algorithmic_bytes_per_launch": 8.0 * (m * n_loc + k * (m + n_loc)),
-                     "kernel": "gemm_skinny_kernel (W'A and H A', 2*k*m*n flop per launch)",
+                     "kernel": "gemm_tma_kernel (W'A and H A', 2*k*m*n flop per launch; tiles by TMA)",
                      "launch_ms": {"WtA": t_wta, "HAt": t_hat}, "peak_source": peak_src,
                      "step_frac_of_peak": flops_per_iter(m, n, k) / world / (ms_per_step * 1e-3) * 1e-12 / peak if peak else None},
         "cpu_baseline": cpu,
@@ -474,7 +474,7 @@ def run_c5(env, args):
                       "sharding": f"A,H by column block over {env.world} GPU(s)", "l2": "inputs larger than L2 (A is %.1f GB per rank)" % (8e-9 * m * n_loc)},
            "gpu_launches": launches,
            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                        "traffic": None, "kernel": "gemm_skinny_kernel (W'A and H A')", "launch_ms": {"WtA": t_wta, "HAt": t_hat},
+                        "traffic": None, "kernel": "gemm_tma_kernel (W'A and H A')", "launch_ms": {"WtA": t_wta, "HAt": t_hat},
                         "peak_source": peak_src,
                         "step_frac_of_peak": flops_per_iter(m, n, k) / env.world / (ms_per_step * 1e-3) * 1e-12 / peak if peak else None},
            "e2e": None, "e2e_note": "not measured: the reference cannot hold this matrix (32-bit offsets, SURVEY section 0) and a 40 GB "

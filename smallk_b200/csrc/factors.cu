@@ -511,7 +511,7 @@ hals_block_sweep_kernel(int k, int q, int c0, int nb, int cpc, double* __restric
                                 if (r2 > r && r2 < ns) sV[r2 * cpc + jl] = fma(gp[r2], y, sV[r2 * cpc + jl]);
                         }
                         double w = xv[c] - v / gcc;
-                        if (isnan(w) || w < 0.0) { w = 0.0; zeros += 1.0; }
+                        if (!(w >= 0.0)) { w = 0.0; zeros += 1.0; }           // NaN or negative (-0.0 passes, as in the reference's test)
                         sV[r * cpc + jl] = w;
                         if (l == nb - 1) xrow[jl] = w;      // the block's last row stays unscaled in Xb
                         sumsq += w * w;

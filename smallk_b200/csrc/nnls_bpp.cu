@@ -646,6 +646,12 @@ __global__ void nnls_bpp_slow_kernel(int k, const double* __restrict__ LHS, long
     }
 }
 
+// the work counters of the two kernels and the per-call flags
+__global__ void nnls_reset_kernel(unsigned int* __restrict__ counter, int* __restrict__ status)
+{
+    if (threadIdx.x == 0) { counter[0] = 0u; counter[1] = 0u; status[ST_ANY_NONOPT] = 0; status[ST_DEFER_COUNT] = 0; }
+}
+
 // Finishes ZeroizeSmallValues(X), ZeroizeSmallValues(Y) for columns that never entered the pivot loop;
 // a no-op unless some column was non-optimal.
 __global__ void zeroize_if_flag_kernel(const int* __restrict__ status, int k, long long q,
@@ -702,9 +708,8 @@ void nnls_bpp(cudaStream_t stream, int k, int q, const double* LHS, long long ld
               int* status, unsigned int* counter, void* deferred, int outer_iter, int num_sms,
               const double* Ginv, const int* ginv_flag)
 {
-    SMK_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned int), stream));
-    SMK_CUDA(cudaMemsetAsync(&status[ST_ANY_NONOPT], 0, sizeof(int), stream));
-    SMK_CUDA(cudaMemsetAsync(&status[ST_DEFER_COUNT], 0, sizeof(int), stream));
+    nnls_reset_kernel<<<1, 32, 0, stream>>>(counter, status);     // one launch instead of three memsets (the solves of a small shard are latency)
+    SMK_LAUNCH_CHECK();
     if (q <= 0) return;          // a rank may own no rows; the flags above are still reset for the reduction that follows
     if (!Ginv && k > 32)
     {
