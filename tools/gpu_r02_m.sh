@@ -21,4 +21,4 @@ PY
 }
 run plain "$EXTRAS_PLAIN"
 run phases "--no-extras --no-e2e" SMK_PHASES=1
-run phases_nosidegram "--no-extras --no-e2e" SMK_PHASES=1 SMK_SIDE_GRAM=0
+[ -n "$SKIP_NOSIDEGRAM" ] || run phases_nosidegram "--no-extras --no-e2e" SMK_PHASES=1 SMK_SIDE_GRAM=0
