@@ -852,7 +852,8 @@ void hals_sweep(cudaStream_t stream, int k, int q, double* X, const double* G, c
         unsigned int* ticket = reinterpret_cast<unsigned int*>(rowinfo + 2 * 256);
         SMK_CUDA(cudaMemsetAsync(ticket, 0, 2 * sizeof(unsigned int), stream));
         // phase B as one cooperative kernel per block when a CTA per SM can hold its share of 4 rows in shared memory (SMK_HALS_SWEEP=0: step kernels)
-        static const bool sweep_on = [] { const char* e = getenv("SMK_HALS_SWEEP"); return !(e && atoi(e) == 0); }();
+        const char* sweep_env = getenv("SMK_HALS_SWEEP");          // read per call: the tests run both forms in one process
+        const bool sweep_on = !(sweep_env && atoi(sweep_env) == 0);
         const int sweep_grid = std::max(1, std::min(num_sms, ceil_div(q, 256)));
         const int cpc = ceil_div(q, sweep_grid);
         const size_t sweep_smem = static_cast<size_t>(kSubB) * cpc * sizeof(double);

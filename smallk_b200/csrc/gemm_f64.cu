@@ -615,7 +615,8 @@ void gemm_f64(cudaStream_t stream, bool nt, int M, int N, int R,
     if (fix) grid = dim3(static_cast<unsigned int>(tiles * splits), 1, 1);
 
     // the A-sized contractions: tiles by TMA (SMK_GEMM_TMA=0 keeps the cp.async kernel: measurements)
-    static const bool tma_on = [] { const char* e = getenv("SMK_GEMM_TMA"); return !(e && atoi(e) == 0); }();
+    const char* tma_env = getenv("SMK_GEMM_TMA");                  // read per call: the tests run both kernels in one process
+    const bool tma_on = !(tma_env && atoi(tma_env) == 0);
     bool launched = false;
     if (tma_on && vec2 && workspace && R >= 4 * BK && M * static_cast<long long>(N) > 65536 && lda < (1LL << 36) && ldb < (1LL << 36))
     {

@@ -34,6 +34,7 @@ def rel(a, b):
     (True, False, 128, 700, 1000),    # the TMA kernel: two M tiles
     (True, False, 72, 1000, 1000),    # the TMA kernel: ragged M (zero-filled boxes)
     (False, True, 40, 2000, 777),     # the TMA kernel: NT, M < one tile, odd reduction length
+    (False, True, 64, 1302, 2050),    # the TMA kernel: NT, N even but not a multiple of the 8-wide boxes
     (True, False, 72, 1000, 999),     # odd leading dimension: back to the cp.async kernel
 ])
 def test_gemm_matches_numpy(gpu, tA, tB, M, N, K):
@@ -51,6 +52,17 @@ def test_gemm_in_kernel_split_reduction_matches_numpy(gpu, tB, M, N, K, monkeypa
     there) forced on one GPU, TMA and cp.async main loops."""
     monkeypatch.setenv("SMK_GEMM_FIXUP", "1")
     rng = np.random.default_rng(M + N + K)
+    A = rng.random((K, M))
+    B = rng.random((N, K) if tB else (K, N))
+    ref = A.T @ (B.T if tB else B)
+    assert rel(gpu.gemm(A, B, transA=True, transB=tB), ref) < REL_PRIM
+
+
+@pytest.mark.parametrize("tB,M,N,K", [(False, 64, 1300, 4100), (True, 64, 1304, 2052)])
+def test_gemm_cp_async_kernel_on_a_sized_products_matches_numpy(gpu, tB, M, N, K, monkeypatch):
+    """SMK_GEMM_TMA=0: the cp.async kernel (the fallback for unaligned operands) on shapes the TMA kernel normally takes."""
+    monkeypatch.setenv("SMK_GEMM_TMA", "0")
+    rng = np.random.default_rng(M + N + K + 1)
     A = rng.random((K, M))
     B = rng.random((N, K) if tB else (K, N))
     ref = A.T @ (B.T if tB else B)
@@ -183,6 +195,24 @@ def test_dense_trace_matches_oracle(gpu, oracle, alg, m, n, k, iters, prog):
         assert abs(metrics[i] - o["metrics"][i]) <= mtol * abs(o["metrics"][i]), (i, metrics[i], o["metrics"][i])
 
 
+@pytest.mark.parametrize("m,n,k,iters", [(260, 200, 40, 15), (3000, 150, 72, 6)])
+def test_hals_w_side_step_kernels_match_oracle(gpu, oracle, m, n, k, iters, monkeypatch):
+    """SMK_HALS_SWEEP=0: the W-side sweep with one launch per step (the form used when the rows of W do not fit the shared memory
+    of the grid) instead of the cooperative block sweep the other HALS tests run."""
+    monkeypatch.setenv("SMK_HALS_SWEEP", "0")
+    rng = np.random.default_rng(m + 3 * n + k)
+    A = rng.random((m, n)); W0 = rng.random((m, k)); H0 = rng.random((k, n)) * (2.0 / k)
+    o = oracle.nmf_dense(A, W0, H0, alg="HALS", prog="DELTA_FNORM", tol=1e-12, min_iter=1, max_iter=iters, trace=True)
+    assert o["rc"] == 0
+    gpu.load_dense(A)
+    opts = sk.make_options(m, n, k, algorithm="HALS", prog="DELTA_FNORM", tol=1e-12, min_iter=1, max_iter=iters, normalize=False)
+    metrics, Ws, Hs = _trace_gpu(gpu, W0, H0, opts, iters)
+    for i in range(iters):
+        assert rel(Ws[i], o["W_trace"][i]) < REL_FACTOR, (i, rel(Ws[i], o["W_trace"][i]))
+        assert rel(Hs[i], o["H_trace"][i]) < REL_FACTOR, (i, rel(Hs[i], o["H_trace"][i]))
+        assert abs(metrics[i] - o["metrics"][i]) <= REL_FACTOR * abs(o["metrics"][i]), (i, metrics[i], o["metrics"][i])
+
+
 @pytest.mark.parametrize("alg,k", [("BPP", 16), ("HALS", 16), ("MU", 8)])
 def test_nmf_call_matches_oracle(gpu, oracle, alg, k):
     """The one-call interface (Nmf): stopping rule, iteration count, final normalisation."""
@@ -197,6 +227,21 @@ def test_nmf_call_matches_oracle(gpu, oracle, alg, k):
     assert st.iteration_count == o["iterations"]
     assert rel(W, o["W"]) < REL_FACTOR and rel(H, o["H"]) < REL_FACTOR
     assert np.allclose(np.linalg.norm(W, axis=0), 1.0, atol=1e-12)
+
+
+def test_nmf_call_with_tma_sized_products_matches_oracle(gpu, oracle):
+    """smk_nmf (the stop-tested loop as one CUDA graph) on a problem whose A-sized products are large enough for the TMA kernel:
+    the tensor maps are kernel parameters of the captured launches."""
+    m, n, k = 1500, 1200, 64
+    rng = np.random.default_rng(5)
+    A = rng.random((m, n)); W0 = rng.random((m, k)); H0 = rng.random((k, n))
+    kw = dict(tol=1e-9, min_iter=3, max_iter=10)            # ten iterations (the limit is a normal exit)
+    o = oracle.nmf_dense(A, W0, H0, alg="BPP", normalize=True, **kw)
+    gpu.load_dense(A)
+    opts = sk.make_options(m, n, k, algorithm="BPP", normalize=True, **kw)
+    W, H, st = gpu.nmf(W0, H0, opts)
+    assert st.iteration_count == o["iterations"]
+    assert rel(W, o["W"]) < REL_FACTOR and rel(H, o["H"]) < REL_FACTOR
 
 
 # ---------------------------------------------------------------------------
