@@ -90,18 +90,26 @@ def test_select_columns_is_submatrix_cols_compact(gpu):
     gpu.select_all()
 
 
-def test_nnls_hals_matches_reference_fixture_shape(gpu, oracle):
-    """smk_nnls_hals (NnlsHals, nnls.hpp:249-316): converges and leaves unit-norm W columns, nonnegative H."""
+def test_nnls_hals_matches_restated_reference_loop(gpu, oracle):
+    """smk_nnls_hals (NnlsHals, nnls.hpp:249-316): converges, leaves unit-norm W columns and nonnegative H, and takes the same
+    number of iterations to the same factors as the NumPy restatement of the reference's loop (oracle/nnls_hals_oracle.py)."""
     rng = np.random.default_rng(9)
     m, n, k = 200, 150, 6
     Wt = rng.random((m, k)); Ht = rng.random((k, n)) * (rng.random((k, n)) < 0.4)
     A = Wt @ Ht
     gpu.load_dense(A)
-    rc, W, H, it = gpu.nnls_hals(Wt, rng.random((k, n)), 1e-6, 5000)
+    H0 = rng.random((k, n))
+    rc, W, H, it = gpu.nnls_hals(Wt, H0, 1e-6, 5000)
     assert rc == 0 and it > 1
     assert np.allclose(np.linalg.norm(W, axis=0), 1.0, rtol=1e-12)
     assert H.min() >= 0.0
     assert np.linalg.norm(W @ H - A) <= 1e-4 * np.linalg.norm(A)
+    # and against the restatement of the reference's loop: same iteration count, same factors
+    from oracle.nnls_hals_oracle import nnls_hals
+    ok, Wo, Ho, ito = nnls_hals(A, Wt, H0, 1e-6, 5000)
+    assert ok and ito == it, (ito, it)
+    assert np.linalg.norm(W - Wo) <= 1e-9 * np.linalg.norm(Wo)
+    assert np.linalg.norm(H - Ho) <= 1e-9 * np.linalg.norm(Ho)
 
 
 def test_priority_score_with_device_sorts_is_bit_identical():
