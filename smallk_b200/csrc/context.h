@@ -155,6 +155,11 @@ struct smk_ctx
     std::vector<std::pair<const char*, cudaEvent_t>> phase_marks;
     std::vector<cudaEvent_t> phase_pool;
     size_t phase_pool_used = 0;
+    // HALS on several GPUs: the W sweep is replicated (its in-sweep norms couple the rows), but W'W and gradW are formed from this
+    // rank's block of x_loc rows only (Gram partials summed over the ranks, PG sum over own rows)
+    bool grad_sharded = false;
+    int g_row0() const { return rank * x_loc; }
+    int g_rows() const { const int r = m - rank * x_loc; return r < 0 ? 0 : (r < x_loc ? r : x_loc); }
     int w_row0() const { return rank * m_loc; }
     int w_rows() const { const int r = m - rank * m_loc; return r < 0 ? 0 : (r < m_loc ? r : m_loc); }
 };
