@@ -13,6 +13,5 @@ SMK_PHASES=1 timeout 300 python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu
 timeout 300 python bench.py --steps 100 --warmup 5 --no-extras --no-cpu-baseline > gpurun_out/a_bench_100.json 2> gpurun_out/a_bench_100.err; echo "bench100 rc=$?"
 SMK_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "pipelined or slabs or residency" > gpurun_out/a_pytest_experimental.log 2>&1
 echo "experimental pytest rc=$?" >> gpurun_out/a_pytest_experimental.log; tail -3 gpurun_out/a_pytest_experimental.log
-SMK_SPMM_PIPE=1 timeout 400 python bench.py --workload c3 --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/a_c3_pipe.json 2> gpurun_out/a_c3_pipe.err; echo "c3 pipe rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/a_launches_bench_c2.csv python bench.py --steps 2 --warmup 3 --no-extras --no-e2e --no-cpu-baseline > gpurun_out/a_ncu_bench.log 2>&1; echo "ncu rc=$?"
 ls -la gpurun_out | tail -20
