@@ -618,7 +618,9 @@ void gemm_f64(cudaStream_t stream, bool nt, int M, int N, int R,
     const char* tma_env = getenv("SMK_GEMM_TMA");                  // read per call: the tests run both kernels in one process
     const bool tma_on = !(tma_env && atoi(tma_env) == 0);
     bool launched = false;
-    if (tma_on && vec2 && workspace && R >= 4 * BK && M * static_cast<long long>(N) > 65536 && lda < (1LL << 36) && ldb < (1LL << 36))
+    const char* tma_small_env = getenv("SMK_GEMM_TMA_SHORT");      // =0: products with a short reduction and no split (G * X - R) stay on the cp.async kernel
+    const bool tma_short = !(tma_small_env && atoi(tma_small_env) == 0);
+    if (tma_on && vec2 && (workspace || tma_short) && R >= 4 * BK && M * static_cast<long long>(N) > 65536 && lda < (1LL << 36) && ldb < (1LL << 36))
     {
         CUtensorMap mapA, mapB;
         const bool ok = make_map_2d(&mapA, A, M, R, lda, 8, BK) &&
