@@ -15,7 +15,6 @@
 #include <limits>
 #include <sstream>
 #include <stdexcept>
-#include <thread>
 
 #include "host_internal.hpp"
 #include "matrix_io.hpp"
@@ -412,17 +411,7 @@ R compute_priority_rows(smk_ctx* ctx, const R* W_parent, const R* W_child, const
     if (static_cast<int>(S.rank_p.size()) < n) { S.rank_p.resize(n); S.rank_1.resize(n); S.rank_2.resize(n); }
     // U = non-zero rows of the parent vector, merged with the child's rows
     Q.pnz.clear();
-    {
-        // deep nodes: the parent vector is zero almost everywhere, so eight entries are tested at once before any is looked at
-        int i = 0;
-        for (; i + 8 <= n; i += 8)
-        {
-            const bool any = (P[i] != 0) | (P[i + 1] != 0) | (P[i + 2] != 0) | (P[i + 3] != 0) | (P[i + 4] != 0) | (P[i + 5] != 0) | (P[i + 6] != 0) | (P[i + 7] != 0);
-            if (!any) continue;
-            for (int t = i; t < i + 8; ++t) if (P[t] != 0) Q.pnz.push_back(t);
-        }
-        for (; i < n; ++i) if (P[i] != 0) Q.pnz.push_back(i);
-    }
+    for (int i = 0; i < n; ++i) if (P[i] != 0) Q.pnz.push_back(i);
     Q.u.clear();
     {
         size_t a = 0; int b = 0;
@@ -516,14 +505,8 @@ R compute_priority_rows(smk_ctx* ctx, const R* W_parent, const R* W_child, const
         }
         return cum;
     };
-    // the two DCG sums read what is final by now (orderings, ranks, wpart) and write nothing shared: on a large node they run on
-    // a second host thread while this one sorts the weights and adds the ideal sum (each is a sequential sum by definition)
-    R dcg1 = 0, dcg2 = 0;
-    std::thread worker;
-    const bool threaded = nu >= 20000;
-    if (threaded) worker = std::thread([&] { dcg1 = dcg(S.pos_1, S.pz_1, S.rank_1, P); dcg2 = dcg(S.pos_2, S.pz_2, S.rank_2, P); });
-    else { dcg1 = dcg(S.pos_1, S.pz_1, S.rank_1, P); dcg2 = dcg(S.pos_2, S.pz_2, S.rank_2, P); }
-    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{worker};
+    const R dcg1 = dcg(S.pos_1, S.pz_1, S.rank_1, P);
+    const R dcg2 = dcg(S.pos_2, S.pz_2, S.rank_2, P);
 
     lap.mark(3);
     // ideal score: sorted irregular weights merged with the all-zero rows' weights, last row first
@@ -563,7 +546,6 @@ R compute_priority_rows(smk_ctx* ctx, const R* W_parent, const R* W_child, const
     }
     if (hi >= 0) run(hi, 0, std::max(n1, n2));
     while (head < nw) { ideal = pos == 0 ? wf[head] : ideal + wf[head] / l2[pos + 1]; ++pos; ++head; }
-    if (worker.joinable()) worker.join();
     lap.mark(5);
     return (dcg1 / ideal) * (dcg2 / ideal);
 }
