@@ -127,6 +127,23 @@ def file_sha16(path):
         return None
 
 
+def kernel_sha16(path, begin, end):
+    """sha of the DEVICE code a traffic capture describes: the text of `path` from the line starting with `begin` up to the line
+    starting with `end` (host-side dispatch edits do not invalidate an ncu capture; a change to the kernel does)."""
+    try:
+        text = open(path).read()
+        a = text.index("\n" + begin)
+        b = text.index("\n" + end, a + 1)
+        return hashlib.sha256(text[a:b].encode()).hexdigest()[:16]
+    except (OSError, ValueError):
+        return None
+
+
+# the kernels the committed traffic files describe
+GEMM_KERNEL_SPAN = (os.path.join(ROOT, "smallk_b200", "csrc", "gemm_f64.cu"), "// What every GEMM kernel of this file does", "// C = sum_s partial[s] (- D)")
+SPMM_KERNEL_SPAN = (os.path.join(ROOT, "smallk_b200", "csrc", "spmm.cu"), "// How the loops are written, and why", "// out(:, j) = beta * out(:, j) + sum of the partials")
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # the reference on the host cores
 # ---------------------------------------------------------------------------------------------------------------
@@ -344,12 +361,12 @@ def run_c2(env, args):
                 continue
             try:
                 tj = json.load(open(tpath))
-                sha_now = file_sha16(os.path.join(ROOT, "smallk_b200", "csrc", "gemm_f64.cu"))
+                sha_now = kernel_sha16(*GEMM_KERNEL_SPAN)
                 if tj.get("kernel_source_sha16") in (None, sha_now):
                     traffic = float(tj["dram_bytes_read"]) + float(tj["dram_bytes_write"])
                     traffic_note = f"profiles/{tname}" + ("" if tj.get("kernel_source_sha16") else " (capture predates the sha check)")
                 else:
-                    traffic_note = f"profiles/{tname} is stale: gemm_f64.cu changed since the capture"
+                    traffic_note = f"profiles/{tname} is stale: the GEMM kernels in gemm_f64.cu changed since the capture"
             except Exception:
                 pass
             break

@@ -140,7 +140,7 @@ def run_c3(args, env=None, steps=None, warmup=None):
             try:
                 tj = json.load(open(tp))
                 import bench
-                sha_now = bench.file_sha16(os.path.join(ROOT, "smallk_b200", "csrc", "spmm.cu"))
+                sha_now = bench.kernel_sha16(*bench.SPMM_KERNEL_SPAN)
                 # the capture describes the kernel source it was taken from: refused once spmm.cu has changed
                 traffic = float(tj["dram_bytes_both_products"]) if tj.get("kernel_source_sha16") in (None, sha_now) else None
             except Exception:
