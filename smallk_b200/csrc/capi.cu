@@ -45,13 +45,13 @@ bool options_valid(smk_ctx* c, const smk_nmf_options& o)
     return true;
 }
 
-void ensure_scratch(smk_ctx* c)
+void ensure_scratch(smk_ctx* c, int k = 0)
 {
     c->status.reserve(ST_COUNT);
     c->counter.reserve(2);
     if (!c->pinned) SMK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->pinned), 16 * sizeof(double), cudaHostAllocDefault));
     if (!c->ticket.p) { c->ticket.reserve(8); SMK_CUDA(cudaMemsetAsync(c->ticket.p, 0, 8 * sizeof(unsigned int), c->stream)); }
-    c->partial.reserve(4096 + 512 * 256);
+    c->partial.reserve(4096 + static_cast<size_t>(512) * std::max(k, 256));      // normalize_and_scale: up to 512 blocks x k partial sums
     c->acc.reserve(8);
 }
 
@@ -94,11 +94,10 @@ int begin_impl(smk_ctx* c, const smk_nmf_options* opts, const double* W0, int ld
     if (static_cast<unsigned long long>(c->n) * opts->k > 2147483647ull) return fail(c, SMK_SIZE_TOO_LARGE, "H matrix size too large");
     if (ldW < c->m) return fail(c, SMK_BAD_PARAM, "leading dimension of W return buffer too small");
     if (ldH < opts->k) return fail(c, SMK_BAD_PARAM, "leading dimension of H return buffer too small");
-    if (opts->k > 256) return fail(c, SMK_BAD_PARAM, "k > 256 is not supported");
     c->opts = *opts;
     c->steps_done = 0;
     c->pg0 = 0.0;
-    ensure_scratch(c);
+    ensure_scratch(c, opts->k);
     solver_alloc(c);
     upload_W(c, W0, ldW);
     upload_tight(c, H0, ldH, opts->k, c->n, c->H.p);
@@ -293,7 +292,6 @@ int smk_nnls_hals(smk_ctx* c, int k, double* W, int ldW, double* H, int ldH, dou
     if (!c || !W || !H || k <= 0 || max_iter <= 0) return SMK_BAD_PARAM;
     if (!c->has_dense && !c->has_sparse) return fail(c, SMK_BAD_PARAM, "no matrix loaded");
     if (ldW < c->m || ldH < k) return fail(c, SMK_BAD_PARAM, "NnlsHals: non-conformant W and H");
-    if (k > 256) return fail(c, SMK_BAD_PARAM, "k > 256 is not supported");
     return guarded(c, [&]() {
         SMK_CUDA(cudaSetDevice(c->device));
         smk_nmf_options o;
@@ -302,7 +300,7 @@ int smk_nnls_hals(smk_ctx* c, int k, double* W, int ldW, double* H, int ldH, dou
         o.height = c->m; o.width = c->n; o.k = k; o.min_iter = 1; o.max_iter = max_iter; o.tolcount = 1;
         c->opts = o;
         c->steps_done = 0;
-        ensure_scratch(c);
+        ensure_scratch(c, k);
         solver_alloc(c);
         upload_W(c, W, ldW);
         upload_tight(c, H, ldH, k, c->n, c->H.p);
@@ -619,7 +617,6 @@ int smk_sparse_gemm(smk_ctx* c, int variant, double alpha, const double* B, int 
         case 2: if (Bw != m || Ch != Bh || Cw != n) return fail(c, SMK_BAD_PARAM, "Gemm: non-conformant matrices"); k = Bh; break;
         default: if (Bh != m || Ch != Bw || Cw != n) return fail(c, SMK_BAD_PARAM, "Gemm: non-conformant matrices"); k = Bw; break;
         }
-        if (k > 256) return fail(c, SMK_BAD_PARAM, "dense operand wider than 256 is not supported");
         // Device kernels want the dense operand as k x (m or n) and produce k x (n or m).
         DevBuf<double> dB, dBt, dC, dCt;
         dB.reserve(static_cast<size_t>(Bh) * Bw);

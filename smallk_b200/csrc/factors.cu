@@ -9,7 +9,7 @@ namespace smk {
 
 namespace {
 
-constexpr int kMaxKPL = 8;          // rows per lane: k <= 256
+constexpr int kMaxKPL = 8;          // rows per lane of the register kernels: k <= 256 (larger k: the *_big fallback kernels)
 constexpr int kSweepBlocks = 2048;  // upper bound on the grid of the per-row sweep kernels
 
 __device__ __forceinline__ double block_sum_f(double v, double* red)
@@ -138,6 +138,103 @@ __global__ void hals_sweep_row_kernel(int k, int q, int r, double* __restrict__ 
         }
         s = warp_sum(s);
         xr = __shfl_sync(0xffffffffu, xr, r & 31);   // only the owning lane had it; others hold 0 -> take owner's
+        if (lane == 0)
+        {
+            double w = xr + (__ldg(R + j * k + r) - s) / grr;
+            if (isnan(w) || w < 0.0) { w = 0.0; zeros += 1.0; }
+            xcol[r] = w;
+            sumsq += w * w;
+        }
+    }
+    sumsq = block_sum_f(sumsq, red);
+    zeros = block_sum_f(zeros, red);
+    if (threadIdx.x == 0)
+    {
+        double* pc = partial + (r & 1) * 2 * kSweepBlocks;
+        pc[blockIdx.x] = sumsq;
+        pc[kSweepBlocks + blockIdx.x] = zeros;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// k > 256 (no k-vector fits the registers of a warp): the same two sweeps with runtime loops over the rows. Fallback
+// forms — correct for any k, not tuned: the H side walks a column in place (it stays in L1 for the k steps of its warp),
+// the W side is k + 1 dependent launches, each of which re-reads X.
+// ---------------------------------------------------------------------------
+__global__ void hals_sweep_cols_big_kernel(int k, int q, double* X, const double* __restrict__ G, const double* __restrict__ R)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    for (long long j = blockIdx.x * static_cast<long long>(warps_per_block) + (threadIdx.x >> 5); j < q;
+         j += static_cast<long long>(gridDim.x) * warps_per_block)
+    {
+        double* xcol = X + j * k;
+        const double* rcol = R + j * k;
+        for (int r = 0; r < k; ++r)
+        {
+            const double* gcol = G + static_cast<long long>(r) * k;
+            double s = 0.0;
+            for (int p = lane; p < k; p += 32) s += __ldg(gcol + p) * xcol[p];
+            s = warp_sum(s);
+            double h = xcol[r] + (__ldg(rcol + r) - s) / __ldg(gcol + r);
+            if (isnan(h) || h < 0.0) h = 0.0;
+            __syncwarp();                       // every lane has read the old column
+            if (lane == 0) xcol[r] = h;
+            __syncwarp();                       // ... and sees the new entry in the next step
+        }
+    }
+}
+
+// pass r of the W-side sweep: same two halves and the same partial layout as hals_sweep_row_kernel
+__global__ void hals_sweep_row_big_kernel(int k, int q, int r, double* X, const double* __restrict__ G,
+                                          const double* __restrict__ R, double* __restrict__ partial, int nblocks_prev,
+                                          double* __restrict__ norms)
+{
+    __shared__ double red[32];
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    double inv_prev = 1.0;
+    bool fill_prev = false;
+    if (r > 0)
+    {
+        const double* pp = partial + ((r - 1) & 1) * 2 * kSweepBlocks;
+        double s = 0.0, z = 0.0;
+        for (int i = threadIdx.x; i < nblocks_prev; i += blockDim.x) { s += pp[i]; z += pp[kSweepBlocks + i]; }
+        s = block_sum_f(s, red);
+        z = block_sum_f(z, red);
+        double norm;
+        if (z == static_cast<double>(q)) { fill_prev = true; norm = DBL_EPSILON * sqrt(static_cast<double>(q)); }
+        else norm = sqrt(s);
+        inv_prev = 1.0 / norm;
+        if (blockIdx.x == 0 && threadIdx.x == 0) norms[r - 1] = norm;
+    }
+    if (r == k)
+    {
+        for (long long j = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; j < q;
+             j += static_cast<long long>(gridDim.x) * blockDim.x)
+        {
+            double* px = X + j * k + (k - 1);
+            *px = (fill_prev ? DBL_EPSILON : *px) * inv_prev;
+        }
+        return;
+    }
+    double sumsq = 0.0, zeros = 0.0;
+    const double* grow = G + static_cast<long long>(r) * k;
+    const double grr = __ldg(grow + r);
+    for (long long j = blockIdx.x * static_cast<long long>(warps_per_block) + (threadIdx.x >> 5); j < q;
+         j += static_cast<long long>(gridDim.x) * warps_per_block)
+    {
+        double* xcol = X + j * k;
+        double s = 0.0, xr = 0.0;
+        for (int p = lane; p < k; p += 32)
+        {
+            double xv = xcol[p];
+            if (p == r - 1) { xv = (fill_prev ? DBL_EPSILON : xv) * inv_prev; xcol[p] = xv; }
+            if (p == r) xr = xv;
+            s += __ldg(grow + p) * xv;
+        }
+        s = warp_sum(s);
+        xr = __shfl_sync(0xffffffffu, xr, r & 31);
         if (lane == 0)
         {
             double w = xr + (__ldg(R + j * k + r) - s) / grr;
@@ -766,6 +863,19 @@ __global__ void row_sumsq_kernel(int k, int q, const double* __restrict__ X, dou
     }
 }
 
+// the same partial sums for k > 256: a thread per row, the block's share of the columns in column order
+__global__ void row_sumsq_big_kernel(int k, int q, const double* __restrict__ X, double* __restrict__ partial)
+{
+    const long long per = (static_cast<long long>(q) + gridDim.x - 1) / gridDim.x;
+    const long long j0 = blockIdx.x * per, j1 = (j0 + per < q) ? j0 + per : q;
+    for (int p = threadIdx.x; p < k; p += blockDim.x)
+    {
+        double s = 0.0;
+        for (long long j = j0; j < j1; ++j) { const double v = X[j * k + p]; s += v * v; }
+        partial[static_cast<long long>(blockIdx.x) * k + p] = s;
+    }
+}
+
 __global__ void norms_finalize_kernel(int k, int nblocks, const double* __restrict__ partial, double* __restrict__ norms,
                                       int* __restrict__ status, double* __restrict__ HHt)
 {
@@ -809,7 +919,7 @@ void dispatch_kpl(int k, F&& f)
     else if (k <= 64) f(std::integral_constant<int, 2>());
     else if (k <= 128) f(std::integral_constant<int, 4>());
     else if (k <= 256) f(std::integral_constant<int, 8>());
-    else throw std::string("k > 256 is not supported");
+    else throw std::string("dispatch_kpl: k > 256 takes the fallback kernels");
 }
 
 int ew_blocks(long long total, int num_sms) { return static_cast<int>(std::max<long long>(1, std::min<long long>((total + 255) / 256, 8LL * num_sms))); }
@@ -836,6 +946,26 @@ void hals_sweep(cudaStream_t stream, int k, int q, double* X, const double* G, c
     const int threads = 256, wpb = threads / 32;
     const char* dbg = getenv("SMK_HALS_DEBUG");
     const int dbgv = dbg ? atoi(dbg) : 0;
+    if (k > kMaxKPL * 32)
+    {
+        // any k: the fallback kernels (runtime loops over the rows of a column)
+        if (!normalize_rows)
+        {
+            const int blocks = std::max(1, std::min(ceil_div(q, wpb), 8 * num_sms));
+            hals_sweep_cols_big_kernel<<<blocks, threads, 0, stream>>>(k, q, X, G, R);
+            SMK_LAUNCH_CHECK();
+        }
+        else
+        {
+            const int blocks = std::max(1, std::min(std::min(ceil_div(q, wpb), 4 * num_sms), kSweepBlocks));
+            for (int r = 0; r <= k; ++r)
+            {
+                hals_sweep_row_big_kernel<<<blocks, threads, 0, stream>>>(k, q, r, X, G, R, partial, blocks, norms);
+                SMK_LAUNCH_CHECK();
+            }
+        }
+        return;
+    }
     if (normalize_rows && scratch && k >= 8 && !(dbgv & 1))
     {
         // blocked sweep (see hals_block_outer_kernel)
@@ -941,8 +1071,14 @@ void normalize_and_scale(cudaStream_t stream, int k, int m, int n, double* Wt, d
                          int* status, double* partial, int num_sms, double* HHt, double* HAt)
 {
     const int threads = 256, wpb = threads / 32;
-    // partial must hold blocks*k doubles: the context allocates 4096 + 512*k, so cap the grid at 512
+    // partial must hold blocks*k doubles: the context allocates 4096 + 512 * max(k, 256), so cap the grid at 512
     int blocks = std::max(1, std::min(std::min(ceil_div(m, wpb), 2 * num_sms), 512));
+    if (k > kMaxKPL * 32)
+    {
+        row_sumsq_big_kernel<<<blocks, threads, 0, stream>>>(k, m, Wt, partial);
+        SMK_LAUNCH_CHECK();
+    }
+    else
     dispatch_kpl(k, [&](auto kpl) {
         constexpr int KPL = decltype(kpl)::value;
         row_sumsq_kernel<KPL><<<blocks, threads, wpb * k * sizeof(double), stream>>>(k, m, Wt, partial);

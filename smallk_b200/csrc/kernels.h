@@ -50,6 +50,8 @@ void nnls_bpp(cudaStream_t stream, int k, int q, const double* LHS, long long ld
 // nnls_bpp forms them itself on `stream`. The solvers run it on a side stream under the big product preceding the solve.
 void nnls_prepare_inverse(cudaStream_t stream, int k, const double* LHS, long long ldl, double* Ginv, int* ok);
 size_t nnls_deferred_bytes(int q, int k, int num_sms);
+// does nnls_bpp use G^-1 at this k? (32 < k <= 256: the complement path of the register / shared-memory kernels)
+inline bool nnls_uses_inverse(int k) { return k > 32 && k <= 256; }
 void nnls_bpp_finish(cudaStream_t stream, int k, int q, double* X, long long ldx, double* Y, long long ldy, int* status, int num_sms);
 
 // ---- elementwise.cu -------------------------------------------------------
@@ -100,6 +102,7 @@ void spmm_gather(cudaStream_t stream, int ncols, const unsigned int* ptr, const 
                  int k, const double* B, long long ldb, double alpha, double beta, double* out, long long ldo, int num_sms);
 struct SegTable;
 constexpr int kSpmmSeg = 512;
+constexpr int kSpmmMaxK = 256;        // rows of the dense operand one kernel pass holds per warp; a wider operand goes in row blocks
 // Segment table of a compressed matrix (ncols compressed columns, offsets ptr[ncols + 1]); synchronises the stream.
 void build_segments(cudaStream_t stream, int ncols, const unsigned int* ptr, SegTable& T, int num_sms);
 // Same product as spmm_gather, one work item per segment; columns cut into several segments are summed from

@@ -678,12 +678,16 @@ void nnls_bpp_wide(cudaStream_t stream, int k, int q, const double* LHS, long lo
                    double* X, long long ldx, double* Y, long long ldy, int* status, unsigned int* counter, void* scratch,
                    int outer_iter, int num_sms, const double* Ginv, const int* ginv_flag);
 void invert_spd_global(cudaStream_t stream, int k, const double* G, long long ldg, double* Ginv, int* ok);
+size_t nnls_big_scratch_bytes(int k, int num_sms);
+void nnls_bpp_big(cudaStream_t stream, int k, int q, const double* LHS, long long ldl, const double* RHS, long long ldr,
+                  double* X, long long ldx, double* Y, long long ldy, int* status, unsigned int* counter, void* scratch,
+                  int outer_iter, int num_sms);
 
 // G^-1 (k x k, tight) and its success flag for nnls_bpp: one launch, meant to run on a side stream under the big product that
 // precedes the NNLS solve (solver.cu). Not needed (and not computed) for k <= 32, where every passive-set system is solved directly.
 void nnls_prepare_inverse(cudaStream_t stream, int k, const double* LHS, long long ldl, double* Ginv, int* ok)
 {
-    if (k <= 32) return;
+    if (!nnls_uses_inverse(k)) return;
     if (k <= kInvSmemMaxK)
     {
         const size_t smem = (static_cast<size_t>(k) * k + 2 * static_cast<size_t>(k)) * sizeof(double);
@@ -698,6 +702,7 @@ void nnls_prepare_inverse(cudaStream_t stream, int k, const double* LHS, long lo
 // + room for G^-1 and its flag when the caller does not bring them
 size_t nnls_deferred_bytes(int q, int k, int num_sms)
 {
+    if (k > 256) return nnls_big_scratch_bytes(k, num_sms);
     return std::max(static_cast<size_t>(q) * sizeof(BppColState), nnls_wide_scratch_bytes(k, num_sms)) +
            static_cast<size_t>(k) * k * sizeof(double) + 64;
 }
@@ -711,6 +716,11 @@ void nnls_bpp(cudaStream_t stream, int k, int q, const double* LHS, long long ld
     nnls_reset_kernel<<<1, 32, 0, stream>>>(counter, status);     // one launch instead of three memsets (the solves of a small shard are latency)
     SMK_LAUNCH_CHECK();
     if (q <= 0) return;          // a rank may own no rows; the flags above are still reset for the reduction that follows
+    if (k > 256)
+    {
+        nnls_bpp_big(stream, k, q, LHS, ldl, RHS, ldr, X, ldx, Y, ldy, status, counter, deferred, outer_iter, num_sms);
+        return;
+    }
     if (!Ginv && k > 32)
     {
         // the caller did not prepare G^-1: form it here, at the tail of the scratch buffer

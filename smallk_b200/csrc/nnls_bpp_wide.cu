@@ -544,6 +544,164 @@ nnls_bpp_wide_kernel(int k, int q, const double* __restrict__ G, long long ldg, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// k > 256: the same pivoting history with nothing sized by k on the chip. A CTA owns a column; its threads take the rows
+// round-robin; the packed Cholesky triangle, the vectors (right-hand side of the solve, row buffer, x, y), the passive
+// list and the three bit masks sit in a per-CTA scratch in global memory (L2). Every solve is the direct one
+// (G_PP x_P = b_P, cta_spd_solve_packed). A fallback: correct for any k, not tuned.
+// ---------------------------------------------------------------------------------------------------------------
+struct BigScratch
+{
+    int k;
+    __host__ __device__ size_t nw() const { return (static_cast<size_t>(k) + 31) >> 5; }
+    __host__ __device__ size_t doubles() const { return static_cast<size_t>(k) * (k + 1) / 2 + 4 * static_cast<size_t>(k); }   // U | vb | rowj | sx | sy
+    __host__ __device__ size_t ints() const { return static_cast<size_t>(k) + 4 * nw() + 4; }                                  // list | passive, nonopt, infeas | prefix
+    __host__ __device__ size_t bytes() const { return ((doubles() * sizeof(double) + ints() * sizeof(int)) + 255) & ~static_cast<size_t>(255); }
+};
+
+__global__ void __launch_bounds__(kWideThreads)
+nnls_bpp_big_kernel(int k, int q, const double* __restrict__ G, long long ldg, const double* __restrict__ RHS, long long ldr,
+                    double* X, long long ldx, double* Y, long long ldy, int* __restrict__ status, unsigned int* __restrict__ counter,
+                    int outer_iter, unsigned char* gscratch)
+{
+    __shared__ unsigned int s_col;
+    __shared__ int s_p, s_ng[kWideThreads / 32];
+    const BigScratch L{k};
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int nw = static_cast<int>(L.nw());
+    const int kr = nw * 32;                       // rows rounded up to whole mask words: the ballot loops run whole warps
+    unsigned char* mine = gscratch + static_cast<size_t>(blockIdx.x) * L.bytes();
+    double* U = reinterpret_cast<double*>(mine);
+    double* vb = U + static_cast<size_t>(k) * (k + 1) / 2;
+    double* rowj = vb + k;
+    double* sx = rowj + k;
+    double* sy = sx + k;
+    int* list = reinterpret_cast<int*>(sy + k);
+    unsigned int* words = reinterpret_cast<unsigned int*>(list + k);      // [0, nw) passive, [nw, 2nw) nonopt, [2nw, 3nw) infeas
+    int* wpre = reinterpret_cast<int*>(words + 3 * nw);                   // passive rows before word w
+    const int max_rounds = 5 * k;
+
+    for (;;)
+    {
+        __syncthreads();
+        if (t == 0) s_col = atomicAdd(counter, 1u);
+        __syncthreads();
+        const unsigned int c = s_col;
+        if (c >= static_cast<unsigned int>(q)) break;
+        const double* rhs = RHS + static_cast<long long>(c) * ldr;
+        double* xcol = X + static_cast<long long>(c) * ldx;
+        double* ycol = Y + static_cast<long long>(c) * ldy;
+        // warm start: passive = (X > 0)   (nnls.hpp:157)
+        for (int r = t; r < kr; r += kWideThreads)
+        {
+            const unsigned int w = __ballot_sync(0xffffffffu, r < k && xcol[r] > 0.0);
+            if (lane == 0) words[r >> 5] = w;
+        }
+        int P = kPbar, Ninf = k + 1, round = 0;
+        bool failed = false;
+        for (;;)
+        {
+            __syncthreads();
+            // ---- passive rows before each mask word (warp 0: a scan over the word counts), then the passive list
+            if (warp == 0)
+            {
+                int run = 0;
+                for (int w0 = 0; w0 < nw; w0 += 32)
+                {
+                    const int w = w0 + lane;
+                    const int pc = (w < nw) ? __popc(words[w]) : 0;
+                    int incl = pc;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                    if (w < nw) wpre[w] = run + incl - pc;
+                    run += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                if (lane == 0) s_p = run;
+            }
+            __syncthreads();
+            const int p = s_p;
+            for (int r = t; r < k; r += kWideThreads)
+            {
+                const unsigned int w = words[r >> 5];
+                if ((w >> (r & 31)) & 1u) list[wpre[r >> 5] + __popc(w & ((1u << (r & 31)) - 1u))] = r;
+            }
+            __syncthreads();
+            if (p > 0)
+            {
+                // ---- G_PP x_P = b_P
+                for (int cc = warp; cc < p; cc += (kWideThreads >> 5))
+                {
+                    const double* gcol = G + static_cast<long long>(list[cc]) * ldg;
+                    double* col = U + (static_cast<size_t>(cc) * (cc + 1) >> 1);
+                    for (int i = lane; i <= cc; i += 32) col[i] = gcol[list[i]];
+                }
+                for (int i = t; i < p; i += kWideThreads) vb[i] = rhs[list[i]];
+                __syncthreads();
+                if (!cta_spd_solve_packed(U, vb, p, rowj)) { failed = true; break; }
+            }
+            for (int r = t; r < k; r += kWideThreads)
+            {
+                const unsigned int w = words[r >> 5];
+                double x = 0.0;
+                if ((w >> (r & 31)) & 1u) x = vb[wpre[r >> 5] + __popc(w & ((1u << (r & 31)) - 1u))];
+                if (round > 0 && fabs(x) < kZeroThresh) x = 0.0;      // ZeroizeSmallValues(Xsub), nnls.hpp:215
+                sx[r] = x;
+            }
+            __syncthreads();
+            // ---- dual y = G x - b (nnls.hpp:168-169, 219-220); nonopt = (Y < 0) & ~P, infeas = (X < 0) & P (nnls.hpp:42-140)
+            int ng = 0;
+            for (int r = t; r < kr; r += kWideThreads)
+            {
+                bool in = false;
+                double x = 0.0, y = 0.0;
+                if (r < k)
+                {
+                    double s = 0.0;
+                    for (int e = 0; e < p; ++e)
+                    {
+                        const int cc = list[e];
+                        s = fma(__ldg(G + static_cast<long long>(cc) * ldg + r), sx[cc], s);
+                    }
+                    y = s - rhs[r];
+                    if (round > 0 && fabs(y) < kZeroThresh) y = 0.0;
+                    sy[r] = y;
+                    in = (words[r >> 5] >> (r & 31)) & 1u;
+                    x = sx[r];
+                }
+                const unsigned int wn = __ballot_sync(0xffffffffu, r < k && !in && y < 0.0);
+                const unsigned int wi = __ballot_sync(0xffffffffu, r < k && in && x < 0.0);
+                if (lane == 0) { words[nw + (r >> 5)] = wn; words[2 * nw + (r >> 5)] = wi; ng += __popc(wn) + __popc(wi); }
+            }
+            if (lane == 0) s_ng[warp] = ng;
+            __syncthreads();
+            int not_good = 0;
+#pragma unroll
+            for (int w = 0; w < kWideThreads / 32; ++w) not_good += s_ng[w];
+            if (not_good == 0) break;
+            if (round == 0 && t == 0) atomicOr(&status[ST_ANY_NONOPT], 1);
+            if (round >= max_rounds) { failed = true; break; }        // nnls.hpp:195-196
+            // ---- UpdatePassiveSet (nnls.cpp:18-74)
+            if (not_good < Ninf || P >= 1)
+            {
+                if (not_good < Ninf) { P = kPbar; Ninf = not_good; } else P -= 1;
+                for (int w = t; w < nw; w += kWideThreads) words[w] = (words[w] | words[nw + w]) & ~words[2 * nw + w];
+            }
+            else if (t == 0)
+            {
+                const int ra = max_row_index_ref_words(words + nw, k), rb = max_row_index_ref_words(words + 2 * nw, k);
+                const int r = ra > rb ? ra : rb;
+                words[r >> 5] ^= (1u << (r & 31));
+                atomicAdd(&status[ST_BACKUP_COUNT], 1);
+            }
+            ++round;
+        }
+        if (failed && t == 0) atomicMin(&status[ST_FAIL_ITER], outer_iter);
+        __syncthreads();
+        if (!failed)
+            for (int r = t; r < k; r += kWideThreads) { xcol[r] = sx[r]; ycol[r] = sy[r]; }
+    }
+}
+
 } // namespace
 
 size_t nnls_wide_scratch_bytes(int k, int num_sms)
@@ -565,7 +723,7 @@ void nnls_bpp_wide(cudaStream_t stream, int k, int q, const double* LHS, long lo
                    double* X, long long ldx, double* Y, long long ldy, int* status, unsigned int* counter, void* scratch,
                    int outer_iter, int num_sms, const double* Ginv, const int* flag)
 {
-    if (k > 256) throw std::string("nnls_bpp: k > 256 is not supported");
+    if (k > 256) throw std::string("nnls_bpp_wide: internal error (k > 256)");
     const size_t tri_k = static_cast<size_t>(k) * (k + 1) / 2;
     double* gscr = static_cast<double*>(scratch);
     const int grid = std::min(3 * num_sms, q);
@@ -574,6 +732,29 @@ void nnls_bpp_wide(cudaStream_t stream, int k, int q, const double* LHS, long lo
     SMK_CUDA(cudaFuncSetAttribute(nnls_bpp_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     nnls_bpp_wide_kernel<<<grid, kWideThreads, smem, stream>>>(k, q, LHS, ldl, Ginv, flag, RHS, ldr, X, ldx, Y, ldy, status,
                                                               counter, outer_iter, gscr, tri_k + 512);
+    SMK_LAUNCH_CHECK();
+}
+
+// k > 256: see nnls_bpp_big_kernel. The grid is what a quarter of a gigabyte of per-CTA scratch allows (at least one CTA).
+constexpr size_t kBigScratchBudget = size_t(256) << 20;
+static int nnls_big_grid(int k, int num_sms)
+{
+    const BigScratch L{k};
+    return static_cast<int>(std::max<size_t>(1, std::min<size_t>(static_cast<size_t>(2 * num_sms), kBigScratchBudget / L.bytes())));
+}
+size_t nnls_big_scratch_bytes(int k, int num_sms)
+{
+    if (k <= 256) return 0;
+    return static_cast<size_t>(nnls_big_grid(k, num_sms)) * BigScratch{k}.bytes() + 256;
+}
+void nnls_bpp_big(cudaStream_t stream, int k, int q, const double* LHS, long long ldl, const double* RHS, long long ldr,
+                  double* X, long long ldx, double* Y, long long ldy, int* status, unsigned int* counter, void* scratch,
+                  int outer_iter, int num_sms)
+{
+    if (k > 32768) throw std::string("nnls_bpp: k > 32768 is not supported");     // the packed triangle is indexed with 32-bit integers
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(scratch) + 255) & ~static_cast<uintptr_t>(255));
+    const int grid = std::min(nnls_big_grid(k, num_sms), q);
+    nnls_bpp_big_kernel<<<grid, kWideThreads, 0, stream>>>(k, q, LHS, ldl, RHS, ldr, X, ldx, Y, ldy, status, counter, outer_iter, base);
     SMK_LAUNCH_CHECK();
 }
 

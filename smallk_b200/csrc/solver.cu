@@ -185,7 +185,7 @@ void inverse_side(smk_ctx* c, const double* G, smk_ctx::InvBuf& b)
 {
     const int k = c->opts.k;
     b.valid = false;
-    if (c->opts.algorithm != SMK_BPP || k <= 32) return;
+    if (c->opts.algorithm != SMK_BPP || !nnls_uses_inverse(k)) return;
     b.Ginv.reserve(static_cast<size_t>(k) * k);
     b.ok.reserve(1);
     nnls_prepare_inverse(c->side, k, G, k, b.Ginv.p, b.ok.p);
@@ -195,7 +195,7 @@ void inverse_side(smk_ctx* c, const double* G, smk_ctx::InvBuf& b)
 // (the inverse was a fixed ~0.19 ms inside every NNLS launch when each CTA formed it for itself)
 void prepare_inverse(smk_ctx* c, const double* G, smk_ctx::InvBuf& b)
 {
-    if (c->opts.algorithm != SMK_BPP || c->opts.k <= 32) return;
+    if (c->opts.algorithm != SMK_BPP || !nnls_uses_inverse(c->opts.k)) return;
     side_begin(c, b);
     inverse_side(c, G, b);
     side_end(c, b);
@@ -259,7 +259,8 @@ void solver_alloc(smk_ctx* c)
     const size_t k = c->opts.k, n = c->n;
     c->w_sharded = c->nranks > 1 && (c->opts.algorithm == SMK_BPP || c->opts.algorithm == SMK_MU);
     c->grad_sharded = c->nranks > 1 && c->opts.algorithm == SMK_HALS;
-    c->use_peer = c->nranks > 1 && peer_enabled_by_env();
+    // the one-shot exchange slots of peer.cu hold a k x k Gram matrix for k <= 256; larger ranks exchange through NCCL
+    c->use_peer = c->nranks > 1 && peer_enabled_by_env() && static_cast<long long>(k) * static_cast<long long>(k) + 64 <= kPeerSmallCap;
     c->x_loc = c->nranks > 1 ? (c->m + c->nranks - 1) / c->nranks : c->m;       // rows per exchanged block
     c->m_loc = c->w_sharded ? c->x_loc : c->m;
     const bool padded = c->w_sharded || c->use_peer;

@@ -582,6 +582,14 @@ void spmm_gather(cudaStream_t stream, int ncols, const unsigned int* ptr, const 
                  int k, const double* B, long long ldb, double alpha, double beta, double* out, long long ldo, int num_sms)
 {
     if (ncols <= 0) return;
+    if (k > kSpmmMaxK)
+    {
+        // any k: the operand in row blocks of kSpmmMaxK (a block of rows of a k x * column-major matrix is the same matrix with
+        // another base pointer); entries are still added in storage order, so nothing changes numerically
+        for (int k0 = 0; k0 < k; k0 += kSpmmMaxK)
+            spmm_gather(stream, ncols, ptr, idx, val, std::min(kSpmmMaxK, k - k0), B + k0, ldb, alpha, beta, out + k0, ldo, num_sms);
+        return;
+    }
 #define SMK_G(L, KPL) launch_gather<L, KPL>(stream, ncols, ptr, idx, val, k, B, ldb, alpha, beta, out, ldo, num_sms)
     if (k <= 2) SMK_G(2, 1);
     else if (k <= 4) SMK_G(4, 1);
@@ -591,7 +599,7 @@ void spmm_gather(cudaStream_t stream, int ncols, const unsigned int* ptr, const 
     else if (k <= 64) SMK_G(32, 2);
     else if (k <= 128) SMK_G(32, 4);
     else if (k <= 256) SMK_G(32, 8);
-    else throw std::string("spmm: k > 256 is not supported");
+    else throw std::string("spmm: internal error (k > kSpmmMaxK reached a register kernel)");
 #undef SMK_G
 }
 
@@ -600,6 +608,14 @@ void spmm_gather_seg(cudaStream_t stream, int ncols, const SegTable& T, const un
                      double* partial, int num_sms, int ngather)
 {
     if (ncols <= 0 || T.nseg <= 0) return;
+    if (k > kSpmmMaxK)
+    {
+        // as in spmm_gather; every row block runs to completion (per-segment partials included) before the next re-uses `partial`
+        for (int k0 = 0; k0 < k; k0 += kSpmmMaxK)
+            spmm_gather_seg(stream, ncols, T, idx, val, std::min(kSpmmMaxK, k - k0), B + k0, ldb, alpha, beta, out + k0, ldo, partial,
+                            num_sms, ngather);
+        return;
+    }
     const uintptr_t addr_bits = reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(partial);
     const bool aligned16 = (addr_bits & 15) == 0;
     const bool wide256 = k >= 64 && k <= 256 && (ldb & 3) == 0 && (ldo & 3) == 0 && (addr_bits & 31) == 0 && ngather > 0 &&
@@ -659,7 +675,7 @@ void spmm_gather_seg(cudaStream_t stream, int ncols, const SegTable& T, const un
     else if (k <= 64) SMK_S(32, 2);
     else if (k <= 128) SMK_S(32, 4);
     else if (k <= 256) SMK_S(32, 8);
-    else throw std::string("spmm: k > 256 is not supported");
+    else throw std::string("spmm: internal error (k > kSpmmMaxK reached a register kernel)");
 #undef SMK_S
     }
     if (T.nmulti > 0)

@@ -53,13 +53,6 @@ Result CheckCommon(const NmfOptions& options, int ldim_w, int ldim_h)
         return Result::NOTINITIALIZED;
     }
     if (!IsValid(options)) return Result::BAD_PARAM;
-    // the one capability limit of this build (not in the reference): the device kernels hold a factor column in registers /
-    // shared memory, k <= 256. Said here, before any upload, in the nmflib wording the other argument errors use.
-    if (options.k > 256)
-    {
-        std::cerr << "nmflib error: k-value larger than 256 is not supported by the GPU kernels of this build (k = " << options.k << ")" << std::endl;
-        return Result::BAD_PARAM;
-    }
     const uint64_t m = options.height, n = options.width, k = options.k;
     if (!FitsWithin<int>(m * k)) { std::cerr << "W matrix size too large" << std::endl; return Result::SIZE_TOO_LARGE; }
     if (!FitsWithin<int>(n * k)) { std::cerr << "H matrix size too large" << std::endl; return Result::SIZE_TOO_LARGE; }

@@ -96,12 +96,18 @@ NNLS_CASES = {"nnls_k16_q64": (21, 16, 64), "nnls_k40_q90": (22, 40, 90), "nnls_
 # toggles is reported by BitMatrix::MaxRowIndex from word 0 / the partial last word (correct) or from a full word > 0
 # (common/src/bit_matrix.cpp:459-467: 32 rows too low -> the wrong row is toggled, the column cycles until MAX_ITER = 5k
 # and the REFERENCE returns failure). name -> (k, at, s, seed); the fixture records the reference's rc, X, Y.
+# k > 256 (the any-k fallback kernel): the same 2000-column problem cut down to 42 columns around the four in which the rule
+# fires (481, 500, 750, 958 for s = 5, seed = 6) — a passive-set solve is a 300 x 300 Cholesky there, on the CPU and on the GPU.
+_BIGK_COLS = tuple(range(470, 510)) + (750, 958)
 BACKUP_CASES = {"nnls_backup_k64_word0": (64, 27, 5, 6), "nnls_backup_k48_partial": (48, 43, 5, 6),
                 "nnls_backup_k100_word0": (100, 10, 5, 6), "nnls_backup_k200_word0": (200, 20, 6, 9),
-                "nnls_backup_k64_defect": (64, 59, 5, 6), "nnls_backup_k100_defect": (100, 60, 5, 6)}
+                "nnls_backup_k64_defect": (64, 59, 5, 6), "nnls_backup_k100_defect": (100, 60, 5, 6),
+                "nnls_backup_k300_word0": (300, 10, 5, 6, _BIGK_COLS), "nnls_backup_k300_partial": (300, 291, 5, 6, _BIGK_COLS)}
+# (no k = 300 defect case: the four columns then cycle through 5k = 1500 solves of a 300 x 300 system each, 40 s on the CPU;
+# the defective MaxRowIndex is one function shared by every k > 64 and covered at k = 100)
 
 
-def backup_inputs(k, at, s, seed, q=2000):
+def backup_inputs(k, at, s, seed, cols=None, q=2000):
     rng = np.random.default_rng(seed * 100 + s)
     rows = s + int(rng.integers(0, 3))
     Ws = rng.standard_normal((rows, s)) + 2.0 * rng.standard_normal((rows, 1))
@@ -115,6 +121,9 @@ def backup_inputs(k, at, s, seed, q=2000):
     RHS[at:at + s] = Rs
     X0 = rng.random((k, q))
     X0[at:at + s] = Xs
+    if cols is not None:
+        cols = np.asarray(cols)
+        RHS, X0 = np.ascontiguousarray(RHS[:, cols]), np.ascontiguousarray(X0[:, cols])
     return LHS, RHS, X0
 
 

@@ -28,7 +28,9 @@ def main():
     orc = Oracle()
     failures = []
     cases = [("BPP", 301, 257, 24, 8, False), ("BPP", 420, 390, 100, 5, False), ("MU", 203, 190, 9, 12, False),
-             ("HALS", 230, 200, 12, 10, False), ("RANK2", 250, 240, 2, 12, False), ("BPP", 300, 280, 16, 8, True)]
+             ("HALS", 230, 200, 12, 10, False), ("RANK2", 250, 240, 2, 12, False), ("BPP", 300, 280, 16, 8, True),
+             # k > 256: the any-k fallback kernels; the exchange goes through NCCL whatever SMK_PEER says (solver_alloc)
+             ("HALS", 330, 300, 260, 3, False), ("MU", 300, 280, 264, 4, False)]
     for peer in ("1", "0"):
         os.environ["SMK_PEER"] = peer          # read by the library at every solver_begin
         for alg, m, n, k, iters, sparse in cases:
