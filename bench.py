@@ -147,19 +147,19 @@ SPMM_KERNEL_SPAN = (os.path.join(ROOT, "smallk_b200", "csrc", "spmm.cu"), "// Ho
 # ---------------------------------------------------------------------------------------------------------------
 # the reference on the host cores
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_reference_run(m, n, k, warm, timed, threads, layouts, seeds=(SEED_A, SEED_W, SEED_H)):
-    """The reference's own NmfSolve (Solver_Generic_BPP) on the FULL m x n workload: `warm` + `timed` iterations per thread
+def cpu_reference_run(m, n, k, warm, timed, threads, layouts, seeds=(SEED_A, SEED_W, SEED_H), alg="BPP", h0_scale=1.0):
+    """The reference's own NmfSolve (Solver_Generic_BPP, or the solver `alg` names) on the FULL m x n workload: `warm` + `timed` iterations per thread
     layout, timed per iteration by stamps taken inside its loop. Returns (mean seconds per timed iteration of the faster
     layout, its BLAS thread count, BLAS backend, per-layout seconds)."""
     import ctypes
     import workloads
-    from oracle import Ref, REF_SO
+    from oracle import Ref, REF_SO, ALG
     if not os.path.exists(REF_SO):
         raise RuntimeError("oracle/_ref/libsmallk_ref.so is missing (built only where /root/reference exists)")
     ref = Ref()
     A_t = workloads.dense_columns(m, 0, n, seed=seeds[0])          # C-ordered (n, m) == column-major m x n
     W0 = np.asfortranarray(np.random.default_rng(seeds[1]).random((m, k)))
-    H0 = np.asfortranarray(np.random.default_rng(seeds[2]).random((k, n)))
+    H0 = np.asfortranarray(np.random.default_rng(seeds[2]).random((k, n))) * h0_scale
     dp = ctypes.POINTER(ctypes.c_double)
     iters = warm + timed
     out = {}
@@ -170,7 +170,7 @@ def cpu_reference_run(m, n, k, warm, timed, threads, layouts, seeds=(SEED_A, SEE
         stamps = np.zeros(iters)
         t0 = ctypes.c_double(0.0)
         it = ctypes.c_int(0)
-        rc = ref.lib.ref_nmf_dense_stamped(3, 0, m, n, k, iters, threads, A_t.ctypes.data_as(dp), m,
+        rc = ref.lib.ref_nmf_dense_stamped(ALG[alg], 0, m, n, k, iters, threads, A_t.ctypes.data_as(dp), m,
                                            W.ctypes.data_as(dp), m, H.ctypes.data_as(dp), k,
                                            ctypes.byref(it), stamps.ctypes.data_as(dp), ctypes.byref(t0))
         if rc != 0:
@@ -371,6 +371,35 @@ def run_c2(env, args):
                 pass
             break
 
+    # ---- the other dense solver of the metric ("BPP/HALS, dense+sparse"): HALS on the same matrix, one GPU ---------------
+    variants = None
+    if world == 1 and not args.no_extras and m == 20000:
+        variants = {}
+        try:
+            hs = 2.0 / k                        # mean(W0 * H0) = mean(A) for U[0,1) factors and entries (HALS note)
+            oh = sk.make_options(m, n, k, algorithm="HALS", prog="PG_RATIO", tol=1e-15, min_iter=1, max_iter=3 + 20, normalize=False)
+            ctx.solver_begin(W0, np.asfortranarray(H0 * hs), oh)
+            ms_h, tr_h, l_h, _, ph_h = env.timed_run(ctx, 3, 20)
+            fl_h = 4.0 * k * m * n + 6.0 * k * k * (m + n)           # two A-sized products; Gram, sweep and gradient per factor
+            v = {"metric": METRIC, "value": 1000.0 / ms_h, "unit": UNIT, "ms_per_step": ms_h, "steps": 20, "warmup": 3, "gpu_launches": l_h,
+                 "config": {"workload": f"dense HALS NMF {m}x{n} FP64 k={k} (C2's matrix, Solver_Generic_HALS_Da)", "algorithm": "HALS", "k": k},
+                 "step_frac_of_fp64_tensor_peak": (fl_h / (ms_h * 1e-3) * 1e-12 / peak) if peak else None,
+                 "progress_metric_last": tr_h[-1]}
+            if ph_h:
+                v["phases_ms_per_step"] = ph_h
+            if not args.no_cpu_baseline:
+                try:
+                    cores = os.cpu_count() or 1
+                    sec, bt, backend, _ = cpu_reference_run(m, n, k, 1, 2, cores, (cores,), alg="HALS", h0_scale=hs)
+                    v["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "reference",
+                                         "sample": f"reference HALS (oracle/_ref, BLAS={backend}, {bt} BLAS threads) on the FULL {m}x{n} workload: "
+                                                   "2 timed iterations after 1 warm-up, Init excluded"}
+                except Exception as ex:
+                    v["cpu_baseline"] = {"value": None, "sample": f"unavailable: {ex}"}
+            variants["dense_hals"] = v
+        except Exception as ex:                       # a variant must never cost the headline line
+            variants["dense_hals"] = {"error": f"{type(ex).__name__}: {ex}"}
+
     # ---- end to end through the host-buffer API -------------------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -450,6 +479,8 @@ def run_c2(env, args):
     }
     if phases:
         line["phases_ms_per_step"] = phases
+    if variants:
+        line["variants"] = variants
     return line
 
 

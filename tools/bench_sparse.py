@@ -146,6 +146,28 @@ def run_c3(args, env=None, steps=None, warmup=None):
             except Exception:
                 traffic = None
             break
+    # ---- the other sparse solver of the metric ("BPP/HALS, dense+sparse"): BPP on the same matrix, one GPU ----------------
+    variants = None
+    if world == 1:
+        variants = {}
+        try:
+            ob = sk.make_options(m, n, k, algorithm="BPP", tol=1e-15, min_iter=1, max_iter=1 + 4, normalize=False)
+            ctx.solver_begin(W0, H0, ob)
+            tr_b = list(ctx.solver_run(1))
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            b0.record(stream)
+            tr_b += list(ctx.solver_run(4))
+            b1.record(stream)
+            torch.cuda.synchronize()
+            ms_b = b0.elapsed_time(b1) / 4
+            variants["sparse_bpp"] = {"metric": METRIC, "value": 1000.0 / ms_b, "unit": UNIT, "ms_per_step": ms_b, "steps": 4, "warmup": 1,
+                                      "gpu_launches": ctx.last_step()[1],
+                                      "config": {"workload": f"sparse BPP NMF {m}x{n} nnz={nnz} k={k} (C3's matrix, Solver_Generic_BPP)",
+                                                 "algorithm": "BPP", "k": k},
+                                      "progress_metric_last": tr_b[-1]}
+        except Exception as ex:                       # a variant must never cost the C3 line
+            variants["sparse_bpp"] = {"error": f"{type(ex).__name__}: {ex}"}
     if env is None:
         ctx.close()
         del ctx
@@ -207,6 +229,8 @@ def run_c3(args, env=None, steps=None, warmup=None):
             "cpu_baseline": cpu, "progress_metric_last": metric}
     if phases:
         line["phases_ms_per_step"] = phases
+    if variants:
+        line["variants"] = variants
     return line
 
 
