@@ -68,6 +68,7 @@ int smk_create(smk_ctx** ctx, int device);
 void smk_destroy(smk_ctx* ctx);
 const char* smk_last_error(const smk_ctx* ctx);
 int smk_device_sm_count(const smk_ctx* ctx);
+int smk_device_index(const smk_ctx* ctx);     /* the CUDA device smk_create was given (-1 for a null context) */
 /* Run on a caller-owned CUDA stream (e.g. torch's current stream); 0 restores the context's own. */
 int smk_set_stream(smk_ctx* ctx, void* cuda_stream);
 int smk_synchronize(smk_ctx* ctx);

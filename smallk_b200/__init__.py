@@ -24,7 +24,7 @@ ALGORITHMS = {"MU": 0, "HALS": 1, "RANK2": 2, "BPP": 3}
 PROGRESS = {"PG_RATIO": 0, "DELTA_FNORM": 1}
 
 EXPORTS = [
-    "smk_create", "smk_destroy", "smk_last_error", "smk_device_sm_count", "smk_set_stream", "smk_synchronize",
+    "smk_create", "smk_destroy", "smk_last_error", "smk_device_sm_count", "smk_device_index", "smk_set_stream", "smk_synchronize",
     "smk_comm_unique_id", "smk_comm_init", "smk_load_dense", "smk_load_dense_device", "smk_load_csc", "smk_nmf",
     "smk_solver_begin", "smk_solver_step", "smk_solver_progress", "smk_solver_get", "smk_solver_normalize",
     "smk_solver_last_step_ms", "smk_solver_time_product", "smk_gemm", "smk_nnls_bpp", "smk_sparse_gemm",
@@ -33,7 +33,7 @@ EXPORTS = [
 ]
 HOST_LIB_PATH = os.path.join(_HERE, "lib", "libsmallk_host.so")
 HOST_EXPORTS = ["smkh_last_error", "smkh_hierclust_sparse", "smkh_hierclust_dense", "smkh_flatclust", "smkh_compute_priority",
-                "smkh_last_hier_profile", "smkh_compute_priority_plain", "smkh_compute_priority_gpu", "smkh_compute_priority_rows", "smkh_load_matrix_market",
+                "smkh_last_hier_profile", "smkh_compute_priority_plain", "smkh_compute_priority_gpu", "smkh_compute_priority_rows", "smkh_compute_priority_rows2", "smkh_load_matrix_market",
                 "smkh_load_delimited", "smkh_write_delimited", "smkh_compute_assignments", "smkh_compute_fuzzy_assignments",
                 "smkh_top_terms_matrix", "smkh_random_matrices", "smkh_is_valid", "smkh_flatclust_write_results", "smkh_tree_script"]
 
@@ -365,11 +365,11 @@ def hierclust(A_dense=None, csc=None, shape=None, num_clusters=4, tol=1e-4, min_
                                        rowi.ctypes.data_as(_up), _d(val), *tail)
     else:
         rc = lib.smkh_hierclust_dense(m, n, _d(A_dense), m, *tail)
-    prof = np.zeros(5)
+    prof = np.zeros(6)
     lib.smkh_last_hier_profile(_d(prof))
     out.update(rc=rc, n_outliers=n_out.value, nmf_count=int(stats[0]), max_count=int(stats[1]),
                iterations=int(stats[2]), elapsed_s=el.value,
-               profile=dict(zip(("extract_s", "init_s", "factor_s", "priority_s", "terms_s"), prof.tolist())))
+               profile=dict(zip(("extract_s", "init_s", "factor_s", "priority_s", "terms_s", "priority_worker_s"), prof.tolist())))
     if flat:
         out.update(W=W, H=H, flat_assignments=fa)
     return out

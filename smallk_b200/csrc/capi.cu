@@ -160,6 +160,7 @@ void smk_destroy(smk_ctx* c)
 
 const char* smk_last_error(const smk_ctx* c) { return c ? c->err.c_str() : "null context"; }
 int smk_device_sm_count(const smk_ctx* c) { return c ? c->num_sms : 0; }
+int smk_device_index(const smk_ctx* c) { return c ? c->device : -1; }
 
 int smk_set_stream(smk_ctx* c, void* s)
 {

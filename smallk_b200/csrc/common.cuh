@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -19,8 +20,9 @@ struct CudaError { cudaError_t code; const char* file; int line; };
         if (_e != cudaSuccess) throw ::smk::CudaError{_e, __FILE__, __LINE__}; \
     } while (0)
 
-// every kernel launch of this library goes through here, so it can be counted (bench.py: gpu_launches)
-inline long long& launch_counter() { static long long n = 0; return n; }
+// every kernel launch of this library goes through here, so it can be counted (bench.py: gpu_launches); atomic because two
+// contexts may launch from two host threads (the hierclust driver's worker thread sorts on its own context)
+inline std::atomic<long long>& launch_counter() { static std::atomic<long long> n{0}; return n; }
 #define SMK_LAUNCH_CHECK()                 \
     do {                                   \
         ++::smk::launch_counter();         \

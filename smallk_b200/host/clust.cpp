@@ -11,8 +11,14 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#endif
+#include <future>
 #include <iostream>
 #include <limits>
+#include <mutex>
 #include <sstream>
 #include <stdexcept>
 
@@ -52,7 +58,8 @@ bool IsValid(const ClustOptions& opts, bool validate_matrix)
 // --------------------------------------------------------------------------------------------------------------
 R compute_priority_on(smk_ctx* ctx, const R* W_parent, const R* W_child, int n);
 R compute_priority_plain(smk_ctx* ctx, const R* W_parent, const R* W_child, int n);
-R compute_priority_rows(smk_ctx* ctx, const R* W_parent, const R* W_child, int n, const unsigned int* child_rows, int n_child_rows);
+R compute_priority_rows(smk_ctx* ctx, const R* W_parent, const R* W_child, int n, const unsigned int* child_rows, int n_child_rows,
+                        const unsigned int* parent_rows = nullptr, int n_parent_rows = 0);
 
 namespace {
 
@@ -195,23 +202,26 @@ struct PriorityScratch
     std::vector<unsigned long long> zero_1, zero_2, zero_all;   // one bit per row: zero in child 1 / child 2 / everywhere
 };
 PriorityScratch g_ps;
+// g_ps / g_rs belong to whoever holds this: every evaluation on the calling thread, and the tree driver's worker thread
+// if it ever has to leave its own scratch for the general evaluation (compute_priority_on)
+std::mutex g_priority_mutex;
 
 // rows[0..cnt) (ascending row order) sorted by decreasing v[row], ties by ascending row
-void sort_rows_desc(const R* v, std::vector<int>& rows, smk_ctx* ctx)
+void sort_rows_desc(const R* v, std::vector<int>& rows, smk_ctx* ctx, PriorityScratch& S = g_ps)
 {
     const int cnt = static_cast<int>(rows.size());
     if (ctx && cnt >= kDeviceSortMin)
     {
-        g_ps.keys.resize(cnt); g_ps.perm.resize(cnt); g_ps.tmp_i.resize(cnt);
-        for (int i = 0; i < cnt; ++i) g_ps.keys[i] = v[rows[i]];
-        if (smk_argsort_desc(ctx, g_ps.keys.data(), cnt, g_ps.perm.data()) != SMK_OK) throw std::runtime_error(smk_last_error(ctx));
-        for (int i = 0; i < cnt; ++i) g_ps.tmp_i[i] = rows[g_ps.perm[i]];
-        rows.swap(g_ps.tmp_i);
+        S.keys.resize(cnt); S.perm.resize(cnt); S.tmp_i.resize(cnt);
+        for (int i = 0; i < cnt; ++i) S.keys[i] = v[rows[i]];
+        if (smk_argsort_desc(ctx, S.keys.data(), cnt, S.perm.data()) != SMK_OK) throw std::runtime_error(smk_last_error(ctx));
+        for (int i = 0; i < cnt; ++i) S.tmp_i[i] = rows[S.perm[i]];
+        rows.swap(S.tmp_i);
     }
     else
     {
         // (value, row) pairs sort on contiguous keys; the order is the same total order
-        std::vector<std::pair<R, int>>& pr = g_ps.pairs;
+        std::vector<std::pair<R, int>>& pr = S.pairs;
         pr.resize(cnt);
         for (int i = 0; i < cnt; ++i) pr[i] = std::make_pair(v[rows[i]], rows[i]);
         std::sort(pr.begin(), pr.end(), [](const std::pair<R, int>& a, const std::pair<R, int>& b) {
@@ -394,24 +404,65 @@ struct PriorityProf
 PriorityProf g_pprof;
 struct Lap
 {
+    bool on;
     std::chrono::steady_clock::time_point t0;
-    Lap() : t0(std::chrono::steady_clock::now()) {}
-    void mark(int i) { if (!g_pprof.on) return; const auto t1 = std::chrono::steady_clock::now(); g_pprof.t[i] += std::chrono::duration<double>(t1 - t0).count(); t0 = t1; }
+    explicit Lap(bool timed) : on(timed && g_pprof.on), t0(std::chrono::steady_clock::now()) {}
+    void mark(int i) { if (!on) return; const auto t1 = std::chrono::steady_clock::now(); g_pprof.t[i] += std::chrono::duration<double>(t1 - t0).count(); t0 = t1; }
 };
 } // namespace
 
-R compute_priority_rows(smk_ctx* ctx, const R* W_parent, const R* W_child, const int n, const unsigned int* child_rows, const int n_child_rows)
+namespace {
+// acc = (...((acc + a[0] / b[0]) + a[1] / b[1]) + ...) + a[c-1] / b[c-1]: the quotients of a block are formed first (independent
+// IEEE divisions, two or four per instruction: the same values a scalar division gives), then added one after the other in
+// the order the reference adds them. The ideal-score sum of compute_priority has one such term per row of the matrix; done one
+// term at a time it is bound by the throughput of the scalar divider.
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("avx"))) void quotients_avx(const double* a, const double* b, const int cnt, double* q)
 {
-    if (!child_rows) return compute_priority_on(ctx, W_parent, W_child, n);
-    Lap lap;
+    int j = 0;
+    for (; j + 4 <= cnt; j += 4) _mm256_storeu_pd(q + j, _mm256_div_pd(_mm256_loadu_pd(a + j), _mm256_loadu_pd(b + j)));
+    for (; j < cnt; ++j) q[j] = a[j] / b[j];
+}
+void quotients_sse2(const double* a, const double* b, const int cnt, double* q)
+{
+    int j = 0;
+    for (; j + 2 <= cnt; j += 2) _mm_storeu_pd(q + j, _mm_div_pd(_mm_loadu_pd(a + j), _mm_loadu_pd(b + j)));
+    for (; j < cnt; ++j) q[j] = a[j] / b[j];
+}
+typedef void (*QuotientFn)(const double*, const double*, int, double*);
+const QuotientFn g_quotients = __builtin_cpu_supports("avx") ? quotients_avx : quotients_sse2;
+#else
+void quotients_plain(const double* a, const double* b, const int cnt, double* q) { for (int j = 0; j < cnt; ++j) q[j] = a[j] / b[j]; }
+typedef void (*QuotientFn)(const double*, const double*, int, double*);
+const QuotientFn g_quotients = quotients_plain;
+#endif
+inline R add_quotients(R acc, const double* a, const double* b, const int c)
+{
+    double q[32];
+    for (int j0 = 0; j0 < c; j0 += 32)
+    {
+        const int cnt = std::min(32, c - j0);
+        g_quotients(a + j0, b + j0, cnt, q);
+        for (int j = 0; j < cnt; ++j) acc = acc + q[j];
+    }
+    return acc;
+}
+
+// The evaluation proper, on the scratch it is given: g_ps / g_rs (the caller holds g_priority_mutex) or the tree driver's
+// worker-thread set. `timed` = this call feeds the SMK_PRIORITY_PROF section timers (the calling thread's evaluations only).
+// parent_rows (optional, ascending): the rows outside of which the parent vector is zero (the row map of the node the vector
+// was factored on) — the scan for its non-zero rows then visits those instead of all n.
+R priority_rows_impl(smk_ctx* ctx, PriorityScratch& S, RowsScratch& Q, const bool timed, const R* W_parent, const R* W_child, const int n,
+                     const unsigned int* child_rows, const int n_child_rows, const unsigned int* parent_rows = nullptr, const int n_parent_rows = 0)
+{
+    Lap lap(timed);
     const R* P = W_parent; const R* C1 = W_child; const R* C2 = W_child + n;
-    PriorityScratch& S = g_ps;
-    RowsScratch& Q = g_rs;
     S.pos_p.clear(); S.pos_1.clear(); S.pos_2.clear(); S.pz_1.clear(); S.pz_2.clear(); S.other.clear();
     if (static_cast<int>(S.rank_p.size()) < n) { S.rank_p.resize(n); S.rank_1.resize(n); S.rank_2.resize(n); }
     // U = non-zero rows of the parent vector, merged with the child's rows
     Q.pnz.clear();
-    for (int i = 0; i < n; ++i) if (P[i] != 0) Q.pnz.push_back(i);
+    if (parent_rows) { for (int t = 0; t < n_parent_rows; ++t) { const int i = static_cast<int>(parent_rows[t]); if (P[i] != 0) Q.pnz.push_back(i); } }
+    else for (int i = 0; i < n; ++i) if (P[i] != 0) Q.pnz.push_back(i);
     Q.u.clear();
     {
         size_t a = 0; int b = 0;
@@ -426,7 +477,7 @@ R compute_priority_rows(smk_ctx* ctx, const R* W_parent, const R* W_child, const
     }
     const int nu = static_cast<int>(Q.u.size());
     lap.mark(0);
-    if (g_pprof.on) { g_pprof.calls += 1; g_pprof.rows += nu; }
+    if (timed && g_pprof.on) { g_pprof.calls += 1; g_pprof.rows += nu; }
     Q.a1.resize(nu); Q.a2.resize(nu); Q.allzero.resize(nu);
     // one pass over U: the lists compute_priority_on builds from all m rows, with the zero-row counts in closed form
     int c1 = 0, c2 = 0;                     // positive rows of child 1 / child 2 seen so far
@@ -448,7 +499,12 @@ R compute_priority_rows(smk_ctx* ctx, const R* W_parent, const R* W_child, const
     }
     // rows outside child_rows must be zero in the child factors (the driver scatters into a zeroed buffer); anything irregular
     // goes the general way
-    if (!regular) return compute_priority_on(ctx, W_parent, W_child, n);
+    if (!regular)
+    {
+        if (&S == &g_ps) return compute_priority_on(ctx, W_parent, W_child, n);        // the caller holds the mutex
+        std::lock_guard<std::mutex> lock(g_priority_mutex);
+        return compute_priority_on(ctx, W_parent, W_child, n);
+    }
     const int np = static_cast<int>(S.pos_p.size()), n1 = static_cast<int>(S.pos_1.size()), n2 = static_cast<int>(S.pos_2.size());
     const int n_part = np;
     if (n_part <= 1) return R(-3);
@@ -466,9 +522,9 @@ R compute_priority_rows(smk_ctx* ctx, const R* W_parent, const R* W_child, const
         if (!(C2[row] > 0)) S.rank_2[row] += n2;
     }
     lap.mark(1);
-    sort_rows_desc(P, S.pos_p, ctx);
-    sort_rows_desc(C1, S.pos_1, ctx);
-    sort_rows_desc(C2, S.pos_2, ctx);
+    sort_rows_desc(P, S.pos_p, ctx, S);
+    sort_rows_desc(C1, S.pos_1, ctx, S);
+    sort_rows_desc(C2, S.pos_2, ctx, S);
     lap.mark(2);
     for (int q = 0; q < np; ++q) S.rank_p[S.pos_p[q]] = q;
     for (int q = 0; q < n1; ++q) S.rank_1[S.pos_1[q]] = q;
@@ -523,17 +579,26 @@ R compute_priority_rows(smk_ctx* ctx, const R* W_parent, const R* W_child, const
     int pos = 0, head = 0;
     // all-zero rows hi, hi - 1, ..., lo with `shift` = max(n1 - positives of child 1 before them, n2 - ... of child 2):
     // rank of row i in the worse child ordering = i + shift
+    // Row i of the run has weight invd[n - (i + shift)]: walking the run (i falling) walks invd upwards, and invd does not
+    // increase with its index, so the rows that come before the next irregular weight wf[head] (those with a strictly larger
+    // weight; an equal irregular weight goes first) are found by bisection and added as one block.
     auto run = [&](const int hi, const int lo, const int shift) {
         int i = hi;
-        for (; i >= lo && head < nw; --i)
+        while (i >= lo)
         {
-            const R w = invd[n - (i + shift)];
-            while (head < nw && wf[head] >= w) { ideal = pos == 0 ? wf[head] : ideal + wf[head] / l2[pos + 1]; ++pos; ++head; }
-            ideal = pos == 0 ? w : ideal + w / l2[pos + 1];
-            ++pos;
+            const double* seg = invd + (n - (i + shift));           // weights of rows i, i - 1, ..., lo
+            const int len = i - lo + 1;
+            int c = len;
+            if (head < nw)
+            {
+                const R wh = wf[head];
+                c = static_cast<int>(std::partition_point(seg, seg + len, [wh](const double v) { return !(wh >= v); }) - seg);
+                if (c == 0) { ideal = pos == 0 ? wh : ideal + wh / l2[pos + 1]; ++pos; ++head; continue; }
+            }
+            if (pos == 0) { ideal = seg[0]; ++pos; --i; continue; }
+            ideal = add_quotients(ideal, seg, l2 + pos + 1, c);
+            pos += c; i -= c;
         }
-        if (i >= lo && pos == 0) { ideal = invd[n - (i + shift)]; ++pos; --i; }
-        for (; i >= lo; --i) { ideal = ideal + invd[n - (i + shift)] / l2[pos + 1]; ++pos; }
     };
     int hi = n - 1;
     for (int t = nu - 1; t >= 0; --t)
@@ -549,11 +614,33 @@ R compute_priority_rows(smk_ctx* ctx, const R* W_parent, const R* W_child, const
     lap.mark(5);
     return (dcg1 / ideal) * (dcg2 / ideal);
 }
+} // namespace
+
+R compute_priority_rows(smk_ctx* ctx, const R* W_parent, const R* W_child, const int n, const unsigned int* child_rows, const int n_child_rows,
+                        const unsigned int* parent_rows, const int n_parent_rows)
+{
+    std::lock_guard<std::mutex> lock(g_priority_mutex);
+    if (!child_rows) return compute_priority_on(ctx, W_parent, W_child, n);
+    return priority_rows_impl(ctx, g_ps, g_rs, true, W_parent, W_child, n, child_rows, n_child_rows, parent_rows, n_parent_rows);
+}
 
 // --------------------------------------------------------------------------------------------------------------
 // tree growing
 // --------------------------------------------------------------------------------------------------------------
 namespace {
+
+// A priority score that may still be on its way: the tree driver lets the score of a left child be evaluated on a worker
+// thread while the calling thread extracts, initialises and factors the right child (the score is host work on three
+// m-vectors, ~5 ms per node at m = 320 000, during which the GPU would sit idle; the factorization is GPU work during which
+// the host would). value is final once fut is no longer valid.
+struct PendingPriority
+{
+    R value = R(0);
+    std::future<R> fut;
+    std::vector<unsigned int> rows;      // the worker's own copy of the node's row map (the driver's is scratch)
+    bool pending() const { return fut.valid(); }
+    R get() { if (fut.valid()) value = fut.get(); return value; }
+};
 
 struct Stopwatch
 {
@@ -567,6 +654,17 @@ struct Factor          // the rank-2 factors of one node: W is m x 2 (ld = m), H
 {
     std::vector<R> W, H;
     unsigned int cols = 0;
+    std::vector<unsigned int> rows;     // the rows W can be non-zero on (ascending); all_rows: every row (the root)
+    bool all_rows = false;
+};
+
+// the rows a parent vector (a column of `f.W`) can be non-zero on, for the priority score of f's children
+struct ParentRows
+{
+    const unsigned int* rows = nullptr;
+    int count = 0;
+    ParentRows() {}
+    explicit ParentRows(const Factor& f) : rows(f.all_rows ? nullptr : f.rows.data()), count(f.all_rows ? 0 : static_cast<int>(f.rows.size())) {}
 };
 
 struct HierRun
@@ -579,9 +677,26 @@ struct HierRun
     std::vector<unsigned int> new_to_old;      // scratch, m entries
     std::vector<R> Wsub, Hsub, Winit_full, Hinit_full;
     int init_counter = 1;                      // Winit_<i>.csv / Hinit_<i>.csv, clust_hier_generic.hpp:586
+    // worker-thread evaluation of priority scores (SMK_HIER_ASYNC=0 turns it off): its own scratch, its own library context
+    // (stream + sort buffers) for the device sorts of large nodes
+    bool async_on = true;
+    smk_ctx* ctx_worker = nullptr;
+    PriorityScratch scratch_worker;
+    RowsScratch rows_worker;
 
     HierRun(smk_ctx* c, const ClustOptions& o, Random& r, ClustStats& s)
-        : ctx(c), opts(o), m(o.nmf_opts.height), n(o.nmf_opts.width), rng(r), stats(s), new_to_old(o.nmf_opts.height) {}
+        : ctx(c), opts(o), m(o.nmf_opts.height), n(o.nmf_opts.width), rng(r), stats(s), new_to_old(o.nmf_opts.height)
+    {
+        const char* e = getenv("SMK_HIER_ASYNC");
+        async_on = !(e && atoi(e) == 0);
+        if (async_on && smk_create(&ctx_worker, smk_device_index(ctx)) != SMK_OK) { ctx_worker = nullptr; async_on = false; }
+        // the log tables are grown here, on this thread, once: afterwards both threads only read them
+        g_logs.ensure(static_cast<int>(m));
+        g_invd.ensure(static_cast<int>(m));
+    }
+    ~HierRun() { if (ctx_worker) smk_destroy(ctx_worker); }
+    HierRun(const HierRun&) = delete;
+    HierRun& operator=(const HierRun&) = delete;
 
     // LoadInitializers, clust_hier_generic.hpp:568-609
     void load_initializers()
@@ -622,12 +737,18 @@ struct HierRun
     }
 
     // clust_hier_generic.hpp:383-517
-    R actual_split(const std::vector<unsigned int>& subset, const R* W_parent, Factor& out, std::vector<unsigned int>& labels)
+    // With `defer`, the score of a regular split (two non-empty clusters, non-negative factors, more than one positive parent
+    // entry — such a score is a product of two ratios of sums of non-negative weights: never negative) is started on the worker
+    // thread and the value returned here is the placeholder 0; everything the worker reads (W_parent, out.W, defer->rows)
+    // must stay untouched until defer->get().
+    R actual_split(const std::vector<unsigned int>& subset, const R* W_parent, const ParentRows pr, Factor& out,
+                   std::vector<unsigned int>& labels, PendingPriority* defer = nullptr)
     {
         const size_t cnt = subset.size();
         out.cols = static_cast<unsigned int>(cnt);
         out.W.assign(static_cast<size_t>(m) * 2, R(0));
         out.H.assign(cnt * 2, R(0));
+        out.rows.clear(); out.all_rows = false;
         if (cnt <= 3) { labels.assign(cnt, 1u); return R(-1); }
 
         int new_height = 0;
@@ -676,13 +797,42 @@ struct HierRun
             out.W[static_cast<size_t>(m) + new_to_old[r]] = Wsub[static_cast<size_t>(new_height) + r];
         }
         out.H = Hsub;
+        out.rows.assign(new_to_old.begin(), new_to_old.begin() + new_height);
         if (!(has_0 && has_1)) return R(-1);
+        if (defer && async_on)
+        {
+            // what decides the sign of the score, and whether the streaming evaluation applies, is cheap to know now
+            bool regular = true;
+            int parent_pos = 0;
+            auto look = [&](const R v) { if (!(v >= 0)) regular = false; parent_pos += (v > 0) ? 1 : 0; };
+            if (pr.rows) { for (int t = 0; t < pr.count; ++t) look(W_parent[pr.rows[t]]); }
+            else for (unsigned int r = 0; r < m; ++r) look(W_parent[r]);
+            for (size_t e = 0; e < Wsub.size() && regular; ++e) if (!(Wsub[e] >= 0)) regular = false;
+            if (regular && parent_pos > 1)
+            {
+                defer->rows.assign(new_to_old.begin(), new_to_old.begin() + new_height);
+                const R* child = out.W.data();
+                const int mm = static_cast<int>(m);
+                PendingPriority* pp = defer;
+                HierRun* self = this;
+                defer->fut = std::async(std::launch::async, [self, pp, W_parent, child, mm, pr]() {
+                    const auto t0 = std::chrono::steady_clock::now();
+                    const R v = priority_rows_impl(self->ctx_worker, self->scratch_worker, self->rows_worker, false, W_parent, child, mm,
+                                                   pp->rows.data(), static_cast<int>(pp->rows.size()), pr.rows, pr.count);
+                    self->stats.t_priority_worker += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                    return v;
+                });
+                return R(0);
+            }
+        }
         Stopwatch sw(stats.t_priority);
-        return compute_priority_rows(ctx, W_parent, out.W.data(), static_cast<int>(m), new_to_old.data(), new_height);
+        return compute_priority_rows(ctx, W_parent, out.W.data(), static_cast<int>(m), new_to_old.data(), new_height, pr.rows, pr.count);
     }
 
     // clust_hier_generic.hpp:245-376
-    R trial_split(std::vector<unsigned int>& subset, const R min_priority, const R* W_parent, Factor& out)
+    // With `defer` the returned score may still be pending (defer->pending()): the caller takes it from defer->get().
+    R trial_split(std::vector<unsigned int>& subset, const R min_priority, const R* W_parent, const ParentRows pr, Factor& out,
+                  PendingPriority* defer = nullptr)
     {
         const std::vector<unsigned int> backup(subset);
         std::vector<unsigned int> labels, small, labels_small;
@@ -691,19 +841,21 @@ struct HierRun
         R priority = R(-2);
         while (trial < opts.trial_allowance)
         {
-            priority = actual_split(subset, W_parent, out, labels);
-            if (priority < R(0)) break;
+            priority = actual_split(subset, W_parent, pr, out, labels, defer);
+            if (priority < R(0)) break;                  // a pending score is not negative (actual_split)
             int counts[2] = {0, 0};
             for (unsigned int l : labels) counts[l] += 1;
             const int smallest = std::min(counts[0], counts[1]);
             if (!(smallest < opts.unbalanced * labels.size())) break;
+            // the unbalanced path re-uses `out`, the row map and the calling thread's score evaluation: finish the pending score first
+            if (defer && defer->pending()) { Stopwatch sw(stats.t_priority); priority = defer->get(); }
 
             const unsigned int small_label = (smallest == counts[0]) ? 0u : 1u;
             small.clear();
             for (size_t q = 0; q < labels.size(); ++q) if (labels[q] == small_label) small.push_back(subset[q]);
             // priority of the small cluster, with its own topic vector (a column of this split's W) as parent
             const std::vector<R> w_col(out.W.begin() + static_cast<size_t>(small_label) * m, out.W.begin() + static_cast<size_t>(small_label + 1) * m);
-            const R priority_small = actual_split(small, w_col.data(), tmp, labels_small);
+            const R priority_small = actual_split(small, w_col.data(), ParentRows(out), tmp, labels_small);
             if (priority_small < min_priority)
             {
                 trial += 1;
@@ -741,7 +893,7 @@ struct HierRun
         // root: the whole matrix
         smk_select_all(ctx);
         Factor root;
-        root.W.resize(static_cast<size_t>(m) * 2); root.H.resize(static_cast<size_t>(n) * 2); root.cols = n;
+        root.W.resize(static_cast<size_t>(m) * 2); root.H.resize(static_cast<size_t>(n) * 2); root.cols = n; root.all_rows = true;
         bool ok = false;
         for (int attempt = 0; attempt < 3 && !ok; ++attempt)
         {
@@ -771,16 +923,19 @@ struct HierRun
             }
             const unsigned int i0 = tree.LeftChildIndex(), i1 = tree.RightChildIndex();
             {
-                const std::vector<R> parent(tree.LeftChildTopicVector());
-                tree.SetNodePriority(i0, trial_split(tree.LeftChildDocs(), min_priority, parent.data(), node_factor[i0]));
-            }
-            {
-                const std::vector<R> parent(tree.RightChildTopicVector());
-                tree.SetNodePriority(i1, trial_split(tree.RightChildDocs(), min_priority, parent.data(), node_factor[i1]));
+                // the left child's score may be evaluated on the worker thread while this thread works on the right child
+                const std::vector<R> parent0(tree.LeftChildTopicVector()), parent1(tree.RightChildTopicVector());
+                const ParentRows pr(0 == i ? root : node_factor[split_index]);      // both vectors are columns of the split node's W
+                PendingPriority pend;
+                R p0 = trial_split(tree.LeftChildDocs(), min_priority, parent0.data(), pr, node_factor[i0], &pend);
+                const R p1 = trial_split(tree.RightChildDocs(), min_priority, parent1.data(), pr, node_factor[i1]);
+                if (pend.pending()) { Stopwatch sw(stats.t_priority); p0 = pend.get(); }
+                tree.SetNodePriority(i0, p0);
+                tree.SetNodePriority(i1, p1);
             }
             if (opts.verbose) { cout << "[" << (i + 1) << "] "; cout.flush(); }
             // the factors of a node that has been split are never read again
-            if (i > 0) { Factor().W.swap(node_factor[split_index].W); Factor().H.swap(node_factor[split_index].H); }
+            if (i > 0) { Factor().W.swap(node_factor[split_index].W); Factor().H.swap(node_factor[split_index].H); Factor().rows.swap(node_factor[split_index].rows); }
         }
         smk_select_all(ctx);
         { Stopwatch sw(stats.t_terms); tree.ComputeTopTerms(opts.maxterms); }

@@ -18,12 +18,13 @@ typedef double R;
 
 struct ClustStats
 {
-    ClustStats() : nmf_count(0), max_count(0), iteration_count(0), t_extract(0), t_init(0), t_factor(0), t_priority(0), t_terms(0) {}
+    ClustStats() : nmf_count(0), max_count(0), iteration_count(0), t_extract(0), t_init(0), t_factor(0), t_priority(0), t_terms(0), t_priority_worker(0) {}
     int nmf_count;        // factorizations performed
     int max_count;        // factorizations that reached the iteration limit
     // not in the reference: throughput accounting
     long long iteration_count;                                  // rank-2 outer iterations over all factorizations
-    double t_extract, t_init, t_factor, t_priority, t_terms;    // seconds: subset extraction, initialisers, smk_nmf, priority scores, top terms
+    double t_extract, t_init, t_factor, t_priority, t_terms;    // seconds on the calling thread: subset extraction, initialisers, smk_nmf, priority scores (evaluating or waiting for one), top terms
+    double t_priority_worker;                                   // seconds of priority-score evaluation that ran on the worker thread, under the other child's factorization
 };
 
 struct ClustOptions

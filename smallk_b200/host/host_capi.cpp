@@ -18,11 +18,12 @@
 
 R compute_priority_on(smk_ctx* ctx, const R* W_parent, const R* W_child, int n);
 R compute_priority_plain(smk_ctx* ctx, const R* W_parent, const R* W_child, int n);
-R compute_priority_rows(smk_ctx* ctx, const R* W_parent, const R* W_child, int n, const unsigned int* child_rows, int n_child_rows);
+R compute_priority_rows(smk_ctx* ctx, const R* W_parent, const R* W_child, int n, const unsigned int* child_rows, int n_child_rows,
+                        const unsigned int* parent_rows = nullptr, int n_parent_rows = 0);
 
 namespace {
 
-double g_profile[5] = {0, 0, 0, 0, 0};
+double g_profile[6] = {0, 0, 0, 0, 0, 0};
 
 void EnsureInit()
 {
@@ -67,7 +68,7 @@ int Finish(Result r, const ClustOptions& o, Tree<R>& tree, ClustStats& cs, int n
            const std::vector<R>& w, const std::vector<R>& h, double* buf_w, double* buf_h, long long* stats, int* flat_assignments)
 {
     if (stats) { stats[0] = cs.nmf_count; stats[1] = cs.max_count; stats[2] = cs.iteration_count; }
-    g_profile[0] = cs.t_extract; g_profile[1] = cs.t_init; g_profile[2] = cs.t_factor; g_profile[3] = cs.t_priority; g_profile[4] = cs.t_terms;
+    g_profile[0] = cs.t_extract; g_profile[1] = cs.t_init; g_profile[2] = cs.t_factor; g_profile[3] = cs.t_priority; g_profile[4] = cs.t_terms; g_profile[5] = cs.t_priority_worker;
     if (Result::OK != r) return static_cast<int>(r);
     ExportTree(tree, o.num_clusters, o.maxterms, n, assignments, parent, left, right, is_left, doc_count, terms, priority, is_leaf, n_outliers);
     if (o.flat)
@@ -91,7 +92,7 @@ extern "C" {
 const char* smkh_last_error() { return NmfLastError(); }
 
 // seconds spent by the last smkh_hierclust_* call in: subset extraction, initialisers, smk_nmf, priority scores, top terms
-void smkh_last_hier_profile(double* out5) { for (int i = 0; i < 5; ++i) out5[i] = g_profile[i]; }
+void smkh_last_hier_profile(double* out6) { for (int i = 0; i < 6; ++i) out6[i] = g_profile[i]; }
 
 // ClustSparse (hierclust/src/clust.cpp:160). stats[0..2] = nmf_count, max_count, total rank-2 iterations.
 int smkh_hierclust_sparse(int m, int n, unsigned int nz, const unsigned int* col_offsets, const unsigned int* row_indices,
@@ -175,6 +176,12 @@ double smkh_compute_priority_plain(const double* W_parent, const double* W_child
 double smkh_compute_priority_rows(const double* W_parent, const double* W_child, int m, const unsigned int* child_rows, int n_child_rows)
 {
     return compute_priority_rows(nullptr, W_parent, W_child, m, child_rows, n_child_rows);
+}
+// ... and with the rows named outside of which the parent vector is zero (what the tree driver passes below the root)
+double smkh_compute_priority_rows2(const double* W_parent, const double* W_child, int m, const unsigned int* child_rows, int n_child_rows,
+                                   const unsigned int* parent_rows, int n_parent_rows)
+{
+    return compute_priority_rows(nullptr, W_parent, W_child, m, child_rows, n_child_rows, parent_rows, n_parent_rows);
 }
 // the same with the large sorts on the GPU (what the tree driver uses): must give the identical value
 double smkh_compute_priority_gpu(const double* W_parent, const double* W_child, int m)

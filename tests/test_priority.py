@@ -19,6 +19,7 @@ def _host():
     lib.smkh_compute_priority.restype = ctypes.c_double
     lib.smkh_compute_priority_plain.restype = ctypes.c_double
     lib.smkh_compute_priority_rows.restype = ctypes.c_double
+    lib.smkh_compute_priority_rows2.restype = ctypes.c_double
     return lib
 
 
@@ -75,6 +76,11 @@ def test_row_list_priority_equals_plain_evaluation_bit_for_bit():
         a = lib.smkh_compute_priority_rows(P.ctypes.data_as(dp), C.ctypes.data_as(dp), n, child_rows.ctypes.data_as(up), len(child_rows))
         b = lib.smkh_compute_priority_plain(P.ctypes.data_as(dp), C.ctypes.data_as(dp), n)
         assert a == b, (n, mode, a, b)
+        # the tree driver also names the rows outside of which the parent vector is zero (a superset of its non-zero rows)
+        parent_rows = np.unique(np.concatenate([np.flatnonzero(P != 0), rng.choice(n, min(n, 29), replace=False)])).astype(np.uint32)
+        c = lib.smkh_compute_priority_rows2(P.ctypes.data_as(dp), C.ctypes.data_as(dp), n, child_rows.ctypes.data_as(up), len(child_rows),
+                                            parent_rows.ctypes.data_as(up), len(parent_rows))
+        assert c == b, (n, mode, c, b)
 
 
 def test_priority_equals_reference_function_bit_for_bit():
