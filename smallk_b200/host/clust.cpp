@@ -580,24 +580,34 @@ R priority_rows_impl(smk_ctx* ctx, PriorityScratch& S, RowsScratch& Q, const boo
     // all-zero rows hi, hi - 1, ..., lo with `shift` = max(n1 - positives of child 1 before them, n2 - ... of child 2):
     // rank of row i in the worse child ordering = i + shift
     // Row i of the run has weight invd[n - (i + shift)]: walking the run (i falling) walks invd upwards, and invd does not
-    // increase with its index, so the rows that come before the next irregular weight wf[head] (those with a strictly larger
-    // weight; an equal irregular weight goes first) are found by bisection and added as one block.
+    // increase with its index. Where at least kStretch rows come before the next irregular weight wf[head] (those with a strictly
+    // larger weight; an equal irregular weight goes first), the end of that stretch is found by bisection and its rows are added
+    // as one block; otherwise one row or one irregular weight at a time (large nodes: the two kinds alternate every few rows).
+    constexpr int kStretch = 24;
     auto run = [&](const int hi, const int lo, const int shift) {
         int i = hi;
         while (i >= lo)
         {
             const double* seg = invd + (n - (i + shift));           // weights of rows i, i - 1, ..., lo
             const int len = i - lo + 1;
-            int c = len;
             if (head < nw)
             {
                 const R wh = wf[head];
-                c = static_cast<int>(std::partition_point(seg, seg + len, [wh](const double v) { return !(wh >= v); }) - seg);
-                if (c == 0) { ideal = pos == 0 ? wh : ideal + wh / l2[pos + 1]; ++pos; ++head; continue; }
+                if (wh >= seg[0]) { ideal = pos == 0 ? wh : ideal + wh / l2[pos + 1]; ++pos; ++head; continue; }
+                if (pos == 0 || len < kStretch || wh >= seg[kStretch - 1])
+                {
+                    ideal = pos == 0 ? seg[0] : ideal + seg[0] / l2[pos + 1];
+                    ++pos; --i;
+                    continue;
+                }
+                const int c = static_cast<int>(std::partition_point(seg + kStretch, seg + len, [wh](const double v) { return !(wh >= v); }) - seg);
+                ideal = add_quotients(ideal, seg, l2 + pos + 1, c);
+                pos += c; i -= c;
+                continue;
             }
             if (pos == 0) { ideal = seg[0]; ++pos; --i; continue; }
-            ideal = add_quotients(ideal, seg, l2 + pos + 1, c);
-            pos += c; i -= c;
+            ideal = add_quotients(ideal, seg, l2 + pos + 1, len);
+            pos += len; i -= len;
         }
     };
     int hi = n - 1;
