@@ -690,6 +690,9 @@ struct HierRun
     // worker-thread evaluation of priority scores (SMK_HIER_ASYNC=0 turns it off): its own scratch, its own library context
     // (stream + sort buffers) for the device sorts of large nodes
     bool async_on = true;
+    // SMK_HIER_PROF=1: seconds of the driver's own host work per kind, on stderr when the run ends
+    bool prof_on = false;
+    double t_tree = 0, t_buffers = 0, t_labels = 0;
     smk_ctx* ctx_worker = nullptr;
     PriorityScratch scratch_worker;
     RowsScratch rows_worker;
@@ -699,12 +702,19 @@ struct HierRun
     {
         const char* e = getenv("SMK_HIER_ASYNC");
         async_on = !(e && atoi(e) == 0);
+        const char* pe = getenv("SMK_HIER_PROF");
+        prof_on = pe && atoi(pe) != 0;
         if (async_on && smk_create(&ctx_worker, smk_device_index(ctx)) != SMK_OK) { ctx_worker = nullptr; async_on = false; }
         // the log tables are grown here, on this thread, once: afterwards both threads only read them
         g_logs.ensure(static_cast<int>(m));
         g_invd.ensure(static_cast<int>(m));
     }
-    ~HierRun() { if (ctx_worker) smk_destroy(ctx_worker); }
+    ~HierRun()
+    {
+        if (ctx_worker) smk_destroy(ctx_worker);
+        if (prof_on) fprintf(stderr, "hierclust driver: tree updates %.3f s, factor buffers (zero fill) %.3f s, labels + scatter %.3f s\n",
+                             t_tree, t_buffers, t_labels);
+    }
     HierRun(const HierRun&) = delete;
     HierRun& operator=(const HierRun&) = delete;
 
@@ -756,8 +766,11 @@ struct HierRun
     {
         const size_t cnt = subset.size();
         out.cols = static_cast<unsigned int>(cnt);
-        out.W.assign(static_cast<size_t>(m) * 2, R(0));
-        out.H.assign(cnt * 2, R(0));
+        {
+            Stopwatch sw(t_buffers);
+            out.W.assign(static_cast<size_t>(m) * 2, R(0));
+            out.H.assign(cnt * 2, R(0));
+        }
         out.rows.clear(); out.all_rows = false;
         if (cnt <= 3) { labels.assign(cnt, 1u); return R(-1); }
 
@@ -795,19 +808,22 @@ struct HierRun
         if (!ok) throw std::runtime_error("HierNMF2: node factorization failed after three attempts.");
 
         bool has_0 = false, has_1 = false;
-        labels.resize(cnt);
-        for (size_t c = 0; c < cnt; ++c)
         {
-            if (Hsub[2 * c] > Hsub[2 * c + 1]) { labels[c] = 0u; has_0 = true; }
-            else { labels[c] = 1u; has_1 = true; }
+            Stopwatch sw_labels(t_labels);
+            labels.resize(cnt);
+            for (size_t c = 0; c < cnt; ++c)
+            {
+                if (Hsub[2 * c] > Hsub[2 * c + 1]) { labels[c] = 0u; has_0 = true; }
+                else { labels[c] = 1u; has_1 = true; }
+            }
+            for (int r = 0; r < new_height; ++r)
+            {
+                out.W[new_to_old[r]] = Wsub[r];
+                out.W[static_cast<size_t>(m) + new_to_old[r]] = Wsub[static_cast<size_t>(new_height) + r];
+            }
+            out.H = Hsub;
+            out.rows.assign(new_to_old.begin(), new_to_old.begin() + new_height);
         }
-        for (int r = 0; r < new_height; ++r)
-        {
-            out.W[new_to_old[r]] = Wsub[r];
-            out.W[static_cast<size_t>(m) + new_to_old[r]] = Wsub[static_cast<size_t>(new_height) + r];
-        }
-        out.H = Hsub;
-        out.rows.assign(new_to_old.begin(), new_to_old.begin() + new_height);
         if (!(has_0 && has_1)) return R(-1);
         if (defer && async_on)
         {
@@ -923,9 +939,10 @@ struct HierRun
         unsigned int split_index = 0;
         for (unsigned int i = 0; i + 1 < num_clusters; ++i)
         {
-            if (0 == i) tree.SplitRoot(root.W.data(), root.H.data(), root.cols);
+            if (0 == i) { Stopwatch sw(t_tree); tree.SplitRoot(root.W.data(), root.H.data(), root.cols); }
             else
             {
+                Stopwatch sw(t_tree);
                 tree.MinMaxLeafPriorities(min_priority, max_priority, split_index);
                 if (max_priority < R(0)) { cout << "\nHierNMF2: no further factorization possible.\n" << endl; break; }
                 const Factor& f = node_factor[split_index];
@@ -934,7 +951,9 @@ struct HierRun
             const unsigned int i0 = tree.LeftChildIndex(), i1 = tree.RightChildIndex();
             {
                 // the left child's score may be evaluated on the worker thread while this thread works on the right child
-                const std::vector<R> parent0(tree.LeftChildTopicVector()), parent1(tree.RightChildTopicVector());
+                // the children's topic vectors live in the tree's nodes, which stay where they are until the next Split
+                const std::vector<R>& parent0 = tree.LeftChildTopicVector();
+                const std::vector<R>& parent1 = tree.RightChildTopicVector();
                 const ParentRows pr(0 == i ? root : node_factor[split_index]);      // both vectors are columns of the split node's W
                 PendingPriority pend;
                 R p0 = trial_split(tree.LeftChildDocs(), min_priority, parent0.data(), pr, node_factor[i0], &pend);
