@@ -652,6 +652,8 @@ struct PendingPriority
     R get() { if (fut.valid()) value = fut.get(); return value; }
 };
 
+double seconds_since(const std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+
 struct Stopwatch
 {
     double& acc;
@@ -917,6 +919,7 @@ struct HierRun
         tree.Init(num_clusters, node_count, m, n);
 
         // root: the whole matrix
+        const auto t_grow0 = std::chrono::steady_clock::now();
         smk_select_all(ctx);
         Factor root;
         root.W.resize(static_cast<size_t>(m) * 2); root.H.resize(static_cast<size_t>(n) * 2); root.cols = n; root.all_rows = true;
@@ -934,6 +937,8 @@ struct HierRun
         }
         if (!ok) throw std::runtime_error("HierNMF2: root node factorization failed after three attempts");
 
+        if (prof_on) fprintf(stderr, "hierclust driver: tree.Init + root factorization (initialisers included) %.3f s\n", seconds_since(t_grow0));
+        const auto t_loop0 = std::chrono::steady_clock::now();
         std::vector<Factor> node_factor(node_count);
         R min_priority = std::numeric_limits<R>::infinity(), max_priority = 0;
         unsigned int split_index = 0;
@@ -966,6 +971,7 @@ struct HierRun
             // the factors of a node that has been split are never read again
             if (i > 0) { Factor().W.swap(node_factor[split_index].W); Factor().H.swap(node_factor[split_index].H); Factor().rows.swap(node_factor[split_index].rows); }
         }
+        if (prof_on) fprintf(stderr, "hierclust driver: split loop %.3f s\n", seconds_since(t_loop0));
         smk_select_all(ctx);
         { Stopwatch sw(stats.t_terms); tree.ComputeTopTerms(opts.maxterms); }
         tree.ComputeAssignments();
@@ -1015,8 +1021,13 @@ Result check_sizes(const ClustOptions& options)
 
 Result run(const ClustOptions& options, R* buf_w, R* buf_h, Tree<R>& tree, ClustStats& stats, Random& rng)
 {
+    const auto t0 = std::chrono::steady_clock::now();
     HierRun job(NmfContext(), options, rng, stats);
-    if (!job.grow(tree)) return Result::FAILURE;
+    const double t_ctor = seconds_since(t0);
+    const auto t1 = std::chrono::steady_clock::now();
+    const bool grown = job.grow(tree);
+    if (job.prof_on) fprintf(stderr, "hierclust driver: set-up %.3f s, grow() %.3f s\n", t_ctor, seconds_since(t1));
+    if (!grown) return Result::FAILURE;
     if (options.flat && !job.flat(tree, buf_w, buf_h))
     {
         cerr << "Flat clustering failed." << endl;
@@ -1043,8 +1054,10 @@ Result ClustSparse(const ClustOptions& options, const SparseMatrix<R>& A, R* buf
 {
     const Result r = check_sizes(options);
     if (Result::OK != r) return r;
+    const auto t0 = std::chrono::steady_clock::now();
     const int rc = smk_load_csc(NmfContext(), static_cast<int>(A.Height()), static_cast<int>(A.Width()), A.Size(),
                                 A.LockedColBuffer(), A.LockedRowBuffer(), A.LockedDataBuffer());
     if (rc != SMK_OK) { NmfSetLastError(smk_last_error(NmfContext())); return NmfFromAbi(rc); }
+    { const char* pe = getenv("SMK_HIER_PROF"); if (pe && atoi(pe) != 0) fprintf(stderr, "hierclust driver: smk_load_csc %.3f s\n", seconds_since(t0)); }
     return run(options, buf_w, buf_h, tree, stats, rng);
 }

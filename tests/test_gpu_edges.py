@@ -26,7 +26,7 @@ def _trace_gpu(ctx, W0, H0, opts, iters):
 
 
 @pytest.mark.parametrize("alg,m,n,k,iters", [
-    ("BPP", 50, 40, 1, 6), ("MU", 50, 40, 1, 6), ("HALS", 50, 40, 1, 6),      # one factor
+    ("BPP", 50, 40, 1, 3), ("MU", 50, 40, 1, 3), ("HALS", 50, 40, 1, 3),      # one factor (three iterations: by the fifth the metric is 1e-7 of its start, rounding noise of a cancelled gradient)
     ("BPP", 7, 6, 3, 5), ("HALS", 6, 5, 2, 6), ("MU", 4, 3, 2, 6), ("RANK2", 6, 5, 2, 6),   # a handful of rows and columns
     ("BPP", 1, 30, 1, 4),                                                      # a single row
 ])
