@@ -647,7 +647,6 @@ struct PendingPriority
 {
     R value = R(0);
     std::future<R> fut;
-    std::vector<unsigned int> rows;      // the worker's own copy of the node's row map (the driver's is scratch)
     bool pending() const { return fut.valid(); }
     R get() { if (fut.valid()) value = fut.get(); return value; }
 };
@@ -662,15 +661,19 @@ struct Stopwatch
     ~Stopwatch() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
 };
 
-struct Factor          // the rank-2 factors of one node: W is m x 2 (ld = m), H is 2 x cols
+// The rank-2 factors of one node. W (m x 2 in the reference) is zero outside the rows of the node's compacted matrix, so it is
+// kept on those rows only: row rows[r] of W is (Wc[r], Wc[nrows + r]). The root (all_rows) holds every row. H is 2 x cols.
+struct Factor
 {
-    std::vector<R> W, H;
-    unsigned int cols = 0;
-    std::vector<unsigned int> rows;     // the rows W can be non-zero on (ascending); all_rows: every row (the root)
+    std::vector<R> Wc, H;
+    std::vector<unsigned int> rows;     // ascending
     bool all_rows = false;
+    unsigned int cols = 0;
+    size_t nrows(const unsigned int m) const { return all_rows ? m : rows.size(); }
+    void release() { std::vector<R>().swap(Wc); std::vector<R>().swap(H); std::vector<unsigned int>().swap(rows); }
 };
 
-// the rows a parent vector (a column of `f.W`) can be non-zero on, for the priority score of f's children
+// the rows a parent vector (a column of `f`'s W) can be non-zero on, for the priority score of f's children
 struct ParentRows
 {
     const unsigned int* rows = nullptr;
@@ -678,6 +681,19 @@ struct ParentRows
     ParentRows() {}
     explicit ParentRows(const Factor& f) : rows(f.all_rows ? nullptr : f.rows.data()), count(f.all_rows ? 0 : static_cast<int>(f.rows.size())) {}
 };
+
+// What one thread needs to evaluate priority scores: a full-height m x 2 buffer that is zero except while a node's W is
+// scattered into it, and — for the worker threads — a scratch set and a library context (stream + sort buffers) of their own.
+struct Evaluator
+{
+    smk_ctx* ctx = nullptr;
+    std::vector<R> dense;
+    PriorityScratch ps;
+    RowsScratch rs;
+    double busy_s = 0;
+};
+
+struct MisSpeculated {};        // thrown (and caught) inside HierRun::grow: the leaf split ahead of time was not the right one
 
 struct HierRun
 {
@@ -687,17 +703,16 @@ struct HierRun
     Random& rng;
     ClustStats& stats;
     std::vector<unsigned int> new_to_old;      // scratch, m entries
-    std::vector<R> Wsub, Hsub, Winit_full, Hinit_full;
+    std::vector<R> Wsub, Hsub, Winit_full, Hinit_full, parent_scratch;
     int init_counter = 1;                      // Winit_<i>.csv / Hinit_<i>.csv, clust_hier_generic.hpp:586
-    // worker-thread evaluation of priority scores (SMK_HIER_ASYNC=0 turns it off): its own scratch, its own library context
-    // (stream + sort buffers) for the device sorts of large nodes
+    // Priority scores off the calling thread (SMK_HIER_ASYNC=0 turns it off): evaluator 0 is the calling thread's, 1 takes the
+    // left children's scores, 2 the right children's.
     bool async_on = true;
+    Evaluator eval[3];
     // SMK_HIER_PROF=1: seconds of the driver's own host work per kind, on stderr when the run ends
     bool prof_on = false;
     double t_tree = 0, t_buffers = 0, t_labels = 0;
-    smk_ctx* ctx_worker = nullptr;
-    PriorityScratch scratch_worker;
-    RowsScratch rows_worker;
+    int speculations = 0, misspeculations = 0;
 
     HierRun(smk_ctx* c, const ClustOptions& o, Random& r, ClustStats& s)
         : ctx(c), opts(o), m(o.nmf_opts.height), n(o.nmf_opts.width), rng(r), stats(s), new_to_old(o.nmf_opts.height)
@@ -706,16 +721,19 @@ struct HierRun
         async_on = !(e && atoi(e) == 0);
         const char* pe = getenv("SMK_HIER_PROF");
         prof_on = pe && atoi(pe) != 0;
-        if (async_on && smk_create(&ctx_worker, smk_device_index(ctx)) != SMK_OK) { ctx_worker = nullptr; async_on = false; }
-        // the log tables are grown here, on this thread, once: afterwards both threads only read them
+        eval[0].ctx = ctx;
+        for (int w = 1; w <= 2 && async_on; ++w)
+            if (smk_create(&eval[w].ctx, smk_device_index(ctx)) != SMK_OK) { eval[w].ctx = nullptr; async_on = false; }
+        for (int w = 0; w < (async_on ? 3 : 1); ++w) eval[w].dense.assign(static_cast<size_t>(m) * 2, R(0));
+        // the log tables are grown here, on this thread, once: afterwards every thread only reads them
         g_logs.ensure(static_cast<int>(m));
         g_invd.ensure(static_cast<int>(m));
     }
     ~HierRun()
     {
-        if (ctx_worker) smk_destroy(ctx_worker);
-        if (prof_on) fprintf(stderr, "hierclust driver: tree updates %.3f s, factor buffers (zero fill) %.3f s, labels + scatter %.3f s\n",
-                             t_tree, t_buffers, t_labels);
+        for (int w = 1; w <= 2; ++w) if (eval[w].ctx) smk_destroy(eval[w].ctx);
+        if (prof_on) fprintf(stderr, "hierclust driver: tree updates %.3f s, factor buffers %.3f s, labels + scatter %.3f s; %d leaves split ahead "
+                                     "of the last score, %d of them taken back\n", t_tree, t_buffers, t_labels, speculations, misspeculations);
     }
     HierRun(const HierRun&) = delete;
     HierRun& operator=(const HierRun&) = delete;
@@ -758,22 +776,47 @@ struct HierRun
         return false;
     }
 
+    // The priority score of `child` against the parent vector, on evaluator E: the child's W is scattered into E's full-height
+    // buffer for the evaluation and taken out again (the buffer is zero between evaluations).
+    R evaluate(Evaluator& E, const bool calling_thread, const R* W_parent, const ParentRows pr, const Factor& child)
+    {
+        const size_t cnt = child.nrows(m);
+        R* D = E.dense.data();
+        struct Scattered
+        {
+            R* D; const Factor& f; size_t cnt, m;
+            Scattered(R* d, const Factor& ff, size_t c, size_t mm) : D(d), f(ff), cnt(c), m(mm)
+            {
+                if (f.all_rows) std::copy(f.Wc.begin(), f.Wc.end(), D);
+                else for (size_t r = 0; r < cnt; ++r) { D[f.rows[r]] = f.Wc[r]; D[m + f.rows[r]] = f.Wc[cnt + r]; }
+            }
+            ~Scattered()
+            {
+                if (f.all_rows) std::fill(D, D + 2 * m, R(0));
+                else for (size_t r = 0; r < cnt; ++r) { D[f.rows[r]] = R(0); D[m + f.rows[r]] = R(0); }
+            }
+        } guard(D, child, cnt, m);
+        const unsigned int* rows = child.all_rows ? nullptr : child.rows.data();
+        if (calling_thread) return compute_priority_rows(E.ctx, W_parent, D, static_cast<int>(m), rows, static_cast<int>(cnt), pr.rows, pr.count);
+        const auto t0 = std::chrono::steady_clock::now();
+        const R v = rows ? priority_rows_impl(E.ctx, E.ps, E.rs, false, W_parent, D, static_cast<int>(m), rows, static_cast<int>(cnt), pr.rows, pr.count)
+                         : compute_priority_rows(E.ctx, W_parent, D, static_cast<int>(m), nullptr, 0);
+        E.busy_s += seconds_since(t0);
+        return v;
+    }
+
     // clust_hier_generic.hpp:383-517
-    // With `defer`, the score of a regular split (two non-empty clusters, non-negative factors, more than one positive parent
-    // entry — such a score is a product of two ratios of sums of non-negative weights: never negative) is started on the worker
-    // thread and the value returned here is the placeholder 0; everything the worker reads (W_parent, out.W, defer->rows)
-    // must stay untouched until defer->get().
+    // With `defer` (and evaluator `widx` free), the score of a regular split (two non-empty clusters, non-negative factors, more
+    // than one positive parent entry — such a score is a product of two ratios of sums of non-negative weights: never negative)
+    // is started on a worker thread and the value returned here is the placeholder 0; what the worker reads (W_parent, the rows
+    // behind `pr`, `out`) must stay untouched until defer->get().
     R actual_split(const std::vector<unsigned int>& subset, const R* W_parent, const ParentRows pr, Factor& out,
-                   std::vector<unsigned int>& labels, PendingPriority* defer = nullptr)
+                   std::vector<unsigned int>& labels, PendingPriority* defer = nullptr, const int widx = 1)
     {
         const size_t cnt = subset.size();
         out.cols = static_cast<unsigned int>(cnt);
-        {
-            Stopwatch sw(t_buffers);
-            out.W.assign(static_cast<size_t>(m) * 2, R(0));
-            out.H.assign(cnt * 2, R(0));
-        }
-        out.rows.clear(); out.all_rows = false;
+        out.Wc.clear(); out.rows.clear(); out.all_rows = false;
+        out.H.assign(cnt * 2, R(0));
         if (cnt <= 3) { labels.assign(cnt, 1u); return R(-1); }
 
         int new_height = 0;
@@ -818,11 +861,7 @@ struct HierRun
                 if (Hsub[2 * c] > Hsub[2 * c + 1]) { labels[c] = 0u; has_0 = true; }
                 else { labels[c] = 1u; has_1 = true; }
             }
-            for (int r = 0; r < new_height; ++r)
-            {
-                out.W[new_to_old[r]] = Wsub[r];
-                out.W[static_cast<size_t>(m) + new_to_old[r]] = Wsub[static_cast<size_t>(new_height) + r];
-            }
+            out.Wc = Wsub;
             out.H = Hsub;
             out.rows.assign(new_to_old.begin(), new_to_old.begin() + new_height);
         }
@@ -838,29 +877,24 @@ struct HierRun
             for (size_t e = 0; e < Wsub.size() && regular; ++e) if (!(Wsub[e] >= 0)) regular = false;
             if (regular && parent_pos > 1)
             {
-                defer->rows.assign(new_to_old.begin(), new_to_old.begin() + new_height);
-                const R* child = out.W.data();
-                const int mm = static_cast<int>(m);
-                PendingPriority* pp = defer;
                 HierRun* self = this;
-                defer->fut = std::async(std::launch::async, [self, pp, W_parent, child, mm, pr]() {
-                    const auto t0 = std::chrono::steady_clock::now();
-                    const R v = priority_rows_impl(self->ctx_worker, self->scratch_worker, self->rows_worker, false, W_parent, child, mm,
-                                                   pp->rows.data(), static_cast<int>(pp->rows.size()), pr.rows, pr.count);
-                    self->stats.t_priority_worker += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-                    return v;
-                });
+                Evaluator* E = &eval[widx];
+                const Factor* child = &out;
+                defer->fut = std::async(std::launch::async, [self, E, W_parent, pr, child]() { return self->evaluate(*E, false, W_parent, pr, *child); });
                 return R(0);
             }
         }
         Stopwatch sw(stats.t_priority);
-        return compute_priority_rows(ctx, W_parent, out.W.data(), static_cast<int>(m), new_to_old.data(), new_height, pr.rows, pr.count);
+        return evaluate(eval[0], true, W_parent, pr, out);
     }
 
     // clust_hier_generic.hpp:245-376
-    // With `defer` the returned score may still be pending (defer->pending()): the caller takes it from defer->get().
-    R trial_split(std::vector<unsigned int>& subset, const R min_priority, const R* W_parent, const ParentRows pr, Factor& out,
-                  PendingPriority* defer = nullptr)
+    // min_priority() is asked for only where the reference uses the value (a small cluster's score is compared with it), which
+    // lets the caller hand in a value that is still being established. With `defer` the returned score may still be pending
+    // (defer->pending()): the caller takes it from defer->get().
+    template <typename MinPriority>
+    R trial_split(std::vector<unsigned int>& subset, MinPriority&& min_priority, const R* W_parent, const ParentRows pr, Factor& out,
+                  PendingPriority* defer = nullptr, const int widx = 1)
     {
         const std::vector<unsigned int> backup(subset);
         std::vector<unsigned int> labels, small, labels_small;
@@ -869,22 +903,32 @@ struct HierRun
         R priority = R(-2);
         while (trial < opts.trial_allowance)
         {
-            priority = actual_split(subset, W_parent, pr, out, labels, defer);
+            priority = actual_split(subset, W_parent, pr, out, labels, defer, widx);
             if (priority < R(0)) break;                  // a pending score is not negative (actual_split)
             int counts[2] = {0, 0};
             for (unsigned int l : labels) counts[l] += 1;
             const int smallest = std::min(counts[0], counts[1]);
             if (!(smallest < opts.unbalanced * labels.size())) break;
-            // the unbalanced path re-uses `out`, the row map and the calling thread's score evaluation: finish the pending score first
+            // the unbalanced path re-uses `out` and the row map: finish the pending score first
             if (defer && defer->pending()) { Stopwatch sw(stats.t_priority); priority = defer->get(); }
 
             const unsigned int small_label = (smallest == counts[0]) ? 0u : 1u;
             small.clear();
             for (size_t q = 0; q < labels.size(); ++q) if (labels[q] == small_label) small.push_back(subset[q]);
             // priority of the small cluster, with its own topic vector (a column of this split's W) as parent
-            const std::vector<R> w_col(out.W.begin() + static_cast<size_t>(small_label) * m, out.W.begin() + static_cast<size_t>(small_label + 1) * m);
-            const R priority_small = actual_split(small, w_col.data(), ParentRows(out), tmp, labels_small);
-            if (priority_small < min_priority)
+            R priority_small;
+            {
+                const size_t cnt = out.rows.size();
+                parent_scratch.resize(m, R(0));
+                for (size_t r = 0; r < cnt; ++r) parent_scratch[out.rows[r]] = out.Wc[small_label * cnt + r];
+                struct Clear
+                {
+                    std::vector<R>& v; const std::vector<unsigned int> rows;
+                    ~Clear() { for (unsigned int r : rows) v[r] = R(0); }
+                } clear{parent_scratch, out.rows};
+                priority_small = actual_split(small, parent_scratch.data(), ParentRows(out), tmp, labels_small);
+            }
+            if (priority_small < min_priority())
             {
                 trial += 1;
                 if (trial < opts.trial_allowance)
@@ -902,7 +946,7 @@ struct HierRun
         {
             if (opts.verbose) cout << "recycling " << small.size() << " items ..." << endl;
             subset = backup;
-            std::fill(out.W.begin(), out.W.end(), R(0));
+            std::fill(out.Wc.begin(), out.Wc.end(), R(0));
             out.cols = static_cast<unsigned int>(subset.size());
             out.H.assign(subset.size() * 2, R(0));
             priority = R(-2);
@@ -922,17 +966,17 @@ struct HierRun
         const auto t_grow0 = std::chrono::steady_clock::now();
         smk_select_all(ctx);
         Factor root;
-        root.W.resize(static_cast<size_t>(m) * 2); root.H.resize(static_cast<size_t>(n) * 2); root.cols = n; root.all_rows = true;
+        root.Wc.resize(static_cast<size_t>(m) * 2); root.H.resize(static_cast<size_t>(n) * 2); root.cols = n; root.all_rows = true;
         bool ok = false;
         for (int attempt = 0; attempt < 3 && !ok; ++attempt)
         {
-            if (!opts.initdir.empty()) { load_initializers(); root.W = Winit_full; root.H = Hinit_full; }
+            if (!opts.initdir.empty()) { load_initializers(); root.Wc = Winit_full; root.H = Hinit_full; }
             else
             {
-                RandomMatrix(root.W.data(), m, m, 2, rng, R(0.5), R(0.5));
+                RandomMatrix(root.Wc.data(), m, m, 2, rng, R(0.5), R(0.5));
                 RandomMatrix(root.H.data(), 2, 2, n, rng, R(0.5), R(0.5));
             }
-            ok = factor(static_cast<int>(m), static_cast<int>(n), root.W.data(), root.H.data());
+            ok = factor(static_cast<int>(m), static_cast<int>(n), root.Wc.data(), root.H.data());
             if (!ok) cout << "\nRoot node factorization failed, retrying with new initializers..." << endl;
         }
         if (!ok) throw std::runtime_error("HierNMF2: root node factorization failed after three attempts");
@@ -942,35 +986,119 @@ struct HierRun
         std::vector<Factor> node_factor(node_count);
         R min_priority = std::numeric_limits<R>::infinity(), max_priority = 0;
         unsigned int split_index = 0;
+        // Scores on their way: the left child's on evaluator 1 (under the right child's factorization), the right child's on
+        // evaluator 2 (under the factorization of the NEXT split's left child, which is started ahead of time — see below).
+        PendingPriority pend_left, pend_right;
+        unsigned int pend_left_node = 0, pend_right_node = 0;
+        int release_after_right = -1;          // the split node whose rows the pending right-child score still reads
+        auto finish_left = [&]() {
+            if (!pend_left.pending()) return;
+            Stopwatch sw(stats.t_priority);
+            tree.SetNodePriority(pend_left_node, pend_left.get());
+        };
+        auto finish_right = [&]() {
+            if (pend_right.pending())
+            {
+                Stopwatch sw(stats.t_priority);
+                tree.SetNodePriority(pend_right_node, pend_right.get());
+            }
+            // the factors of a node that has been split are never read again
+            if (release_after_right >= 0) { node_factor[release_after_right].release(); release_after_right = -1; }
+        };
+        auto split_leaf = [&](const unsigned int q) {
+            Stopwatch sw(t_tree);
+            const Factor& f = node_factor[q];
+            tree.SplitCompact(q, f.rows.data(), static_cast<unsigned int>(f.rows.size()), f.Wc.data(), f.H.data(), f.cols);
+        };
+        auto plain_min = [&]() { return min_priority; };
+
+        bool ahead = false;                    // this iteration's split and left child were already done (ahead of time, confirmed)
+        unsigned int i0 = 0, i1 = 0;
         for (unsigned int i = 0; i + 1 < num_clusters; ++i)
         {
-            if (0 == i) { Stopwatch sw(t_tree); tree.SplitRoot(root.W.data(), root.H.data(), root.cols); }
-            else
+            if (!ahead)
             {
-                Stopwatch sw(t_tree);
-                tree.MinMaxLeafPriorities(min_priority, max_priority, split_index);
-                if (max_priority < R(0)) { cout << "\nHierNMF2: no further factorization possible.\n" << endl; break; }
-                const Factor& f = node_factor[split_index];
-                tree.Split(split_index, f.W.data(), f.H.data(), f.cols);
+                finish_left(); finish_right();
+                if (0 == i) { Stopwatch sw(t_tree); tree.SplitRoot(root.Wc.data(), root.H.data(), root.cols); }
+                else
+                {
+                    { Stopwatch sw(t_tree); tree.MinMaxLeafPriorities(min_priority, max_priority, split_index); }
+                    if (max_priority < R(0)) { cout << "\nHierNMF2: no further factorization possible.\n" << endl; break; }
+                    split_leaf(split_index);
+                }
+                i0 = tree.LeftChildIndex(); i1 = tree.RightChildIndex();
+                const ParentRows pr(0 == i ? root : node_factor[split_index]);      // both topic vectors are columns of the split node's W
+                const R p0 = trial_split(tree.LeftChildDocs(), plain_min, tree.LeftChildTopicVector().data(), pr, node_factor[i0], &pend_left, 1);
+                if (pend_left.pending()) pend_left_node = i0; else tree.SetNodePriority(i0, p0);
             }
-            const unsigned int i0 = tree.LeftChildIndex(), i1 = tree.RightChildIndex();
+            ahead = false;
             {
-                // the left child's score may be evaluated on the worker thread while this thread works on the right child
-                // the children's topic vectors live in the tree's nodes, which stay where they are until the next Split
-                const std::vector<R>& parent0 = tree.LeftChildTopicVector();
-                const std::vector<R>& parent1 = tree.RightChildTopicVector();
-                const ParentRows pr(0 == i ? root : node_factor[split_index]);      // both vectors are columns of the split node's W
-                PendingPriority pend;
-                R p0 = trial_split(tree.LeftChildDocs(), min_priority, parent0.data(), pr, node_factor[i0], &pend);
-                const R p1 = trial_split(tree.RightChildDocs(), min_priority, parent1.data(), pr, node_factor[i1]);
-                if (pend.pending()) { Stopwatch sw(stats.t_priority); p0 = pend.get(); }
-                tree.SetNodePriority(i0, p0);
-                tree.SetNodePriority(i1, p1);
+                // the children's topic vectors live in the tree's nodes, which stay where they are
+                const ParentRows pr(0 == i ? root : node_factor[split_index]);
+                const R p1 = trial_split(tree.RightChildDocs(), plain_min, tree.RightChildTopicVector().data(), pr, node_factor[i1], &pend_right, 2);
+                if (pend_right.pending()) pend_right_node = i1; else tree.SetNodePriority(i1, p1);
+                if (i > 0) release_after_right = static_cast<int>(split_index);
             }
+            finish_left();
             if (opts.verbose) { cout << "[" << (i + 1) << "] "; cout.flush(); }
-            // the factors of a node that has been split are never read again
-            if (i > 0) { Factor().W.swap(node_factor[split_index].W); Factor().H.swap(node_factor[split_index].H); Factor().rows.swap(node_factor[split_index].rows); }
+
+            // Ahead of time: while the right child's score is evaluated, the leaf that will be split next UNLESS that score beats it
+            // (the best of all the others, the reference's scan and tie rule) is split and its left child factored. When the
+            // score arrives it either confirms the choice — the work is exactly what the next iteration would have done, from the same
+            // generator state — or the tree, the generator and the counters are put back and the next iteration starts over.
+            if (!(async_on && pend_right.pending() && i + 2 < num_clusters && opts.initdir.empty())) continue;
+            R min_wo = 0, max_wo = 0;
+            unsigned int best = 0;
+            { Stopwatch sw(t_tree); tree.MinMaxLeafPrioritiesWithout(i1, min_wo, max_wo, best); }
+            if (max_wo < R(0)) continue;
+            const Random saved_rng = rng;
+            const int saved_nmf = stats.nmf_count, saved_max = stats.max_count;
+            const long long saved_iters = stats.iteration_count;
+            speculations += 1;
+            split_leaf(best);
+            const unsigned int s0 = tree.LeftChildIndex(), s1 = tree.RightChildIndex();
+            bool confirmed = false;
+            R next_min = 0;
+            // the right child's score is in: was `best` the right leaf to split? if so, what MinMaxLeafPriorities would have found
+            auto confirm = [&]() {
+                if (confirmed) return next_min;
+                finish_right();
+                const R p1 = tree.NodePriority(i1);
+                if (p1 > max_wo) throw MisSpeculated();
+                next_min = (p1 > R(0) && p1 < min_wo) ? p1 : min_wo;
+                confirmed = true;
+                return next_min;
+            };
+            auto take_back = [&]() {
+                if (pend_left.pending()) { try { pend_left.get(); } catch (...) {} }
+                { Stopwatch sw(t_tree); tree.UndoSplit(best); }
+                node_factor[s0] = Factor();
+                rng = saved_rng;
+                stats.nmf_count = saved_nmf; stats.max_count = saved_max; stats.iteration_count = saved_iters;
+                misspeculations += 1;
+            };
+            try
+            {
+                const ParentRows pr(node_factor[best]);
+                const R p0 = trial_split(tree.LeftChildDocs(), confirm, tree.LeftChildTopicVector().data(), pr, node_factor[s0], &pend_left, 1);
+                if (pend_left.pending()) pend_left_node = s0; else tree.SetNodePriority(s0, p0);
+                confirm();
+            }
+            catch (MisSpeculated&) { take_back(); continue; }
+            catch (...)
+            {
+                // an error of a factorization that should never have been started is not an error
+                bool wrong = false;
+                if (!confirmed) { try { confirm(); } catch (MisSpeculated&) { wrong = true; } }
+                if (wrong) { take_back(); continue; }
+                throw;
+            }
+            ahead = true;
+            split_index = best; i0 = s0; i1 = s1;
+            min_priority = next_min; max_priority = max_wo;
         }
+        finish_left(); finish_right();
+        stats.t_priority_worker += eval[1].busy_s + eval[2].busy_s;
         if (prof_on) fprintf(stderr, "hierclust driver: split loop %.3f s\n", seconds_since(t_loop0));
         smk_select_all(ctx);
         { Stopwatch sw(stats.t_terms); tree.ComputeTopTerms(opts.maxterms); }

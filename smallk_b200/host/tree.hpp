@@ -99,16 +99,45 @@ public:
 
     void Split(const unsigned int node_index, const T* W, const T* H, const unsigned int h_width)
     {
-        index0_ = active_nodes_; index1_ = active_nodes_ + 1;
-        active_nodes_ += 2;
-        nodes_[node_index].left_child_index = index0_;
-        nodes_[node_index].right_child_index = index1_;
-        is_leaf_[node_index] = false;
-        MakeLeaf(index0_, node_index, true); MakeLeaf(index1_, node_index, false);
-        const std::vector<unsigned int>& src = nodes_[node_index].docs;
-        for (unsigned int c = 0; c < h_width; ++c)
-            nodes_[(H[2 * c] > H[2 * c + 1]) ? index0_ : index1_].docs.push_back(src[c]);   // tree.hpp:308-314
+        SplitDocs(node_index, H, h_width);
         TakeTopicVectors(W);
+    }
+
+    // Split with the node's W held on its own rows only (the hierclust driver's node factors): rows[r] of the full m x 2 matrix
+    // is (Wc[r], Wc[count + r]); every other row is zero.
+    void SplitCompact(const unsigned int node_index, const unsigned int* rows, const unsigned int count, const T* Wc, const T* H,
+                      const unsigned int h_width)
+    {
+        SplitDocs(node_index, H, h_width);
+        std::vector<T>& t0 = nodes_[index0_].topic_vector;
+        std::vector<T>& t1 = nodes_[index1_].topic_vector;
+        t0.assign(term_count_, T(0)); t1.assign(term_count_, T(0));
+        for (unsigned int r = 0; r < count; ++r) { t0[rows[r]] = Wc[r]; t1[rows[r]] = Wc[static_cast<size_t>(count) + r]; }
+    }
+
+    // Takes back the most recent Split / SplitCompact (of node_index): the driver splits the most promising leaf ahead of time
+    // while the last score is still being evaluated, and must be able to return to the tree as it was.
+    void UndoSplit(const unsigned int node_index)
+    {
+        nodes_[index0_] = NodeRec(); nodes_[index1_] = NodeRec();
+        is_leaf_[index0_] = false; is_leaf_[index1_] = false;
+        active_nodes_ -= 2;
+        nodes_[node_index].left_child_index = NONE; nodes_[node_index].right_child_index = NONE;
+        is_leaf_[node_index] = true;
+    }
+
+    // MinMaxLeafPriorities over every leaf but `skip` (same scan, same tie rule)
+    void MinMaxLeafPrioritiesWithout(const unsigned int skip, T& min_priority, T& max_priority, unsigned int& max_priority_index)
+    {
+        min_priority = std::numeric_limits<T>::max();
+        max_priority = std::numeric_limits<T>::lowest();
+        for (unsigned int q = 0; q < is_leaf_.size(); ++q)
+        {
+            if (!is_leaf_[q] || q == skip) continue;
+            const T p = nodes_[q].priority;
+            if (p > T(0) && p < min_priority) min_priority = p;
+            if (p > max_priority) { max_priority = p; max_priority_index = q; }
+        }
     }
 
     void SetNodePriority(const unsigned int node_index, const T priority) { nodes_[node_index].priority = priority; }
@@ -242,6 +271,19 @@ private:
         nd.parent_index = parent; nd.left_child_index = NONE; nd.right_child_index = NONE;
         nd.is_valid = true; nd.is_left_child = is_left;
         is_leaf_[q] = true;
+    }
+    // the two new leaves of node_index and their documents
+    void SplitDocs(const unsigned int node_index, const T* H, const unsigned int h_width)
+    {
+        index0_ = active_nodes_; index1_ = active_nodes_ + 1;
+        active_nodes_ += 2;
+        nodes_[node_index].left_child_index = index0_;
+        nodes_[node_index].right_child_index = index1_;
+        is_leaf_[node_index] = false;
+        MakeLeaf(index0_, node_index, true); MakeLeaf(index1_, node_index, false);
+        const std::vector<unsigned int>& src = nodes_[node_index].docs;
+        for (unsigned int c = 0; c < h_width; ++c)
+            nodes_[(H[2 * c] > H[2 * c + 1]) ? index0_ : index1_].docs.push_back(src[c]);   // tree.hpp:308-314
     }
     // left child <- W(:,0), right child <- W(:,1)   (tree.hpp:332-349)
     void TakeTopicVectors(const T* W)
