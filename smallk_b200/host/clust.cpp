@@ -693,6 +693,28 @@ struct Evaluator
     double busy_s = 0;
 };
 
+// The worker threads' library contexts are made by the first Clust call on a device and kept for the later ones (creating and
+// destroying two contexts is tens of milliseconds each way); NmfFinalize releases them (HierReleaseWorkers).
+struct WorkerContexts
+{
+    smk_ctx* ctx[2] = {nullptr, nullptr};
+    int device = -1;
+    bool acquire(const int dev)
+    {
+        if (device == dev && ctx[0] && ctx[1]) return true;
+        release();
+        for (int w = 0; w < 2; ++w) if (smk_create(&ctx[w], dev) != SMK_OK) { ctx[w] = nullptr; release(); return false; }
+        device = dev;
+        return true;
+    }
+    void release()
+    {
+        for (int w = 0; w < 2; ++w) { if (ctx[w]) smk_destroy(ctx[w]); ctx[w] = nullptr; }
+        device = -1;
+    }
+};
+WorkerContexts g_workers;
+
 struct MisSpeculated {};        // thrown (and caught) inside HierRun::grow: the leaf split ahead of time was not the right one
 
 struct HierRun
@@ -722,8 +744,8 @@ struct HierRun
         const char* pe = getenv("SMK_HIER_PROF");
         prof_on = pe && atoi(pe) != 0;
         eval[0].ctx = ctx;
-        for (int w = 1; w <= 2 && async_on; ++w)
-            if (smk_create(&eval[w].ctx, smk_device_index(ctx)) != SMK_OK) { eval[w].ctx = nullptr; async_on = false; }
+        if (async_on && !g_workers.acquire(smk_device_index(ctx))) async_on = false;
+        if (async_on) { eval[1].ctx = g_workers.ctx[0]; eval[2].ctx = g_workers.ctx[1]; }
         for (int w = 0; w < (async_on ? 3 : 1); ++w) eval[w].dense.assign(static_cast<size_t>(m) * 2, R(0));
         // the log tables are grown here, on this thread, once: afterwards every thread only reads them
         g_logs.ensure(static_cast<int>(m));
@@ -731,7 +753,6 @@ struct HierRun
     }
     ~HierRun()
     {
-        for (int w = 1; w <= 2; ++w) if (eval[w].ctx) smk_destroy(eval[w].ctx);
         if (prof_on) fprintf(stderr, "hierclust driver: tree updates %.3f s, factor buffers %.3f s, labels + scatter %.3f s; %d leaves split ahead "
                                      "of the last score, %d of them taken back\n", t_tree, t_buffers, t_labels, speculations, misspeculations);
     }
@@ -1186,6 +1207,12 @@ Result ClustSparse(const ClustOptions& options, const SparseMatrix<R>& A, R* buf
     const int rc = smk_load_csc(NmfContext(), static_cast<int>(A.Height()), static_cast<int>(A.Width()), A.Size(),
                                 A.LockedColBuffer(), A.LockedRowBuffer(), A.LockedDataBuffer());
     if (rc != SMK_OK) { NmfSetLastError(smk_last_error(NmfContext())); return NmfFromAbi(rc); }
-    { const char* pe = getenv("SMK_HIER_PROF"); if (pe && atoi(pe) != 0) fprintf(stderr, "hierclust driver: smk_load_csc %.3f s\n", seconds_since(t0)); }
-    return run(options, buf_w, buf_h, tree, stats, rng);
+    const char* pe = getenv("SMK_HIER_PROF");
+    const bool prof = pe && atoi(pe) != 0;
+    if (prof) fprintf(stderr, "hierclust driver: smk_load_csc %.3f s\n", seconds_since(t0));
+    const Result res = run(options, buf_w, buf_h, tree, stats, rng);
+    if (prof) fprintf(stderr, "hierclust driver: ClustSparse %.3f s in all\n", seconds_since(t0));
+    return res;
 }
+
+void HierReleaseWorkers() { g_workers.release(); }

@@ -7,3 +7,4 @@ smk_ctx* NmfContext();                 // the context NmfInitialize created, or 
 smk_nmf_options NmfToAbi(const NmfOptions& o);
 Result NmfFromAbi(int rc);
 void NmfSetLastError(const char* msg);
+void HierReleaseWorkers();             // clust.cpp: the score workers' library contexts (kept from one Clust call to the next)

@@ -95,6 +95,7 @@ Result NmfIsInitialized() { return g_ctx ? Result::INITIALIZED : Result::NOTINIT
 
 void NmfFinalize()
 {
+    HierReleaseWorkers();
     if (g_ctx) smk_destroy(g_ctx);
     g_ctx = nullptr;
 }
