@@ -63,7 +63,9 @@ typedef struct
     int iteration_count;
 } smk_nmf_stats;
 
-/* ---- lifecycle: NmfInitialize / NmfIsInitialized / NmfFinalize (common/src/nmf.cpp:36-52) ---- */
+/* ---- lifecycle: NmfInitialize / NmfIsInitialized / NmfFinalize (common/src/nmf.cpp:36-52) ----
+ * A context is used by one host thread at a time; different contexts (own stream, own scratch) may be used from different host
+ * threads concurrently (the hierclust driver sorts on two worker contexts while the main one factors). ---- */
 int smk_create(smk_ctx** ctx, int device);
 void smk_destroy(smk_ctx* ctx);
 const char* smk_last_error(const smk_ctx* ctx);
