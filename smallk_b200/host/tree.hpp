@@ -11,6 +11,8 @@
 #include <iostream>
 #include <limits>
 #include <string>
+#include <cstdlib>
+#include <new>
 #include <vector>
 
 #include "hierclust_writer.hpp"
@@ -42,6 +44,37 @@ inline void TopTerms(const int maxterms, const T* v, const int height, std::vect
     for (int q = 0; q < keep; ++q) term_indices[q] = scratch[q];
 }
 
+// n zero-initialised elements straight from calloc. A topic vector of a deep node is zero on all but a few rows: pages that
+// are never written stay unmapped (std::vector would write every one of them), and a later full read maps the shared zero page.
+template <typename T>
+class ZeroArray
+{
+public:
+    ZeroArray() {}
+    ~ZeroArray() { std::free(p_); }
+    ZeroArray(const ZeroArray& o) { reset(o.n_); for (size_t i = 0; i < n_; ++i) p_[i] = o.p_[i]; }
+    ZeroArray(ZeroArray&& o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+    ZeroArray& operator=(ZeroArray o) noexcept { std::swap(p_, o.p_); std::swap(n_, o.n_); return *this; }
+    void reset(const size_t n)
+    {
+        std::free(p_); p_ = nullptr; n_ = 0;
+        if (n == 0) return;
+        p_ = static_cast<T*>(std::calloc(n, sizeof(T)));
+        if (!p_) throw std::bad_alloc();
+        n_ = n;
+    }
+    T* data() { return p_; }
+    const T* data() const { return p_; }
+    size_t size() const { return n_; }
+    T* begin() { return p_; }
+    T* end() { return p_ + n_; }
+    const T* begin() const { return p_; }
+    const T* end() const { return p_ + n_; }
+private:
+    T* p_ = nullptr;
+    size_t n_ = 0;
+};
+
 template <typename T>
 class Tree
 {
@@ -50,8 +83,8 @@ public:
 
     unsigned int LeftChildIndex() { return index0_; }
     unsigned int RightChildIndex() { return index1_; }
-    std::vector<T>& LeftChildTopicVector() { return nodes_[index0_].topic_vector; }
-    std::vector<T>& RightChildTopicVector() { return nodes_[index1_].topic_vector; }
+    ZeroArray<T>& LeftChildTopicVector() { return nodes_[index0_].topic_vector; }
+    ZeroArray<T>& RightChildTopicVector() { return nodes_[index1_].topic_vector; }
     std::vector<unsigned int>& LeftChildDocs() { return nodes_[index0_].docs; }
     std::vector<unsigned int>& RightChildDocs() { return nodes_[index1_].docs; }
     std::vector<unsigned int>& Outliers() { return outliers_; }
@@ -109,10 +142,11 @@ public:
                       const unsigned int h_width)
     {
         SplitDocs(node_index, H, h_width);
-        std::vector<T>& t0 = nodes_[index0_].topic_vector;
-        std::vector<T>& t1 = nodes_[index1_].topic_vector;
-        t0.assign(term_count_, T(0)); t1.assign(term_count_, T(0));
-        for (unsigned int r = 0; r < count; ++r) { t0[rows[r]] = Wc[r]; t1[rows[r]] = Wc[static_cast<size_t>(count) + r]; }
+        ZeroArray<T>& t0 = nodes_[index0_].topic_vector;
+        ZeroArray<T>& t1 = nodes_[index1_].topic_vector;
+        t0.reset(term_count_); t1.reset(term_count_);
+        T* d0 = t0.data(); T* d1 = t1.data();
+        for (unsigned int r = 0; r < count; ++r) { d0[rows[r]] = Wc[r]; d1[rows[r]] = Wc[static_cast<size_t>(count) + r]; }
     }
 
     // Takes back the most recent Split / SplitCompact (of node_index): the driver splits the most promising leaf ahead of time
@@ -126,14 +160,15 @@ public:
         is_leaf_[node_index] = true;
     }
 
-    // MinMaxLeafPriorities over every leaf but `skip` (same scan, same tie rule)
-    void MinMaxLeafPrioritiesWithout(const unsigned int skip, T& min_priority, T& max_priority, unsigned int& max_priority_index)
+    // MinMaxLeafPriorities over every leaf but skip_a and skip_b (NONE: nothing to skip); same scan, same tie rule
+    void MinMaxLeafPrioritiesWithout(const unsigned int skip_a, const unsigned int skip_b, T& min_priority, T& max_priority,
+                                     unsigned int& max_priority_index)
     {
         min_priority = std::numeric_limits<T>::max();
         max_priority = std::numeric_limits<T>::lowest();
         for (unsigned int q = 0; q < is_leaf_.size(); ++q)
         {
-            if (!is_leaf_[q] || q == skip) continue;
+            if (!is_leaf_[q] || q == skip_a || q == skip_b) continue;
             const T p = nodes_[q].priority;
             if (p > T(0) && p < min_priority) min_priority = p;
             if (p > max_priority) { max_priority = p; max_priority_index = q; }
@@ -260,7 +295,7 @@ private:
         T priority = T(0);
         unsigned int parent_index = NONE, left_child_index = NONE, right_child_index = NONE;
         bool is_valid = false, is_left_child = false;
-        std::vector<T> topic_vector;
+        ZeroArray<T> topic_vector;
         std::vector<int> term_indices;
         std::vector<unsigned int> docs;
     };
@@ -288,8 +323,10 @@ private:
     // left child <- W(:,0), right child <- W(:,1)   (tree.hpp:332-349)
     void TakeTopicVectors(const T* W)
     {
-        nodes_[index0_].topic_vector.assign(W, W + term_count_);
-        nodes_[index1_].topic_vector.assign(W + term_count_, W + 2 * static_cast<size_t>(term_count_));
+        nodes_[index0_].topic_vector.reset(term_count_);
+        nodes_[index1_].topic_vector.reset(term_count_);
+        std::copy(W, W + term_count_, nodes_[index0_].topic_vector.data());
+        std::copy(W + term_count_, W + 2 * static_cast<size_t>(term_count_), nodes_[index1_].topic_vector.data());
     }
 
     std::vector<NodeRec> nodes_;
