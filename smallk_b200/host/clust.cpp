@@ -694,22 +694,22 @@ struct Evaluator
 };
 
 // The worker threads' library contexts are made by the first Clust call on a device and kept for the later ones (creating and
-// destroying them is tens of milliseconds each way); NmfFinalize releases them (HierReleaseWorkers).
+// destroying two contexts is tens of milliseconds each way); NmfFinalize releases them (HierReleaseWorkers).
 struct WorkerContexts
 {
-    smk_ctx* ctx[3] = {nullptr, nullptr, nullptr};
+    smk_ctx* ctx[2] = {nullptr, nullptr};
     int device = -1;
     bool acquire(const int dev)
     {
-        if (device == dev && ctx[0] && ctx[1] && ctx[2]) return true;
+        if (device == dev && ctx[0] && ctx[1]) return true;
         release();
-        for (int w = 0; w < 3; ++w) if (smk_create(&ctx[w], dev) != SMK_OK) { ctx[w] = nullptr; release(); return false; }
+        for (int w = 0; w < 2; ++w) if (smk_create(&ctx[w], dev) != SMK_OK) { ctx[w] = nullptr; release(); return false; }
         device = dev;
         return true;
     }
     void release()
     {
-        for (int w = 0; w < 3; ++w) { if (ctx[w]) smk_destroy(ctx[w]); ctx[w] = nullptr; }
+        for (int w = 0; w < 2; ++w) { if (ctx[w]) smk_destroy(ctx[w]); ctx[w] = nullptr; }
         device = -1;
     }
 };
@@ -728,9 +728,9 @@ struct HierRun
     std::vector<R> Wsub, Hsub, Winit_full, Hinit_full, parent_scratch;
     int init_counter = 1;                      // Winit_<i>.csv / Hinit_<i>.csv, clust_hier_generic.hpp:586
     // Priority scores off the calling thread (SMK_HIER_ASYNC=0 turns it off): evaluator 0 is the calling thread's, 1 takes the
-    // left children's scores in turn with 3, 2 the right children's.
+    // left children's scores, 2 the right children's.
     bool async_on = true;
-    Evaluator eval[4];
+    Evaluator eval[3];
     // SMK_HIER_PROF=1: seconds of the driver's own host work per kind, on stderr when the run ends
     bool prof_on = false;
     double t_tree = 0, t_buffers = 0, t_labels = 0;
@@ -745,8 +745,8 @@ struct HierRun
         prof_on = pe && atoi(pe) != 0;
         eval[0].ctx = ctx;
         if (async_on && !g_workers.acquire(smk_device_index(ctx))) async_on = false;
-        if (async_on) for (int w = 1; w <= 3; ++w) eval[w].ctx = g_workers.ctx[w - 1];
-        for (int w = 0; w < (async_on ? 4 : 1); ++w) eval[w].dense.assign(static_cast<size_t>(m) * 2, R(0));
+        if (async_on) { eval[1].ctx = g_workers.ctx[0]; eval[2].ctx = g_workers.ctx[1]; }
+        for (int w = 0; w < (async_on ? 3 : 1); ++w) eval[w].dense.assign(static_cast<size_t>(m) * 2, R(0));
         // the log tables are grown here, on this thread, once: afterwards every thread only reads them
         g_logs.ensure(static_cast<int>(m));
         g_invd.ensure(static_cast<int>(m));
@@ -1007,25 +1007,24 @@ struct HierRun
         std::vector<Factor> node_factor(node_count);
         R min_priority = std::numeric_limits<R>::infinity(), max_priority = 0;
         unsigned int split_index = 0;
-        // Scores on their way. Both children's scores are evaluated on worker threads (left children on evaluators 1 and 3 in turn,
-        // right children on evaluator 2) while the calling thread goes on: to the right child's factorization, and then to the NEXT
-        // split, which is made ahead of time (see below) — so the two scores of a split have the next left child's factorization to
-        // run under, side by side.
-        PendingPriority pend_left, pend_right, pend_ahead;
+        // Scores on their way: the left child's on evaluator 1 (under the right child's factorization), the right child's on
+        // evaluator 2 (under the factorization of the NEXT split's left child, which is started ahead of time — see below).
+        PendingPriority pend_left, pend_right;
         unsigned int pend_left_node = 0, pend_right_node = 0;
-        int left_eval = 1;
-        int release_after = -1;                // the split node whose rows the pending scores of its children still read
-        auto release_split = [&]() {
-            // the factors of a node that has been split are never read again
-            if (release_after >= 0 && !pend_left.pending() && !pend_right.pending()) { node_factor[release_after].release(); release_after = -1; }
-        };
+        int release_after_right = -1;          // the split node whose rows the pending right-child score still reads
         auto finish_left = [&]() {
-            if (pend_left.pending()) { Stopwatch sw(stats.t_priority); tree.SetNodePriority(pend_left_node, pend_left.get()); }
-            release_split();
+            if (!pend_left.pending()) return;
+            Stopwatch sw(stats.t_priority);
+            tree.SetNodePriority(pend_left_node, pend_left.get());
         };
         auto finish_right = [&]() {
-            if (pend_right.pending()) { Stopwatch sw(stats.t_priority); tree.SetNodePriority(pend_right_node, pend_right.get()); }
-            release_split();
+            if (pend_right.pending())
+            {
+                Stopwatch sw(stats.t_priority);
+                tree.SetNodePriority(pend_right_node, pend_right.get());
+            }
+            // the factors of a node that has been split are never read again
+            if (release_after_right >= 0) { node_factor[release_after_right].release(); release_after_right = -1; }
         };
         auto split_leaf = [&](const unsigned int q) {
             Stopwatch sw(t_tree);
@@ -1050,7 +1049,7 @@ struct HierRun
                 }
                 i0 = tree.LeftChildIndex(); i1 = tree.RightChildIndex();
                 const ParentRows pr(0 == i ? root : node_factor[split_index]);      // both topic vectors are columns of the split node's W
-                const R p0 = trial_split(tree.LeftChildDocs(), plain_min, tree.LeftChildTopicVector().data(), pr, node_factor[i0], &pend_left, left_eval);
+                const R p0 = trial_split(tree.LeftChildDocs(), plain_min, tree.LeftChildTopicVector().data(), pr, node_factor[i0], &pend_left, 1);
                 if (pend_left.pending()) pend_left_node = i0; else tree.SetNodePriority(i0, p0);
             }
             ahead = false;
@@ -1059,20 +1058,19 @@ struct HierRun
                 const ParentRows pr(0 == i ? root : node_factor[split_index]);
                 const R p1 = trial_split(tree.RightChildDocs(), plain_min, tree.RightChildTopicVector().data(), pr, node_factor[i1], &pend_right, 2);
                 if (pend_right.pending()) pend_right_node = i1; else tree.SetNodePriority(i1, p1);
-                if (i > 0) release_after = static_cast<int>(split_index);
+                if (i > 0) release_after_right = static_cast<int>(split_index);
             }
+            finish_left();
             if (opts.verbose) { cout << "[" << (i + 1) << "] "; cout.flush(); }
 
-            // Ahead of time: while the children's scores are evaluated, the leaf that will be split next UNLESS one of those scores
-            // beats it (the best of all the other leaves, by the reference's scan and tie rule: a newer node loses a tie) is split
-            // and its left child factored. When the scores arrive they either confirm the choice — the work is exactly what the next
-            // iteration would have done, from the same generator state — or the tree, the generator and the counters are put back
-            // and the next iteration starts over.
-            if (!(async_on && (pend_left.pending() || pend_right.pending()) && i + 2 < num_clusters && opts.initdir.empty())) continue;
-            const unsigned int skip_l = pend_left.pending() ? i0 : Tree<R>::NONE, skip_r = pend_right.pending() ? i1 : Tree<R>::NONE;
+            // Ahead of time: while the right child's score is evaluated, the leaf that will be split next UNLESS that score beats it
+            // (the best of all the others, the reference's scan and tie rule) is split and its left child factored. When the
+            // score arrives it either confirms the choice — the work is exactly what the next iteration would have done, from the same
+            // generator state — or the tree, the generator and the counters are put back and the next iteration starts over.
+            if (!(async_on && pend_right.pending() && i + 2 < num_clusters && opts.initdir.empty())) continue;
             R min_wo = 0, max_wo = 0;
             unsigned int best = 0;
-            { Stopwatch sw(t_tree); tree.MinMaxLeafPrioritiesWithout(skip_l, skip_r, min_wo, max_wo, best); }
+            { Stopwatch sw(t_tree); tree.MinMaxLeafPrioritiesWithout(i1, Tree<R>::NONE, min_wo, max_wo, best); }
             if (max_wo < R(0)) continue;
             const Random saved_rng = rng;
             const int saved_nmf = stats.nmf_count, saved_max = stats.max_count;
@@ -1080,37 +1078,31 @@ struct HierRun
             speculations += 1;
             split_leaf(best);
             const unsigned int s0 = tree.LeftChildIndex(), s1 = tree.RightChildIndex();
-            const int ahead_eval = (left_eval == 1) ? 3 : 1;
             bool confirmed = false;
             R next_min = 0;
-            // the scores are in: was `best` the right leaf to split? if so, what MinMaxLeafPriorities would have found
+            // the right child's score is in: was `best` the right leaf to split? if so, what MinMaxLeafPriorities would have found
             auto confirm = [&]() {
                 if (confirmed) return next_min;
-                finish_left(); finish_right();
-                next_min = min_wo;
-                for (const unsigned int q : {skip_l, skip_r})
-                {
-                    if (q == Tree<R>::NONE) continue;
-                    const R pq = tree.NodePriority(q);
-                    if (pq > max_wo) throw MisSpeculated();
-                    if (pq > R(0) && pq < next_min) next_min = pq;
-                }
+                finish_right();
+                const R p1 = tree.NodePriority(i1);
+                if (p1 > max_wo) throw MisSpeculated();
+                next_min = (p1 > R(0) && p1 < min_wo) ? p1 : min_wo;
                 confirmed = true;
                 return next_min;
             };
             auto take_back = [&]() {
-                if (pend_ahead.pending()) { try { pend_ahead.get(); } catch (...) {} }
+                if (pend_left.pending()) { try { pend_left.get(); } catch (...) {} }
                 { Stopwatch sw(t_tree); tree.UndoSplit(best); }
                 node_factor[s0] = Factor();
                 rng = saved_rng;
                 stats.nmf_count = saved_nmf; stats.max_count = saved_max; stats.iteration_count = saved_iters;
                 misspeculations += 1;
             };
-            R p_ahead = 0;
             try
             {
                 const ParentRows pr(node_factor[best]);
-                p_ahead = trial_split(tree.LeftChildDocs(), confirm, tree.LeftChildTopicVector().data(), pr, node_factor[s0], &pend_ahead, ahead_eval);
+                const R p0 = trial_split(tree.LeftChildDocs(), confirm, tree.LeftChildTopicVector().data(), pr, node_factor[s0], &pend_left, 1);
+                if (pend_left.pending()) pend_left_node = s0; else tree.SetNodePriority(s0, p0);
                 confirm();
             }
             catch (MisSpeculated&) { take_back(); continue; }
@@ -1125,12 +1117,9 @@ struct HierRun
             ahead = true;
             split_index = best; i0 = s0; i1 = s1;
             min_priority = next_min; max_priority = max_wo;
-            left_eval = ahead_eval;
-            if (pend_ahead.pending()) { pend_left = std::move(pend_ahead); pend_ahead = PendingPriority(); pend_left_node = s0; }
-            else tree.SetNodePriority(s0, p_ahead);
         }
         finish_left(); finish_right();
-        stats.t_priority_worker += eval[1].busy_s + eval[2].busy_s + eval[3].busy_s;
+        stats.t_priority_worker += eval[1].busy_s + eval[2].busy_s;
         if (prof_on) fprintf(stderr, "hierclust driver: split loop %.3f s\n", seconds_since(t_loop0));
         smk_select_all(ctx);
         { Stopwatch sw(stats.t_terms); tree.ComputeTopTerms(opts.maxterms); }
