@@ -35,7 +35,7 @@ HOST_LIB_PATH = os.path.join(_HERE, "lib", "libsmallk_host.so")
 HOST_EXPORTS = ["smkh_last_error", "smkh_hierclust_sparse", "smkh_hierclust_dense", "smkh_flatclust", "smkh_compute_priority",
                 "smkh_last_hier_profile", "smkh_compute_priority_plain", "smkh_compute_priority_gpu", "smkh_compute_priority_rows", "smkh_compute_priority_rows2", "smkh_load_matrix_market",
                 "smkh_load_delimited", "smkh_write_delimited", "smkh_compute_assignments", "smkh_compute_fuzzy_assignments",
-                "smkh_top_terms_matrix", "smkh_random_matrices", "smkh_is_valid", "smkh_flatclust_write_results", "smkh_tree_script"]
+                "smkh_top_terms_matrix", "smkh_random_matrices", "smkh_is_valid", "smkh_flatclust_write_results", "smkh_tree_script", "smkh_tree_script_compact"]
 
 
 class SmallkError(RuntimeError):

@@ -299,7 +299,11 @@ int smkh_flatclust_write_results(const char* outdir, const unsigned int* assignm
 }
 
 // ---- the tree and its writers driven by a script (host/tree.hpp, hierclust_writer.hpp), same contract as oracle/ref_io_capi.cpp ----
-int smkh_tree_script(int seed, int m, int n, int num_clusters, int maxterms, int format, const char* assign_path, const char* tree_path)
+// compact != 0: the same script through the operations the hierclust driver uses — every split goes in with W held on its non-zero
+// rows only (SplitCompact), and before it another leaf (the next best one, if there is one) is split and taken back again
+// (UndoSplit), as the driver does when a split made ahead of time turns out wrong. The files must not change.
+static int tree_script(int seed, int m, int n, int num_clusters, int maxterms, int format, const char* assign_path, const char* tree_path,
+                       int compact)
 {
     // deterministic pseudo-random stream shared by both drivers (values in (0, 1), a quarter of them exactly 0)
     unsigned long long state = 0x9E3779B97F4A7C15ull * static_cast<unsigned long long>(seed + 1);
@@ -329,7 +333,24 @@ int smkh_tree_script(int seed, int m, int n, int num_clusters, int maxterms, int
         if (mx < 0.0) break;
         std::vector<double> Hs;
         fill(W, static_cast<size_t>(m) * 2); fill(Hs, static_cast<size_t>(doc_count[idx]) * 2);
-        tree.Split(idx, W.data(), Hs.data(), doc_count[idx]);
+        if (!compact) { tree.Split(idx, W.data(), Hs.data(), doc_count[idx]); continue; }
+        std::vector<unsigned int> rows;
+        std::vector<double> Wc;
+        for (int r = 0; r < m; ++r) if (W[r] != 0.0 || W[static_cast<size_t>(m) + r] != 0.0) rows.push_back(static_cast<unsigned int>(r));
+        Wc.resize(rows.size() * 2);
+        for (size_t r = 0; r < rows.size(); ++r) { Wc[r] = W[rows[r]]; Wc[rows.size() + r] = W[static_cast<size_t>(m) + rows[r]]; }
+        double mn2 = 0, mx2 = 0; unsigned int other = 0;
+        tree.MinMaxLeafPrioritiesWithout(idx, Tree<double>::NONE, mn2, mx2, other);
+        if (mx2 >= 0.0 && doc_count[other] > 0)
+        {
+            // a decoy: split the runner-up with some factors, look at its children, take it back
+            std::vector<double> Hd(static_cast<size_t>(doc_count[other]) * 2);
+            for (size_t q = 0; q < Hd.size(); ++q) Hd[q] = static_cast<double>((q * 7 + split) % 5);
+            tree.SplitCompact(other, rows.data(), static_cast<unsigned int>(rows.size()), Wc.data(), Hd.data(), doc_count[other]);
+            if (tree.LeftChildDocs().size() + tree.RightChildDocs().size() != doc_count[other]) return -3;
+            tree.UndoSplit(other);
+        }
+        tree.SplitCompact(idx, rows.data(), static_cast<unsigned int>(rows.size()), Wc.data(), Hs.data(), doc_count[idx]);
     }
     tree.ComputeTopTerms(maxterms);
     tree.ComputeAssignments();
@@ -340,6 +361,15 @@ int smkh_tree_script(int seed, int m, int n, int num_clusters, int maxterms, int
     const bool ok = tree.WriteTree(writer, std::string(tree_path), dict);
     delete writer;
     return ok ? 0 : -2;
+}
+
+int smkh_tree_script(int seed, int m, int n, int num_clusters, int maxterms, int format, const char* assign_path, const char* tree_path)
+{
+    return tree_script(seed, m, n, num_clusters, maxterms, format, assign_path, tree_path, 0);
+}
+int smkh_tree_script_compact(int seed, int m, int n, int num_clusters, int maxterms, int format, const char* assign_path, const char* tree_path)
+{
+    return tree_script(seed, m, n, num_clusters, maxterms, format, assign_path, tree_path, 1);
 }
 
 // dictionary files (host/flat_clust_output.hpp LoadStringsFromFile): the strings joined by '\n' into out (capacity cap)

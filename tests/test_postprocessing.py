@@ -182,3 +182,9 @@ def test_tree_and_its_writers_are_byte_identical(tmp_path, fmt):
         if complete:
             assert files[0][1] == files[1][1], ("tree", seed, fmt)
         assert len(files[0][1]) > 100
+        # the same script through the hierclust driver's own tree operations (SplitCompact: W on its non-zero rows; a decoy split
+        # taken back by UndoSplit before every real one): not a byte may change
+        a, t = tmp_path / f"compact_{seed}_{fmt}_assign.csv", tmp_path / f"compact_{seed}_{fmt}_tree.out"
+        rc = host.smkh_tree_script_compact(seed, m, n, clusters, maxterms, fmt, str(a).encode(), str(t).encode())
+        assert rc == 0, ("compact", seed, rc)
+        assert a.read_bytes() == files[1][0] and t.read_bytes() == files[1][1], ("compact", seed, fmt)
