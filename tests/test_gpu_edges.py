@@ -91,3 +91,20 @@ def test_sparse_gemm_on_input_with_empty_rows_and_columns_matches_oracle(gpu, or
             got = gpu.sparse_gemm(variant, alpha, B, beta, C)
             want = oracle.sparse_gemm(variant, alpha, (m, n), S.indptr, S.indices, S.data, B, beta, C)
             assert rel(got, want) < 1e-12
+
+
+@pytest.mark.parametrize("k,q,seed", [(8, 20, 1), (40, 90, 3), (100, 60, 4), (300, 40, 6)])
+def test_nnls_bpp_from_an_all_zero_warm_start_matches_oracle(gpu, oracle, k, q, seed):
+    """X0 = 0: every passive set starts empty (the case of zero initialisers read from a file; DESIGN.md section 7 — the oracle and
+    the reference reach the same solution from it, tests/test_oracle_golden.py). All three NNLS kernels (k <= 64, <= 256, any k)."""
+    rng = np.random.default_rng(seed)
+    W = rng.random((4 * k, k)); A = rng.random((4 * k, q))
+    LHS = W.T @ W
+    RHS = W.T @ A - 0.35 * rng.random((k, q)) * np.abs(W.T @ A).mean()
+    X0 = np.zeros((k, q))
+    rc, Xo, Yo = oracle.nnls_bpp(LHS, RHS, X0.copy())
+    assert rc == 0
+    X, Y = gpu.nnls_bpp(LHS, RHS, X0.copy())
+    assert np.array_equal(X > 0, Xo > 0)
+    assert rel(X, Xo) < 1e-9
+    assert np.abs(Y - Yo).max() <= 1e-8 * max(1.0, np.abs(Yo).max())

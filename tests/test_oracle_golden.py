@@ -124,3 +124,24 @@ def test_oracle_nnls_matches_reference_live(oracle):
         assert rc1 == rc2 == 0
         assert np.array_equal(X1 > 0, X2 > 0)
         assert rel(X1, X2) < 1e-10
+
+
+@needs_ref
+def test_all_zero_warm_start_reaches_the_reference_solution(oracle):
+    """X0 = 0 (zero initialisers read from a file): every passive set starts empty. The reference then takes its global branch —
+    the unconstrained solve for all columns while the BitMatrix stays empty (nmf_solver_bpp.hpp:174-178) — and pivots on the signs
+    of a residual that is rounding noise; the restatement (and the CUDA kernels) start such a column from x = 0 instead (DESIGN.md
+    section 7). The paths differ; the solution BPP converges to is the NNLS optimum either way: same support, same values."""
+    ref = Ref()
+    for k, q, seed in [(8, 20, 1), (16, 64, 2), (40, 90, 3), (100, 60, 4), (200, 30, 5)]:
+        rng = np.random.default_rng(seed)
+        W = rng.random((4 * k, k)); A = rng.random((4 * k, q))
+        LHS = W.T @ W
+        RHS = W.T @ A - 0.35 * rng.random((k, q)) * np.abs(W.T @ A).mean()
+        X0 = np.zeros((k, q))
+        rc1, X1, Y1 = oracle.nnls_bpp(LHS, RHS, X0.copy())
+        rc2, X2, Y2 = ref.nnls_bpp(LHS, RHS, X0.copy(), max_threads=1)
+        assert rc1 == rc2 == 0
+        assert np.array_equal(X1 > 0, X2 > 0)
+        assert rel(X1, X2) < 1e-10
+        assert np.abs(Y1 - Y2).max() <= 1e-9 * max(1.0, np.abs(Y2).max())
