@@ -14,6 +14,7 @@
 //                  test; a column that fails it (ill-conditioned G), or any solve when G^-1 could not be formed,
 //                  falls back to the direct method with the packed triangle in a per-CTA global scratch (L2).
 // The dual y = G x - b is always formed as the full product, as the reference does (nnls.hpp:168-169, 219-220).
+#include <cstdlib>
 #include "nnls_common.cuh"
 
 namespace smk {
@@ -299,18 +300,26 @@ __device__ __forceinline__ int max_row_index_ref_words(const unsigned int* w, in
     return (wd > 0) ? h - 32 : h;
 }
 
+// NMAX = the largest system solved in shared memory: 128 for k <= 256 (a passive set or its complement has at most 128 rows), 64 for
+// k <= 128 — there a CTA of 128 threads (one per row) and a 64 x 64 triangle leave room for six columns in flight per SM instead of
+// three (r02 ncu of the 128 / 256 form at k = 128, profiles/ncu_r02_c3_sparse_bpp_nnls_wide*.txt: 66 % of the stall samples were block
+// barriers, seven warps waiting for the one that factors a diagonal block; more columns per SM fill those slots), and a passive set of
+// more than 64 rows goes through its complement, which is the smaller system.
+constexpr int kWideRowj = 2 * kPBS;      // two published diagonal blocks of the blocked solve; also the scratch of the CTA-wide max reductions
+template <int NMAX>
 struct WideSmem
 {
-    int k;
-    __host__ __device__ size_t tri_doubles() const { return static_cast<size_t>(kWideNmax) * (kWideNmax + 1) / 2; }
-    __host__ __device__ size_t total_bytes() const
+    __host__ __device__ static constexpr size_t tri_doubles() { return static_cast<size_t>(NMAX) * (NMAX + 1) / 2; }
+    __host__ __device__ static constexpr size_t total_bytes()
     {
-        // U | rowj[144] | vb[128] | sb[256] | sx[256] | su[256] | list[256] shorts | words[64]   (75,136 bytes: 3 CTAs per SM)
-        return (tri_doubles() + 2 * kWideNmax + 16 + 3 * 256) * sizeof(double) + 256 * sizeof(unsigned short) + 64 * sizeof(unsigned int);
+        // U | rowj[144] | vb[NMAX] | sb[256] | sx[256] | su[256] | list[256] shorts | words[64]
+        // (NMAX = 128: 75,136 bytes, 3 CTAs per SM; NMAX = 64: 25,472 bytes)
+        return (tri_doubles() + kWideRowj + NMAX + 3 * 256) * sizeof(double) + 256 * sizeof(unsigned short) + 64 * sizeof(unsigned int);
     }
 };
 
-__global__ void __launch_bounds__(kWideThreads, 3)
+template <int NMAX, int THREADS>
+__global__ void __launch_bounds__(THREADS, (THREADS == 256 ? 3 : 6))
 nnls_bpp_wide_kernel(int k, int q, const double* __restrict__ G, long long ldg, const double* __restrict__ Ginv,
                      const int* __restrict__ ginv_flag, const double* __restrict__ RHS, long long ldr,
                      double* __restrict__ X, long long ldx, double* __restrict__ Y, long long ldy,
@@ -318,11 +327,11 @@ nnls_bpp_wide_kernel(int k, int q, const double* __restrict__ G, long long ldg, 
                      double* __restrict__ gscratch, size_t gscratch_stride)
 {
     extern __shared__ __align__(16) double smem[];
-    const WideSmem L{k};
+    using L = WideSmem<NMAX>;
     double* sU = smem;
-    double* s_rowj = sU + L.tri_doubles();
-    double* s_vb = s_rowj + kWideNmax + 16;     // s_rowj: 144 doubles (two published diagonal blocks of the blocked solve)
-    double* sb = s_vb + kWideNmax;
+    double* s_rowj = sU + L::tri_doubles();
+    double* s_vb = s_rowj + kWideRowj;
+    double* sb = s_vb + NMAX;
     double* sx = sb + 256;
     double* su = sx + 256;
     unsigned short* list = reinterpret_cast<unsigned short*>(su + 256);
@@ -362,7 +371,7 @@ nnls_bpp_wide_kernel(int k, int q, const double* __restrict__ G, long long ldg, 
         if (lane == 0) rowj[warp] = bmax;
         __syncthreads();
         bmax = 0.0;
-        for (int w = 0; w < 8; ++w) bmax = fmax(bmax, rowj[w]);
+        for (int w = 0; w < THREADS / 32; ++w) bmax = fmax(bmax, rowj[w]);
         __syncthreads();
 
         int P = kPbar, Ninf = k + 1, round = 0;
@@ -383,22 +392,22 @@ nnls_bpp_wide_kernel(int k, int q, const double* __restrict__ G, long long ldg, 
             const bool in = valid && ((myword >> lane) & 1u);
             const int pos_in = before + __popc(myword & ((1u << lane) - 1u));
             const int pos_out = t - pos_in;                 // rows t' < t that are not passive (t < k)
-            bool use_complement = (p > kWideNmax) && ginv_ok;
+            bool use_complement = (p > NMAX) && ginv_ok;
             bool solved = false;
 
             if (p == 0) { x = 0.0; solved = true; }
             while (!solved)
             {
-                if (p <= kWideNmax || !use_complement)
+                if (p <= NMAX || !use_complement)
                 {
                     // ---- direct: G_PP x_P = b_P
-                    const bool small = p <= kWideNmax;
+                    const bool small = p <= NMAX;
                     double* M = small ? sU : gU;
                     double* vb = small ? s_vb : g_vb;
                     __syncthreads();
                     if (in) list[pos_in] = t;
                     __syncthreads();
-                    for (int cc = warp; cc < p; cc += (kWideThreads >> 5))
+                    for (int cc = warp; cc < p; cc += (THREADS >> 5))
                     {
                         const double* gcol = G + static_cast<long long>(list[cc]) * ldg;
                         double* col = M + tri(cc);
@@ -430,7 +439,7 @@ nnls_bpp_wide_kernel(int k, int q, const double* __restrict__ G, long long ldg, 
                     __syncthreads();
                     if (valid && !in) list[pos_out] = t;
                     __syncthreads();
-                    for (int cc = warp; cc < na; cc += (kWideThreads >> 5))
+                    for (int cc = warp; cc < na; cc += (THREADS >> 5))
                     {
                         const double* gcol = Ginv + static_cast<long long>(list[cc]) * k;
                         double* col = sU + tri(cc);
@@ -467,7 +476,7 @@ nnls_bpp_wide_kernel(int k, int q, const double* __restrict__ G, long long ldg, 
                 }
             }
             y = s - b;
-            if (use_complement && p > kWideNmax)
+            if (use_complement && p > NMAX)
             {
                 // acceptance of the complement path: rounding-level residual on the passive rows
                 double res = in ? fabs(y) : 0.0;
@@ -477,13 +486,13 @@ nnls_bpp_wide_kernel(int k, int q, const double* __restrict__ G, long long ldg, 
                 if (lane == 0) rowj[warp] = res;
                 __syncthreads();
                 res = 0.0;
-                for (int w = 0; w < 8; ++w) res = fmax(res, rowj[w]);
+                for (int w = 0; w < THREADS / 32; ++w) res = fmax(res, rowj[w]);
                 if (!(res <= 1.0e-11 * bmax))
                 {
                     // redo this round with the direct method in global scratch (uniform decision)
                     __syncthreads();
                     double* M = gU;
-                    for (int cc = warp; cc < p; cc += (kWideThreads >> 5))
+                    for (int cc = warp; cc < p; cc += (THREADS >> 5))
                     {
                         const double* gcol = G + static_cast<long long>(list[cc]) * ldg;
                         double* col = M + tri(cc);
@@ -708,7 +717,7 @@ size_t nnls_wide_scratch_bytes(int k, int num_sms)
 {
     if (k <= 64) return 0;
     const size_t tri_k = static_cast<size_t>(k) * (k + 1) / 2;
-    return static_cast<size_t>(3 * num_sms) * (tri_k + 512) * sizeof(double) + 64;
+    return static_cast<size_t>((k <= 128 ? 6 : 3) * num_sms) * (tri_k + 512) * sizeof(double) + 64;
 }
 
 // G^-1 by one CTA working in global memory (k > 160: the matrix does not fit shared memory)
@@ -726,12 +735,25 @@ void nnls_bpp_wide(cudaStream_t stream, int k, int q, const double* LHS, long lo
     if (k > 256) throw std::string("nnls_bpp_wide: internal error (k > 256)");
     const size_t tri_k = static_cast<size_t>(k) * (k + 1) / 2;
     double* gscr = static_cast<double*>(scratch);
-    const int grid = std::min(3 * num_sms, q);
-    const WideSmem L{k};
-    const size_t smem = L.total_bytes();
-    SMK_CUDA(cudaFuncSetAttribute(nnls_bpp_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    nnls_bpp_wide_kernel<<<grid, kWideThreads, smem, stream>>>(k, q, LHS, ldl, Ginv, flag, RHS, ldr, X, ldx, Y, ldy, status,
-                                                              counter, outer_iter, gscr, tri_k + 512);
+    // SMK_NNLS_WIDE128=0: the 256-thread / 128 x 128 form for every k (A/B measurements; the tests run both)
+    const char* e = getenv("SMK_NNLS_WIDE128");
+    const bool narrow = k <= 128 && !(e && atoi(e) == 0);
+    if (narrow)
+    {
+        const int grid = std::min(6 * num_sms, q);
+        const size_t smem = WideSmem<64>::total_bytes();
+        auto kern = nnls_bpp_wide_kernel<64, 128>;
+        SMK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        kern<<<grid, 128, smem, stream>>>(k, q, LHS, ldl, Ginv, flag, RHS, ldr, X, ldx, Y, ldy, status, counter, outer_iter, gscr, tri_k + 512);
+    }
+    else
+    {
+        const int grid = std::min(3 * num_sms, q);
+        const size_t smem = WideSmem<128>::total_bytes();
+        auto kern = nnls_bpp_wide_kernel<128, 256>;
+        SMK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        kern<<<grid, 256, smem, stream>>>(k, q, LHS, ldl, Ginv, flag, RHS, ldr, X, ldx, Y, ldy, status, counter, outer_iter, gscr, tri_k + 512);
+    }
     SMK_LAUNCH_CHECK();
 }
 

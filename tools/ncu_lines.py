@@ -100,6 +100,10 @@ def main():
         why = max(stalls, key=lambda h: g(r, h))
         print(f"  {g(r, '# Samples'):8d} samples {g(r, 'Instructions Executed'):11d} exec  {r[ix['Source']].strip()[:64]:64s} ({why[6:]})")
     ins = line_table(lib, kernel)
+    if 0 < abs(len(ins) - len(data)) <= 2:
+        # nvdisasm and the report disagree about a trailing padding instruction or two: the common prefix is the same code
+        keep = min(len(ins), len(data))
+        ins, data = ins[:keep], data[:keep]
     if len(ins) != len(data):
         print(f"\n(the library's kernel has {len(ins)} SASS instructions, the report {len(data)}: not the profiled build, no per-line table)")
         return
