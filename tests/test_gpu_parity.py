@@ -115,6 +115,20 @@ def test_nnls_bpp_wide_mostly_passive_matches_oracle(gpu, oracle, k, q, frac, se
     assert np.abs(Y - Yo).max() <= 1e-8 * max(1.0, np.abs(Yo).max())
 
 
+@pytest.mark.parametrize("k,q,seed", [(100, 500, 8), (128, 150, 12)])
+def test_nnls_bpp_wide_256_thread_form_at_k_le_128_matches_oracle(gpu, oracle, k, q, seed, monkeypatch):
+    """SMK_NNLS_WIDE128=0: the 256-thread / 128 x 128 form of nnls_bpp_wide_kernel at 64 < k <= 128, where the other tests run the
+    128-thread / 64 x 64 form."""
+    monkeypatch.setenv("SMK_NNLS_WIDE128", "0")
+    LHS, RHS, X0 = _nnls_problem(k, q, seed)
+    rc, Xo, Yo = oracle.nnls_bpp(LHS, RHS, X0)
+    assert rc == 0
+    X, Y = gpu.nnls_bpp(LHS, RHS, X0)
+    assert np.array_equal(X > 0, Xo > 0)
+    assert rel(X, Xo) < 1e-10
+    assert np.abs(Y - Yo).max() <= 1e-9 * max(1.0, np.abs(Yo).max())
+
+
 def test_nnls_bpp_all_optimal_after_first_solve_keeps_tiny_values(gpu, oracle):
     """nnls.hpp:192,226-227: X,Y are zeroized only if some column was non-optimal."""
     k, q = 8, 16
