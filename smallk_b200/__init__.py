@@ -333,10 +333,11 @@ def _i(a):
 
 
 def hierclust(A_dense=None, csc=None, shape=None, num_clusters=4, tol=1e-4, min_iter=5, max_iter=5000, maxterms=5,
-              unbalanced=0.1, trial_allowance=3, flat=False, normalize=False, seed=1, verbose=False):
+              unbalanced=0.1, trial_allowance=3, flat=False, normalize=False, seed=1, verbose=False, lib=None):
     """HierNMF2 through the C++ host driver (host/clust.cpp): Clust for a dense array, ClustSparse for a
-    (col_offsets, row_indices, data) triple. Returns the tree as arrays, like oracle.Ref.hierclust."""
-    lib = load_host_library()
+    (col_offsets, row_indices, data) triple. Returns the tree as arrays, like oracle.Ref.hierclust.
+    lib: another build of the host library (tests/test_host_driver_cpu.py runs the driver over a CPU mock of the C ABI)."""
+    lib = lib or load_host_library()
     if csc is not None:
         m, n = shape
     else:
