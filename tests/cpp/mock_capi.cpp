@@ -7,6 +7,7 @@
 // smk_select_columns restates SubMatrixColsCompact (common/include/sparse_matrix_impl.hpp:479-591: the listed columns in list
 // order, rows left without entries dropped, the rest renumbered in ascending order; dense_matrix_impl.hpp:224-285: all rows kept).
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -151,10 +152,84 @@ int smk_sort_desc(smk_ctx* c, double* v, int n)
     return SMK_OK;
 }
 
-// NnlsHals (the flat-clustering step after the tree) is not restated in C: the CPU tests run the tree driver without it
-int smk_nnls_hals(smk_ctx* c, int, double*, int, double*, int, double, int, int*)
+// NnlsHals (common/include/nnls.hpp:249-316; the flat-clustering step after the tree, clust_flat_generic.hpp:33-74), restated
+// as in oracle/nnls_hals_oracle.py: W'W and W'A once; per iteration one HALS sweep over the rows of H (updated rows feed the later
+// ones, NaN / negative -> 0), gradH = W'W H - W'A, the projected-gradient norm; stop when it falls below tol times its first value,
+// then NormalizeAndScale(W, H).
+int smk_nnls_hals(smk_ctx* c, int k, double* W, int ldW, double* H, int ldH, double tol, int max_iter, int* iterations)
 {
-    return c ? fail(c, SMK_FAILURE, "NnlsHals is not part of the CPU mock") : SMK_BAD_PARAM;
+    if (!c || !W || !H || k <= 0 || max_iter <= 0) return SMK_BAD_PARAM;
+    const int m = c->sub ? c->am : c->m, n = c->sub ? c->an : c->n;
+    if (ldW < m || ldH < k) return fail(c, SMK_BAD_PARAM, "NnlsHals: non-conformant W and H");
+    std::vector<double> WtW(static_cast<size_t>(k) * k, 0.0), WtA(static_cast<size_t>(k) * n, 0.0);
+    for (int a = 0; a < k; ++a)
+        for (int b = 0; b < k; ++b)
+        {
+            double s = 0.0;
+            for (int i = 0; i < m; ++i) s += W[static_cast<size_t>(a) * ldW + i] * W[static_cast<size_t>(b) * ldW + i];
+            WtW[static_cast<size_t>(b) * k + a] = s;
+        }
+    for (int j = 0; j < n; ++j)
+    {
+        double* out = &WtA[static_cast<size_t>(j) * k];
+        if (c->dense)
+        {
+            const double* col = (c->sub ? c->subA.data() : c->A.data()) + static_cast<size_t>(j) * m;
+            for (int a = 0; a < k; ++a) { double s = 0.0; for (int i = 0; i < m; ++i) s += W[static_cast<size_t>(a) * ldW + i] * col[i]; out[a] = s; }
+        }
+        else
+        {
+            const unsigned* cp = c->sub ? c->scolp.data() : c->colp.data();
+            const unsigned* ri = c->sub ? c->srowi.data() : c->rowi.data();
+            const double* va = c->sub ? c->sval.data() : c->val.data();
+            for (unsigned e = cp[j]; e < cp[j + 1]; ++e)
+                for (int a = 0; a < k; ++a) out[a] += va[e] * W[static_cast<size_t>(a) * ldW + ri[e]];
+        }
+    }
+    double pg0 = 0.0;
+    for (int it = 0; it < max_iter; ++it)
+    {
+        for (int r = 0; r < k; ++r)
+            for (int j = 0; j < n; ++j)
+            {
+                double* h = H + static_cast<size_t>(j) * ldH;
+                double s = 0.0;
+                for (int p = 0; p < k; ++p) s += WtW[static_cast<size_t>(p) * k + r] * h[p];
+                double v = h[r] + (WtA[static_cast<size_t>(j) * k + r] - s) / WtW[static_cast<size_t>(r) * k + r];
+                if (!(v >= 0.0)) v = 0.0;
+                h[r] = v;
+            }
+        double sum = 0.0;
+        for (int j = 0; j < n; ++j)
+        {
+            const double* h = H + static_cast<size_t>(j) * ldH;
+            for (int r = 0; r < k; ++r)
+            {
+                double g = -WtA[static_cast<size_t>(j) * k + r];
+                for (int p = 0; p < k; ++p) g += WtW[static_cast<size_t>(p) * k + r] * h[p];
+                if (g < 0.0 || h[r] > 0.0) sum += g * g;
+            }
+        }
+        const double pg = std::sqrt(sum);
+        if (pg != pg) { if (iterations) *iterations = it + 1; return fail(c, SMK_FAILURE, "ProjectedGradientNorm: NaN"); }
+        if (it == 0) { pg0 = pg; continue; }
+        if (pg < tol * pg0)
+        {
+            if (iterations) *iterations = it + 1;
+            for (int a = 0; a < k; ++a)
+            {
+                double s = 0.0;
+                for (int i = 0; i < m; ++i) s += W[static_cast<size_t>(a) * ldW + i] * W[static_cast<size_t>(a) * ldW + i];
+                const double nr = std::sqrt(s);
+                if (nr < 2.220446049250313e-16) return fail(c, SMK_FAILURE, "Normalize: column norm < machine epsilon");
+                for (int i = 0; i < m; ++i) W[static_cast<size_t>(a) * ldW + i] /= nr;
+                for (int j = 0; j < n; ++j) H[static_cast<size_t>(j) * ldH + a] *= nr;
+            }
+            return SMK_OK;
+        }
+    }
+    if (iterations) *iterations = max_iter;
+    return fail(c, SMK_FAILURE, "NNLS solver reached iteration limit.");
 }
 
 } // extern "C"

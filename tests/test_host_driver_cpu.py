@@ -52,7 +52,7 @@ def check_tree(got, want, name):
     assert np.allclose(got["priority"], want["priority"], rtol=1e-4, atol=0), (name, got["priority"], want["priority"])
 
 
-CASES = [name for name in sorted(mh.HIER_CASES) if not mh.HIER_CASES[name][-1].get("flat")]
+CASES = sorted(mh.HIER_CASES)
 
 
 @pytest.mark.parametrize("workers", ["1", "0"])
@@ -63,6 +63,11 @@ def test_tree_driver_over_the_cpu_mock_grows_the_reference_tree(mock_host, name,
     z = np.load(os.path.join(HERE, "golden", name + ".npz"))
     got = sk.hierclust(A_dense=g["A"], csc=g["csc"], shape=g["shape"], num_clusters=g["num_clusters"], seed=g["seed"], lib=mock_host, **g["extra"])
     check_tree(got, z, name)
+    if g["extra"].get("flat"):
+        # HierNmf2WithFlat: the leaves' topic vectors as W, NnlsHals for H (the mock's restatement of it), flat assignments
+        assert np.array_equal(got["flat_assignments"], z["flat_assignments"])
+        assert np.linalg.norm(got["H"] - z["H"]) <= 1e-7 * np.linalg.norm(z["H"])
+        assert np.linalg.norm(got["W"] - z["W"]) <= 1e-9 * np.linalg.norm(z["W"])
 
 
 def test_tree_driver_over_the_cpu_mock_matches_live_reference_on_fresh_seeds(mock_host):
