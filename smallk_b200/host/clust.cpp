@@ -194,8 +194,13 @@ R compute_priority_plain(smk_ctx* ctx, const R* W_parent, const R* W_child, cons
 // --------------------------------------------------------------------------------------------------------------
 namespace {
 
+// the three ranks of a row side by side (one cache line per row where three arrays were three): rank among the parent's positive
+// entries (-1: the parent entry is not positive), rank in the ordering of child 1 / child 2
+struct RowRanks { int p, c1, c2, pad; };
+
 struct PriorityScratch
 {
+    std::vector<RowRanks> rr;
     std::vector<int> pos_p, pos_1, pos_2, pz_1, pz_2, other, rank_p, rank_1, rank_2, perm, tmp_i;
     std::vector<R> keys, wfull, wpart, wsort;
     std::vector<std::pair<R, int>> pairs;
@@ -458,7 +463,8 @@ R priority_rows_impl(smk_ctx* ctx, PriorityScratch& S, RowsScratch& Q, const boo
     Lap lap(timed);
     const R* P = W_parent; const R* C1 = W_child; const R* C2 = W_child + n;
     S.pos_p.clear(); S.pos_1.clear(); S.pos_2.clear(); S.pz_1.clear(); S.pz_2.clear(); S.other.clear();
-    if (static_cast<int>(S.rank_p.size()) < n) { S.rank_p.resize(n); S.rank_1.resize(n); S.rank_2.resize(n); }
+    if (static_cast<int>(S.rr.size()) < n) S.rr.resize(n);
+    RowRanks* const rr = S.rr.data();
     // U = non-zero rows of the parent vector, merged with the child's rows
     Q.pnz.clear();
     if (parent_rows) { for (int t = 0; t < n_parent_rows; ++t) { const int i = static_cast<int>(parent_rows[t]); if (P[i] != 0) Q.pnz.push_back(i); } }
@@ -489,9 +495,9 @@ R priority_rows_impl(smk_ctx* ctx, PriorityScratch& S, RowsScratch& Q, const boo
         if (!(pv >= 0) || !(av >= 0) || !(bv >= 0)) { regular = false; break; }
         const bool p = pv > 0, a = av > 0, b = bv > 0;
         if (p) S.pos_p.push_back(i);
-        if (a) S.pos_1.push_back(i); else { if (p || b) S.rank_1[i] = i - c1; if (p) S.pz_1.push_back(i); }
-        if (b) S.pos_2.push_back(i); else { if (p || a) S.rank_2[i] = i - c2; if (p) S.pz_2.push_back(i); }
-        if (!p && (a || b)) S.other.push_back(i);
+        if (a) S.pos_1.push_back(i); else { if (p || b) rr[i].c1 = i - c1; if (p) S.pz_1.push_back(i); }
+        if (b) S.pos_2.push_back(i); else { if (p || a) rr[i].c2 = i - c2; if (p) S.pz_2.push_back(i); }
+        if (!p && (a || b)) { S.other.push_back(i); rr[i].p = -1; }
         Q.allzero[t] = (!p && !a && !b) ? 1 : 0;
         if (a) ++c1;
         if (b) ++c2;
@@ -514,55 +520,57 @@ R priority_rows_impl(smk_ctx* ctx, PriorityScratch& S, RowsScratch& Q, const boo
     const std::vector<double>& lg2 = g_logs.lg2;
     const double* invd = g_invd.inv.data();
     auto discount_of = [&](const int worst) { const R d = ln[n - worst]; return d == 0 ? ln[2] : d; };
-    for (const int row : S.pz_1) S.rank_1[row] += n1;
-    for (const int row : S.pz_2) S.rank_2[row] += n2;
+    for (const int row : S.pz_1) rr[row].c1 += n1;
+    for (const int row : S.pz_2) rr[row].c2 += n2;
     for (const int row : S.other)
     {
-        if (!(C1[row] > 0)) S.rank_1[row] += n1;
-        if (!(C2[row] > 0)) S.rank_2[row] += n2;
+        if (!(C1[row] > 0)) rr[row].c1 += n1;
+        if (!(C2[row] > 0)) rr[row].c2 += n2;
     }
     lap.mark(1);
     sort_rows_desc(P, S.pos_p, ctx, S);
     sort_rows_desc(C1, S.pos_1, ctx, S);
     sort_rows_desc(C2, S.pos_2, ctx, S);
     lap.mark(2);
-    for (int q = 0; q < np; ++q) S.rank_p[S.pos_p[q]] = q;
-    for (int q = 0; q < n1; ++q) S.rank_1[S.pos_1[q]] = q;
-    for (int q = 0; q < n2; ++q) S.rank_2[S.pos_2[q]] = q;
+    for (int q = 0; q < np; ++q) rr[S.pos_p[q]].p = q;
+    for (int q = 0; q < n1; ++q) rr[S.pos_1[q]].c1 = q;
+    for (int q = 0; q < n2; ++q) rr[S.pos_2[q]].c2 = q;
 
     S.wfull.resize(static_cast<size_t>(np) + S.other.size()); S.wpart.resize(np);
     for (int i = 0; i < np; ++i)
     {
         const int row = S.pos_p[i];
-        const R d = discount_of(std::max(S.rank_1[row], S.rank_2[row]));
+        const R d = discount_of(std::max(rr[row].c1, rr[row].c2));
         S.wfull[i] = ln[n - i] / d;
         S.wpart[i] = ln[n_part - i] / d;
     }
     for (size_t u = 0; u < S.other.size(); ++u)
     {
         const int row = S.other[u];
-        S.wfull[np + u] = R(1) / discount_of(std::max(S.rank_1[row], S.rank_2[row]));
+        S.wfull[np + u] = R(1) / discount_of(std::max(rr[row].c1, rr[row].c2));
     }
-    auto dcg = [&](const std::vector<int>& pos, const std::vector<int>& pz, const std::vector<int>& rank_c, const R* Pv) {
+    // a row of a child's ordering counts where the parent entry is positive (p >= 0: "other" rows were marked -1 above)
+    auto dcg = [&](const std::vector<int>& pos, const std::vector<int>& pz, int RowRanks::*rank_c) {
         R cum = 0;
         const int cnt = static_cast<int>(pos.size());
         for (int q = 0; q < cnt; ++q)
         {
-            const int row = pos[q];
-            if (!(Pv[row] > 0)) continue;
-            const R g = S.wpart[S.rank_p[row]];
+            const int rp = rr[pos[q]].p;
+            if (rp < 0) continue;
+            const R g = S.wpart[rp];
             cum = q == 0 ? g : cum + g / lg2[q + 1];
         }
         for (const int row : pz)
         {
-            const int q = rank_c[row];
-            const R g = S.wpart[S.rank_p[row]];
+            const RowRanks& x = rr[row];
+            const int q = x.*rank_c;
+            const R g = S.wpart[x.p];
             cum = q == 0 ? g : cum + g / lg2[q + 1];
         }
         return cum;
     };
-    const R dcg1 = dcg(S.pos_1, S.pz_1, S.rank_1, P);
-    const R dcg2 = dcg(S.pos_2, S.pz_2, S.rank_2, P);
+    const R dcg1 = dcg(S.pos_1, S.pz_1, &RowRanks::c1);
+    const R dcg2 = dcg(S.pos_2, S.pz_2, &RowRanks::c2);
 
     lap.mark(3);
     // ideal score: sorted irregular weights merged with the all-zero rows' weights, last row first
